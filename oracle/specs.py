@@ -1,0 +1,376 @@
+"""
+TEST INFRASTRUCTURE (oracle).  The BASELINE.json configs as term-table specs.
+
+Each spec is a plain dict transcribed from the `config()` method of the reference example it names
+(the examples ARE the benchmark definitions).  The same spec drives
+  * oracle/env_builder.py  -> a ManagedEnvironment built from the reference's (or the drop-in's)
+                              own manager classes and mdp functions,
+  * oracle/manager_port.py -> the torch-CPU oracle port.
+Manager references inside params are written "@<manager name>".
+"""
+from __future__ import annotations
+
+import copy
+
+GO2_JOINTS = ["FL_.*_joint", "FR_.*_joint", "RL_.*_joint", "RR_.*_joint"]
+GO2_DEFAULT_POS = {
+    ".*_hip_joint": 0.0,
+    "FL_thigh_joint": 0.8,
+    "FR_thigh_joint": 0.8,
+    "RL_thigh_joint": 1.0,
+    "RR_thigh_joint": 1.0,
+    ".*_calf_joint": -1.5,
+}
+INITIAL_POS = [0.0, 0.0, 0.4]
+INITIAL_QUAT = [1.0, 0.0, 0.0, 0.0]
+
+_RESET_FIXED = {
+    "position": {
+        "fn": "position",
+        "params": {"position": INITIAL_POS, "quat": INITIAL_QUAT, "zero_velocity": True},
+    }
+}
+
+_OBS_48 = {
+    "velocity_cmd": {"fn": "command", "mgr": "velocity_command"},
+    "angle_velocity": {"fn": "ang_vel"},
+    "linear_velocity": {"fn": "lin_vel"},
+    "projected_gravity": {"fn": "gravity"},
+    "dof_position": {"fn": "dof_pos"},
+    "dof_velocity": {"fn": "dof_vel", "scale": 0.05},
+    "actions": {"fn": "actions"},
+}
+
+_EM = "@robot_manager"
+_VC = "@velocity_command"
+_AM = "@action_manager"
+
+
+def _track(weight_lin, weight_ang):
+    return {
+        "tracking_lin_vel": {
+            "fn": "command_tracking_lin_vel", "weight": weight_lin,
+            "params": {"vel_cmd_manager": _VC, "entity_manager": _EM},
+        },
+        "tracking_ang_vel": {
+            "fn": "command_tracking_ang_vel", "weight": weight_ang,
+            "params": {"vel_cmd_manager": _VC, "entity_manager": _EM},
+        },
+    }
+
+
+def simple() -> dict:
+    """examples/simple/environment.py:96-243 (config 1; fixed target command, no command manager)."""
+    return {
+        "name": "simple", "robot": "go2", "dt": 1 / 50,
+        "max_episode_length_sec": 20, "max_episode_random_scaling": 0.1,
+        "fixed_command": [0.5, 0.0, 0.0],
+        "entity": {"on_reset": _RESET_FIXED},
+        "action": {
+            "type": "position", "joint_names": GO2_JOINTS, "default_pos": GO2_DEFAULT_POS,
+            "scale": 0.25, "clip": (-100.0, 100.0), "use_default_offset": True, "pd_kp": 20, "pd_kv": 0.5,
+        },
+        "commands": {},
+        "contacts": {},
+        "rewards": {
+            "base_height_target": {
+                "fn": "base_height", "weight": -50.0, "params": {"target_height": 0.3, "entity_attr": "robot"},
+            },
+            "tracking_lin_vel": {
+                "fn": "command_tracking_lin_vel", "weight": 1.0,
+                "params": {"command": "@fixed_command[:, :2]", "entity_manager": _EM},
+            },
+            "tracking_ang_vel": {
+                "fn": "command_tracking_ang_vel", "weight": 0.2,
+                "params": {"commanded_ang_vel": "@fixed_command[:, 2]", "entity_manager": _EM},
+            },
+            "lin_vel_z": {"fn": "lin_vel_z_l2", "weight": -1.0, "params": {"entity_manager": _EM}},
+            "action_rate": {"fn": "action_rate_l2", "weight": -0.005},
+            "similar_to_default": {"fn": "dof_similar_to_default", "weight": -0.1, "params": {"action_manager": _AM}},
+        },
+        "terminations": {
+            "timeout": {"fn": "timeout", "time_out": True},
+            "fall_over": {"fn": "bad_orientation", "params": {"limit_angle": 10.0, "entity_manager": _EM}},
+        },
+        "observations": {
+            "policy": {
+                "terms": {
+                    "angle_velocity": {"fn": "ang_vel", "scale": 0.25},
+                    "linear_velocity": {"fn": "lin_vel", "scale": 2.0},
+                    "projected_gravity": {"fn": "gravity"},
+                    "dof_position": {"fn": "dof_pos"},
+                    "dof_velocity": {"fn": "dof_vel", "scale": 0.05},
+                    "actions": {"fn": "actions"},
+                }
+            }
+        },
+    }
+
+
+def command_direction() -> dict:
+    """examples/command_direction/environment.py:85-247 (config 2)."""
+    return {
+        "name": "command_direction", "robot": "go2", "dt": 1 / 50,
+        "max_episode_length_sec": 20, "max_episode_random_scaling": 0.1,
+        "entity": {"on_reset": _RESET_FIXED},
+        "action": {
+            "type": "position", "joint_names": GO2_JOINTS, "default_pos": GO2_DEFAULT_POS,
+            "scale": 0.25, "use_default_offset": True, "pd_kp": 20, "pd_kv": 0.5,
+        },
+        "commands": {
+            "velocity_command": {
+                "type": "velocity",
+                "range": {"lin_vel_x": [-1.0, 1.0], "lin_vel_y": [-1.0, 1.0], "ang_vel_z": [-1.0, 1.0]},
+                "standing_probability": 0.02, "resample_time_sec": 5.0,
+            }
+        },
+        "contacts": {},
+        "rewards": {
+            "base_height_target": {
+                "fn": "base_height", "weight": -50.0, "params": {"target_height": 0.3, "entity_attr": "robot"},
+            },
+            **_track(1.0, 0.5),
+            "lin_vel_z": {"fn": "lin_vel_z_l2", "weight": -1.0, "params": {"entity_manager": _EM}},
+            "action_rate": {"fn": "action_rate_l2", "weight": -0.005},
+            "similar_to_default": {"fn": "dof_similar_to_default", "weight": -0.1, "params": {"action_manager": _AM}},
+        },
+        "terminations": {
+            "timeout": {"fn": "timeout", "time_out": True},
+            "fall_over": {"fn": "bad_orientation", "params": {"limit_angle": 10.0, "entity_manager": _EM}},
+        },
+        "observations": {"policy": {"terms": copy.deepcopy(_OBS_48)}},
+    }
+
+
+def contacts() -> dict:
+    """examples/contacts/environment.py:89-272 (config 3a)."""
+    return {
+        "name": "contacts", "robot": "go2", "dt": 1 / 50,
+        "max_episode_length_sec": 20, "max_episode_random_scaling": 0.1,
+        "entity": {"on_reset": _RESET_FIXED},
+        "action": {
+            "type": "position", "joint_names": GO2_JOINTS, "default_pos": GO2_DEFAULT_POS,
+            "scale": 0.5, "use_default_offset": True, "pd_kp": 20, "pd_kv": 0.5,
+        },
+        "commands": {
+            "velocity_command": {
+                "type": "velocity",
+                "range": {"lin_vel_x": [-1.0, 1.0], "lin_vel_y": [0.0, 0.0], "ang_vel_z": [-0.5, 0.5]},
+                "standing_probability": 0.02, "resample_time_sec": 5.0,
+            }
+        },
+        "contacts": {
+            "foot_contact_manager": {
+                "link_names": [".*_calf"], "track_air_time": True, "air_time_contact_threshold": 5.0,
+            }
+        },
+        "rewards": {
+            "foot_air_time": {
+                "fn": "feet_air_time", "weight": 2.5,
+                "params": {"contact_manager": "@foot_contact_manager", "vel_cmd_manager": _VC, "time_threshold": 0.5},
+            },
+            **_track(1.0, 0.5),
+            "lin_vel_z": {"fn": "lin_vel_z_l2", "weight": -1.0, "params": {"entity_manager": _EM}},
+            "ang_vel_xy": {"fn": "ang_vel_xy_l2", "weight": -0.05, "params": {"entity_manager": _EM}},
+            "action_rate": {"fn": "action_rate_l2", "weight": -0.005},
+            "similar_to_default": {"fn": "dof_similar_to_default", "weight": -0.1, "params": {"action_manager": _AM}},
+            "flat_orientation": {"fn": "flat_orientation_l2", "weight": -2.5},
+        },
+        "terminations": {
+            "timeout": {"fn": "timeout", "time_out": True},
+            "fall_over": {"fn": "bad_orientation", "params": {"limit_angle": 20.0, "entity_manager": _EM}},
+        },
+        "observations": {"policy": {"terms": copy.deepcopy(_OBS_48)}},
+    }
+
+
+def rough_terrain() -> dict:
+    """examples/rough_terrain/environment.py:86-321 (config 4)."""
+    return {
+        "name": "rough_terrain", "robot": "go2", "dt": 1 / 50,
+        "max_episode_length_sec": 20, "max_episode_random_scaling": 0.1,
+        "terrain": {
+            "pos": (-12.0, -12.0, 0.0), "n_subterrains": (1, 1), "subterrain_size": (24.0, 24.0),
+            "vertical_scale": 0.001,
+        },
+        "xy_range": 12.5,
+        "entity": {
+            "on_reset": {
+                "position": {
+                    "fn": "randomize_terrain_position",
+                    "params": {"height_offset": 0.4, "terrain_manager": "@terrain_manager"},
+                }
+            }
+        },
+        "action": {
+            "type": "position", "joint_names": GO2_JOINTS, "default_pos": GO2_DEFAULT_POS,
+            "scale": 0.25, "use_default_offset": True, "pd_kp": 20, "pd_kv": 0.5, "max_force": 23.5,
+        },
+        "commands": {
+            "velocity_command": {
+                "type": "velocity",
+                "range": {"lin_vel_x": [-1.0, 1.0], "lin_vel_y": [-1.0, 1.0], "ang_vel_z": [-0.5, 0.5]},
+                "standing_probability": 0.05, "resample_time_sec": 5.0,
+            }
+        },
+        "contacts": {
+            "foot_contact_manager": {
+                "link_names": [".*_calf"], "track_air_time": True, "air_time_contact_threshold": 5.0,
+            },
+            "undesired_contacts": {"link_names": [".*_thigh", "base"]},
+        },
+        "rewards": {
+            **_track(1.5, 0.75),
+            "lin_vel_z": {"fn": "lin_vel_z_l2", "weight": -2.0, "params": {"entity_manager": _EM}},
+            "ang_vel_xy": {"fn": "ang_vel_xy_l2", "weight": -0.05, "params": {"entity_manager": _EM}},
+            "undesired_contacts": {
+                "fn": "has_contact", "weight": -1.0,
+                "params": {"contact_manager": "@undesired_contacts", "threshold": 5.0},
+            },
+            "action_rate": {"fn": "action_rate_l2", "weight": -0.01},
+            "similar_to_default": {"fn": "dof_similar_to_default", "weight": -0.1, "params": {"action_manager": _AM}},
+            "flat_orientation": {"fn": "flat_orientation_l2", "weight": -1.5},
+            "terminated": {"fn": "terminated", "weight": -100.0},
+        },
+        "terminations": {
+            "timeout": {"fn": "timeout", "time_out": True},
+            "out_of_bounds": {"fn": "out_of_bounds", "params": {"terrain_manager": "@terrain_manager"}},
+            "bad_orientation": {
+                "fn": "bad_orientation",
+                "params": {"limit_angle": 30.0, "entity_manager": _EM, "grace_steps": 20},
+            },
+        },
+        "observations": {"policy": {"terms": copy.deepcopy(_OBS_48)}},
+    }
+
+
+def berkeley_humanoid() -> dict:
+    """examples/berkeley_humanoid/environment.py:85-274 (config 5)."""
+    return {
+        "name": "berkeley_humanoid", "robot": "berkeley_humanoid", "dt": 1 / 50,
+        "max_episode_length_sec": 20, "max_episode_random_scaling": 0.1,
+        "entity": {
+            "on_reset": {
+                "position": {
+                    "fn": "position",
+                    "params": {"position": [0.0, 0.0, 0.55], "quat": INITIAL_QUAT, "zero_velocity": True},
+                }
+            }
+        },
+        "action": {
+            "type": "position", "joint_names": [".*"],
+            "default_pos": {
+                "LL_HR": -0.071, "LR_HR": 0.071, "LL_HAA": 0.103, "LR_HAA": -0.103,
+                "LL_HFE": -0.463, "LR_HFE": -0.463, "LL_KFE": 0.983, "LR_KFE": 0.983,
+                "LL_FFE": -0.350, "LR_FFE": -0.350, "LL_FAA": 0.126, "LR_FAA": -0.126,
+            },
+            "scale": 0.5, "use_default_offset": True, "pd_kp": 15.0, "pd_kv": 1.0,
+            "max_force": {".*_HR": 20.0, ".*_HAA": 20.0, ".*_HFE": 30.0, ".*_KFE": 30.0, ".*_FFE": 20.0, ".*_FAA": 5.0},
+        },
+        "commands": {
+            "velocity_command": {
+                "type": "velocity",
+                "range": {"lin_vel_x": [0.0, 1.0], "lin_vel_y": [0.0, 0.0], "ang_vel_z": [-0.5, 0.5]},
+                "standing_probability": 0.02, "resample_time_sec": 5.0,
+            }
+        },
+        "contacts": {
+            "torso_contact_manager": {"link_names": ["torso"]},
+            "feet_contact_manager": {"link_names": [".*_faa"], "track_air_time": True},
+        },
+        "rewards": {
+            **_track(1.0, 0.5),
+            "lin_vel_z": {"fn": "lin_vel_z_l2", "weight": -2.0, "params": {"entity_manager": _EM}},
+            "ang_vel_xy_l2": {"fn": "ang_vel_xy_l2", "weight": -0.05, "params": {"entity_manager": _EM}},
+            "action_rate": {"fn": "action_rate_l2", "weight": -0.005},
+            "similar_to_default": {"fn": "dof_similar_to_default", "weight": -0.05, "params": {"action_manager": _AM}},
+            "feet_air_time": {
+                "fn": "feet_air_time", "weight": 2.0,
+                "params": {
+                    "time_threshold": 0.2, "time_threshold_max": 0.5,
+                    "contact_manager": "@feet_contact_manager", "vel_cmd_manager": _VC,
+                },
+            },
+        },
+        "terminations": {
+            "timeout": {"fn": "timeout", "time_out": True},
+            "torso_contact": {"fn": "contact_force", "params": {"contact_manager": "@torso_contact_manager"}},
+        },
+        "observations": {"policy": {"terms": copy.deepcopy(_OBS_48)}},
+    }
+
+
+def kitchen_sink() -> dict:
+    """
+    Not a BASELINE config: a Go2 table that exercises every remaining mdp term of SURVEY.md 8(a)
+    (is_alive, stand_still, contact_force reward, feet_slide, base_height_below_minimum, has_contact
+    / contact_force_with_grace_period terminations, observation noise + history, dof_force and
+    contact-force observations, a with-entity contact filter, a height command, action delay).
+    """
+    s = contacts()
+    s["name"] = "kitchen_sink"
+    s["action"]["delay_step"] = 2
+    s["action"]["noise_scale"] = 0.05
+    s["commands"]["height_command"] = {"type": "uniform", "range": (0.25, 0.35), "resample_time_sec": 3.0}
+    s["contacts"]["thigh_ground"] = {"link_names": [".*_thigh"], "with_entity_attr": "terrain"}
+    s["contacts"]["body"] = {"link_names": ["base", ".*_hip"], "with_links_names": [".*_calf", ".*_foot"]}
+    s["rewards"].update({
+        "alive": {"fn": "is_alive", "weight": 0.5},
+        "height_cmd": {
+            "fn": "base_height", "weight": -10.0,
+            "params": {"height_command": "@height_command", "entity_manager": _EM},
+        },
+        "stand_still": {
+            "fn": "stand_still_joint_deviation_l1", "weight": -0.2,
+            "params": {"command_threshold": 0.3, "vel_cmd_manager": _VC, "action_manager": _AM},
+        },
+        "thigh_force": {
+            "fn": "contact_force", "weight": -0.01,
+            "params": {"contact_manager": "@thigh_ground", "threshold": 2.0},
+        },
+        "feet_slide": {"fn": "feet_slide", "weight": -0.1, "params": {"contact_manager": "@foot_contact_manager"}},
+        "zero_weight": {"fn": "lin_vel_z_l2", "weight": 0.0, "params": {"entity_manager": _EM}},
+    })
+    s["terminations"].update({
+        "too_low": {"fn": "base_height_below_minimum", "params": {"minimum_height": 0.24, "entity_manager": _EM}},
+        "body_hit": {
+            "fn": "has_contact", "params": {"contact_manager": "@body", "threshold": 40.0, "min_contacts": 2},
+        },
+        "thigh_hit": {
+            "fn": "contact_force_with_grace_period",
+            "params": {"contact_manager": "@thigh_ground", "threshold": 90.0, "grace_steps": 5},
+        },
+    })
+    terms = s["observations"]["policy"]["terms"]
+    terms["angle_velocity"]["noise"] = 0.1
+    terms["dof_position"]["noise"] = 0.01
+    terms["dof_force"] = {"fn": "dof_force", "scale": 0.1}
+    terms["foot_force"] = {"fn": "contact_force", "mgr": "foot_contact_manager", "scale": 0.01}
+    terms["height_cmd"] = {"fn": "command", "mgr": "height_command"}
+    # (mdp.observations.current_actions without an action manager cannot be used: env.actions is
+    #  still None during ObservationManager.build()'s dry run in the reference.)
+    terms["actions2"] = {"fn": "current_actions"}
+    s["observations"]["policy"]["history_len"] = 3
+    s["observations"]["critic"] = {
+        "noise": 0.02,
+        "terms": {
+            "linear_velocity": {"fn": "lin_vel"},
+            "projected_gravity": {"fn": "gravity", "noise": 0.05},
+            "dof_velocity": {"fn": "dof_vel", "scale": 0.05, "noise": 0.0},
+        },
+    }
+    return s
+
+
+ALL = {
+    "simple": simple,
+    "command_direction": command_direction,
+    "contacts": contacts,
+    "rough_terrain": rough_terrain,
+    "berkeley_humanoid": berkeley_humanoid,
+    "kitchen_sink": kitchen_sink,
+}
+
+
+def get(name: str) -> dict:
+    return ALL[name]()
