@@ -424,8 +424,10 @@ class SyntheticScene:
         source: Callable[[int], dict] | None = None,
         copy_on_get: bool = False,
         pool: int = 0,
+        source_kw: dict | None = None,
     ):
         self.dt = dt
+        self._source_kw = source_kw or {}
         self.n_contacts = n_contacts
         self.seed = seed
         self.device = torch.device(device) if device is not None else gs.device
@@ -461,7 +463,7 @@ class SyntheticScene:
         assert self.robot is not None, "add_robot() first"
         self.n_envs = n_envs
         if self._source is None:
-            self._source = StateSource(self.robot.model, n_envs, self.n_contacts, self.seed)
+            self._source = StateSource(self.robot.model, n_envs, self.n_contacts, self.seed, **self._source_kw)
         self.envs_offset = torch.zeros(n_envs, 3, device=self.device)
         if self.pool_size > 0:
             self._pool = [self._to_device(self._source(k)) for k in range(self.pool_size)]

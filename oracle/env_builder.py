@@ -62,6 +62,7 @@ def make_scene(spec: dict, device, source=None, copy_on_get=False, n_contacts=8,
     scene = SyntheticScene(
         dt=spec["dt"], n_contacts=n_contacts, seed=seed, device=device, source=source,
         copy_on_get=copy_on_get, pool=pool,
+        source_kw={"xy_range": spec["xy_range"]} if "xy_range" in spec else None,
     )
     if "terrain" in spec:
         terrain = scene.add_terrain(**spec["terrain"])
@@ -89,6 +90,10 @@ def build_env(spec: dict, ns, num_envs: int, device, **scene_kw):
                     self.fixed_command[:, i] = v
 
         # ---- helpers --------------------------------------------------------------------------
+        def managers_by_name(self, kind):
+            """Attribute names of the command / contact managers, in creation order."""
+            return list(spec["commands" if kind == "command" else "contacts"].keys())
+
         def _resolve(self, value):
             if isinstance(value, str) and value.startswith("@"):
                 ref = value[1:]
