@@ -1,0 +1,401 @@
+// Pre-physics action kernel, finalize (ordered compaction + logging reductions), the sparse
+// re-observation kernel and the stand-alone contact scatter.
+#pragma once
+#include "device_utils.cuh"
+#include "plan.h"
+
+namespace gfb {
+
+// ---------------------------------------------------------------------------------------------
+// action_kernel: GenesisEnv.step bookkeeping + action manager (pre-physics)
+//   genesis_env.py:196       episode_length += 1
+//   genesis_env.py:202-203   last_actions <- actions ; actions <- raw
+//   position_action_manager.py:402-414   NaN/Inf flags; t = a*scale + offset; clamp(lo, hi)
+//   position_within_limits.py:125-126    clamp(a,-1,1) * scale + offset
+//   rewards.py:267-271       action_rate = sum((last_actions - actions)^2)   (consumed post-physics)
+// One slab of TILE envs per block: the raw and previous action slabs are contiguous -> TMA in;
+// last_actions / actions are pure copies -> TMA out of the very same shared-memory slabs.
+// ---------------------------------------------------------------------------------------------
+struct ActionParams {
+  gfb_program_head P;
+  const float* raw_env;
+  const float* raw_mgr;  // == raw_env unless a delay FIFO is active
+  float* env_actions;
+  float* env_last_actions;
+  float* targets;
+  float* action_rate;
+  int32_t* episode_length;
+  uint32_t* status;
+  int32_t tma_ok;
+  int32_t check_finite;
+};
+
+template <int TILE>
+__global__ void __launch_bounds__(TILE) action_kernel(const __grid_constant__ ActionParams A) {
+  extern __shared__ __align__(128) float S[];
+  __shared__ __align__(8) uint64_t bar;
+  const gfb_program_head& P = A.P;
+  const int tid = threadIdx.x;
+  const int N = P.num_envs, D = P.num_dofs;
+  const int e0 = blockIdx.x * TILE;
+  const int valid = min(TILE, N - e0);
+  const bool active = tid < valid;
+  const int e = e0 + tid;
+  const bool use_tma = A.tma_ok && valid == TILE;
+  const bool two_raw = A.raw_mgr != A.raw_env;
+
+  float* s_raw = S;                   // (TILE, D) raw env actions
+  float* s_prev = S + TILE * D;       // (TILE, D) previous env.actions
+  float* s_tgt = S + 2 * TILE * D;    // (TILE, D) targets out
+  float* s_rawm = S + 3 * TILE * D;   // (TILE, D) delayed raw (only with a FIFO)
+  const uint32_t slab_bytes = (uint32_t)TILE * D * 4u;
+  const size_t goff = (size_t)e0 * D;
+
+  if (use_tma) {
+    if (tid == 0) {
+      mbar_init(&bar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&bar, slab_bytes * (two_raw ? 3u : 2u));
+      bulk_load(s_raw, A.raw_env + goff, slab_bytes, &bar);
+      bulk_load(s_prev, A.env_actions + goff, slab_bytes, &bar);
+      if (two_raw) bulk_load(s_rawm, A.raw_mgr + goff, slab_bytes, &bar);
+    }
+  } else {
+    const int words = valid * D;
+    for (int w = tid; w < words; w += TILE) {
+      s_raw[w] = A.raw_env[goff + w];
+      s_prev[w] = A.env_actions[goff + w];
+      if (two_raw) s_rawm[w] = A.raw_mgr[goff + w];
+    }
+  }
+  if (active && A.episode_length) A.episode_length[e] += 1;
+  if (use_tma) mbar_wait(&bar, 0);
+  __syncthreads();
+
+  // pure copies first: last_actions <- previous actions, actions <- raw
+  if (use_tma) {
+    if (tid == 0) {
+      bulk_store(A.env_last_actions + goff, s_prev, slab_bytes);
+      bulk_store(A.env_actions + goff, s_raw, slab_bytes);
+      bulk_commit();
+    }
+  } else {
+    const int words = valid * D;
+    for (int w = tid; w < words; w += TILE) {
+      A.env_last_actions[goff + w] = s_prev[w];
+      A.env_actions[goff + w] = s_raw[w];
+    }
+  }
+
+  if (active) {
+    const float* a = s_raw + tid * D;
+    const float* p = s_prev + tid * D;
+    const float* am = (two_raw ? s_rawm : s_raw) + tid * D;
+    float* t = s_tgt + tid * D;
+    float rate = 0.0f;
+    uint32_t status = 0;
+    for (int d = 0; d < D; ++d) {
+      const float x = a[d];
+      rate = add(rate, sq(sub(p[d], x)));
+      float y = am[d];
+      if (A.check_finite) {
+        if (y != y) status |= GFB_STATUS_NAN_ACTION;
+        if (fabsf(y) == __int_as_float(0x7f800000)) status |= GFB_STATUS_INF_ACTION;
+      }
+      if (P.action_mode == 2) {
+        // torch.clamp_ propagates NaN
+        y = (y != y) ? y : fminf(fmaxf(y, -1.0f), 1.0f);
+        y = add(mul(y, P.action_scale[d]), P.action_offset[d]);
+      } else {
+        y = add(mul(y, P.action_scale[d]), P.action_offset[d]);
+        y = (y != y) ? y : fminf(fmaxf(y, P.action_clip_lo[d]), P.action_clip_hi[d]);
+      }
+      t[d] = y;
+    }
+    if (A.action_rate) A.action_rate[e] = rate;
+    if (status) atomicOr(A.status, status);
+  }
+
+  if (A.targets && P.action_mode != 0) {
+    if (use_tma) {
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        bulk_store(A.targets + goff, s_tgt, slab_bytes);
+        bulk_commit();
+      }
+    } else {
+      __syncthreads();
+      const int words = valid * D;
+      for (int w = tid; w < words; w += TILE) A.targets[goff + w] = s_tgt[w];
+    }
+  }
+  if (use_tma && tid == 0) bulk_wait_all();
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize_kernel: one block.  Turns the per-slab partials of post_kernel into
+//   * the ascending int64 reset index list, identical to (terminated|truncated).nonzero()
+//     (managed_env.py:308-310)
+//   * per-termination fire counts / fractions (termination_manager.py:178-182)
+//   * per-reward-term episode means over the reset envs (reward_manager.py:205-216)
+//   * the report block (n_reset, status bits)
+// Reductions are fixed-order (lane-strided partial sums in double, then a shuffle tree), so the
+// logged values are run-to-run deterministic.
+// ---------------------------------------------------------------------------------------------
+struct FinalizeParams {
+  Scratch s;
+  int64_t* reset_idx;
+  float* log_out;
+  double* log_acc;
+  int32_t tile;
+  int32_t num_envs;
+  int32_t n_reward;
+  int32_t n_termination;
+  uint32_t phases;
+  uint32_t reward_weight_mask;  // bit r set: term r has weight != 0 (mean is logged)
+};
+
+constexpr int FIN_THREADS = 1024;
+
+__global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinalizeParams F) {
+  __shared__ int s_warp_sum[FIN_THREADS / 32];
+  __shared__ int s_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nt = F.s.n_tiles;
+  const int words = F.tile / 32;
+
+  // ---- ordered compaction ---------------------------------------------------------------------
+  const int per = (nt + FIN_THREADS - 1) / FIN_THREADS;
+  const int t0 = min(tid * per, nt), t1 = min(t0 + per, nt);
+  int local = 0;
+  for (int t = t0; t < t1; ++t) local += F.s.tile_reset_count[t];
+  int incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp_sum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = s_warp_sum[lane];
+    int inc2 = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, inc2, o);
+      if (lane >= o) inc2 += u;
+    }
+    s_warp_sum[lane] = inc2 - v;  // exclusive warp offsets
+    if (lane == 31) s_total = inc2;
+  }
+  __syncthreads();
+  int offset = s_warp_sum[warp] + incl - local;
+  if (F.reset_idx) {
+    for (int t = t0; t < t1; ++t) {
+      if (F.s.tile_reset_count[t] == 0) continue;
+      for (int w = 0; w < words; ++w) {
+        uint32_t bits = F.s.tile_reset_bits[(size_t)t * words + w];
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          F.reset_idx[offset++] = (int64_t)t * F.tile + w * 32 + b;
+        }
+      }
+    }
+  }
+  const int n_reset = s_total;
+
+  // ---- logging reductions: one warp per term ----------------------------------------------------
+  gfb_report* rep = F.s.report;
+  if (warp < F.n_termination) {
+    int acc = 0;
+    if (F.phases & GFB_PHASE_TERMINATION)
+      for (int t = lane; t < nt; t += 32) acc += F.s.tile_term_count[(size_t)warp * nt + t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      rep->termination_count[warp] = acc;
+      if (F.log_out) F.log_out[F.n_reward + warp] = fdiv((float)acc, (float)F.num_envs);
+      if (F.log_acc) F.log_acc[F.n_reward + warp] = (double)acc;
+    }
+  }
+  for (int r = warp; r < F.n_reward; r += FIN_THREADS / 32) {
+    double acc = 0.0;
+    if (F.phases & GFB_PHASE_RESET)
+      for (int t = lane; t < nt; t += 32) acc += F.s.tile_rew_sum[(size_t)r * nt + t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const bool logged = (F.reward_weight_mask >> r) & 1u;
+      const float mean = (n_reset > 0 && logged) ? (float)(acc / (double)n_reset) : 0.0f;
+      rep->reward_episode_mean[r] = mean;
+      if (F.log_out) F.log_out[r] = mean;
+      if (F.log_acc) F.log_acc[r] = acc;
+    }
+  }
+  if (tid == 0) {
+    rep->n_reset = n_reset;
+    rep->status = atomicExch(F.s.status, 0u);
+    if (F.log_acc) F.log_acc[F.n_reward + F.n_termination] = (double)n_reset;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// observe_kernel: frame 0 of every observation group for a LIST of envs (or all envs), from the
+// current engine state and the CACHED inverse base quaternion.  The reference observes after
+// reset (managed_env.py:322-326) with post-reset engine getters but the pre-reset cached
+// quaternion (entity_manager.py:134-146 vs :189-195; EntityManager.reset does not refresh it).
+// ---------------------------------------------------------------------------------------------
+struct ObserveParams {
+  gfb_program_head P;
+  gfb_buffers b;
+  Plan plan;
+  const DevObsCol* cols;
+  const int64_t* idx;
+  int32_t n;
+};
+
+template <int TILE>
+__global__ void __launch_bounds__(TILE) observe_kernel(const __grid_constant__ ObserveParams K) {
+  extern __shared__ __align__(128) float S[];  // (TILE, stash_stride)
+  __shared__ long long s_env[TILE];
+  const gfb_program_head& P = K.P;
+  const Plan& plan = K.plan;
+  const int tid = threadIdx.x;
+  const int i0 = blockIdx.x * TILE;
+  const int valid = min(TILE, K.n - i0);
+  if (tid < valid) {
+    const long long e = K.idx ? (long long)K.idx[i0 + tid] : (long long)(i0 + tid);
+    s_env[tid] = e;
+    float* st = S + tid * plan.stash_stride;
+    const float4 q = GFB_BUF(const float4, GFB_B_INV_BASE_QUAT)[e];
+    const V3 iq = {q.y, q.z, q.w};
+    if (plan.needs & NEED_ANG) {
+      const float* v = GFB_BUF(const float, GFB_B_ANG) + e * 3;
+      const V3 r = rotate(V3{v[0], v[1], v[2]}, q.x, iq);
+      st[0] = r.x; st[1] = r.y; st[2] = r.z;
+    }
+    if (plan.needs & NEED_LIN) {
+      const float* v = GFB_BUF(const float, GFB_B_VEL) + e * 3;
+      const V3 r = rotate(V3{v[0], v[1], v[2]}, q.x, iq);
+      st[3] = r.x; st[4] = r.y; st[5] = r.z;
+    }
+    if (plan.needs & NEED_GRAV) {
+      const V3 r = rotate(V3{0.f, 0.f, -1.f}, q.x, iq);
+      st[6] = r.x; st[7] = r.y; st[8] = r.z;
+    }
+    for (int m = 0; m < P.n_contact; ++m) {
+      const float* cg = GFB_BUF(const float, GFB_B_CONTACTS0 + m);
+      if (!cg) continue;
+      cg += e * P.contact[m].n_links * 3;
+      for (int t = 0; t < P.contact[m].n_links; ++t)
+        st[plan.st_cnorm[m] + t] = norm3(cg[t * 3], cg[t * 3 + 1], cg[t * 3 + 2]);
+    }
+  }
+  __syncthreads();
+  const Philox rng(P.rng_seed);
+  for (int g = 0; g < P.n_obs_groups; ++g) {
+    const gfb_obs_group& og = P.obs_group[g];
+    const int O = og.n_cols, OH = og.n_cols * og.history;
+    const DevObsCol* cols = K.cols + og.col_begin;
+    float* out = GFB_BUF(float, GFB_B_OBS_OUT0 + g);
+    const float* noise = GFB_BUF(const float, GFB_B_OBS_NOISE0 + g);
+    const int total = valid * O;
+    for (int f = tid; f < total; f += TILE) {
+      const int row = f / O, col = f - row * O;
+      const long long e = s_env[row];
+      const DevObsCol d = cols[col];
+      float v = 0.0f;
+      if (d.kind == 1 || d.kind == 2)
+        v = reinterpret_cast<const float*>(K.b.buf[d.gbuf])[e * d.row_words + d.col];
+      else if (d.kind == 3)
+        v = S[row * plan.stash_stride + d.a];
+      v = mul(v, d.scale);
+      if (d.noise != 0.f) {
+        float u;
+        if (P.rng_mode == 0) {
+          u = noise ? noise[e * O + col] : 0.f;
+        } else {
+          const uint4 x = rng((uint32_t)e, (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32),
+                              0x1000u + (uint32_t)(og.col_begin + (col & ~3)));
+          const int j = col & 3;
+          const uint32_t xj = j == 0 ? x.x : (j == 1 ? x.y : (j == 2 ? x.z : x.w));
+          u = sub(mul(u01(xj), 2.f), 1.f);
+        }
+        v = add(v, mul(u, d.noise));
+      }
+      out[e * OH + col] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// contact_kernel: the reference's Taichi kernel (contact/kernel.py:5-90) on its own, with its
+// argument list.  One thread per env, targets outer / contact slots inner, ordered sums.
+// ---------------------------------------------------------------------------------------------
+__global__ void contact_kernel(const float* __restrict__ force, const float* __restrict__ position,
+                               const int32_t* __restrict__ link_a, const int32_t* __restrict__ link_b,
+                               const float4* __restrict__ links_quat, const int32_t* __restrict__ targets,
+                               const int32_t* __restrict__ withs, float* __restrict__ out_f,
+                               float* __restrict__ out_p, float* __restrict__ counts, int n_envs, int C, int L,
+                               int Lc, int Lw, int has_filter) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_envs) return;
+  const int32_t* la = link_a + (size_t)e * C;
+  const int32_t* lb = link_b + (size_t)e * C;
+  const float* cf = force + (size_t)e * C * 3;
+  const float* cp = position + (size_t)e * C * 3;
+  for (int t = 0; t < Lc; ++t) {
+    const int target = targets[t];
+    const float4 tq = links_quat[(size_t)e * L + target];
+    float fx = 0.f, fy = 0.f, fz = 0.f, px = 0.f, py = 0.f, pz = 0.f, cnt = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const int a = la[c], b = lb[c];
+      const bool is_a = a == target, is_b = b == target;
+      bool hit = is_a | is_b;
+      if (hit && has_filter) {
+        bool keep = false;
+        for (int w = 0; w < Lw; ++w) keep |= (is_a && b == withs[w]) || (is_b && a == withs[w]);
+        hit = keep;
+      }
+      if (hit) {
+        const float x = cf[c * 3], y = cf[c * 3 + 1], z = cf[c * 3 + 2];
+        V3 f = is_b ? V3{x, y, z} : V3{-x, -y, -z};
+        f = inv_rotate_ti(f, tq.x, V3{tq.y, tq.z, tq.w});
+        fx = add(fx, f.x); fy = add(fy, f.y); fz = add(fz, f.z);
+        px = add(px, cp[c * 3]); py = add(py, cp[c * 3 + 1]); pz = add(pz, cp[c * 3 + 2]);
+        cnt = add(cnt, 1.0f);
+      }
+    }
+    if (cnt > 0.f) {
+      px = fdiv(px, cnt); py = fdiv(py, cnt); pz = fdiv(pz, cnt);
+    }
+    float* of = out_f + ((size_t)e * Lc + t) * 3;
+    float* op = out_p + ((size_t)e * Lc + t) * 3;
+    of[0] = fx; of[1] = fy; of[2] = fz;
+    op[0] = px; op[1] = py; op[2] = pz;
+    counts[(size_t)e * Lc + t] = cnt;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rotate_kernel: transform_by_quat(vec, q or conj(q)) for stand-alone getter calls
+// ---------------------------------------------------------------------------------------------
+__global__ void rotate_kernel(const float* __restrict__ vec, const float4* __restrict__ quat,
+                              float* __restrict__ out, int n, int conjugate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 q = quat[i];
+  const V3 qv = conjugate ? V3{-q.y, -q.z, -q.w} : V3{q.y, q.z, q.w};
+  const V3 v = vec ? V3{vec[i * 3], vec[i * 3 + 1], vec[i * 3 + 2]} : V3{0.f, 0.f, -1.f};
+  const V3 r = rotate(v, q.x, qv);
+  out[i * 3] = r.x;
+  out[i * 3 + 1] = r.y;
+  out[i * 3 + 2] = r.z;
+}
+
+}  // namespace gfb

@@ -1,0 +1,149 @@
+// Device helpers for the fused manager-step kernels (sm_100a).
+//
+//  * rn-intrinsic arithmetic recipes that reproduce torch-CPU eager results bit for bit
+//    (re-probed in DESIGN.md): every multiply/add separately rounded, never
+//    left to nvcc's fmad contraction; cross products and short norms as the FMA chains the ATen
+//    CPU kernels compile to.
+//  * quaternion rotation following oracle/geom.py op for op.
+//  * mbarrier + cp.async.bulk (TMA, non-tensor form) wrappers for slab loads/stores.
+//  * Philox4x32-10 for the production (non-injected) random draws.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gfb {
+
+// ---------------------------------------------------------------------------------------------
+// exact-rounding arithmetic
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float sq(float a) { return __fmul_rn(a, a); }
+
+struct V3 {
+  float x, y, z;
+};
+
+// torch.cross(a, b) on CPU evaluates each component as fma(a1, b2, -(a2*b1)).
+__device__ __forceinline__ V3 cross(const V3& a, const V3& b) {
+  V3 r;
+  r.x = __fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y));
+  r.y = __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z));
+  r.z = __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x));
+  return r;
+}
+
+// torch.norm(v, dim=-1) over 3 / 2 components: sqrt(fma(z,z,fma(y,y,x*x))).
+__device__ __forceinline__ float norm3(float x, float y, float z) {
+  return __fsqrt_rn(__fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x))));
+}
+__device__ __forceinline__ float norm2(float x, float y) {
+  return __fsqrt_rn(__fmaf_rn(y, y, __fmul_rn(x, x)));
+}
+
+// oracle/geom.py transform_by_quat: t = cross(q_xyz, v) * 2; out = (v + w*t) + cross(q_xyz, t)
+__device__ __forceinline__ V3 rotate(const V3& v, float w, const V3& q) {
+  V3 t = cross(q, v);
+  t.x = mul(t.x, 2.0f);
+  t.y = mul(t.y, 2.0f);
+  t.z = mul(t.z, 2.0f);
+  V3 c = cross(q, t);
+  V3 r;
+  r.x = add(add(v.x, mul(w, t.x)), c.x);
+  r.y = add(add(v.y, mul(w, t.y)), c.y);
+  r.z = add(add(v.z, mul(w, t.z)), c.z);
+  return r;
+}
+
+// oracle/geom.py ti_inv_transform_by_quat: q* = conj(q); u = q* x v; uu = q* x u; v + (w*u + uu)*2
+__device__ __forceinline__ V3 inv_rotate_ti(const V3& v, float w, const V3& qv) {
+  V3 q = {-qv.x, -qv.y, -qv.z};
+  V3 u = cross(q, v);
+  V3 uu = cross(q, u);
+  V3 r;
+  r.x = add(v.x, mul(add(mul(w, u.x), uu.x), 2.0f));
+  r.y = add(v.y, mul(add(mul(w, u.y), uu.y), 2.0f));
+  r.z = add(v.z, mul(add(mul(w, u.z), uu.z), 2.0f));
+  return r;
+}
+
+__device__ __forceinline__ bool finite_f(float x) { return (__float_as_uint(x) & 0x7f800000u) != 0x7f800000u; }
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + bulk async copies (TMA, linear form).  SASS: SYNCS.* / UBLKCP.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+// global -> shared, completion counted on `bar`.  dst/src 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// shared -> global.
+__device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (before a bulk_store)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10
+// ---------------------------------------------------------------------------------------------
+struct Philox {
+  uint32_t k0, k1;
+  __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+  __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      uint32_t n0 = hi1 ^ c1 ^ a, n1 = lo1, n2 = hi0 ^ c3 ^ b, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      a += 0x9E3779B9u;
+      b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+// uint32 -> [0, 1)
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+}  // namespace gfb

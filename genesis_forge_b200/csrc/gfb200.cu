@@ -1,0 +1,777 @@
+// libgfb200: C ABI + launch logic (see include/gfb200.h).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gfb200.h"
+#include "aux_kernels.cuh"
+#include "plan.h"
+#include "post_kernel.cuh"
+
+using namespace gfb;
+
+namespace {
+
+constexpr int kMaxSmemBytes = 227 * 1024;
+constexpr int kPlanSlots = 6;
+constexpr int kEventPairs = 2048;
+constexpr int kObserveTile = 128;
+
+inline int align4(int w) { return (w + 3) & ~3; }
+
+struct PlanSlot {
+  bool used = false;
+  uint32_t phases = 0;
+  int tile = 0;
+  std::vector<DevObsCol> cols_host;
+  DevObsCol* cols_dev = nullptr;
+};
+
+}  // namespace
+
+struct gfb_handle {
+  int device = 0;
+  int num_envs = 0;
+  std::string err;
+  gfb_program prog;
+  bool has_prog = false;
+  Scratch scratch{};
+  int scratch_tiles = 0;
+  gfb_report* report_host = nullptr;  // pinned
+  PlanSlot slots[kPlanSlots];
+  PlanSlot observe_slot;
+  bool disable_tma = false;
+  int force_tile = 0;
+  int64_t launches = 0;
+  // profiling
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_post, ev_action;
+  int n_post = 0, n_action = 0;
+  float post_ms = 0.f, action_ms = 0.f;
+  int post_count = 0, action_count = 0;
+  int smem_attr_post[3] = {0, 0, 0};
+  int smem_attr_action[3] = {0, 0, 0};
+};
+
+namespace {
+
+int fail(gfb_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                     \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess)                                                                                 \
+      return fail(h, GFB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+  } while (0)
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int tile_index(int tile) { return tile == 32 ? 0 : (tile == 64 ? 1 : 2); }
+
+// ---------------------------------------------------------------------------------------------
+// term-table analysis: which derived vectors / staged slabs does the program need
+// ---------------------------------------------------------------------------------------------
+uint32_t compute_needs(const gfb_program& prog, uint32_t phases) {
+  const gfb_program_head& P = prog.head;
+  uint32_t needs = 0;
+  if (phases & GFB_PHASE_REWARD)
+    for (int r = 0; r < P.n_reward; ++r) {
+      const gfb_reward_term& t = P.reward[r];
+      if (t.weight == 0.0f) continue;
+      switch (t.op) {
+        case GFB_R_LIN_VEL_Z:
+        case GFB_R_TRACK_LIN_VEL:
+          needs |= NEED_LIN;
+          break;
+        case GFB_R_ANG_VEL_XY:
+        case GFB_R_TRACK_ANG_VEL:
+          needs |= NEED_ANG;
+          break;
+        case GFB_R_FLAT_ORIENTATION:
+          needs |= NEED_GRAV;
+          break;
+        case GFB_R_BODY_ACC_EXP:
+          needs |= NEED_LIN | NEED_ANG;
+          break;
+        case GFB_R_BASE_HEIGHT:
+          needs |= NEED_POS;
+          break;
+        case GFB_R_DOF_SIMILAR:
+        case GFB_R_STAND_STILL:
+          needs |= NEED_DOF_POS;
+          break;
+        default:
+          break;
+      }
+    }
+  if (phases & GFB_PHASE_TERMINATION)
+    for (int t = 0; t < P.n_termination; ++t) {
+      switch (P.termination[t].op) {
+        case GFB_T_BAD_ORIENTATION:
+          needs |= NEED_GRAV;
+          break;
+        case GFB_T_BASE_HEIGHT_MIN:
+        case GFB_T_OUT_OF_BOUNDS:
+          needs |= NEED_POS;
+          break;
+        default:
+          break;
+      }
+    }
+  if (phases & GFB_PHASE_OBSERVE)
+    for (int g = 0; g < P.n_obs_groups; ++g)
+      for (int c = 0; c < P.obs_group[g].n_cols; ++c) {
+        switch (prog.obs_cols[P.obs_group[g].col_begin + c].src) {
+          case GFB_O_LIN_VEL_B:
+            needs |= NEED_LIN;
+            break;
+          case GFB_O_ANG_VEL_B:
+            needs |= NEED_ANG;
+            break;
+          case GFB_O_GRAVITY_B:
+            needs |= NEED_GRAV;
+            break;
+          default:
+            break;
+        }
+      }
+  return needs;
+}
+
+// Lay out the shared-memory slab for one (program, phases, tile) combination and lower the
+// observation columns to device descriptors.
+int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, Plan& plan,
+               std::vector<DevObsCol>& cols) {
+  const gfb_program& prog = h->prog;
+  const gfb_program_head& P = prog.head;
+  memset(&plan, 0, sizeof(plan));
+  plan.tile = tile;
+  plan.needs = compute_needs(prog, phases);
+  plan.off_pos = plan.off_quat = plan.off_vel = plan.off_ang = plan.off_dof_pos = -1;
+  plan.off_cforce = plan.off_cpos = plan.off_cla = plan.off_clb = -1;
+  for (int k = 0; k < GFB_MAX_COMMANDS; ++k) plan.off_cmd[k] = -1;
+  int cursor = 0;
+  auto stage = [&](int buf, int words, int store) -> int {
+    if (plan.n_staged >= GFB_MAX_STAGED) return -1;
+    const int i = plan.n_staged++;
+    plan.staged_buf[i] = buf;
+    plan.staged_words[i] = words;
+    plan.staged_off[i] = cursor;
+    plan.staged_store[i] = store;
+    const int off = cursor;
+    cursor = align4(cursor + words * tile);
+    return off;
+  };
+  const bool entity = phases & GFB_PHASE_ENTITY;
+  if (entity) {
+    if (!b.buf[GFB_B_QUAT]) return fail(h, GFB_ERR_INVALID, "GFB_B_QUAT is required for the entity phase");
+    plan.off_quat = stage(GFB_B_QUAT, 4, GFB_B_BASE_QUAT);
+  }
+  if ((plan.needs & NEED_POS) || (entity && b.buf[GFB_B_BASE_POS])) {
+    if (!b.buf[GFB_B_POS]) return fail(h, GFB_ERR_INVALID, "GFB_B_POS missing");
+    plan.off_pos = stage(GFB_B_POS, 3, entity ? GFB_B_BASE_POS : -1);
+  }
+  if (plan.needs & NEED_LIN) {
+    if (!b.buf[GFB_B_VEL]) return fail(h, GFB_ERR_INVALID, "GFB_B_VEL missing");
+    plan.off_vel = stage(GFB_B_VEL, 3, -1);
+  }
+  if (plan.needs & NEED_ANG) {
+    if (!b.buf[GFB_B_ANG]) return fail(h, GFB_ERR_INVALID, "GFB_B_ANG missing");
+    plan.off_ang = stage(GFB_B_ANG, 3, -1);
+  }
+  if (plan.needs & NEED_DOF_POS) {
+    if (!b.buf[GFB_B_DOF_POS]) return fail(h, GFB_ERR_INVALID, "GFB_B_DOF_POS missing");
+    plan.off_dof_pos = stage(GFB_B_DOF_POS, P.num_dofs, -1);
+  }
+  if (phases & (GFB_PHASE_REWARD | GFB_PHASE_COMMAND | GFB_PHASE_RESET | GFB_PHASE_OBSERVE))
+    for (int k = 0; k < P.n_command; ++k) {
+      if (!b.buf[GFB_B_COMMAND0 + k]) return fail(h, GFB_ERR_INVALID, "command buffer missing");
+      plan.off_cmd[k] = stage(GFB_B_COMMAND0 + k, P.command[k].n_dims, -1);
+    }
+  const bool contact = (phases & GFB_PHASE_CONTACT) && P.n_contact > 0;
+  if (contact) {
+    for (int id : {GFB_B_C_FORCE, GFB_B_C_POS, GFB_B_C_LINK_A, GFB_B_C_LINK_B, GFB_B_LINKS_QUAT})
+      if (!b.buf[id]) return fail(h, GFB_ERR_INVALID, "contact input buffer missing");
+    const int C = P.n_contact_slots;
+    plan.off_cforce = stage(GFB_B_C_FORCE, 3 * C, -1);
+    plan.off_cpos = stage(GFB_B_C_POS, 3 * C, -1);
+    plan.off_cla = stage(GFB_B_C_LINK_A, C, -1);
+    plan.off_clb = stage(GFB_B_C_LINK_B, C, -1);
+  }
+  // stash
+  int stride = 9;
+  for (int m = 0; m < P.n_contact; ++m) {
+    plan.st_cnorm[m] = stride;
+    stride += P.contact[m].n_links;
+    plan.st_air[m] = stride;
+    if (P.contact[m].track_air_time) stride += 4 * P.contact[m].n_links;
+  }
+  if ((stride & 1) == 0) ++stride;  // odd stride: conflict-free per-thread rows
+  plan.stash_stride = stride;
+  plan.stash_off = cursor;
+  cursor = align4(cursor + stride * tile);
+  plan.sums_off = cursor;
+  if ((phases & (GFB_PHASE_REWARD | GFB_PHASE_RESET)) && P.n_reward > 0) cursor = align4(cursor + P.n_reward * tile);
+  for (int m = 0; m < P.n_contact; ++m) {
+    plan.cout_off[m] = cursor;
+    if (contact) cursor = align4(cursor + 3 * P.contact[m].n_links * tile);
+    plan.cposout_off[m] = cursor;
+    if (contact) cursor = align4(cursor + 3 * P.contact[m].n_links * tile);
+  }
+
+  // observation columns
+  cols.clear();
+  int n_cols_total = 0;
+  for (int g = 0; g < P.n_obs_groups; ++g) n_cols_total = std::max(n_cols_total, P.obs_group[g].col_begin + P.obs_group[g].n_cols);
+  if (n_cols_total > GFB_MAX_OBS_COLS) return fail(h, GFB_ERR_INVALID, "too many observation columns");
+  cols.resize(n_cols_total);
+  for (int i = 0; i < n_cols_total; ++i) {
+    const gfb_obs_col& oc = prog.obs_cols[i];
+    DevObsCol d{};
+    d.scale = oc.scale;
+    d.noise = oc.noise;
+    d.col = oc.col;
+    auto global_src = [&](int buf, int row_words) {
+      d.kind = 2;
+      d.gbuf = buf;
+      d.row_words = row_words;
+    };
+    switch (oc.src) {
+      case GFB_O_COMMAND:
+        if (oc.mgr < 0 || oc.mgr >= P.n_command) return fail(h, GFB_ERR_INVALID, "obs: bad command manager");
+        global_src(GFB_B_COMMAND0 + oc.mgr, P.command[oc.mgr].n_dims);
+        if (plan.off_cmd[oc.mgr] >= 0) {
+          d.kind = 1;
+          d.a = plan.off_cmd[oc.mgr];
+        }
+        break;
+      case GFB_O_ANG_VEL_B:
+        d.kind = 3; d.a = 0 + oc.col;
+        break;
+      case GFB_O_LIN_VEL_B:
+        d.kind = 3; d.a = 3 + oc.col;
+        break;
+      case GFB_O_GRAVITY_B:
+        d.kind = 3; d.a = 6 + oc.col;
+        break;
+      case GFB_O_DOF_POS:
+        global_src(GFB_B_DOF_POS, P.num_dofs);
+        if (plan.off_dof_pos >= 0) {
+          d.kind = 1;
+          d.a = plan.off_dof_pos;
+        }
+        break;
+      case GFB_O_DOF_VEL:
+        global_src(GFB_B_DOF_VEL, P.num_dofs);
+        break;
+      case GFB_O_DOF_FORCE:
+        global_src(GFB_B_DOF_FORCE, P.num_dofs);
+        break;
+      case GFB_O_TARGETS:
+        global_src(GFB_B_TARGETS, P.num_dofs);
+        break;
+      case GFB_O_ENV_ACTIONS:
+        global_src(GFB_B_ENV_ACTIONS, P.num_dofs);
+        break;
+      case GFB_O_CONTACT_NORM:
+        if (oc.mgr < 0 || oc.mgr >= P.n_contact) return fail(h, GFB_ERR_INVALID, "obs: bad contact manager");
+        d.kind = 3;
+        d.a = plan.st_cnorm[oc.mgr] + oc.col;
+        break;
+      case GFB_O_ZERO:
+        d.kind = 0;
+        break;
+      default:
+        return fail(h, GFB_ERR_UNSUPPORTED, "obs: unsupported column source");
+    }
+    if ((d.kind == 2 || d.kind == 1) && (phases & GFB_PHASE_OBSERVE) && !b.buf[d.gbuf])
+      return fail(h, GFB_ERR_INVALID, "obs: source buffer " + std::to_string(d.gbuf) + " is NULL");
+    cols[i] = d;
+  }
+  // mark 4-aligned runs that can move as one 16-byte piece
+  for (int g = 0; g < P.n_obs_groups; ++g) {
+    const gfb_obs_group& og = P.obs_group[g];
+    if (og.n_cols & 3) continue;
+    for (int c = 0; c + 3 < og.n_cols; c += 4) {
+      DevObsCol* d = &cols[og.col_begin + c];
+      bool ok = (d[0].kind == 1 || d[0].kind == 2) && (d[0].col & 3) == 0 && (d[0].row_words & 3) == 0;
+      if (d[0].kind == 1) ok = ok && (d[0].a & 3) == 0;
+      for (int j = 1; j < 4 && ok; ++j)
+        ok = d[j].kind == d[0].kind && d[j].a == d[0].a && d[j].gbuf == d[0].gbuf &&
+             d[j].row_words == d[0].row_words && d[j].col == d[0].col + j && d[j].scale == d[0].scale &&
+             d[j].noise == d[0].noise;
+      if (ok && d[0].kind == 2) ok = aligned16(b.buf[d[0].gbuf]);
+      d[0].vec = ok ? 1 : 0;
+    }
+  }
+  plan.n_cols_total = n_cols_total;
+  plan.cols_off = cursor;
+  cursor = align4(cursor + n_cols_total * (int)(sizeof(DevObsCol) / 4));
+  plan.smem_words = cursor;
+  return GFB_OK;
+}
+
+bool tma_eligible(const gfb_handle* h, const gfb_buffers& b, const Plan& plan, uint32_t phases) {
+  if (h->disable_tma) return false;
+  const gfb_program_head& P = h->prog.head;
+  if (P.num_envs & 3) return false;
+  for (int i = 0; i < plan.n_staged; ++i) {
+    if (!aligned16(b.buf[plan.staged_buf[i]])) return false;
+    if ((phases & GFB_PHASE_ENTITY) && plan.staged_store[i] >= 0 && b.buf[plan.staged_store[i]] &&
+        !aligned16(b.buf[plan.staged_store[i]]))
+      return false;
+  }
+  if ((phases & (GFB_PHASE_REWARD | GFB_PHASE_RESET)) && P.n_reward > 0 && !aligned16(b.buf[GFB_B_EP_SUMS])) return false;
+  if ((phases & GFB_PHASE_CONTACT))
+    for (int m = 0; m < P.n_contact; ++m)
+      if (!aligned16(b.buf[GFB_B_CONTACTS0 + m]) || !aligned16(b.buf[GFB_B_CONTACT_POS0 + m])) return false;
+  return true;
+}
+
+int choose_tile(const gfb_handle* h) {
+  if (h->force_tile == 32 || h->force_tile == 64 || h->force_tile == 128) return h->force_tile;
+  return h->num_envs >= 32768 ? 128 : 32;
+}
+
+template <int TILE>
+int launch_post(gfb_handle* h, const KParams& kp, size_t smem, cudaStream_t stream, int grid) {
+  int& cur = h->smem_attr_post[tile_index(TILE)];
+  if ((int)smem > 48 * 1024 && (int)smem > cur) {
+    CUDA_TRY(cudaFuncSetAttribute(post_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cur = (int)smem;
+  }
+  post_kernel<TILE><<<grid, TILE, smem, stream>>>(kp);
+  CUDA_TRY(cudaGetLastError());
+  return GFB_OK;
+}
+
+template <int TILE>
+int launch_action(gfb_handle* h, const ActionParams& ap, size_t smem, cudaStream_t stream, int grid) {
+  int& cur = h->smem_attr_action[tile_index(TILE)];
+  if ((int)smem > 48 * 1024 && (int)smem > cur) {
+    CUDA_TRY(cudaFuncSetAttribute(action_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cur = (int)smem;
+  }
+  action_kernel<TILE><<<grid, TILE, smem, stream>>>(ap);
+  CUDA_TRY(cudaGetLastError());
+  return GFB_OK;
+}
+
+int upload_cols(gfb_handle* h, PlanSlot& slot, const std::vector<DevObsCol>& cols, cudaStream_t stream) {
+  const size_t bytes = cols.size() * sizeof(DevObsCol);
+  if (!slot.cols_dev) CUDA_TRY(cudaMalloc(&slot.cols_dev, GFB_MAX_OBS_COLS * sizeof(DevObsCol)));
+  if (slot.cols_host.size() != cols.size() || (bytes && memcmp(slot.cols_host.data(), cols.data(), bytes) != 0)) {
+    slot.cols_host = cols;
+    if (bytes) CUDA_TRY(cudaMemcpyAsync(slot.cols_dev, slot.cols_host.data(), bytes, cudaMemcpyHostToDevice, stream));
+  }
+  return GFB_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int gfb_abi_version(void) { return GFB_ABI_VERSION; }
+
+int64_t gfb_abi_sizeof(int32_t which) {
+  switch (which) {
+    case 0: return (int64_t)sizeof(gfb_program);
+    case 1: return (int64_t)sizeof(gfb_buffers);
+    case 2: return (int64_t)sizeof(gfb_report);
+    case 3: return (int64_t)sizeof(gfb_program_head);
+    case 4: return (int64_t)GFB_B_COUNT;
+    default: return -1;
+  }
+}
+
+const char* gfb_last_error(const gfb_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int gfb_create(int32_t num_envs, int32_t device, gfb_handle** out) {
+  if (!out || num_envs <= 0) return GFB_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device >= count) return GFB_ERR_NO_DEVICE;
+  gfb_handle* h = new gfb_handle();
+  h->device = device;
+  h->num_envs = num_envs;
+  *out = h;  // returned even on failure so that gfb_last_error() works; caller destroys it
+  CUDA_TRY(cudaSetDevice(device));
+  const int nt = (num_envs + 31) / 32;
+  h->scratch_tiles = nt;
+  CUDA_TRY(cudaMalloc(&h->scratch.tile_reset_bits, (size_t)nt * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&h->scratch.tile_reset_count, (size_t)nt * sizeof(int32_t)));
+  CUDA_TRY(cudaMalloc(&h->scratch.tile_term_count, (size_t)nt * GFB_MAX_TERMINATION_TERMS * sizeof(int32_t)));
+  CUDA_TRY(cudaMalloc(&h->scratch.tile_rew_sum, (size_t)nt * GFB_MAX_REWARD_TERMS * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->scratch.status, sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&h->scratch.report, sizeof(gfb_report)));
+  CUDA_TRY(cudaMemset(h->scratch.status, 0, sizeof(uint32_t)));
+  CUDA_TRY(cudaMemset(h->scratch.report, 0, sizeof(gfb_report)));
+  CUDA_TRY(cudaMemset(h->scratch.tile_reset_count, 0, (size_t)nt * sizeof(int32_t)));
+  CUDA_TRY(cudaMemset(h->scratch.tile_reset_bits, 0, (size_t)nt * sizeof(uint32_t)));
+  CUDA_TRY(cudaMallocHost(&h->report_host, sizeof(gfb_report)));
+  const char* env = getenv("GFB_DISABLE_TMA");
+  h->disable_tma = env && env[0] == '1';
+  env = getenv("GFB_TILE");
+  h->force_tile = env ? atoi(env) : 0;
+  return GFB_OK;
+}
+
+void gfb_destroy(gfb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->scratch.tile_reset_bits);
+  cudaFree(h->scratch.tile_reset_count);
+  cudaFree(h->scratch.tile_term_count);
+  cudaFree(h->scratch.tile_rew_sum);
+  cudaFree(h->scratch.status);
+  cudaFree(h->scratch.report);
+  if (h->report_host) cudaFreeHost(h->report_host);
+  for (auto& s : h->slots)
+    if (s.cols_dev) cudaFree(s.cols_dev);
+  if (h->observe_slot.cols_dev) cudaFree(h->observe_slot.cols_dev);
+  for (auto e : h->ev_post) cudaEventDestroy(e);
+  for (auto e : h->ev_action) cudaEventDestroy(e);
+  delete h;
+}
+
+int gfb_set_program(gfb_handle* h, const gfb_program* program) {
+  if (!h || !program) return GFB_ERR_INVALID;
+  const gfb_program_head& P = program->head;
+  if (P.num_envs != h->num_envs) return fail(h, GFB_ERR_INVALID, "program.num_envs differs from the handle's");
+  if (P.num_dofs < 0 || P.num_dofs > GFB_MAX_DOFS) return fail(h, GFB_ERR_INVALID, "num_dofs out of range");
+  if (P.n_reward < 0 || P.n_reward > GFB_MAX_REWARD_TERMS) return fail(h, GFB_ERR_INVALID, "n_reward out of range");
+  if (P.n_termination < 0 || P.n_termination > GFB_MAX_TERMINATION_TERMS)
+    return fail(h, GFB_ERR_INVALID, "n_termination out of range");
+  if (P.n_command < 0 || P.n_command > GFB_MAX_COMMANDS) return fail(h, GFB_ERR_INVALID, "n_command out of range");
+  if (P.n_contact < 0 || P.n_contact > GFB_MAX_CONTACT_MANAGERS) return fail(h, GFB_ERR_INVALID, "n_contact out of range");
+  if (P.n_obs_groups < 0 || P.n_obs_groups > GFB_MAX_OBS_GROUPS) return fail(h, GFB_ERR_INVALID, "n_obs_groups out of range");
+  for (int k = 0; k < P.n_command; ++k) {
+    if (P.command[k].n_dims <= 0 || P.command[k].n_dims > GFB_MAX_COMMAND_DIMS)
+      return fail(h, GFB_ERR_INVALID, "command n_dims out of range");
+    if (P.command[k].enabled && P.command[k].resample_steps <= 0)
+      return fail(h, GFB_ERR_INVALID, "command resample_steps must be positive");
+  }
+  for (int m = 0; m < P.n_contact; ++m) {
+    if (P.contact[m].n_links <= 0 || P.contact[m].n_links > GFB_MAX_CONTACT_LINKS)
+      return fail(h, GFB_ERR_INVALID, "contact n_links out of range");
+    if (P.contact[m].n_with < 0 || P.contact[m].n_with > GFB_MAX_WITH_LINKS)
+      return fail(h, GFB_ERR_INVALID, "contact n_with out of range");
+    for (int t = 0; t < P.contact[m].n_links; ++t)
+      if (P.contact[m].link_ids[t] < 0 || P.contact[m].link_ids[t] >= P.n_links_total)
+        return fail(h, GFB_ERR_INVALID, "contact link id outside [0, n_links_total)");
+  }
+  for (int g = 0; g < P.n_obs_groups; ++g)
+    if (P.obs_group[g].n_cols <= 0 || P.obs_group[g].history < 1 ||
+        P.obs_group[g].col_begin + P.obs_group[g].n_cols > GFB_MAX_OBS_COLS)
+      return fail(h, GFB_ERR_INVALID, "observation group out of range");
+  for (int r = 0; r < P.n_reward; ++r) {
+    const gfb_reward_term& t = P.reward[r];
+    const bool contact_op = t.op == GFB_R_HAS_CONTACT || t.op == GFB_R_CONTACT_FORCE ||
+                            t.op == GFB_R_FEET_AIR_TIME || t.op == GFB_R_FEET_SLIDE;
+    if (contact_op && (t.mgr < 0 || t.mgr >= P.n_contact)) return fail(h, GFB_ERR_INVALID, "reward: bad contact manager");
+    if (t.op == GFB_R_FEET_AIR_TIME && !P.contact[t.mgr].track_air_time)
+      return fail(h, GFB_ERR_INVALID, "feet_air_time needs a contact manager with track_air_time");
+    const bool cmd_op = t.op == GFB_R_STAND_STILL ||
+                        ((t.op == GFB_R_TRACK_LIN_VEL || t.op == GFB_R_TRACK_ANG_VEL) && !(t.flags & GFB_RF_FIXED_COMMAND)) ||
+                        (t.op == GFB_R_BASE_HEIGHT && (t.flags & GFB_RF_TARGET_FROM_COMMAND));
+    if (cmd_op && (t.mgr < 0 || t.mgr >= P.n_command)) return fail(h, GFB_ERR_INVALID, "reward: bad command manager");
+    if (t.op == GFB_R_FEET_AIR_TIME && t.i0 >= P.n_command) return fail(h, GFB_ERR_INVALID, "feet_air_time: bad command manager");
+    if (t.op == GFB_R_BODY_ACC_EXP || t.op == GFB_R_EXTERNAL)
+      return fail(h, GFB_ERR_UNSUPPORTED, "reward op not implemented in this build");
+  }
+  for (int t = 0; t < P.n_termination; ++t) {
+    const gfb_termination_term& tt = P.termination[t];
+    const bool contact_op = tt.op == GFB_T_HAS_CONTACT || tt.op == GFB_T_CONTACT_FORCE || tt.op == GFB_T_CONTACT_FORCE_GRACE;
+    if (contact_op && (tt.mgr < 0 || tt.mgr >= P.n_contact)) return fail(h, GFB_ERR_INVALID, "termination: bad contact manager");
+    if (tt.op == GFB_T_EXTERNAL) return fail(h, GFB_ERR_UNSUPPORTED, "termination op not implemented in this build");
+  }
+  h->prog = *program;
+  h->has_prog = true;
+  return GFB_OK;
+}
+
+int gfb_action_step(gfb_handle* h, const gfb_buffers* b, const float* raw_env, const float* raw_mgr, void* stream_) {
+  if (!h || !b || !raw_env) return GFB_ERR_INVALID;
+  if (!h->has_prog) return fail(h, GFB_ERR_INVALID, "gfb_set_program() first");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const gfb_program_head& P = h->prog.head;
+  if (!raw_mgr) raw_mgr = raw_env;
+  ActionParams ap{};
+  ap.P = P;
+  ap.raw_env = raw_env;
+  ap.raw_mgr = raw_mgr;
+  ap.env_actions = static_cast<float*>(b->buf[GFB_B_ENV_ACTIONS]);
+  ap.env_last_actions = static_cast<float*>(b->buf[GFB_B_ENV_LAST_ACTIONS]);
+  ap.targets = static_cast<float*>(b->buf[GFB_B_TARGETS]);
+  ap.action_rate = static_cast<float*>(b->buf[GFB_B_ACTION_RATE]);
+  ap.episode_length = static_cast<int32_t*>(b->buf[GFB_B_EPISODE_LENGTH]);
+  ap.status = h->scratch.status;
+  ap.check_finite = 1;
+  if (!ap.env_actions || !ap.env_last_actions) return fail(h, GFB_ERR_INVALID, "env action buffers missing");
+  if (P.action_mode != 0 && !ap.targets) return fail(h, GFB_ERR_INVALID, "GFB_B_TARGETS missing");
+  const int tile = choose_tile(h);
+  const int D = P.num_dofs;
+  ap.tma_ok = !h->disable_tma && ((tile * D) % 4 == 0) && aligned16(raw_env) && aligned16(raw_mgr) &&
+              aligned16(ap.env_actions) && aligned16(ap.env_last_actions) && (!ap.targets || aligned16(ap.targets));
+  const size_t smem = (size_t)tile * D * 4 * 4;
+  const int grid = (P.num_envs + tile - 1) / tile;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->profiling && h->n_action + 2 <= (int)h->ev_action.size()) {
+    e0 = h->ev_action[h->n_action++];
+    e1 = h->ev_action[h->n_action++];
+    cudaEventRecord(e0, stream);
+  }
+  int rc;
+  if (tile == 32) rc = launch_action<32>(h, ap, smem, stream, grid);
+  else if (tile == 64) rc = launch_action<64>(h, ap, smem, stream, grid);
+  else rc = launch_action<128>(h, ap, smem, stream, grid);
+  if (rc != GFB_OK) return rc;
+  if (e1) cudaEventRecord(e1, stream);
+  h->launches += 1;
+  return GFB_OK;
+}
+
+int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void* stream_) {
+  if (!h || !b) return GFB_ERR_INVALID;
+  if (!h->has_prog) return fail(h, GFB_ERR_INVALID, "gfb_set_program() first");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const gfb_program_head& P = h->prog.head;
+
+  // required buffers for the requested phases
+  auto need = [&](int id, const char* name) -> bool {
+    if (b->buf[id]) return true;
+    h->err = std::string("buffer ") + name + " is NULL";
+    return false;
+  };
+  if (!need(GFB_B_EPISODE_LENGTH, "EPISODE_LENGTH")) return GFB_ERR_INVALID;
+  if (P.base_max_episode_length > 0 && !need(GFB_B_MAX_EPISODE_LENGTH, "MAX_EPISODE_LENGTH")) return GFB_ERR_INVALID;
+  if (phases & GFB_PHASE_TERMINATION)
+    if (!need(GFB_B_TERMINATED, "TERMINATED") || !need(GFB_B_TRUNCATED, "TRUNCATED")) return GFB_ERR_INVALID;
+  if (phases & GFB_PHASE_REWARD)
+    if (!need(GFB_B_REWARD, "REWARD")) return GFB_ERR_INVALID;
+  if ((phases & (GFB_PHASE_REWARD | GFB_PHASE_RESET)) && P.n_reward > 0)
+    if (!need(GFB_B_EP_SUMS, "EP_SUMS") || !need(GFB_B_EP_SECONDS, "EP_SECONDS")) return GFB_ERR_INVALID;
+  if (phases & GFB_PHASE_RESET)
+    if (!need(GFB_B_RESET_IDX, "RESET_IDX")) return GFB_ERR_INVALID;
+  if (phases & GFB_PHASE_CONTACT)
+    for (int m = 0; m < P.n_contact; ++m) {
+      if (!need(GFB_B_CONTACTS0 + m, "CONTACTS") || !need(GFB_B_CONTACT_POS0 + m, "CONTACT_POS")) return GFB_ERR_INVALID;
+      if (P.contact[m].track_air_time && !need(GFB_B_AIR0 + m, "AIR")) return GFB_ERR_INVALID;
+    }
+  if (phases & GFB_PHASE_OBSERVE)
+    for (int g = 0; g < P.n_obs_groups; ++g) {
+      if (!need(GFB_B_OBS_OUT0 + g, "OBS_OUT")) return GFB_ERR_INVALID;
+      if (P.obs_group[g].history > 1 && !need(GFB_B_OBS_PREV0 + g, "OBS_PREV")) return GFB_ERR_INVALID;
+    }
+  if (!(phases & GFB_PHASE_ENTITY) && (phases & (GFB_PHASE_REWARD | GFB_PHASE_TERMINATION | GFB_PHASE_OBSERVE)))
+    if (!need(GFB_B_INV_BASE_QUAT, "INV_BASE_QUAT")) return GFB_ERR_INVALID;
+  for (int r = 0; r < P.n_reward; ++r) {
+    if (!(phases & GFB_PHASE_REWARD) || P.reward[r].weight == 0.0f) continue;
+    const gfb_reward_term& t = P.reward[r];
+    if (t.op == GFB_R_ACTION_RATE && !need(GFB_B_ACTION_RATE, "ACTION_RATE")) return GFB_ERR_INVALID;
+    if (t.op == GFB_R_FEET_SLIDE && !need(GFB_B_LINKS_VEL, "LINKS_VEL")) return GFB_ERR_INVALID;
+    if ((t.flags & GFB_RF_FIXED_COMMAND) && (t.op == GFB_R_TRACK_LIN_VEL || t.op == GFB_R_TRACK_ANG_VEL) &&
+        !need(GFB_B_FIXED_COMMAND, "FIXED_COMMAND"))
+      return GFB_ERR_INVALID;
+    if (t.op == GFB_R_BASE_HEIGHT && (t.flags & GFB_RF_TARGET_FROM_TENSOR) && !need(GFB_B_TARGET_HEIGHT, "TARGET_HEIGHT"))
+      return GFB_ERR_INVALID;
+    if (t.op == GFB_R_BASE_HEIGHT && (t.flags & GFB_RF_TERRAIN_HEIGHT) && !need(GFB_B_HEIGHT_FIELD, "HEIGHT_FIELD"))
+      return GFB_ERR_INVALID;
+  }
+
+  // tile: shrink until the slab fits comfortably
+  int tile = choose_tile(h);
+  KParams kp{};
+  std::vector<DevObsCol> cols;
+  for (;;) {
+    int rc = build_plan(h, *b, phases, tile, kp.plan, cols);
+    if (rc != GFB_OK) return rc;
+    if ((size_t)kp.plan.smem_words * 4 <= (size_t)kMaxSmemBytes / 2 || tile == 32) break;
+    tile = tile / 2;
+  }
+  const size_t smem = (size_t)kp.plan.smem_words * 4;
+  if (smem > (size_t)kMaxSmemBytes) return fail(h, GFB_ERR_UNSUPPORTED, "slab does not fit in shared memory");
+
+  PlanSlot* slot = nullptr;
+  for (auto& s : h->slots)
+    if (s.used && s.phases == phases && s.tile == tile) slot = &s;
+  if (!slot)
+    for (auto& s : h->slots)
+      if (!s.used) {
+        slot = &s;
+        break;
+      }
+  if (!slot) slot = &h->slots[0];
+  slot->used = true;
+  slot->phases = phases;
+  slot->tile = tile;
+  int rc = upload_cols(h, *slot, cols, stream);
+  if (rc != GFB_OK) return rc;
+
+  const int n_tiles = (P.num_envs + tile - 1) / tile;
+  kp.P = P;
+  kp.b = *b;
+  kp.s = h->scratch;
+  kp.s.n_tiles = n_tiles;
+  kp.cols = slot->cols_dev;
+  kp.phases = phases;
+  kp.tma_ok = tma_eligible(h, *b, kp.plan, phases) ? 1 : 0;
+
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->profiling && h->n_post + 2 <= (int)h->ev_post.size()) {
+    e0 = h->ev_post[h->n_post++];
+    e1 = h->ev_post[h->n_post++];
+    cudaEventRecord(e0, stream);
+  }
+  if (tile == 32) rc = launch_post<32>(h, kp, smem, stream, n_tiles);
+  else if (tile == 64) rc = launch_post<64>(h, kp, smem, stream, n_tiles);
+  else rc = launch_post<128>(h, kp, smem, stream, n_tiles);
+  if (rc != GFB_OK) return rc;
+  if (e1) cudaEventRecord(e1, stream);
+
+  FinalizeParams fp{};
+  fp.s = kp.s;
+  fp.reset_idx = static_cast<int64_t*>(b->buf[GFB_B_RESET_IDX]);
+  fp.log_out = static_cast<float*>(b->buf[GFB_B_LOG_OUT]);
+  fp.log_acc = static_cast<double*>(b->buf[GFB_B_LOG_ACC]);
+  fp.tile = tile;
+  fp.num_envs = P.num_envs;
+  fp.n_reward = P.n_reward;
+  fp.n_termination = P.n_termination;
+  fp.phases = phases;
+  fp.reward_weight_mask = 0;
+  for (int r = 0; r < P.n_reward; ++r)
+    if (P.reward[r].weight != 0.0f) fp.reward_weight_mask |= (1u << r);
+  finalize_kernel<<<1, FIN_THREADS, 0, stream>>>(fp);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 2;
+  return GFB_OK;
+}
+
+int gfb_read_report(gfb_handle* h, gfb_report* out, void* stream_) {
+  if (!h || !out) return GFB_ERR_INVALID;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CUDA_TRY(cudaMemcpyAsync(h->report_host, h->scratch.report, sizeof(gfb_report), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  *out = *h->report_host;
+  return GFB_OK;
+}
+
+int gfb_observe(gfb_handle* h, const gfb_buffers* b, const int64_t* idx, int32_t n, void* stream_) {
+  if (!h || !b) return GFB_ERR_INVALID;
+  if (!h->has_prog) return fail(h, GFB_ERR_INVALID, "gfb_set_program() first");
+  if (n <= 0) return GFB_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const gfb_program_head& P = h->prog.head;
+  if (!b->buf[GFB_B_INV_BASE_QUAT]) return fail(h, GFB_ERR_INVALID, "INV_BASE_QUAT missing");
+  ObserveParams op{};
+  std::vector<DevObsCol> cols;
+  // observe-only plan: nothing is staged, every staged-kind column falls back to its global buffer
+  gfb_buffers probe = *b;
+  int rc = build_plan(h, probe, GFB_PHASE_OBSERVE, kObserveTile, op.plan, cols);
+  if (rc != GFB_OK) return rc;
+  for (auto& c : cols) {
+    if (c.kind == 1) c.kind = 2;
+    c.vec = 0;
+  }
+  if ((op.plan.needs & NEED_LIN) && !b->buf[GFB_B_VEL]) return fail(h, GFB_ERR_INVALID, "VEL missing");
+  if ((op.plan.needs & NEED_ANG) && !b->buf[GFB_B_ANG]) return fail(h, GFB_ERR_INVALID, "ANG missing");
+  rc = upload_cols(h, h->observe_slot, cols, stream);
+  if (rc != GFB_OK) return rc;
+  op.P = P;
+  op.b = *b;
+  op.cols = h->observe_slot.cols_dev;
+  op.idx = idx;
+  op.n = n;
+  const size_t smem = (size_t)op.plan.stash_stride * kObserveTile * 4;
+  const int grid = (n + kObserveTile - 1) / kObserveTile;
+  observe_kernel<kObserveTile><<<grid, kObserveTile, smem, stream>>>(op);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GFB_OK;
+}
+
+int gfb_contact_forces(gfb_handle* h, const float* force, const float* position, const int32_t* link_a,
+                       const int32_t* link_b, const float* links_quat, const int32_t* target_link_ids,
+                       const int32_t* with_link_ids, float* out_forces, float* out_positions,
+                       float* position_counts, int32_t n_envs, int32_t n_slots, int32_t n_links_total,
+                       int32_t n_targets, int32_t n_with, int32_t has_with_filter, void* stream_) {
+  if (!h || !force || !position || !link_a || !link_b || !links_quat || !target_link_ids || !out_forces ||
+      !out_positions || !position_counts)
+    return fail(h, GFB_ERR_INVALID, "gfb_contact_forces: null argument");
+  if (n_envs <= 0 || n_targets <= 0) return GFB_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int threads = 128;
+  contact_kernel<<<(n_envs + threads - 1) / threads, threads, 0, stream>>>(
+      force, position, link_a, link_b, reinterpret_cast<const float4*>(links_quat), target_link_ids, with_link_ids,
+      out_forces, out_positions, position_counts, n_envs, n_slots, n_links_total, n_targets, n_with, has_with_filter);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GFB_OK;
+}
+
+int gfb_rotate(gfb_handle* h, const float* vec, const float* quat, float* out, int32_t n, int32_t conjugate,
+               void* stream_) {
+  if (!h || !quat || !out) return fail(h, GFB_ERR_INVALID, "gfb_rotate: null argument");
+  if (n <= 0) return GFB_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  rotate_kernel<<<(n + 255) / 256, 256, 0, stream>>>(vec, reinterpret_cast<const float4*>(quat), out, n, conjugate);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GFB_OK;
+}
+
+int gfb_profile_enable(gfb_handle* h, int32_t enabled) {
+  if (!h) return GFB_ERR_INVALID;
+  if (enabled && h->ev_post.empty()) {
+    h->ev_post.resize(kEventPairs * 2);
+    h->ev_action.resize(kEventPairs * 2);
+    for (auto& e : h->ev_post) CUDA_TRY(cudaEventCreate(&e));
+    for (auto& e : h->ev_action) CUDA_TRY(cudaEventCreate(&e));
+  }
+  h->profiling = enabled != 0;
+  h->n_post = h->n_action = 0;
+  h->post_ms = h->action_ms = 0.f;
+  h->post_count = h->action_count = 0;
+  return GFB_OK;
+}
+
+int gfb_profile_read(gfb_handle* h, float* post_ms_total, int32_t* post_launches, float* action_ms_total,
+                     int32_t* action_launches) {
+  if (!h) return GFB_ERR_INVALID;
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (int i = 0; i + 1 < h->n_post; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_post[i], h->ev_post[i + 1]) == cudaSuccess) {
+      h->post_ms += ms;
+      h->post_count += 1;
+    }
+  }
+  for (int i = 0; i + 1 < h->n_action; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_action[i], h->ev_action[i + 1]) == cudaSuccess) {
+      h->action_ms += ms;
+      h->action_count += 1;
+    }
+  }
+  h->n_post = h->n_action = 0;
+  if (post_ms_total) *post_ms_total = h->post_ms;
+  if (post_launches) *post_launches = h->post_count;
+  if (action_ms_total) *action_ms_total = h->action_ms;
+  if (action_launches) *action_launches = h->action_count;
+  return GFB_OK;
+}
+
+int64_t gfb_launch_count(const gfb_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

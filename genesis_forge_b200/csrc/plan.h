@@ -1,0 +1,84 @@
+// Host/device shared structures internal to libgfb200 (not part of the ABI).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/gfb200.h"
+
+// typed view of an entry of the buffer table of the kernel parameter `K`
+#define GFB_BUF(T_, id) (reinterpret_cast<T_*>(K.b.buf[id]))
+
+namespace gfb {
+
+// Observation column as the kernels consume it (built on the host from gfb_obs_col).
+//   kind 0: constant zero
+//   kind 1: slab-staged array: post kernel reads shared memory at `a + row*row_words + col`,
+//           the observe kernel reads global buffer `gbuf`
+//   kind 2: global buffer `gbuf` in both kernels
+//   kind 3: per-env stash (derived values) at `stash + row*stash_stride + a`
+//   vec  1: this column starts a 4-aligned run of 4 columns with the same contiguous source
+struct DevObsCol {
+  int32_t kind;
+  int32_t a;
+  int32_t row_words;
+  int32_t col;
+  float scale;
+  float noise;
+  int32_t gbuf;
+  int32_t vec;
+};
+
+// needs mask: which body-frame vectors the term table uses
+enum : uint32_t {
+  NEED_LIN = 1u,
+  NEED_ANG = 2u,
+  NEED_GRAV = 4u,
+  NEED_POS = 8u,
+  NEED_DOF_POS = 16u,
+  NEED_CONTACT_DATA = 32u,
+};
+
+// stash row layout (words, per env): [ang_b 3][lin_b 3][grav_b 3][per contact manager: norm[Lc], state 4*Lc]
+struct Plan {
+  int32_t tile;          // envs per thread block
+  uint32_t needs;
+  int32_t n_staged;
+  int32_t staged_buf[GFB_MAX_STAGED];
+  int32_t staged_words[GFB_MAX_STAGED];
+  int32_t staged_off[GFB_MAX_STAGED];
+  int32_t staged_store[GFB_MAX_STAGED];  // output buffer that receives a copy of the slab, or -1
+  int32_t off_pos, off_quat, off_vel, off_ang, off_dof_pos;
+  int32_t off_cmd[GFB_MAX_COMMANDS];
+  int32_t off_cforce, off_cpos, off_cla, off_clb;
+  int32_t stash_off, stash_stride;
+  int32_t st_cnorm[GFB_MAX_CONTACT_MANAGERS];  // offsets inside a stash row
+  int32_t st_air[GFB_MAX_CONTACT_MANAGERS];    // 4*Lc words: last_air, cur_air, last_contact, cur_contact
+  int32_t sums_off;                            // (n_reward, tile) episode-sum slab
+  int32_t cout_off[GFB_MAX_CONTACT_MANAGERS];  // (tile, 3*Lc) contact force output slab
+  int32_t cposout_off[GFB_MAX_CONTACT_MANAGERS];
+  int32_t cols_off;                            // DevObsCol table copy
+  int32_t n_cols_total;
+  int32_t smem_words;
+};
+
+struct Scratch {
+  uint32_t* tile_reset_bits;  // (n_tiles, tile/32)
+  int32_t* tile_reset_count;  // (n_tiles)
+  int32_t* tile_term_count;   // (GFB_MAX_TERMINATION_TERMS, n_tiles)
+  double* tile_rew_sum;       // (GFB_MAX_REWARD_TERMS, n_tiles)
+  uint32_t* status;           // sticky status bits
+  gfb_report* report;         // device copy of the report
+  int32_t n_tiles;
+  int32_t _pad;
+};
+
+struct KParams {
+  gfb_program_head P;
+  gfb_buffers b;
+  Plan plan;
+  Scratch s;
+  const DevObsCol* cols;
+  uint32_t phases;
+  int32_t tma_ok;
+};
+
+}  // namespace gfb

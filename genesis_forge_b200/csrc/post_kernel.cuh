@@ -1,0 +1,778 @@
+// The fused post-physics kernel: one thread block per slab of TILE environments, one thread per
+// environment for the per-env arithmetic, all threads together for slab loads/stores and for the
+// observation assembly.
+//
+// Replaces, in one launch, managed_env.py:294-326 of the reference:
+//   entity cache            entity_manager.py:189-195
+//   contact net forces      contact_manager.py:384-432 + contact/kernel.py:35-90 (ordered sums)
+//   air-time state machine  contact_manager.py:434-477
+//   terminations            termination_manager.py:151-190, mdp/terminations.py
+//   rewards + episode sums  reward_manager.py:166-195, mdp/rewards.py
+//   command resample        command_manager.py:152-162, 290-303
+//   in-library reset        genesis_env.py:233-252, contact_manager.py:316-329,
+//                           reward_manager.py:197-222, command_manager.py:164-170
+//   observations            observation_manager.py:218-256 (reset envs are re-observed afterwards by
+//                           observe_kernel, because the reference observes after reset)
+//
+// Data movement: AoS rows ((N,3), (N,4), (N,D), (N,C,3) ...) of one slab are contiguous in HBM, so
+// each staged array is ONE cp.async.bulk (TMA) transfer into shared memory, completion on one
+// mbarrier; slab outputs go back with cp.async.bulk stores; (N,) arrays are plain coalesced
+// accesses; observation rows are written with coalesced 16-byte stores straight from the gather.
+#pragma once
+#include "device_utils.cuh"
+#include "plan.h"
+
+namespace gfb {
+
+// fetch one observation value for slab row `row` (post kernel: staged arrays live in shared memory)
+__device__ __forceinline__ float obs_fetch_post(const DevObsCol& d, const float* S, const gfb_buffers& b,
+                                                const Plan& plan, int row, long long env) {
+  switch (d.kind) {
+    case 1:
+      return S[d.a + row * d.row_words + d.col];
+    case 2:
+      return reinterpret_cast<const float*>(b.buf[d.gbuf])[env * d.row_words + d.col];
+    case 3:
+      return S[plan.stash_off + row * plan.stash_stride + d.a];
+    default:
+      return 0.0f;
+  }
+}
+
+template <int TILE>
+__global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KParams K) {
+  extern __shared__ __align__(128) float S[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int32_t s_term_count[GFB_MAX_TERMINATION_TERMS];
+  __shared__ double s_rew_part[GFB_MAX_REWARD_TERMS][TILE / 32];
+  __shared__ uint32_t s_reset_bits[TILE / 32];
+  __shared__ uint32_t s_status;
+
+  const gfb_program_head& P = K.P;
+  const Plan& plan = K.plan;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = P.num_envs;
+  const int tile = blockIdx.x;
+  const int e0 = tile * TILE;
+  const int valid = min(TILE, N - e0);
+  const bool active = tid < valid;
+  const int e = active ? e0 + tid : N - 1;  // inactive lanes shadow the last env and never write
+  const uint32_t ph = K.phases;
+  const bool use_tma = K.tma_ok && valid == TILE;
+  const int D = P.num_dofs;
+  const bool stage_sums = (ph & (GFB_PHASE_REWARD | GFB_PHASE_RESET)) != 0 && P.n_reward > 0;
+
+  if (tid < GFB_MAX_TERMINATION_TERMS) s_term_count[tid] = 0;
+  if (tid == 0) s_status = 0;
+
+  // ------------------------------------------------------------------------------------------
+  // slab loads
+  // ------------------------------------------------------------------------------------------
+  if (use_tma) {
+    if (tid == 0) {
+      mbar_init(&bar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t total = 0;
+      for (int i = 0; i < plan.n_staged; ++i) total += (uint32_t)plan.staged_words[i] * TILE * 4u;
+      if (stage_sums) total += (uint32_t)P.n_reward * TILE * 4u;
+      mbar_expect_tx(&bar, total);
+      for (int i = 0; i < plan.n_staged; ++i) {
+        const float* src = reinterpret_cast<const float*>(K.b.buf[plan.staged_buf[i]]) +
+                           (size_t)e0 * plan.staged_words[i];
+        bulk_load(S + plan.staged_off[i], src, (uint32_t)plan.staged_words[i] * TILE * 4u, &bar);
+      }
+      if (stage_sums) {
+        const float* sums = GFB_BUF(const float, GFB_B_EP_SUMS);
+        for (int r = 0; r < P.n_reward; ++r)
+          bulk_load(S + plan.sums_off + r * TILE, sums + (size_t)r * N + e0, TILE * 4u, &bar);
+      }
+    }
+  } else {
+    for (int i = 0; i < plan.n_staged; ++i) {
+      const int words = plan.staged_words[i] * valid;
+      const float* src = reinterpret_cast<const float*>(K.b.buf[plan.staged_buf[i]]) +
+                         (size_t)e0 * plan.staged_words[i];
+      float* dst = S + plan.staged_off[i];
+      for (int w = tid; w < words; w += TILE) dst[w] = src[w];
+    }
+    if (stage_sums) {
+      const float* sums = GFB_BUF(const float, GFB_B_EP_SUMS);
+      for (int r = 0; r < P.n_reward; ++r)
+        if (active) S[plan.sums_off + r * TILE + tid] = sums[(size_t)r * N + e];
+    }
+  }
+  // observation descriptor table -> shared memory (per-thread-varying index later on)
+  {
+    const int32_t* src = reinterpret_cast<const int32_t*>(K.cols);
+    int32_t* dst = reinterpret_cast<int32_t*>(S + plan.cols_off);
+    const int words = plan.n_cols_total * (int)(sizeof(DevObsCol) / 4);
+    for (int w = tid; w < words; w += TILE) dst[w] = src[w];
+  }
+
+  // per-env scalars straight into registers while the slab is in flight
+  int ep_len = GFB_BUF(const int32_t, GFB_B_EPISODE_LENGTH)[e];
+  int max_len = P.base_max_episode_length > 0 ? GFB_BUF(const int32_t, GFB_B_MAX_EPISODE_LENGTH)[e] : 0;
+  float ep_secs = 0.0f, action_rate = 0.0f;
+  if (ph & (GFB_PHASE_REWARD | GFB_PHASE_RESET)) {
+    if (K.b.buf[GFB_B_EP_SECONDS]) ep_secs = GFB_BUF(const float, GFB_B_EP_SECONDS)[e];
+  }
+  if ((ph & GFB_PHASE_REWARD) && K.b.buf[GFB_B_ACTION_RATE])
+    action_rate = GFB_BUF(const float, GFB_B_ACTION_RATE)[e];
+
+  if (use_tma) {
+    mbar_wait(&bar, 0);
+  }
+  __syncthreads();
+
+  // slab copies that need no arithmetic (entity cache: base_pos / base_quat are copies of pos / quat)
+  if (ph & GFB_PHASE_ENTITY) {
+    if (use_tma) {
+      if (tid == 0) {
+        for (int i = 0; i < plan.n_staged; ++i)
+          if (plan.staged_store[i] >= 0 && K.b.buf[plan.staged_store[i]]) {
+            float* dst = reinterpret_cast<float*>(K.b.buf[plan.staged_store[i]]) + (size_t)e0 * plan.staged_words[i];
+            bulk_store(dst, S + plan.staged_off[i], (uint32_t)plan.staged_words[i] * TILE * 4u);
+          }
+        bulk_commit();
+      }
+    } else {
+      for (int i = 0; i < plan.n_staged; ++i)
+        if (plan.staged_store[i] >= 0 && K.b.buf[plan.staged_store[i]]) {
+          float* dst = reinterpret_cast<float*>(K.b.buf[plan.staged_store[i]]) + (size_t)e0 * plan.staged_words[i];
+          const float* src = S + plan.staged_off[i];
+          const int words = plan.staged_words[i] * valid;
+          for (int w = tid; w < words; w += TILE) dst[w] = src[w];
+        }
+    }
+  }
+
+  float* st = S + plan.stash_off + tid * plan.stash_stride;
+  uint32_t status = 0;
+
+  // ------------------------------------------------------------------------------------------
+  // entity: inverse base quaternion and body-frame vectors
+  // ------------------------------------------------------------------------------------------
+  float iw = 1.0f;
+  V3 iq = {0.f, 0.f, 0.f};
+  if (ph & GFB_PHASE_ENTITY) {
+    const float4 q = *reinterpret_cast<const float4*>(S + plan.off_quat + tid * 4);
+    iw = q.x;  // q * (1,-1,-1,-1)
+    iq.x = -q.y;
+    iq.y = -q.z;
+    iq.z = -q.w;
+    if (active && K.b.buf[GFB_B_INV_BASE_QUAT])
+      GFB_BUF(float4, GFB_B_INV_BASE_QUAT)[e] = make_float4(iw, iq.x, iq.y, iq.z);
+  } else if (K.b.buf[GFB_B_INV_BASE_QUAT]) {
+    const float4 q = GFB_BUF(const float4, GFB_B_INV_BASE_QUAT)[e];
+    iw = q.x;
+    iq.x = q.y;
+    iq.y = q.z;
+    iq.z = q.w;
+  }
+  V3 lin_b = {0.f, 0.f, 0.f}, ang_b = {0.f, 0.f, 0.f}, grav_b = {0.f, 0.f, 0.f};
+  if (plan.needs & NEED_LIN) {
+    const float* v = S + plan.off_vel + tid * 3;
+    lin_b = rotate(V3{v[0], v[1], v[2]}, iw, iq);
+    st[3] = lin_b.x; st[4] = lin_b.y; st[5] = lin_b.z;
+  }
+  if (plan.needs & NEED_ANG) {
+    const float* v = S + plan.off_ang + tid * 3;
+    ang_b = rotate(V3{v[0], v[1], v[2]}, iw, iq);
+    st[0] = ang_b.x; st[1] = ang_b.y; st[2] = ang_b.z;
+  }
+  if (plan.needs & NEED_GRAV) {
+    grav_b = rotate(V3{0.0f, 0.0f, -1.0f}, iw, iq);
+    st[6] = grav_b.x; st[7] = grav_b.y; st[8] = grav_b.z;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // contacts: ordered net force / mean position per tracked link, then air time
+  // ------------------------------------------------------------------------------------------
+  if ((ph & GFB_PHASE_CONTACT) && P.n_contact > 0) {
+    const int C = P.n_contact_slots, L = P.n_links_total;
+    const int32_t* la = reinterpret_cast<const int32_t*>(S + plan.off_cla) + tid * C;
+    const int32_t* lb = reinterpret_cast<const int32_t*>(S + plan.off_clb) + tid * C;
+    const float* cf = S + plan.off_cforce + tid * C * 3;
+    const float* cp = S + plan.off_cpos + tid * C * 3;
+    // contact_manager.py:401-403: any NaN/Inf force is zeroed (and reported)
+    bool bad = false;
+    for (int k = 0; k < C * 3; ++k) bad |= !finite_f(cf[k]);
+    if (bad && active) status |= GFB_STATUS_BAD_CONTACT;
+    const float4* lq = GFB_BUF(const float4, GFB_B_LINKS_QUAT) + (size_t)e * L;
+
+    for (int m = 0; m < P.n_contact; ++m) {
+      const gfb_contact_manager& cm = P.contact[m];
+      const int Lc = cm.n_links;
+      float* fout = S + plan.cout_off[m] + tid * Lc * 3;
+      float* pout = S + plan.cposout_off[m] + tid * Lc * 3;
+      for (int t = 0; t < Lc; ++t) {
+        const int target = cm.link_ids[t];
+        const float4 tq = lq[target];
+        float fx = 0.f, fy = 0.f, fz = 0.f, px = 0.f, py = 0.f, pz = 0.f, cnt = 0.f;
+        for (int c = 0; c < C; ++c) {
+          const int a = la[c], b2 = lb[c];
+          const bool is_a = a == target, is_b = b2 == target;
+          bool hit = is_a | is_b;
+          if (hit && cm.has_with_filter) {
+            bool keep = false;
+            for (int w = 0; w < cm.n_with; ++w) {
+              const int wl = cm.with_ids[w];
+              keep |= (is_a && b2 == wl) || (is_b && a == wl);
+            }
+            hit = keep;
+          }
+          if (hit) {
+            float x = cf[c * 3 + 0], y = cf[c * 3 + 1], z = cf[c * 3 + 2];
+            if (bad) {
+              x = finite_f(x) ? x : 0.f;
+              y = finite_f(y) ? y : 0.f;
+              z = finite_f(z) ? z : 0.f;
+            }
+            V3 f = is_b ? V3{x, y, z} : V3{-x, -y, -z};  // kernel.py:75-78
+            f = inv_rotate_ti(f, tq.x, V3{tq.y, tq.z, tq.w});
+            fx = add(fx, f.x); fy = add(fy, f.y); fz = add(fz, f.z);
+            px = add(px, cp[c * 3 + 0]); py = add(py, cp[c * 3 + 1]); pz = add(pz, cp[c * 3 + 2]);
+            cnt = add(cnt, 1.0f);
+          }
+        }
+        if (cnt > 0.f) {  // kernel.py:85-90
+          px = fdiv(px, cnt); py = fdiv(py, cnt); pz = fdiv(pz, cnt);
+        }
+        fout[t * 3 + 0] = fx; fout[t * 3 + 1] = fy; fout[t * 3 + 2] = fz;
+        pout[t * 3 + 0] = px; pout[t * 3 + 1] = py; pout[t * 3 + 2] = pz;
+        const float nrm = norm3(fx, fy, fz);
+        st[plan.st_cnorm[m] + t] = nrm;
+
+        if (cm.track_air_time) {  // contact_manager.py:434-477
+          const float* air = GFB_BUF(const float, GFB_B_AIR0 + m);
+          const size_t base = (size_t)e * Lc + t, plane = (size_t)N * Lc;
+          float last_air = air[base], cur_air = air[plane + base];
+          float last_con = air[2 * plane + base], cur_con = air[3 * plane + base];
+          const float dt = cm.scene_dt;
+          const bool is_contact = nrm > cm.air_time_threshold;
+          const bool new_contact = (cur_air > 0.f) && is_contact;
+          const bool new_detach = (cur_con > 0.f) && !is_contact;
+          last_air = new_contact ? add(cur_air, dt) : last_air;
+          const float cur_air2 = !is_contact ? add(cur_air, dt) : 0.f;
+          last_con = new_detach ? add(cur_con, dt) : last_con;
+          const float cur_con2 = is_contact ? add(cur_con, dt) : 0.f;
+          float* sa = st + plan.st_air[m] + t * 4;
+          sa[0] = last_air; sa[1] = cur_air2; sa[2] = last_con; sa[3] = cur_con2;
+        }
+      }
+    }
+  } else if (P.n_contact > 0 && (ph & (GFB_PHASE_REWARD | GFB_PHASE_TERMINATION | GFB_PHASE_OBSERVE))) {
+    // split execution: contact results of an earlier launch come back from global memory
+    for (int m = 0; m < P.n_contact; ++m) {
+      const gfb_contact_manager& cm = P.contact[m];
+      const float* cg = GFB_BUF(const float, GFB_B_CONTACTS0 + m) + (size_t)e * cm.n_links * 3;
+      for (int t = 0; t < cm.n_links; ++t) {
+        st[plan.st_cnorm[m] + t] = norm3(cg[t * 3], cg[t * 3 + 1], cg[t * 3 + 2]);
+        if (cm.track_air_time) {
+          const float* air = GFB_BUF(const float, GFB_B_AIR0 + m);
+          const size_t base = (size_t)e * cm.n_links + t, plane = (size_t)N * cm.n_links;
+          float* sa = st + plan.st_air[m] + t * 4;
+          sa[0] = air[base]; sa[1] = air[plane + base]; sa[2] = air[2 * plane + base]; sa[3] = air[3 * plane + base];
+        }
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // terminations
+  // ------------------------------------------------------------------------------------------
+  bool terminated = false, truncated = false;
+  if (ph & GFB_PHASE_TERMINATION) {
+    for (int t = 0; t < P.n_termination; ++t) {
+      const gfb_termination_term& tt = P.termination[t];
+      bool v = false;
+      switch (tt.op) {
+        case GFB_T_TIMEOUT:
+          v = P.base_max_episode_length > 0 && ep_len > max_len;
+          break;
+        case GFB_T_BAD_ORIENTATION: {
+          const float tilt = fminf(norm2(grav_b.x, grav_b.y), 0.99f);
+          v = !(ep_len <= tt.i0) && (tilt >= tt.p[0]);
+        } break;
+        case GFB_T_BASE_HEIGHT_MIN:
+          v = S[plan.off_pos + tid * 3 + 2] < tt.p[0];
+          break;
+        case GFB_T_OUT_OF_BOUNDS: {
+          const float x = S[plan.off_pos + tid * 3], y = S[plan.off_pos + tid * 3 + 1];
+          v = (x < tt.p[0]) | (x > tt.p[1]) | (y < tt.p[2]) | (y > tt.p[3]);
+        } break;
+        case GFB_T_HAS_CONTACT: {
+          int n = 0;
+          for (int l = 0; l < P.contact[tt.mgr].n_links; ++l) n += st[plan.st_cnorm[tt.mgr] + l] > tt.p[0];
+          v = n >= tt.i0;
+        } break;
+        case GFB_T_CONTACT_FORCE:
+        case GFB_T_CONTACT_FORCE_GRACE: {
+          bool any = false;
+          for (int l = 0; l < P.contact[tt.mgr].n_links; ++l) any |= st[plan.st_cnorm[tt.mgr] + l] > tt.p[0];
+          v = any && (tt.op == GFB_T_CONTACT_FORCE || !(ep_len <= tt.i0));
+        } break;
+        default:
+          break;
+      }
+      v = v && active;
+      if (tt.time_out) truncated |= v; else terminated |= v;
+      const uint32_t votes = __ballot_sync(0xffffffffu, v);
+      if (lane == 0 && votes) atomicAdd(&s_term_count[t], __popc(votes));
+    }
+  } else if (ph & (GFB_PHASE_REWARD | GFB_PHASE_RESET)) {
+    if (K.b.buf[GFB_B_TERMINATED]) terminated = GFB_BUF(const uint8_t, GFB_B_TERMINATED)[e] != 0;
+    if (K.b.buf[GFB_B_TRUNCATED]) truncated = GFB_BUF(const uint8_t, GFB_B_TRUNCATED)[e] != 0;
+  }
+
+  bool reset = false;
+  if (ph & GFB_PHASE_RESET) {
+    if (ph & GFB_PHASE_FORCED_RESET) {
+      const uint8_t* mask = GFB_BUF(const uint8_t, GFB_B_FORCE_RESET);
+      reset = mask ? (mask[e] != 0) : true;
+    } else {
+      reset = terminated | truncated;  // managed_env.py:308-310
+    }
+    reset = reset && active;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // rewards
+  // ------------------------------------------------------------------------------------------
+  float reward = 0.0f;
+  if (ph & GFB_PHASE_REWARD) {
+    ep_secs = add(ep_secs, P.env_dt);  // reward_manager.py:178
+    float dof_dev = 0.0f;
+    bool have_dof_dev = false;
+    for (int r = 0; r < P.n_reward; ++r) {
+      const gfb_reward_term& rt = P.reward[r];
+      if (rt.weight == 0.0f || rt.op == GFB_R_NONE) continue;  // reward_manager.py:181-182
+      float v = 0.0f;
+      switch (rt.op) {
+        case GFB_R_IS_ALIVE:
+          v = terminated ? 0.0f : 1.0f;
+          break;
+        case GFB_R_TERMINATED:
+          v = terminated ? 1.0f : 0.0f;
+          break;
+        case GFB_R_BASE_HEIGHT: {
+          float z = S[plan.off_pos + tid * 3 + 2];
+          float off = 0.0f;
+          if (rt.flags & GFB_RF_TERRAIN_FLAT) off = rt.p[1];
+          if (rt.flags & GFB_RF_TERRAIN_HEIGHT) {
+            // terrain_manager.py:100-166: normalise to [-1,1], bilinear grid_sample(align_corners, border)
+            const float x = S[plan.off_pos + tid * 3], y = S[plan.off_pos + tid * 3 + 1];
+            const float xmin = P.terrain_bounds[0], xmax = P.terrain_bounds[1];
+            const float ymin = P.terrain_bounds[2], ymax = P.terrain_bounds[3];
+            const float gx = sub(mul(fdiv(sub(x, xmin), sub(xmax, xmin)), 2.0f), 1.0f);
+            const float gy = sub(mul(fdiv(sub(y, ymin), sub(ymax, ymin)), 2.0f), 1.0f);
+            const int Hf = P.height_field_rows, Wf = P.height_field_cols;
+            float ix = mul(fdiv(add(gx, 1.0f), 2.0f), (float)(Wf - 1));
+            float iy = mul(fdiv(add(gy, 1.0f), 2.0f), (float)(Hf - 1));
+            ix = fminf(fmaxf(ix, 0.0f), (float)(Wf - 1));
+            iy = fminf(fmaxf(iy, 0.0f), (float)(Hf - 1));
+            const float fx0 = floorf(ix), fy0 = floorf(iy);
+            const int x0 = (int)fx0, y0 = (int)fy0;
+            const int x1 = min(x0 + 1, Wf - 1), y1 = min(y0 + 1, Hf - 1);
+            const float tx = sub(ix, fx0), ty = sub(iy, fy0);
+            const float* hf = GFB_BUF(const float, GFB_B_HEIGHT_FIELD);
+            const float h00 = hf[y0 * Wf + x0], h01 = hf[y0 * Wf + x1];
+            const float h10 = hf[y1 * Wf + x0], h11 = hf[y1 * Wf + x1];
+            const float wx0 = sub(1.0f, tx), wy0 = sub(1.0f, ty);
+            off = add(add(mul(h00, mul(wx0, wy0)), mul(h01, mul(tx, wy0))),
+                      add(mul(h10, mul(wx0, ty)), mul(h11, mul(tx, ty))));
+          }
+          float target = rt.p[0];
+          if (rt.flags & GFB_RF_TARGET_FROM_COMMAND) target = S[plan.off_cmd[rt.mgr] + tid * P.command[rt.mgr].n_dims];
+          if (rt.flags & GFB_RF_TARGET_FROM_TENSOR) target = GFB_BUF(const float, GFB_B_TARGET_HEIGHT)[e];
+          v = sq(sub(sub(z, off), target));
+        } break;
+        case GFB_R_DOF_SIMILAR:
+        case GFB_R_STAND_STILL: {
+          if (!have_dof_dev) {
+            const float* q = S + plan.off_dof_pos + tid * D;
+            if ((D & 3) == 0) {
+              for (int d4 = 0; d4 < D; d4 += 4) {
+                const float4 qv = *reinterpret_cast<const float4*>(q + d4);
+                dof_dev = add(dof_dev, fabsf(sub(qv.x, P.default_dof_pos[d4])));
+                dof_dev = add(dof_dev, fabsf(sub(qv.y, P.default_dof_pos[d4 + 1])));
+                dof_dev = add(dof_dev, fabsf(sub(qv.z, P.default_dof_pos[d4 + 2])));
+                dof_dev = add(dof_dev, fabsf(sub(qv.w, P.default_dof_pos[d4 + 3])));
+              }
+            } else {
+              for (int d = 0; d < D; ++d) dof_dev = add(dof_dev, fabsf(sub(q[d], P.default_dof_pos[d])));
+            }
+            have_dof_dev = true;
+          }
+          v = dof_dev;
+          if (rt.op == GFB_R_STAND_STILL) {
+            const float* c = S + plan.off_cmd[rt.mgr] + tid * P.command[rt.mgr].n_dims;
+            v = mul(dof_dev, norm2(c[0], c[1]) < rt.p[0] ? 1.0f : 0.0f);
+          }
+        } break;
+        case GFB_R_LIN_VEL_Z:
+          v = sq(lin_b.z);
+          break;
+        case GFB_R_ANG_VEL_XY:
+          v = add(sq(ang_b.x), sq(ang_b.y));
+          break;
+        case GFB_R_FLAT_ORIENTATION:
+          v = add(sq(grav_b.x), sq(grav_b.y));
+          break;
+        case GFB_R_ACTION_RATE:
+          v = action_rate;
+          break;
+        case GFB_R_TRACK_LIN_VEL:
+        case GFB_R_TRACK_ANG_VEL: {
+          float c0, c1, c2;
+          if (rt.flags & GFB_RF_FIXED_COMMAND) {
+            const float* c = GFB_BUF(const float, GFB_B_FIXED_COMMAND) + (size_t)e * 3;
+            c0 = c[0]; c1 = c[1]; c2 = c[2];
+          } else {
+            const float* c = S + plan.off_cmd[rt.mgr] + tid * P.command[rt.mgr].n_dims;
+            c0 = c[0]; c1 = c[1]; c2 = c[2];
+          }
+          float err;
+          if (rt.op == GFB_R_TRACK_LIN_VEL)
+            err = add(sq(sub(c0, lin_b.x)), sq(sub(c1, lin_b.y)));
+          else
+            err = sq(sub(c2, ang_b.z));
+          v = expf(fdiv(-err, rt.p[0]));
+        } break;
+        case GFB_R_HAS_CONTACT: {
+          int n = 0;
+          for (int l = 0; l < P.contact[rt.mgr].n_links; ++l) n += st[plan.st_cnorm[rt.mgr] + l] > rt.p[0];
+          v = n >= rt.i0 ? 1.0f : 0.0f;
+        } break;
+        case GFB_R_CONTACT_FORCE: {
+          for (int l = 0; l < P.contact[rt.mgr].n_links; ++l)
+            v = add(v, fmaxf(sub(st[plan.st_cnorm[rt.mgr] + l], rt.p[0]), 0.0f));
+        } break;
+        case GFB_R_FEET_AIR_TIME: {
+          for (int l = 0; l < P.contact[rt.mgr].n_links; ++l) {
+            const float* sa = st + plan.st_air[rt.mgr] + l * 4;
+            const bool made = (sa[3] > 0.0f) && (sa[3] < rt.p[2]);  // contact_manager.py:198-224
+            float a = mul(sub(sa[0], rt.p[0]), made ? 1.0f : 0.0f);
+            if (rt.flags & GFB_RF_HAS_MAX) a = fminf(a, rt.p[1]);
+            v = add(v, a);
+          }
+          if (rt.i0 >= 0) {
+            const float* c = S + plan.off_cmd[rt.i0] + tid * P.command[rt.i0].n_dims;
+            v = mul(v, norm2(c[0], c[1]) > 0.1f ? 1.0f : 0.0f);
+          }
+        } break;
+        case GFB_R_FEET_SLIDE: {
+          const int Lc = P.contact[rt.mgr].n_links;
+          const float* lv = GFB_BUF(const float, GFB_B_LINKS_VEL) + (size_t)e * Lc * 3;
+          for (int l = 0; l < Lc; ++l) {
+            const float speed = norm3(lv[l * 3], lv[l * 3 + 1], lv[l * 3 + 2]);
+            v = add(v, mul(speed, st[plan.st_cnorm[rt.mgr] + l] > 1.0f ? 1.0f : 0.0f));
+          }
+        } break;
+        case GFB_R_EXTERNAL:
+          v = GFB_BUF(const float, GFB_B_OBS_EXT3)[(size_t)e * GFB_MAX_REWARD_TERMS + rt.ext_col];
+          break;
+        default:
+          break;
+      }
+      v = mul(v, rt.weight);
+      reward = add(reward, v);                 // reward_manager.py:188-189
+      float* sum = S + plan.sums_off + r * TILE + tid;
+      *sum = add(*sum, v);                      // reward_manager.py:192-193
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // command resample on the resample boundary (command_manager.py:152-162)
+  // ------------------------------------------------------------------------------------------
+  const Philox rng(P.rng_seed);
+  if (ph & GFB_PHASE_COMMAND) {
+    for (int k = 0; k < P.n_command; ++k) {
+      const gfb_command_manager& cm = P.command[k];
+      if (!cm.enabled) continue;
+      if (active && (ep_len % cm.resample_steps) == 0) {
+        float* cs = S + plan.off_cmd[k] + tid * cm.n_dims;
+        float* cg = GFB_BUF(float, GFB_B_COMMAND0 + k) + (size_t)e * cm.n_dims;
+        const float* inj = GFB_BUF(const float, GFB_B_INJ_CMD_STEP0 + k);
+        for (int i = 0; i < cm.n_dims; ++i) {
+          float val;
+          if (P.rng_mode == 0) {
+            val = inj ? inj[(size_t)e * cm.n_dims + i] : cs[i];
+          } else {
+            const uint4 x = rng((uint32_t)e, (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32), 0x100u + k * 16 + i);
+            val = add(mul(u01(x.x), sub(cm.hi[i], cm.lo[i])), cm.lo[i]);
+          }
+          cs[i] = val;
+          cg[i] = val;
+        }
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // in-library part of reset() for the envs that terminated / truncated
+  // ------------------------------------------------------------------------------------------
+  const uint32_t reset_votes = __ballot_sync(0xffffffffu, reset);
+  if (lane == 0) s_reset_bits[warp] = reset_votes;
+  if (ph & GFB_PHASE_RESET) {
+    if (reset) {
+      // genesis_env.py:233-252
+      if (K.b.buf[GFB_B_ENV_ACTIONS]) {
+        float* a = GFB_BUF(float, GFB_B_ENV_ACTIONS) + (size_t)e * D;
+        float* la = GFB_BUF(float, GFB_B_ENV_LAST_ACTIONS) + (size_t)e * D;
+        for (int d = 0; d < D; ++d) { a[d] = 0.0f; la[d] = 0.0f; }
+      }
+      ep_len = 0;
+      if (P.max_len_random_span > 0.0f && P.base_max_episode_length > 0) {
+        float u;
+        if (P.rng_mode == 0) {
+          const float* inj = GFB_BUF(const float, GFB_B_INJ_MAX_LEN);
+          u = inj ? inj[e] : 0.0f;
+        } else {
+          const uint4 x = rng((uint32_t)e, (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32), 0x200u);
+          u = sub(mul(u01(x.x), 2.0f), 1.0f);
+        }
+        max_len = (int)rintf(add((float)P.base_max_episode_length, mul(u, P.max_len_random_span)));
+        GFB_BUF(int32_t, GFB_B_MAX_EPISODE_LENGTH)[e] = max_len;
+      }
+      GFB_BUF(int32_t, GFB_B_EPISODE_LENGTH)[e] = 0;
+      // command_manager.py:164-170
+      for (int k = 0; k < P.n_command; ++k) {
+        const gfb_command_manager& cm = P.command[k];
+        if (!cm.enabled) continue;
+        float* cs = S + plan.off_cmd[k] + tid * cm.n_dims;
+        float* cg = GFB_BUF(float, GFB_B_COMMAND0 + k) + (size_t)e * cm.n_dims;
+        const float* inj = GFB_BUF(const float, GFB_B_INJ_CMD_RESET0 + k);
+        for (int i = 0; i < cm.n_dims; ++i) {
+          float val;
+          if (P.rng_mode == 0) {
+            val = inj ? inj[(size_t)e * cm.n_dims + i] : cs[i];
+          } else {
+            const uint4 x = rng((uint32_t)e, (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32), 0x300u + k * 16 + i);
+            val = add(mul(u01(x.x), sub(cm.hi[i], cm.lo[i])), cm.lo[i]);
+          }
+          cs[i] = val;
+          cg[i] = val;
+        }
+      }
+      // contact_manager.py:316-329
+      for (int m = 0; m < P.n_contact; ++m)
+        if (P.contact[m].track_air_time)
+          for (int k = 0; k < P.contact[m].n_links * 4; ++k) st[plan.st_air[m] + k] = 0.0f;
+    }
+    // reward_manager.py:197-222: per-term episode mean over the reset envs, then clear
+    if (P.n_reward > 0) {
+      if (reset_votes) {
+        for (int r = 0; r < P.n_reward; ++r) {
+          float* sum = S + plan.sums_off + r * TILE + tid;
+          double q = 0.0;
+          if (reset) {
+            if (P.reward[r].weight != 0.0f) q = (double)fdiv(*sum, ep_secs);
+            *sum = 0.0f;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+          if (lane == 0) s_rew_part[r][warp] = q;
+        }
+      } else if (lane == 0) {
+        for (int r = 0; r < P.n_reward; ++r) s_rew_part[r][warp] = 0.0;
+      }
+      if (reset) ep_secs = 1e-10f;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // per-env outputs
+  // ------------------------------------------------------------------------------------------
+  if (active) {
+    if (ph & GFB_PHASE_TERMINATION) {
+      GFB_BUF(uint8_t, GFB_B_TERMINATED)[e] = terminated;
+      GFB_BUF(uint8_t, GFB_B_TRUNCATED)[e] = truncated;
+    }
+    if (ph & GFB_PHASE_REWARD) GFB_BUF(float, GFB_B_REWARD)[e] = reward;
+    if ((ph & (GFB_PHASE_REWARD | GFB_PHASE_RESET)) && K.b.buf[GFB_B_EP_SECONDS])
+      GFB_BUF(float, GFB_B_EP_SECONDS)[e] = ep_secs;
+    if (ph & (GFB_PHASE_CONTACT | GFB_PHASE_RESET)) {
+      for (int m = 0; m < P.n_contact; ++m) {
+        const gfb_contact_manager& cm = P.contact[m];
+        if (!cm.track_air_time) continue;
+        if (!(ph & GFB_PHASE_CONTACT) && !reset) continue;
+        float* air = GFB_BUF(float, GFB_B_AIR0 + m);
+        const size_t plane = (size_t)N * cm.n_links;
+        for (int t = 0; t < cm.n_links; ++t) {
+          const float* sa = st + plan.st_air[m] + t * 4;
+          const size_t base = (size_t)e * cm.n_links + t;
+          air[base] = sa[0]; air[plane + base] = sa[1]; air[2 * plane + base] = sa[2]; air[3 * plane + base] = sa[3];
+        }
+      }
+    }
+  }
+  if (status) atomicOr(&s_status, status);
+
+  if (use_tma) fence_async_smem();
+  __syncthreads();
+
+  // ------------------------------------------------------------------------------------------
+  // slab outputs: episode sums, contact forces / positions
+  // ------------------------------------------------------------------------------------------
+  const bool store_contacts = (ph & GFB_PHASE_CONTACT) && P.n_contact > 0;
+  if (use_tma) {
+    if (tid == 0) {
+      if (stage_sums) {
+        float* sums = GFB_BUF(float, GFB_B_EP_SUMS);
+        for (int r = 0; r < P.n_reward; ++r)
+          bulk_store(sums + (size_t)r * N + e0, S + plan.sums_off + r * TILE, TILE * 4u);
+      }
+      if (store_contacts)
+        for (int m = 0; m < P.n_contact; ++m) {
+          const uint32_t bytes = (uint32_t)P.contact[m].n_links * 3u * TILE * 4u;
+          const size_t goff = (size_t)e0 * P.contact[m].n_links * 3;
+          bulk_store(GFB_BUF(float, GFB_B_CONTACTS0 + m) + goff, S + plan.cout_off[m], bytes);
+          bulk_store(GFB_BUF(float, GFB_B_CONTACT_POS0 + m) + goff, S + plan.cposout_off[m], bytes);
+        }
+      bulk_commit();
+    }
+  } else {
+    if (stage_sums && active) {
+      float* sums = GFB_BUF(float, GFB_B_EP_SUMS);
+      for (int r = 0; r < P.n_reward; ++r) sums[(size_t)r * N + e] = S[plan.sums_off + r * TILE + tid];
+    }
+    if (store_contacts)
+      for (int m = 0; m < P.n_contact; ++m) {
+        const int words = P.contact[m].n_links * 3 * valid;
+        const size_t goff = (size_t)e0 * P.contact[m].n_links * 3;
+        float* g1 = GFB_BUF(float, GFB_B_CONTACTS0 + m) + goff;
+        float* g2 = GFB_BUF(float, GFB_B_CONTACT_POS0 + m) + goff;
+        for (int w = tid; w < words; w += TILE) {
+          g1[w] = S[plan.cout_off[m] + w];
+          g2[w] = S[plan.cposout_off[m] + w];
+        }
+      }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // slab partials for the finalize kernel (ordered compaction + logging reductions)
+  // ------------------------------------------------------------------------------------------
+  {
+    const Scratch& sc = K.s;
+    const int nt = sc.n_tiles;
+    if (tid < TILE / 32) sc.tile_reset_bits[(size_t)tile * (TILE / 32) + tid] = s_reset_bits[tid];
+    if (tid == 0) {
+      int n = 0;
+      for (int w = 0; w < TILE / 32; ++w) n += __popc(s_reset_bits[w]);
+      sc.tile_reset_count[tile] = n;
+      if (s_status) atomicOr(sc.status, s_status);
+    }
+    if ((ph & GFB_PHASE_TERMINATION) && tid < P.n_termination)
+      sc.tile_term_count[(size_t)tid * nt + tile] = s_term_count[tid];
+    if ((ph & GFB_PHASE_RESET) && tid < P.n_reward) {
+      double acc = 0.0;
+      for (int w = 0; w < TILE / 32; ++w) acc += s_rew_part[tid][w];
+      sc.tile_rew_sum[(size_t)tid * nt + tile] = acc;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // observations: every thread assembles 16-byte pieces of the slab's rows
+  // (observation_manager.py:232-256: value * scale (+ U(-1,1) * noise), concatenated; history
+  //  frames 1..H-1 are the previous step's frames 0..H-2, observation_manager.py:223-226)
+  // ------------------------------------------------------------------------------------------
+  if (ph & GFB_PHASE_OBSERVE) {
+    const DevObsCol* cols_all = reinterpret_cast<const DevObsCol*>(S + plan.cols_off);
+    for (int g = 0; g < P.n_obs_groups; ++g) {
+      const gfb_obs_group& og = P.obs_group[g];
+      const int O = og.n_cols, OH = og.n_cols * og.history;
+      const DevObsCol* cols = cols_all + og.col_begin;
+      float* out = GFB_BUF(float, GFB_B_OBS_OUT0 + g) + (size_t)e0 * OH;
+      const float* prev = GFB_BUF(const float, GFB_B_OBS_PREV0 + g);
+      if (prev) prev += (size_t)e0 * OH;
+      const float* noise = GFB_BUF(const float, GFB_B_OBS_NOISE0 + g);
+      if (noise) noise += (size_t)e0 * O;
+      if ((O & 3) == 0) {
+        const int W = OH >> 2;
+        const int total = valid * W;
+        int row = tid / W, c4 = tid - row * W;
+        const int drow = TILE / W, dc = TILE - drow * W;
+        for (int f = tid; f < total; f += TILE) {
+          const int col = c4 << 2;
+          float4 v;
+          if (col < O) {
+            const DevObsCol d0 = cols[col];
+            float s1 = d0.scale, s2 = d0.scale, s3 = d0.scale;
+            float n1 = d0.noise, n2 = d0.noise, n3 = d0.noise;
+            if (d0.vec) {
+              if (d0.kind == 1)
+                v = *reinterpret_cast<const float4*>(S + d0.a + row * d0.row_words + d0.col);
+              else
+                v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(K.b.buf[d0.gbuf]) +
+                                                      (size_t)(e0 + row) * d0.row_words + d0.col);
+            } else {
+              const DevObsCol d1 = cols[col + 1], d2 = cols[col + 2], d3 = cols[col + 3];
+              v.x = obs_fetch_post(d0, S, K.b, plan, row, e0 + row);
+              v.y = obs_fetch_post(d1, S, K.b, plan, row, e0 + row);
+              v.z = obs_fetch_post(d2, S, K.b, plan, row, e0 + row);
+              v.w = obs_fetch_post(d3, S, K.b, plan, row, e0 + row);
+              s1 = d1.scale; s2 = d2.scale; s3 = d3.scale;
+              n1 = d1.noise; n2 = d2.noise; n3 = d3.noise;
+            }
+            v.x = mul(v.x, d0.scale); v.y = mul(v.y, s1); v.z = mul(v.z, s2); v.w = mul(v.w, s3);
+            if (d0.noise != 0.f || n1 != 0.f || n2 != 0.f || n3 != 0.f) {
+              float4 u;
+              if (P.rng_mode == 0) {
+                u = noise ? *reinterpret_cast<const float4*>(noise + (size_t)row * O + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+              } else {
+                const uint4 x = rng((uint32_t)(e0 + row), (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32),
+                                    0x1000u + (uint32_t)(og.col_begin + col));
+                u = make_float4(sub(mul(u01(x.x), 2.f), 1.f), sub(mul(u01(x.y), 2.f), 1.f),
+                                sub(mul(u01(x.z), 2.f), 1.f), sub(mul(u01(x.w), 2.f), 1.f));
+              }
+              if (d0.noise != 0.f) v.x = add(v.x, mul(u.x, d0.noise));
+              if (n1 != 0.f) v.y = add(v.y, mul(u.y, n1));
+              if (n2 != 0.f) v.z = add(v.z, mul(u.z, n2));
+              if (n3 != 0.f) v.w = add(v.w, mul(u.w, n3));
+            }
+          } else {
+            v = *reinterpret_cast<const float4*>(prev + (size_t)row * OH + (col - O));
+          }
+          *reinterpret_cast<float4*>(out + (size_t)row * OH + col) = v;
+          row += drow;
+          c4 += dc;
+          if (c4 >= W) { c4 -= W; ++row; }
+        }
+      } else {
+        const int total = valid * OH;
+        for (int f = tid; f < total; f += TILE) {
+          const int row = f / OH, col = f - row * OH;
+          float v;
+          if (col < O) {
+            const DevObsCol d = cols[col];
+            v = mul(obs_fetch_post(d, S, K.b, plan, row, e0 + row), d.scale);
+            if (d.noise != 0.f) {
+              float u;
+              if (P.rng_mode == 0) {
+                u = noise ? noise[(size_t)row * O + col] : 0.f;
+              } else {
+                const uint4 x = rng((uint32_t)(e0 + row), (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32),
+                                    0x1000u + (uint32_t)(og.col_begin + (col & ~3)));
+                const int j = col & 3;
+                const uint32_t xj = j == 0 ? x.x : (j == 1 ? x.y : (j == 2 ? x.z : x.w));
+                u = sub(mul(u01(xj), 2.f), 1.f);
+              }
+              v = add(v, mul(u, d.noise));
+            }
+          } else {
+            v = prev[(size_t)row * OH + (col - O)];
+          }
+          out[(size_t)row * OH + col] = v;
+        }
+      }
+    }
+  }
+
+  if (use_tma && tid == 0) bulk_wait_all();
+}
+
+}  // namespace gfb

@@ -1,0 +1,698 @@
+"""
+The fused manager step: term compiler + per-step driver on top of libgfb200 (include/gfb200.h).
+
+`FusedStep` is created by ManagedEnvironment.build().  It
+  * compiles the manager objects (their live config items) into the packed term table
+    (`gfb_program`): one opcode per recognised mdp function, one column descriptor per observation
+    column, per-DOF action parameters, command ranges, contact link ids;
+  * owns the small auxiliary tensors the kernels need (action-rate scratch, reset index list,
+    logging vectors, injected-draw buffers);
+  * drives the launches of one environment step:
+        gfb_action_step -> engine PD target write -> scene.step() -> gfb_post_physics
+        -> gfb_read_report (the single host sync) -> host-side reset fan-out for the compacted
+        reset indices -> gfb_observe for those envs.
+
+Random draws made inside the kernels come either from Philox (default) or from dense injected
+buffers (`inject()`), which is how the parity harness feeds the reference's own draws through.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from ._gs import gs
+
+try:  # pragma: no cover - depends on the environment
+    from tensordict import TensorDict as _TensorDict  # type: ignore
+
+    def make_obs_dict(device):
+        return _TensorDict({}, device=device)
+
+except Exception:
+
+    def make_obs_dict(device):
+        return {}
+
+
+_F32 = np.float32
+
+
+def _f32(x) -> float:
+    """Python float -> the fp32 value torch uses when a Python scalar meets a float32 tensor."""
+    return float(_F32(x))
+
+
+def asin_tilt_threshold(limit_angle_deg: float) -> float:
+    """
+    Smallest fp32 tilt t in [0, 0.99] for which the reference's test
+        torch.asin(torch.clamp(tilt, max=0.99)) > math.radians(limit_angle)
+    (mdp/terminations.py:63-71) is true under THIS host's torch-CPU asin; +inf if none.
+
+    The kernel then evaluates `min(tilt, 0.99) >= threshold`, which is the same predicate without
+    depending on device asin bits (asin is monotonic).  Bisection over the fp32 bit patterns.
+    """
+    limit = math.radians(limit_angle_deg)
+
+    def fires(bits: int) -> bool:
+        t = torch.tensor([bits], dtype=torch.int32).view(torch.float32)
+        return bool((torch.asin(torch.clamp(t, max=0.99)) > limit).item())
+
+    hi = int(np.array([0.99], dtype=np.float32).view(np.int32)[0])
+    if not fires(hi):
+        return float("inf")
+    if fires(0):
+        return 0.0
+    lo = 0  # fires(lo) False, fires(hi) True
+    while hi - lo > 1:
+        mid = (lo + hi) // 2
+        if fires(mid):
+            hi = mid
+        else:
+            lo = mid
+    return float(np.array([hi], dtype=np.int32).view(np.float32)[0])
+
+
+class UnsupportedTermError(NotImplementedError):
+    pass
+
+
+class FusedStep:
+    def __init__(self, env, dry_run: bool = False):
+        """`dry_run` compiles and packs the term table without a device (host-logic tests only)."""
+        self.env = env
+        self.device = torch.device(gs.device)
+        self.N = env.num_envs
+        self.dry_run = dry_run
+        if dry_run:
+            self.lib = self.handle = None
+        else:
+            if self.device.type != "cuda":
+                raise nat.NativeLibraryError(
+                    f"the fused manager step runs on a CUDA device (gs.device is {self.device}); "
+                    "there is no CPU implementation in this package"
+                )
+            self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            self.lib = nat.lib()
+            self.handle = nat.Handle(self.N, self.index)
+        self.program = nat.Program()
+        self.buffers = nat.Buffers()
+        self.report = nat.Report()
+        self._fingerprint = None
+        self._threshold_cache: dict[float, float] = {}
+        self._keepalive: list = []
+        self.injected: dict[str, torch.Tensor] | None = None
+        self.rng_seed = 0x5EED
+        self.dist = None  # (process group) when envs are sharded over ranks
+        self._contact_dims = None
+        self._feet_slide_manager = None
+        self._compile()
+
+    # ------------------------------------------------------------------------------------------
+    # compile: static structure
+    # ------------------------------------------------------------------------------------------
+    def _compile(self):
+        env, M = self.env, self.env.managers
+        self.action = M["action"]
+        self.commands = list(M["command"])
+        self.contacts = list(M["contact"])
+        self.entities = list(M["entity"])
+        self.reward = M["reward"]
+        self.termination = M["termination"]
+        self.observations = list(M["observation"])
+        self.terrains = list(M["terrain"])
+        if len(self.commands) > nat.MAX_COMMANDS:
+            raise UnsupportedTermError(f"at most {nat.MAX_COMMANDS} command managers are supported")
+        if len(self.contacts) > nat.MAX_CONTACT:
+            raise UnsupportedTermError(f"at most {nat.MAX_CONTACT} contact managers are supported")
+        if len(self.observations) > nat.MAX_OBS_GROUPS:
+            raise UnsupportedTermError(f"at most {nat.MAX_OBS_GROUPS} observation managers are supported")
+        self.primary_entity = self.entities[0].entity if self.entities else getattr(env, "robot", None)
+        self.entity_manager = self.entities[0] if self.entities else None
+        if len(self.entities) > 1:
+            others = {id(e.entity) for e in self.entities}
+            if len(others) > 1:
+                raise UnsupportedTermError("the fused step supports EntityManagers of a single entity")
+        self.D = self.action.num_actions if self.action is not None else 0
+        if self.D > nat.MAX_DOFS:
+            raise UnsupportedTermError(f"at most {nat.MAX_DOFS} controlled DOFs are supported")
+
+        dev = self.device
+        N = self.N
+        self.action_rate = torch.zeros(N, device=dev)
+        self.reset_idx = torch.zeros(N, device=dev, dtype=torch.int64)
+        n_r = len(self.reward.cfg) if self.reward is not None else 0
+        n_t = len(self.termination.term_cfg) if self.termination is not None else 0
+        self.n_reward, self.n_termination = n_r, n_t
+        self.log_out = torch.zeros(max(n_r + n_t, 1), device=dev)
+        self.log_acc = torch.zeros(n_r + n_t + 1, device=dev, dtype=torch.float64)
+        # entity cache tensors when there is no EntityManager to own them
+        if self.entity_manager is None:
+            self._inv_base_quat = torch.zeros((N, 4), device=dev)
+        self._fixed_command = None
+        self._fixed_command_parts = None
+        # terms
+        self.reward_terms = []
+        if self.reward is not None:
+            for name, item in self.reward.cfg.items():
+                self.reward_terms.append((name, item, self._opcode_of(item.fn, "reward", name)))
+        self.termination_terms = []
+        if self.termination is not None:
+            for name, item in self.termination.term_cfg.items():
+                self.termination_terms.append((name, item, self._opcode_of(item.fn, "termination", name)))
+        self._static_buffers()
+
+    @staticmethod
+    def _opcode_of(fn, kind: str, name: str) -> int:
+        target = getattr(fn, "__func__", fn)
+        opcode = getattr(target, "gfb_opcode", None)
+        if opcode is None or getattr(target, "gfb_kind", None) != kind:
+            mod = getattr(target, "__module__", "?")
+            raise UnsupportedTermError(
+                f"{kind} term '{name}': function {mod}.{getattr(target, '__name__', target)} is not one of the "
+                f"mdp.{kind}s functions of genesis_forge_b200; user-defined terms are not supported by the "
+                "fused step yet"
+            )
+        return nat.K[opcode]
+
+    def _set(self, buf_id: int, tensor: torch.Tensor | None, dtype=None, keep: bool = False):
+        if tensor is None:
+            self.buffers.buf[buf_id] = None
+            return
+        if tensor.device != self.device:
+            raise ValueError(f"buffer {buf_id}: tensor on {tensor.device}, expected {self.device}")
+        if dtype is not None and tensor.dtype != dtype:
+            tensor = tensor.to(dtype)
+            keep = True
+        if not tensor.is_contiguous():
+            tensor = tensor.contiguous()
+            keep = True
+        if keep:
+            self._keepalive.append(tensor)
+        self.buffers.buf[buf_id] = tensor.data_ptr()
+
+    def _static_buffers(self):
+        """Pointers that never change: tensors owned by the env / managers / this object."""
+        env, K = self.env, nat.K
+        s = self._set
+        s(K["GFB_B_EPISODE_LENGTH"], env.episode_length)
+        s(K["GFB_B_MAX_EPISODE_LENGTH"], env.max_episode_length)
+        s(K["GFB_B_ACTION_RATE"], self.action_rate)
+        s(K["GFB_B_RESET_IDX"], self.reset_idx)
+        s(K["GFB_B_LOG_OUT"], self.log_out)
+        s(K["GFB_B_LOG_ACC"], self.log_acc)
+        for k, mgr in enumerate(self.commands):
+            s(K["GFB_B_COMMAND0"] + k, mgr._command)
+        if self.entity_manager is not None:
+            s(K["GFB_B_BASE_POS"], self.entity_manager._base_pos)
+            s(K["GFB_B_BASE_QUAT"], self.entity_manager._base_quat)
+            s(K["GFB_B_INV_BASE_QUAT"], self.entity_manager._inv_base_quat)
+        else:
+            s(K["GFB_B_INV_BASE_QUAT"], self._inv_base_quat)
+        for m, mgr in enumerate(self.contacts):
+            s(K["GFB_B_CONTACTS0"] + m, mgr.contacts)
+            s(K["GFB_B_CONTACT_POS0"] + m, mgr.contact_positions)
+            s(K["GFB_B_AIR0"] + m, mgr._air)
+        if self.termination is not None:
+            # torch.bool is one byte per element, 0/1
+            s(K["GFB_B_TERMINATED"], self.termination._terminated_buf)
+            s(K["GFB_B_TRUNCATED"], self.termination._truncated_buf)
+        else:
+            s(K["GFB_B_TERMINATED"], env._terminated_buf)
+            s(K["GFB_B_TRUNCATED"], env._truncated_buf)
+        if self.reward is not None:
+            s(K["GFB_B_REWARD"], self.reward._reward_buf)
+            s(K["GFB_B_EP_SECONDS"], self.reward._episode_seconds)
+            s(K["GFB_B_EP_SUMS"], self.reward._episode_sums)
+        else:
+            s(K["GFB_B_REWARD"], env._reward_buf)
+        for t in self.terrains:
+            if t.height_field is not None:
+                s(K["GFB_B_HEIGHT_FIELD"], t.height_field)
+
+    def bind_action_buffers(self):
+        K = nat.K
+        self._set(K["GFB_B_ENV_ACTIONS"], self.env._actions)
+        self._set(K["GFB_B_ENV_LAST_ACTIONS"], self.env._last_actions)
+        if self.action is not None:
+            self._set(K["GFB_B_TARGETS"], self.action._actions)
+
+    # ------------------------------------------------------------------------------------------
+    # pack: live config -> gfb_program
+    # ------------------------------------------------------------------------------------------
+    def _live_fingerprint(self):
+        fp = [self.env.dt, self.env._base_max_episode_length, self.env._max_episode_random_scaling,
+              self.injected is not None, self.rng_seed]
+        for _, item, _ in self.reward_terms:
+            fp.append(item.weight)
+            fp.append(item.version)
+        for _, item, _ in self.termination_terms:
+            fp.append(item.time_out)
+            fp.append(item.version)
+        for mgr in self.commands:
+            fp.append(tuple(map(tuple, mgr.ranges_list())))
+            fp.append(mgr._resample_steps)
+            fp.append(mgr._external_controller is None)
+        for mgr in self.contacts:
+            fp.append(mgr._air_time_contact_threshold)
+        for om in self.observations:
+            fp.append(om.noise)
+            for item in om.cfg.values():
+                fp.append(item.scale)
+                fp.append(item.noise)
+        return tuple(fp)
+
+    def _entity_ok(self, params: dict, what: str):
+        em = params.get("entity_manager")
+        if em is not None:
+            if em.entity is not self.primary_entity:
+                raise UnsupportedTermError(f"{what}: entity_manager of a second entity is not supported")
+            return
+        attr = params.get("entity_attr", "robot")
+        if getattr(self.env, attr, None) is not self.primary_entity:
+            raise UnsupportedTermError(f"{what}: entity_attr '{attr}' is not the fused step's entity")
+
+    def _command_index(self, mgr, what: str) -> int:
+        for k, m in enumerate(self.commands):
+            if m is mgr:
+                return k
+        raise UnsupportedTermError(f"{what}: command manager is not registered with this environment")
+
+    def _contact_index(self, mgr, what: str) -> int:
+        for k, m in enumerate(self.contacts):
+            if m is mgr:
+                return k
+        raise UnsupportedTermError(f"{what}: contact manager is not registered with this environment")
+
+    def _tilt_threshold(self, limit_angle: float) -> float:
+        key = float(limit_angle)
+        if key not in self._threshold_cache:
+            self._threshold_cache[key] = asin_tilt_threshold(key)
+        return self._threshold_cache[key]
+
+    def pack(self):
+        fp = self._live_fingerprint()
+        if fp == self._fingerprint:
+            return
+        env, K, P = self.env, nat.K, self.program.head
+        C.memset(C.byref(self.program), 0, C.sizeof(self.program))
+        P.num_envs, P.num_dofs = self.N, self.D
+        P.env_dt = env.dt
+        P.base_max_episode_length = env._base_max_episode_length or 0
+        if env._base_max_episode_length and env._max_episode_random_scaling > 0.0:
+            P.max_len_random_span = env._base_max_episode_length * env._max_episode_random_scaling
+        P.rng_mode = 0 if self.injected is not None else 1
+        P.rng_seed = self.rng_seed
+
+        # action
+        if self.action is not None:
+            P.action_mode = self.action.kernel_mode
+            kp = {k: v.detach().cpu().tolist() for k, v in self.action.kernel_params().items()}
+            for d in range(self.D):
+                P.action_scale[d] = kp["scale"][d]
+                P.action_offset[d] = kp["offset"][d]
+                P.action_clip_lo[d] = kp["clip_lo"][d]
+                P.action_clip_hi[d] = kp["clip_hi"][d]
+                P.default_dof_pos[d] = kp["default"][d]
+
+        # commands
+        P.n_command = len(self.commands)
+        for k, mgr in enumerate(self.commands):
+            cm = P.command[k]
+            ranges = mgr.ranges_list()
+            if len(ranges) > nat.MAX_COMMAND_DIMS:
+                raise UnsupportedTermError("command manager with too many ranges")
+            cm.n_dims = len(ranges)
+            cm.resample_steps = mgr._resample_steps
+            cm.enabled = 1 if (mgr.enabled and mgr._external_controller is None) else 0
+            for i, (lo, hi) in enumerate(ranges):
+                cm.lo[i], cm.hi[i] = lo, hi
+
+        # contacts
+        P.n_contact = len(self.contacts)
+        scene = env.scene
+        for m, mgr in enumerate(self.contacts):
+            cm = P.contact[m]
+            ids = mgr._link_ids.tolist()
+            local = mgr._local_link_ids.tolist()
+            withs = [int(w) for w in mgr._with_link_ids.tolist()]
+            if len(ids) > nat.MAX_CONTACT_LINKS or len(withs) > nat.MAX_WITH_LINKS:
+                raise UnsupportedTermError("contact manager tracks too many links")
+            cm.n_links, cm.n_with = len(ids), len(withs)
+            cm.has_with_filter = 1 if mgr._has_with_filter else 0
+            cm.track_air_time = 1 if mgr._track_air_time else 0
+            cm.air_time_threshold = mgr._air_time_contact_threshold
+            cm.scene_dt = scene.dt
+            for i, v in enumerate(ids):
+                cm.link_ids[i] = v
+                cm.local_link_ids[i] = local[i]
+            for i, v in enumerate(withs):
+                cm.with_ids[i] = v
+
+        # rewards
+        P.n_reward = len(self.reward_terms)
+        if P.n_reward > nat.MAX_REWARD:
+            raise UnsupportedTermError(f"at most {nat.MAX_REWARD} reward terms are supported")
+        self._feet_slide_manager = None
+        self._fixed_command_parts = None
+        for r, (name, item, opcode) in enumerate(self.reward_terms):
+            t = P.reward[r]
+            t.op, t.mgr, t.i0 = opcode, -1, 0
+            t.weight = item.weight * env.dt  # reward_manager.py:184
+            if not self.reward.enabled:
+                t.weight = 0.0
+            sig = getattr(item.fn, "gfb_signature", None) or item.fn.__func__.gfb_signature
+            p = sig(env, **item.params)
+            what = f"reward '{name}'"
+            if opcode in (K["GFB_R_LIN_VEL_Z"], K["GFB_R_ANG_VEL_XY"], K["GFB_R_FLAT_ORIENTATION"],
+                          K["GFB_R_TRACK_LIN_VEL"], K["GFB_R_TRACK_ANG_VEL"], K["GFB_R_BASE_HEIGHT"]):
+                self._entity_ok(p, what)
+            if opcode == K["GFB_R_BASE_HEIGHT"]:
+                if p["height_command"] is not None:
+                    t.flags |= K["GFB_RF_TARGET_FROM_COMMAND"]
+                    t.mgr = self._command_index(p["height_command"], what)
+                elif torch.is_tensor(p["target_height"]):
+                    t.flags |= K["GFB_RF_TARGET_FROM_TENSOR"]
+                    self._set(K["GFB_B_TARGET_HEIGHT"], p["target_height"].expand(self.N), torch.float32, keep=True)
+                else:
+                    t.p[0] = p["target_height"]
+                tm = p["terrain_manager"]
+                if tm is not None:
+                    if tm.height_field is None:
+                        t.flags |= K["GFB_RF_TERRAIN_FLAT"]
+                        t.p[1] = float(tm._origin[2])
+                    else:
+                        t.flags |= K["GFB_RF_TERRAIN_HEIGHT"]
+                        P.height_field_rows, P.height_field_cols = tm.height_field.shape
+                        for i, b in enumerate(tm.get_bounds()):
+                            P.terrain_bounds[i] = b
+                        self._set(K["GFB_B_HEIGHT_FIELD"], tm.height_field)
+            elif opcode in (K["GFB_R_TRACK_LIN_VEL"], K["GFB_R_TRACK_ANG_VEL"]):
+                t.p[0] = p["sensitivity"]
+                if p["vel_cmd_manager"] is not None:
+                    t.mgr = self._command_index(p["vel_cmd_manager"], what)
+                else:
+                    t.flags |= K["GFB_RF_FIXED_COMMAND"]
+                    parts = self._fixed_command_parts or {}
+                    if opcode == K["GFB_R_TRACK_LIN_VEL"]:
+                        parts["lin"] = p["command"]
+                    else:
+                        parts["ang"] = p["commanded_ang_vel"]
+                    self._fixed_command_parts = parts
+            elif opcode == K["GFB_R_STAND_STILL"]:
+                t.p[0] = p["command_threshold"]
+                t.mgr = self._command_index(p["vel_cmd_manager"], what)
+            elif opcode == K["GFB_R_HAS_CONTACT"]:
+                t.mgr = self._contact_index(p["contact_manager"], what)
+                t.p[0], t.i0 = p["threshold"], int(p["min_contacts"])
+            elif opcode == K["GFB_R_CONTACT_FORCE"]:
+                t.mgr = self._contact_index(p["contact_manager"], what)
+                t.p[0] = p["threshold"]
+            elif opcode == K["GFB_R_FEET_AIR_TIME"]:
+                t.mgr = self._contact_index(p["contact_manager"], what)
+                t.p[0] = p["time_threshold"]
+                if p["time_threshold_max"] is not None:
+                    t.flags |= K["GFB_RF_HAS_MAX"]
+                    t.p[1] = p["time_threshold_max"] - p["time_threshold"]
+                t.p[2] = env.dt + 1.0e-8  # has_made_contact(env.dt), contact_manager.py:198-224
+                t.i0 = self._command_index(p["vel_cmd_manager"], what) if p["vel_cmd_manager"] is not None else -1
+            elif opcode == K["GFB_R_FEET_SLIDE"]:
+                t.mgr = self._contact_index(p["contact_manager"], what)
+                self._feet_slide_manager = (p["contact_manager"], p["entity_attr"])
+
+        # terminations
+        P.n_termination = len(self.termination_terms)
+        if P.n_termination > nat.MAX_TERMINATION:
+            raise UnsupportedTermError(f"at most {nat.MAX_TERMINATION} termination terms are supported")
+        for i, (name, item, opcode) in enumerate(self.termination_terms):
+            t = P.termination[i]
+            t.op, t.mgr, t.time_out = opcode, -1, 1 if item.time_out else 0
+            sig = getattr(item.fn, "gfb_signature", None) or item.fn.__func__.gfb_signature
+            p = sig(env, **item.params)
+            what = f"termination '{name}'"
+            if opcode == K["GFB_T_BAD_ORIENTATION"]:
+                self._entity_ok(p, what)
+                t.p[0] = self._tilt_threshold(p["limit_angle"])
+                t.i0 = int(p["grace_steps"])
+            elif opcode == K["GFB_T_BASE_HEIGHT_MIN"]:
+                self._entity_ok(p, what)
+                t.p[0] = p["minimum_height"]
+            elif opcode == K["GFB_T_OUT_OF_BOUNDS"]:
+                self._entity_ok(p, what)
+                x_min, x_max, y_min, y_max = p["terrain_manager"].get_bounds(p["subterrain"])
+                margin = p["border_margin"]
+                t.p[0], t.p[1] = x_min + margin, x_max - margin
+                t.p[2], t.p[3] = y_min + margin, y_max - margin
+            elif opcode == K["GFB_T_HAS_CONTACT"]:
+                t.mgr = self._contact_index(p["contact_manager"], what)
+                t.p[0], t.i0 = p["threshold"], int(p["min_contacts"])
+            elif opcode == K["GFB_T_CONTACT_FORCE"]:
+                t.mgr = self._contact_index(p["contact_manager"], what)
+                t.p[0] = p["threshold"]
+            elif opcode == K["GFB_T_CONTACT_FORCE_GRACE"]:
+                t.mgr = self._contact_index(p["contact_manager"], what)
+                t.p[0], t.i0 = p["threshold"], int(p["grace_steps"])
+
+        # observations
+        P.n_obs_groups = len(self.observations)
+        col = 0
+        src_of = {
+            "targets": K["GFB_O_TARGETS"], "dof_pos": K["GFB_O_DOF_POS"], "dof_vel": K["GFB_O_DOF_VEL"],
+            "dof_force": K["GFB_O_DOF_FORCE"], "lin_vel_b": K["GFB_O_LIN_VEL_B"], "ang_vel_b": K["GFB_O_ANG_VEL_B"],
+            "gravity_b": K["GFB_O_GRAVITY_B"], "env_actions": K["GFB_O_ENV_ACTIONS"],
+        }
+        for g, om in enumerate(self.observations):
+            og = P.obs_group[g]
+            cols = om.columns() if om.enabled else []
+            og.n_cols, og.history, og.col_begin = len(cols), om._history_len, col
+            if col + len(cols) > nat.MAX_OBS_COLS:
+                raise UnsupportedTermError(f"more than {nat.MAX_OBS_COLS} observation columns")
+            for c in cols:
+                oc = self.program.obs_cols[col]
+                key = c["key"]
+                oc.col, oc.scale, oc.noise, oc.mgr = c["col"], c["scale"], c["noise"], -1
+                if isinstance(key, tuple) and key[0] == "command":
+                    oc.src, oc.mgr = K["GFB_O_COMMAND"], self._command_index(key[1], "observation")
+                elif isinstance(key, tuple) and key[0] == "contact_norm":
+                    oc.src, oc.mgr = K["GFB_O_CONTACT_NORM"], self._contact_index(key[1], "observation")
+                elif key in src_of:
+                    oc.src = src_of[key]
+                else:
+                    raise UnsupportedTermError(f"observation source {key!r} is not supported by the fused step")
+                col += 1
+        self._fingerprint = fp
+
+    # ------------------------------------------------------------------------------------------
+    # per-step pointers
+    # ------------------------------------------------------------------------------------------
+    def _engine_buffers(self, post_reset: bool = False):
+        """Pointers to the engine's state tensors (zero-copy; getters are called once per launch)."""
+        K, s = nat.K, self._set
+        self._keepalive = []
+        robot = self.primary_entity
+        f32 = torch.float32
+        s(K["GFB_B_POS"], robot.get_pos(), f32, keep=True)
+        s(K["GFB_B_QUAT"], robot.get_quat(), f32, keep=True)
+        s(K["GFB_B_VEL"], robot.get_vel(), f32, keep=True)
+        s(K["GFB_B_ANG"], robot.get_ang(), f32, keep=True)
+        if self.action is not None:
+            idx = self.action.dofs_idx
+            s(K["GFB_B_DOF_POS"], robot.get_dofs_position(idx), f32, keep=True)
+            s(K["GFB_B_DOF_VEL"], robot.get_dofs_velocity(idx), f32, keep=True)
+            if self._uses_dof_force:
+                s(K["GFB_B_DOF_FORCE"], robot.get_dofs_force(idx), f32, keep=True)
+        if self.contacts and not post_reset:
+            solver = self.env.scene.rigid_solver
+            c = solver.collider.get_contacts(as_tensor=True, to_torch=True)
+            s(K["GFB_B_C_FORCE"], c["force"], f32, keep=True)
+            s(K["GFB_B_C_POS"], c["position"], f32, keep=True)
+            s(K["GFB_B_C_LINK_A"], c["link_a"], torch.int32, keep=True)
+            s(K["GFB_B_C_LINK_B"], c["link_b"], torch.int32, keep=True)
+            lq = solver.get_links_quat()
+            s(K["GFB_B_LINKS_QUAT"], lq, f32, keep=True)
+            self._contact_dims = (c["link_a"].shape[-1], lq.shape[1])
+            if self._feet_slide_manager is not None:
+                mgr, attr = self._feet_slide_manager
+                vel = getattr(self.env, attr).get_links_vel(links_idx_local=mgr.local_link_ids)
+                s(K["GFB_B_LINKS_VEL"], vel, f32, keep=True)
+        if self._fixed_command_parts:
+            s(K["GFB_B_FIXED_COMMAND"], self._resolve_fixed_command(), f32, keep=True)
+
+    def _resolve_fixed_command(self) -> torch.Tensor:
+        """(N,3) tensor [cmd_x, cmd_y, cmd_yaw] for tracking terms configured with fixed tensors."""
+        parts = self._fixed_command_parts
+        lin, ang = parts.get("lin"), parts.get("ang")
+        base = None
+        for t in (lin, ang):
+            if t is not None and t._base is not None and tuple(t._base.shape) == (self.N, 3):
+                base = t._base
+        if base is not None and base.is_contiguous():
+            ok_lin = lin is None or (lin._base is base and lin.data_ptr() == base.data_ptr() and lin.stride() == (3, 1))
+            ok_ang = ang is None or (ang._base is base and ang.data_ptr() == base.data_ptr() + 8 and ang.stride() == (3,))
+            if ok_lin and ok_ang:
+                return base  # zero-copy: both are views of one (N,3) command tensor
+        if self._fixed_command is None:
+            self._fixed_command = torch.zeros((self.N, 3), device=self.device)
+        if lin is not None:
+            self._fixed_command[:, :2] = lin
+        if ang is not None:
+            self._fixed_command[:, 2] = ang.reshape(self.N)
+        return self._fixed_command
+
+    @property
+    def _uses_dof_force(self) -> bool:
+        return any(key == "dof_force" for om in self.observations for (_, key, _) in om._sources)
+
+    def _obs_buffers(self):
+        K, s = nat.K, self._set
+        for g, om in enumerate(self.observations):
+            cur = om._current
+            s(K["GFB_B_OBS_PREV0"] + g, om._buffers[cur])
+            s(K["GFB_B_OBS_OUT0"] + g, om._buffers[1 - cur])
+
+    def _injection_buffers(self):
+        K, s = nat.K, self._set
+        inj = self.injected or {}
+        for k in range(len(self.commands)):
+            s(K["GFB_B_INJ_CMD_STEP0"] + k, inj.get(f"cmd_step{k}"))
+            s(K["GFB_B_INJ_CMD_RESET0"] + k, inj.get(f"cmd_reset{k}"))
+        s(K["GFB_B_INJ_MAX_LEN"], inj.get("max_len"))
+        for g in range(len(self.observations)):
+            s(K["GFB_B_OBS_NOISE0"] + g, inj.get(f"obs_noise{g}"))
+
+    def inject(self, draws: dict[str, torch.Tensor] | None):
+        """
+        Parity mode: dense buffers holding the reference's own draws.
+            cmd_step<k>, cmd_reset<k>   (N, K_k)  command values for resampled / reset envs
+            max_len                     (N,)      U(-1,1) draws of genesis_env.py:249
+            obs_noise<g>                (N, O_g)  U(-1,1) draws of observation_manager.py:249
+        None returns to in-kernel Philox.
+        """
+        self.injected = draws
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------------------------------
+    # launches
+    # ------------------------------------------------------------------------------------------
+    def _set_program(self):
+        self.pack()
+        P = self.program.head
+        P.step_index = self.env.step_count
+        if self.contacts:
+            if self._contact_dims is None:
+                solver = self.env.scene.rigid_solver
+                c = solver.collider.get_contacts(as_tensor=True, to_torch=True)
+                self._contact_dims = (c["link_a"].shape[-1], solver.get_links_quat().shape[1])
+            P.n_contact_slots, P.n_links_total = self._contact_dims
+        if self.dry_run:
+            return
+        self.handle.check(self.lib.gfb_set_program(self.handle.ptr, C.byref(self.program)), "gfb_set_program")
+
+    def cache_entity(self):
+        """Entity phase alone (EntityManager.build() caches the pose before the first reset)."""
+        self._engine_buffers()
+        self._set_program()
+        self.handle.check(
+            self.lib.gfb_post_physics(self.handle.ptr, C.byref(self.buffers), nat.K["GFB_PHASE_ENTITY"], self._stream()),
+            "gfb_post_physics(entity)",
+        )
+
+    def action_step(self, actions: torch.Tensor):
+        env = self.env
+        if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
+            actions = actions.to(self.device, torch.float32).contiguous()
+        raw_mgr = self.action._delayed(actions) if self.action is not None else actions
+        if raw_mgr is not actions and (raw_mgr.dtype != torch.float32 or not raw_mgr.is_contiguous()):
+            raw_mgr = raw_mgr.to(self.device, torch.float32).contiguous()
+        self._action_keep = (actions, raw_mgr)
+        self._set_program()
+        self.handle.check(
+            self.lib.gfb_action_step(
+                self.handle.ptr, C.byref(self.buffers), C.c_void_p(actions.data_ptr()),
+                C.c_void_p(raw_mgr.data_ptr()), self._stream(),
+            ),
+            "gfb_action_step",
+        )
+        if self.action is not None:
+            env.robot.control_dofs_position(self.action._actions, self.action.dofs_idx)
+
+    def post_physics(self, phases: int) -> nat.Report:
+        self._engine_buffers()
+        self._obs_buffers()
+        self._injection_buffers()
+        self._set_program()
+        stream = self._stream()
+        self.handle.check(
+            self.lib.gfb_post_physics(self.handle.ptr, C.byref(self.buffers), phases, stream), "gfb_post_physics"
+        )
+        if self.dist is not None:
+            self._allreduce_logging()
+        self.handle.check(self.lib.gfb_read_report(self.handle.ptr, C.byref(self.report), stream), "gfb_read_report")
+        return self.report
+
+    def observe(self, idx: torch.Tensor | None, n: int):
+        self._engine_buffers(post_reset=True)
+        self._obs_buffers()
+        self._injection_buffers()
+        self._set_program()
+        ptr = C.c_void_p(idx.data_ptr()) if idx is not None else None
+        self.handle.check(
+            self.lib.gfb_observe(self.handle.ptr, C.byref(self.buffers), ptr, n, self._stream()), "gfb_observe"
+        )
+
+    def rotate_by_inv_base_quat(self, vec: torch.Tensor | None) -> torch.Tensor:
+        quat = self.entity_manager._inv_base_quat if self.entity_manager is not None else self._inv_base_quat
+        return self._rotate(vec, quat, conjugate=0)
+
+    def rotate_by_inv_quat(self, vec: torch.Tensor | None, quat: torch.Tensor) -> torch.Tensor:
+        return self._rotate(vec, quat, conjugate=1)
+
+    def _rotate(self, vec, quat, conjugate: int) -> torch.Tensor:
+        quat = quat.to(self.device, torch.float32).contiguous()
+        n = quat.shape[0]
+        out = torch.empty((n, 3), device=self.device)
+        vptr = None
+        if vec is not None:
+            vec = vec.to(self.device, torch.float32).contiguous()
+            vptr = C.c_void_p(vec.data_ptr())
+        self.handle.check(
+            self.lib.gfb_rotate(self.handle.ptr, vptr, C.c_void_p(quat.data_ptr()), C.c_void_p(out.data_ptr()),
+                                n, conjugate, self._stream()),
+            "gfb_rotate",
+        )
+        return out
+
+    def evaluate_single_term(self, kind, fn, params):
+        raise NotImplementedError(
+            f"direct evaluation of mdp {kind} terms outside the fused step is not available in this build"
+        )
+
+    # ------------------------------------------------------------------------------------------
+    # multi-GPU logging
+    # ------------------------------------------------------------------------------------------
+    def _allreduce_logging(self):
+        """Sum per-term partials over ranks so that logged means are global."""
+        import torch.distributed as dist
+
+        dist.all_reduce(self.log_acc, op=dist.ReduceOp.SUM, group=self.dist)
+
+    def launch_count(self) -> int:
+        return int(self.lib.gfb_launch_count(self.handle.ptr))
+
+    def profile(self, enabled: bool):
+        self.handle.check(self.lib.gfb_profile_enable(self.handle.ptr, 1 if enabled else 0), "gfb_profile_enable")
+
+    def profile_read(self) -> dict:
+        post_ms, act_ms = C.c_float(), C.c_float()
+        n_post, n_act = C.c_int32(), C.c_int32()
+        self.handle.check(
+            self.lib.gfb_profile_read(self.handle.ptr, C.byref(post_ms), C.byref(n_post), C.byref(act_ms), C.byref(n_act)),
+            "gfb_profile_read",
+        )
+        return {"post_ms": post_ms.value, "post_launches": n_post.value,
+                "action_ms": act_ms.value, "action_launches": n_act.value}

@@ -1,0 +1,322 @@
+"""
+ManagedEnvironment: the reference's manager-driven environment
+(genesis_forge/managed_env.py:32-398) with its step pipeline executed by the fused CUDA step.
+
+Public surface kept: constructor arguments, `managers` registry and add_manager(), config(),
+build() (manager build order terrain, action, contact, termination, reward, command, entity,
+observation -- managed_env.py:257-272), step() returning
+(obs, rewards, terminated, truncated, extras), reset(env_ids), get_observations(), the
+action_space / observation_space properties, and the `extras` keys "episode", "observations",
+"terminations", "time_outs".
+
+What differs is who does the work.  The reference's step() walks the managers and issues a few
+hundred eager torch ops with 6+ host syncs; here step() is
+    gfb_action_step -> control_dofs_position -> scene.step() -> gfb_post_physics -> one report
+    read-back -> host reset fan-out for the compacted reset indices -> gfb_observe on those envs.
+Ordering facts of the reference that are preserved are listed in DESIGN.md (rewards see the
+pre-resample command; timeout sees the incremented episode length; reset envs are observed after
+the engine reset but with the pre-reset cached quaternion; ...).
+"""
+from __future__ import annotations
+
+from typing import Any
+
+import torch
+
+from . import _native as nat
+from ._gs import gs
+from .fused import FusedStep, UnsupportedTermError, make_obs_dict
+from .genesis_env import GenesisEnv
+from .managers.base import BaseManager, ManagerType
+
+
+class ManagedEnvironment(GenesisEnv):
+    def __init__(
+        self,
+        num_envs: int = 1,
+        dt: float = 1 / 100,
+        max_episode_length_sec: int | None = 10,
+        max_episode_random_scaling: float = 0.0,
+        extras_logging_key: str = "episode",
+    ):
+        super().__init__(
+            num_envs=num_envs,
+            dt=dt,
+            max_episode_length_sec=max_episode_length_sec,
+            max_episode_random_scaling=max_episode_random_scaling,
+            extras_logging_key=extras_logging_key,
+        )
+        self.managers: dict[str, Any] = {
+            "contact": [], "entity": [], "command": [], "terrain": [],
+            "action": None, "observation": [], "reward": None, "termination": None,
+        }
+        self._action_space = None
+        self._observation_space = None
+        self._reward_buf = torch.zeros((num_envs,), device=gs.device, dtype=gs.tc_float)
+        self._terminated_buf = torch.zeros((num_envs,), device=gs.device, dtype=gs.tc_bool)
+        self._truncated_buf = torch.zeros((num_envs,), device=gs.device, dtype=gs.tc_bool)
+        self._fused: FusedStep | None = None
+        self._tracing: dict | None = None
+
+    # -- spaces ---------------------------------------------------------------------------------
+    @property
+    def action_space(self):
+        if self.managers["action"] is not None:
+            return self.managers["action"].action_space
+        return self._action_space
+
+    @action_space.setter
+    def action_space(self, space):
+        self._action_space = space
+
+    @property
+    def observation_space(self):
+        if self.managers["observation"]:
+            for obs in self.managers["observation"]:
+                if obs.name == "policy":
+                    return obs.observation_space
+            return self.managers["observation"][0].observation_space
+        return self._observation_space
+
+    @observation_space.setter
+    def observation_space(self, space):
+        self._observation_space = space
+
+    # -- manager registry -----------------------------------------------------------------------
+    def add_manager(self, manager_type: ManagerType, manager: BaseManager):
+        if manager_type not in self.managers:
+            raise ValueError(f"'{manager_type}' is not a valid manager type.")
+        slot = self.managers[manager_type]
+        if isinstance(slot, list):
+            slot.append(manager)
+        elif slot is None:
+            self.managers[manager_type] = manager
+        else:
+            raise ValueError(
+                f"Manager type '{manager_type}' already has a manager, and an environment cannot have "
+                f"multiple {manager_type} managers."
+            )
+
+    def config(self):
+        """Override and create the managers here."""
+
+    # -- tracing of observation term functions ----------------------------------------------------
+    def _trace_width(self, key) -> int:
+        if isinstance(key, tuple):
+            kind, mgr = key
+            if kind == "command":
+                return mgr._command.shape[1]
+            if kind == "contact_norm":
+                return mgr._link_ids.shape[0]
+        if key in ("lin_vel_b", "ang_vel_b", "gravity_b", "lin_vel_uncached", "ang_vel_uncached", "gravity_uncached"):
+            return 3
+        return self.managers["action"].num_actions
+
+    def _trace_or(self, key, compute):
+        """Manager getters call this: a tagged placeholder while tracing, the real value otherwise."""
+        if self._tracing is None:
+            return compute()
+        if key not in self._tracing:
+            self._tracing[key] = torch.empty((0, self._trace_width(key)))
+        return self._tracing[key]
+
+    def _trace_term(self, fn, params: dict, what: str):
+        """Run an observation term once under tracing and identify which manager value it returns."""
+        self._tracing = {}
+        try:
+            result = fn(env=self, **params)
+            for key, sentinel in self._tracing.items():
+                if result is sentinel:
+                    if isinstance(key, str) and key.endswith("_uncached"):
+                        raise UnsupportedTermError(
+                            f"{what}: body-frame observations without an entity_manager are not supported by "
+                            "the fused step (pass entity_manager=...)"
+                        )
+                    return key, sentinel.shape[1]
+        finally:
+            self._tracing = None
+        raise UnsupportedTermError(
+            f"{what}: the term function does not return a manager value the fused step recognises "
+            "(EntityManager.get_*, action manager getters, CommandManager.observation, "
+            "mdp.observations.*); user-defined observation terms are not supported yet"
+        )
+
+    # -- build ------------------------------------------------------------------------------------
+    def build(self):
+        super().build()
+        if hasattr(self.scene, "_env"):
+            pass
+        try:
+            self.scene._env = self
+        except Exception:
+            pass
+        self.config()
+        M = self.managers
+        for terrain_manager in M["terrain"]:
+            terrain_manager.build()
+        if M["action"] is not None:
+            M["action"].build()
+        for contact_manager in M["contact"]:
+            contact_manager.build()
+        if M["termination"] is not None:
+            M["termination"].build()
+        if M["reward"] is not None:
+            M["reward"].build()
+        for command_manager in M["command"]:
+            command_manager.build()
+        for entity_manager in M["entity"]:
+            entity_manager.build()
+        for obs in M["observation"]:
+            obs.build()
+        self._fused = FusedStep(self, dry_run=getattr(self, "_dry_run", False))
+        # EntityManager.build() caches the base pose once (entity_manager.py:157-167)
+        if not self._fused.dry_run:
+            self._fused.cache_entity()
+
+    # -- step -------------------------------------------------------------------------------------
+    def step(self, actions: torch.Tensor):
+        fused = self._fused
+        if fused is None:
+            raise RuntimeError("build() the environment before stepping it")
+        self._begin_step()
+        if self._actions is None:
+            self._allocate_action_buffers(actions.shape[1])
+            fused.bind_action_buffers()
+        self.extras["observations"] = make_obs_dict(gs.device)
+
+        fused.action_step(actions)
+        self.scene.step()
+        report = fused.post_physics(nat.K["GFB_PHASE_ALL"])
+        self._publish(report, step=True)
+
+        n_reset = report.n_reset
+        if n_reset > 0:
+            reset_idx = fused.reset_idx[:n_reset]
+            self._host_reset(reset_idx)
+            fused.observe(reset_idx, n_reset)
+
+        obs = None
+        for om in self.managers["observation"]:
+            om._current = 1 - om._current
+            self.extras["observations"][om.name] = om.get_observations()
+            if om.name == "policy":
+                obs = om.get_observations()
+        term = self.managers["termination"]
+        terminated = term._terminated_buf if term is not None else self._terminated_buf
+        truncated = term._truncated_buf if term is not None else self._truncated_buf
+        rew = self.managers["reward"]
+        rewards = rew._reward_buf if rew is not None else self._reward_buf
+        return obs, rewards, terminated, truncated, self.extras
+
+    def _publish(self, report, step: bool):
+        """Logging entries of `extras` (termination_manager.py:178-189, reward_manager.py:205-216)."""
+        fused = self._fused
+        logging = self.extras[self.extras_logging_key]
+        term, rew = self.managers["termination"], self.managers["reward"]
+        status = report.status
+        if status:
+            action = self.managers["action"]
+            quiet = action is not None and action._quiet_action_errors
+            if not quiet and status & nat.K["GFB_STATUS_NAN_ACTION"]:
+                print("ERROR: NaN actions received!")
+            if not quiet and status & nat.K["GFB_STATUS_INF_ACTION"]:
+                print("ERROR: Infinite actions received!")
+            if status & nat.K["GFB_STATUS_BAD_CONTACT"]:
+                print("Warning: Invalid contact forces detected (NaN/inf) and sanitized")
+        snapshot = None
+        n_r = fused.n_reward
+        if step and term is not None:
+            self.extras["terminations"] = term._terminated_buf
+            self.extras["time_outs"] = term._truncated_buf
+            if term.logging_enabled:
+                for i, (name, _, _) in enumerate(fused.termination_terms):
+                    if report.termination_count[i] > 0:
+                        if snapshot is None:
+                            snapshot = self._log_snapshot()
+                        logging[f"{term.logging_tag} / {name}"] = snapshot[n_r + i]
+        if rew is not None and rew.enabled and rew.logging_enabled and report.n_reset > 0:
+            index = {}
+            for i, (name, item, _) in enumerate(fused.reward_terms):
+                if item.weight != 0:
+                    if snapshot is None:
+                        snapshot = self._log_snapshot()
+                    logging[f"{rew.logging_tag} / {name}"] = snapshot[i]
+                    index[name] = i
+            if index:
+                rew._last_log = (snapshot, index)
+
+    def _log_snapshot(self) -> torch.Tensor:
+        """Copy of the kernel's logging vector (entries are handed out as 0-dim views)."""
+        fused = self._fused
+        if fused.dist is None:
+            return fused.log_out.clone()
+        acc = fused.log_acc
+        n_r, n_t = fused.n_reward, fused.n_termination
+        out = torch.empty(n_r + n_t, device=acc.device, dtype=torch.float32)
+        n_reset = acc[n_r + n_t].clamp(min=1.0)
+        out[:n_r] = (acc[:n_r] / n_reset).float()
+        out[n_r:] = (acc[n_r:n_r + n_t] / float(fused.global_num_envs)).float()
+        return out
+
+    def _host_reset(self, env_ids: torch.Tensor | None):
+        """Engine-side part of reset(): action manager gains / joint positions, entity on_reset items."""
+        if self.managers["action"] is not None:
+            self.managers["action"].reset(env_ids)
+        for entity_manager in self.managers["entity"]:
+            entity_manager.reset(env_ids)
+
+    # -- reset ------------------------------------------------------------------------------------
+    def reset(self, env_ids=None):
+        """
+        Reset some (or, with None, all) environments.  The in-library part (counters, action
+        buffers, episode sums + their logged means, air-time state, command resample) is one launch
+        of the post-physics kernel restricted to the reset phase; engine writes follow on the host.
+        """
+        fused = self._fused
+        if fused is None:
+            raise RuntimeError("build() the environment before resetting it")
+        if self.step_count == 0 and self._actions is None and self.action_space is not None:
+            self._allocate_action_buffers(self.action_space.shape[0])
+            fused.bind_action_buffers()
+        K = nat.K
+        mask = None
+        if env_ids is not None:
+            env_ids = torch.as_tensor(env_ids, device=gs.device, dtype=torch.int64)
+            mask = torch.zeros(self.num_envs, device=gs.device, dtype=torch.bool)
+            mask[env_ids] = True
+        fused._set(K["GFB_B_FORCE_RESET"], mask)
+        self._reset_mask_keep = mask
+        if env_ids is None or env_ids.numel() > 0:
+            report = fused.post_physics(K["GFB_PHASE_RESET"] | K["GFB_PHASE_FORCED_RESET"])
+            self._publish(report, step=False)
+            self._host_reset(env_ids)
+        obs = None
+        if env_ids is None:
+            self.extras.pop("observations", None)
+            obs = self.get_observations()
+        return obs, self.extras
+
+    # -- observations -------------------------------------------------------------------------------
+    def get_observations(self) -> torch.Tensor:
+        if not self.managers["observation"]:
+            return super().get_observations()
+        if "observations" in self.extras and "policy" in self.extras["observations"]:
+            return self.extras["observations"]["policy"]
+        if "observations" not in self.extras:
+            self.extras["observations"] = make_obs_dict(gs.device)
+        fused = self._fused
+        # shift history (observation_manager.py:223-226), then frame 0 for every env
+        for om in self.managers["observation"]:
+            cur, nxt = om._buffers[om._current], om._buffers[1 - om._current]
+            single = om.frame_size
+            if om._history_len > 1:
+                nxt[:, single:] = cur[:, : single * (om._history_len - 1)]
+        fused.observe(None, self.num_envs)
+        policy = None
+        for om in self.managers["observation"]:
+            om._current = 1 - om._current
+            obs = om.get_observations()
+            self.extras["observations"][om.name] = obs
+            if om.name == "policy":
+                policy = obs
+        return policy

@@ -1,0 +1,104 @@
+"""
+EntityManager on_reset items, by the reference's names (genesis_forge/mdp/reset.py).  These end in
+engine setters (`set_pos`, `set_quat`, ...) for the compacted list of reset envs that the fused
+kernel produced; they are host-side consumers of the hot path, not part of it.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable
+
+import torch
+
+from .._gs import gs
+from ..managers.config import ResetMdpFnClass
+from ..utils import links_by_name_pattern, xyz_to_quat
+
+
+def zero_all_dofs_velocity(env, entity, envs_idx):
+    entity.zero_all_dofs_velocity(envs_idx)
+
+
+def set_rotation(env, entity, envs_idx, x=0, y=0, z=0):
+    """Set (or uniformly randomise, when a (min, max) tuple is given) the entity's Euler rotation."""
+    angles = torch.zeros((len(envs_idx), 3), device=gs.device)
+    for col, (axis, value) in enumerate((("x", x), ("y", y), ("z", z))):
+        if isinstance(value, tuple):
+            angles[:, col] = env.rng.uniform(f"set_rotation_{axis}", angles[:, col], *value)
+    entity.set_quat(xyz_to_quat(angles), envs_idx=envs_idx)
+
+
+class position(ResetMdpFnClass):
+    """Reset to a fixed position and (optional) rotation (reset.py:67-124)."""
+
+    def __init__(self, env, entity, position, quat=None, zero_velocity: bool = True):
+        self.env = env
+        self.zero_velocity = zero_velocity
+        self.reset_pos = torch.tensor(position, device=gs.device, dtype=gs.tc_float)
+        self.reset_quat = None if quat is None else torch.tensor(quat, device=gs.device, dtype=gs.tc_float)
+
+    def __call__(self, env, entity, envs_idx, position, quat=None, zero_velocity: bool = True):
+        n = len(envs_idx)
+        entity.set_pos(self.reset_pos.expand(n, 3).contiguous(), envs_idx=envs_idx, zero_velocity=self.zero_velocity)
+        if self.reset_quat is not None:
+            entity.set_quat(
+                self.reset_quat.expand(n, 4).contiguous(), envs_idx=envs_idx, zero_velocity=self.zero_velocity
+            )
+
+
+class randomize_terrain_position(ResetMdpFnClass):
+    """Random spot on the terrain with a random yaw by default (reset.py:127-226)."""
+
+    def __init__(self, env, entity, terrain_manager, height_offset: float = 0.1e-3,
+                 subterrain: str | Callable[[], str] | None = None,
+                 rotation: dict | None = {"z": (0, 2 * math.pi)}, zero_velocity: bool = True):
+        self.env = env
+        self.rotation = rotation
+        self._rotation_buffer = None
+
+    def build(self):
+        self._rotation_buffer = torch.zeros((self.env.num_envs, 3), device=gs.device, dtype=gs.tc_float)
+
+    def __call__(self, env, entity, envs_idx, terrain_manager, height_offset: float = 0.1e-3, subterrain=None,
+                 rotation: dict | None = {"z": (0, 2 * math.pi)}, zero_velocity: bool = True):
+        if subterrain is not None and callable(subterrain):
+            subterrain = subterrain()
+        pos = terrain_manager.generate_random_env_pos(
+            envs_idx=envs_idx, subterrain=subterrain, height_offset=height_offset
+        )
+        entity.set_pos(pos, envs_idx=envs_idx, zero_velocity=zero_velocity)
+        if rotation is not None:
+            for col, axis in enumerate(("x", "y", "z")):
+                value = rotation.get(axis, 0)
+                if isinstance(value, tuple):
+                    like = torch.empty(len(envs_idx), device=gs.device)
+                    self._rotation_buffer[envs_idx, col] = env.rng.uniform(f"spawn_rot_{axis}", like, *value)
+            quat = xyz_to_quat(self._rotation_buffer[envs_idx])
+            entity.set_quat(quat, envs_idx=envs_idx, zero_velocity=zero_velocity)
+
+
+class randomize_link_mass_shift(ResetMdpFnClass):
+    """Add a random mass shift to the links matching `link_name` on every reset (reset.py:229-284)."""
+
+    def __init__(self, _env, entity, link_name: str, add_mass_range=(-0.2, 0.2)):
+        self.env = _env
+        self.add_mass_range = add_mass_range
+        self._entity = entity
+        self._link_name = link_name
+        self.build()
+
+    def build(self):
+        self._links_idx_local = []
+        self._mass_shift_buffer = None
+        if self._link_name is not None:
+            links = links_by_name_pattern(self._entity, self._link_name)
+            if links:
+                self._links_idx_local = [link.idx_local for link in links]
+                self._mass_shift_buffer = torch.zeros(
+                    (self.env.num_envs, len(self._links_idx_local)), device=gs.device
+                )
+
+    def __call__(self, env, entity, envs_idx, link_name: str, add_mass_range=(-0.2, 0.2)):
+        like = self._mass_shift_buffer[envs_idx, :]
+        self._mass_shift_buffer[envs_idx, :] = env.rng.uniform("mass_shift", like, *self.add_mass_range)
+        self._entity.set_mass_shift(self._mass_shift_buffer, links_idx_local=self._links_idx_local, envs_idx=envs_idx)

@@ -390,8 +390,10 @@ class PortEnv:
 
         rewards = self._rewards()                             # reward_manager.py:166-195
 
+        self.resample_idx = {}
         for name, c in self.command.items():                  # command_manager.py:152-162
             idx = (self.episode_length % c["resample_steps"] == 0).nonzero(as_tuple=False).reshape((-1,))
+            self.resample_idx[name] = idx
             self._resample(name, c, idx, "cmd_step")
 
         if reset_idx.numel() > 0:
