@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""
+bench.py -- manager env-steps/s of the fused B200 manager step, on synthetic physics state.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--config command_direction] [--num-envs 1048576] [--no-sweep]
+
+One "step" = one full `env.step(actions)` of the drop-in ManagedEnvironment through its public API
+(gfb_action_step -> synthetic scene.step() -> gfb_post_physics -> report read-back -> host reset
+fan-out -> gfb_observe), on a pool of pre-generated synthetic state sets that is larger than L2.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means.
+
+  value      whole-job env-steps/s, inputs resident in HBM, device-timed (CUDA events), max over ranks
+  roofline   the post-physics kernel: its algorithmic bytes / its CUDA-event time / measured HBM peak
+  e2e        same metric with HOST state + action buffers: H2D of the step's inputs and D2H of
+             obs/reward/masks inside the timed region
+  cpu_baseline   the oracle port (torch-CPU restatement of the reference managers, bit-identical to
+             the reference) timed on this box's host cores on the same workload
+  --impl reference   times only that CPU path and prints the same line shape
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "manager env-steps/sec"
+UNIT = "env-steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="command_direction")
+    ap.add_argument("--num-envs", type=int, default=1 << 20, help="envs per GPU (weak scaling)")
+    ap.add_argument("--pool", type=int, default=4, help="pre-generated state sets rotated by scene.step()")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 4096 / 65536 env points")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-envs", type=int, default=0, help="envs for the CPU baseline (0 = same as --num-envs)")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[2:6]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# --------------------------------------------------------------------------------------------------
+# environments
+# --------------------------------------------------------------------------------------------------
+def make_dropin_env(spec, num_envs, device, pool, seed):
+    import genesis_forge_b200 as gfb
+    from oracle.env_builder import build_env, dropin_namespace
+
+    gfb.set_device(device)
+    env = build_env(spec, dropin_namespace(), num_envs, device, pool=pool, seed=seed,
+                    n_contacts=8 if spec["contacts"] else 0)
+    env.build()
+    env.reset()
+    return env
+
+
+def time_dropin(env, actions, steps, warmup, dist_on):
+    """CUDA-event time of `steps` full env.step() calls; returns ms per step (max over ranks)."""
+    import torch.distributed as dist
+
+    dev = env._fused.device
+    for i in range(warmup):
+        env.step(actions[i % len(actions)])
+    torch.cuda.synchronize(dev)
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_reset = 0
+    start.record()
+    for i in range(steps):
+        env.step(actions[i % len(actions)])
+        n_reset += env._fused.report.n_reset
+    end.record()
+    torch.cuda.synchronize(dev)
+    if dist_on:
+        dist.barrier()
+    ms = start.elapsed_time(end) / steps
+    if dist_on:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, n_reset / max(steps, 1)
+
+
+def time_e2e(env, actions_host, steps, warmup, dist_on):
+    """
+    Same step with HOST buffers: every step copies that step's engine state and actions from pinned
+    host memory to the device (inside scene.step(), i.e. where the physics engine would produce
+    them) and reads obs / reward / masks back to pinned host memory.
+    """
+    import torch.distributed as dist
+
+    fused = env._fused
+    dev = fused.device
+    scene = env.scene
+    host_pool = [{k: v.cpu().pin_memory() for k, v in st.items()} for st in scene._pool]
+    dev_state = {k: torch.empty_like(v) for k, v in scene._pool[0].items()}
+    h2d_state = sum(v.numel() * v.element_size() for v in dev_state.values())
+    counter = {"i": 0}
+
+    def host_fed_step():
+        counter["i"] += 1
+        src = host_pool[counter["i"] % len(host_pool)]
+        for k, v in src.items():
+            dev_state[k].copy_(v, non_blocking=True)
+        scene.state = dev_state
+
+    original_step = scene.step
+    scene.step = host_fed_step
+    obs_dev = env.managers["observation"][0]._buffers[0]
+    out_host = {
+        "obs": torch.empty_like(obs_dev, device="cpu").pin_memory(),
+        "rew": torch.empty(env.num_envs, dtype=torch.float32).pin_memory(),
+        "term": torch.empty(env.num_envs, dtype=torch.bool).pin_memory(),
+        "trunc": torch.empty(env.num_envs, dtype=torch.bool).pin_memory(),
+    }
+    act_dev = torch.empty((env.num_envs, fused.D), device=dev)
+    h2d = h2d_state + act_dev.numel() * 4
+    d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+
+    def one(i):
+        act_dev.copy_(actions_host[i % len(actions_host)], non_blocking=True)
+        obs, rew, term, trunc, _ = env.step(act_dev)
+        out_host["obs"].copy_(obs, non_blocking=True)
+        out_host["rew"].copy_(rew, non_blocking=True)
+        out_host["term"].copy_(term, non_blocking=True)
+        out_host["trunc"].copy_(trunc, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    try:
+        for i in range(warmup):
+            one(i)
+        torch.cuda.synchronize(dev)
+        if dist_on:
+            dist.barrier()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for i in range(steps):
+            one(i)
+        end.record()
+        torch.cuda.synchronize(dev)
+        ms = start.elapsed_time(end) / steps
+        if dist_on:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+    finally:
+        scene.step = original_step
+    return ms, h2d, d2h
+
+
+def time_cpu_port(spec, num_envs, pool, steps, warmup, seed):
+    """The oracle port (== reference managers, bit for bit) on the host cores."""
+    from oracle.env_builder import make_scene
+    from oracle.manager_port import PortEnv
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    scene, terrain, robot = make_scene(spec, torch.device("cpu"), copy_on_get=True, pool=pool, seed=seed,
+                                       n_contacts=8 if spec["contacts"] else 0)
+    env = PortEnv(spec, num_envs, scene, terrain, robot)
+    env.build()
+    env.reset()
+    gen = torch.Generator().manual_seed(seed)
+    actions = [torch.randn(num_envs, env.num_actions, generator=gen) for _ in range(2)]
+    for i in range(warmup):
+        env.step(actions[i % 2])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        env.step(actions[i % 2])
+    dt = (time.perf_counter() - t0) / steps
+    return num_envs / dt, threads, dt * 1e3
+
+
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    from oracle import specs
+
+    if rank != 0:
+        return
+    spec = specs.get(args.config)
+    n = args.cpu_envs or args.num_envs
+    steps = max(3, min(args.steps, 12))
+    warmup = max(3, min(args.warmup, 3))
+    value, threads, ms = time_cpu_port(spec, n, 2, steps, warmup, 1234)
+    sample = f"{steps} steps of {n} envs ({args.config} term table), oracle port on torch-CPU"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config} Go2 manager step, num_envs={n}", "cpu": cpu_model()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, local_rank, world):
+    import torch.distributed as dist
+
+    from genesis_forge_b200 import roofline
+    from oracle import specs
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist_on = world > 1
+    if dist_on:
+        dist.init_process_group("nccl", device_id=dev)
+    spec = specs.get(args.config)
+    N = args.num_envs
+    seed = 1234 + rank
+
+    env = make_dropin_env(spec, N, dev, args.pool, seed)
+    fused = env._fused
+    if dist_on:
+        fused.dist = dist.group.WORLD
+        fused.global_num_envs = N * world
+    gen = torch.Generator().manual_seed(seed)
+    actions_host = [torch.randn(N, fused.D, generator=gen).pin_memory() for _ in range(4)]
+    actions = [a.to(dev) for a in actions_host]
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = fused.launch_count()
+    fused.profile(True)
+    ms, resets_per_step = time_dropin(env, actions, args.steps, args.warmup, dist_on)
+    prof = fused.profile_read()
+    fused.profile(False)
+    launches = fused.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+
+    value = N * world / (ms / 1e3)
+    peak, peak_src = peaks()
+    post_ms = prof["post_ms"] / max(prof["post_launches"], 1)
+    act_ms = prof["action_ms"] / max(prof["action_launches"], 1)
+    post_bytes = roofline.post_kernel_bytes(fused)
+    achieved = post_bytes * N / (post_ms / 1e3) / 1e9 if post_ms > 0 else 0.0
+    step_bytes = roofline.step_bytes(fused)
+
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(3, min(args.steps, 10))
+        e2e_ms, h2d, d2h = time_e2e(env, actions_host, e2e_steps, 3, dist_on)
+        e2e = {"value": N * world / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps}
+
+    sweep = {}
+    if not args.no_sweep and not dist_on:
+        for n_small in (4096, 65536):
+            if n_small >= N:
+                continue
+            small = make_dropin_env(spec, n_small, dev, max(args.pool, 4), seed)
+            acts = [torch.randn(n_small, fused.D, device=dev) for _ in range(4)]
+            small._fused.profile(True)
+            ms_s, _ = time_dropin(small, acts, max(args.steps, 100), max(args.warmup, 10), False)
+            p = small._fused.profile_read()
+            sweep[str(n_small)] = {
+                "value": n_small / (ms_s / 1e3), "ms_per_step": ms_s,
+                "post_kernel_us": 1e3 * p["post_ms"] / max(p["post_launches"], 1),
+                "action_kernel_us": 1e3 * p["action_ms"] / max(p["action_launches"], 1),
+            }
+            del small
+
+    cpu = None
+    if rank == 0 and not dist_on and not args.no_cpu:
+        n_cpu = args.cpu_envs or N
+        v, threads, cpu_ms = time_cpu_port(spec, n_cpu, 2, 10, 3, 1234)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": cpu_ms,
+               "sample": f"10 steps of {n_cpu} envs ({args.config} term table), oracle port on torch-CPU, {cpu_model()}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"{args.config} Go2 manager step (full reward/termination/observation table), "
+                            f"num_envs={N} per GPU",
+                "l2_policy": f"{args.pool} pre-generated state sets rotated per step, each set > L2 at this size",
+                "resets_per_step": resets_per_step,
+                "step_algorithmic_bytes_per_env": step_bytes,
+                "step_roofline_frac": step_bytes * N / (ms / 1e3) / 1e9 / peak,
+            },
+            "roofline": {
+                "kernel": "post_kernel (gfb_post_physics)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_env": post_bytes, "kernel_us": post_ms * 1e3,
+                "action_kernel": {"bytes_per_env": roofline.action_kernel_bytes(fused), "kernel_us": act_ms * 1e3,
+                                  "achieved": roofline.action_kernel_bytes(fused) * N / max(act_ms, 1e-9) / 1e6,
+                                  "frac": roofline.action_kernel_bytes(fused) * N / max(act_ms, 1e-9) / 1e6 / peak},
+            },
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "sweep": sweep,
+        }
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (the manager step has no CPU fallback)")
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -98,7 +98,9 @@ def generate_state(
 ) -> dict[str, torch.Tensor]:
     """One synthetic physics state (CPU tensors) for `n_envs` copies of `model`."""
     N, D, C = n_envs, len(model.joint_names), n_contacts
-    L = 1 + len(model.link_names)  # + ground plane, global link idx 0
+    # + ground plane, global link idx 0.  Without contact slots nothing reads per-link state: keep
+    # those arrays minimal so million-env benchmarks of contact-free configs do not carry them.
+    L = 1 + len(model.link_names) if C > 0 else 1
     f32 = torch.float32
 
     def randn(*shape):
@@ -125,13 +127,14 @@ def generate_state(
 
     n_valid = torch.randint(0, C + 1, (N, 1), generator=gen)
     valid = torch.arange(C).unsqueeze(0) < n_valid  # (N, C)
-    link_b = torch.randint(1, L, (N, C), generator=gen)
+    Lr = max(L, 3)
+    link_b = torch.randint(1, Lr, (N, C), generator=gen)
     # the base/torso link (global idx 1) rarely touches anything: keep one in ten of its draws
     demote = (link_b == 1) & (rand(N, C) > 0.1)
-    link_b = torch.where(demote, torch.randint(2, L, (N, C), generator=gen), link_b)
+    link_b = torch.where(demote, torch.randint(2, Lr, (N, C), generator=gen), link_b)
     # mostly ground contacts (link_a = plane = 0); one in five is a self contact
     self_contact = rand(N, C) < 0.2
-    link_a = torch.where(self_contact, torch.randint(2, L, (N, C), generator=gen), 0)
+    link_a = torch.where(self_contact, torch.randint(2, Lr, (N, C), generator=gen), 0)
     s["c_link_a"] = torch.where(valid, link_a, 0).to(torch.int32)
     s["c_link_b"] = torch.where(valid, link_b, 0).to(torch.int32)
     s["c_force"] = (30.0 * randn(N, C, 3)) * valid.unsqueeze(-1)
