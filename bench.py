@@ -117,8 +117,10 @@ def make_dropin_env(spec, num_envs, device, pool, seed):
     from oracle.env_builder import build_env, dropin_namespace
 
     gfb.set_device(device)
+    # apply_setters=False: see SyntheticScene -- the pool's state sets are reused, so engine-side
+    # reset writes are accepted but not applied (keeps the reset rate stationary over the run)
     env = build_env(spec, dropin_namespace(), num_envs, device, pool=pool, seed=seed,
-                    n_contacts=8 if spec["contacts"] else 0)
+                    n_contacts=8 if spec["contacts"] else 0, apply_setters=False)
     env.build()
     env.reset()
     return env
@@ -228,7 +230,7 @@ def time_cpu_port(spec, num_envs, pool, steps, warmup, seed):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     scene, terrain, robot = make_scene(spec, torch.device("cpu"), copy_on_get=True, pool=pool, seed=seed,
-                                       n_contacts=8 if spec["contacts"] else 0)
+                                       n_contacts=8 if spec["contacts"] else 0, apply_setters=False)
     env = PortEnv(spec, num_envs, scene, terrain, robot)
     env.build()
     env.reset()

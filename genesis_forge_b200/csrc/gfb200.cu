@@ -27,8 +27,8 @@ struct PlanSlot {
   bool used = false;
   uint32_t phases = 0;
   int tile = 0;
-  std::vector<DevObsCol> cols_host;
-  DevObsCol* cols_dev = nullptr;
+  std::vector<int32_t> table_host;
+  int32_t* table_dev = nullptr;
 };
 
 }  // namespace
@@ -148,7 +148,8 @@ uint32_t compute_needs(const gfb_program& prog, uint32_t phases) {
 // Lay out the shared-memory slab for one (program, phases, tile) combination and lower the
 // observation columns to device descriptors.
 int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, Plan& plan,
-               std::vector<DevObsCol>& cols) {
+               std::vector<int32_t>& table) {
+  std::vector<DevObsCol> cols;
   const gfb_program& prog = h->prog;
   const gfb_program_head& P = prog.head;
   memset(&plan, 0, sizeof(plan));
@@ -312,8 +313,89 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, P
     }
   }
   plan.n_cols_total = n_cols_total;
+
+  // 16-byte group path: every frame-0 group of 4 columns is either a contiguous run of a staged /
+  // global array, or 4 "head" columns that the owner thread evaluates into the head tile.
+  std::vector<HeadCol> head;
+  struct Group { int32_t base, stride, kindcol; float scale; float noise[4]; };
+  std::vector<Group> groups;
+  for (int g = 0; g < P.n_obs_groups; ++g) {
+    const gfb_obs_group& og = P.obs_group[g];
+    plan.grp_begin[g] = -1;
+    if ((og.n_cols & 3) || !(phases & GFB_PHASE_OBSERVE)) continue;
+    // count the head columns this group would need
+    int need_head = 0;
+    for (int c = 0; c < og.n_cols; c += 4)
+      if (!cols[og.col_begin + c].vec) need_head += 4;
+    if ((int)head.size() + need_head > kMaxHeadCols) continue;  // falls back to the scalar path
+    plan.grp_begin[g] = (int)groups.size();
+    for (int c = 0; c < og.n_cols; c += 4) {
+      const DevObsCol* d = &cols[og.col_begin + c];
+      Group G{};
+      if (d[0].vec) {
+        if (d[0].kind == 1) {
+          G.base = d[0].a + d[0].col;
+          G.kindcol = 1;
+        } else {
+          G.base = d[0].gbuf;
+          G.kindcol = 2 | (d[0].col << 4);
+        }
+        G.stride = d[0].row_words;
+        G.scale = d[0].scale;
+      } else {
+        G.base = (int)head.size();  // patched to a shared offset below
+        G.kindcol = 3;
+        G.stride = 0;
+        G.scale = 1.0f;
+        for (int j = 0; j < 4; ++j) {
+          HeadCol hc{};
+          hc.kind = d[j].kind;
+          hc.a = d[j].a;
+          hc.row_words = d[j].row_words;
+          hc.col = d[j].col;
+          hc.gbuf = d[j].gbuf;
+          hc.scale = d[j].scale;
+          head.push_back(hc);
+        }
+      }
+      for (int j = 0; j < 4; ++j) G.noise[j] = d[j].noise;
+      groups.push_back(G);
+    }
+  }
+  plan.n_head = (int)head.size();
+  plan.n_groups = (int)groups.size();
+  plan.head_tile_off = cursor;
+  cursor = align4(cursor + plan.n_head * tile);
+  for (auto& G : groups)
+    if ((G.kindcol & 15) == 3) {
+      G.base = plan.head_tile_off + G.base;
+      G.stride = plan.n_head;
+      G.kindcol = 1;
+    }
+
+  // descriptor table: [DevObsCol x n_cols][HeadCol x n_head][group SoA]
+  table.clear();
+  auto push_words = [&](const void* p, size_t bytes) {
+    const int32_t* w = static_cast<const int32_t*>(p);
+    table.insert(table.end(), w, w + bytes / 4);
+  };
+  if (!cols.empty()) push_words(cols.data(), cols.size() * sizeof(DevObsCol));
+  plan.head_desc_off = (int)table.size();
+  if (!head.empty()) push_words(head.data(), head.size() * sizeof(HeadCol));
+  while (table.size() & 3) table.push_back(0);
+  plan.grp_off = (int)table.size();
+  const int G = plan.n_groups;
+  for (int i = 0; i < G; ++i) table.push_back(groups[i].base);
+  for (int i = 0; i < G; ++i) table.push_back(groups[i].stride);
+  for (int i = 0; i < G; ++i) table.push_back(groups[i].kindcol);
+  for (int i = 0; i < G; ++i) { int32_t w; memcpy(&w, &groups[i].scale, 4); table.push_back(w); }
+  while (table.size() & 3) table.push_back(0);
+  for (int i = 0; i < G; ++i)
+    for (int j = 0; j < 4; ++j) { int32_t w; memcpy(&w, &groups[i].noise[j], 4); table.push_back(w); }
+  // (the noise block starts 16-byte aligned: grp_off and 4*G... are padded above)
+  plan.table_words = (int)table.size();
   plan.cols_off = cursor;
-  cursor = align4(cursor + n_cols_total * (int)(sizeof(DevObsCol) / 4));
+  cursor = align4(cursor + plan.table_words);
   plan.smem_words = cursor;
   return GFB_OK;
 }
@@ -364,12 +446,17 @@ int launch_action(gfb_handle* h, const ActionParams& ap, size_t smem, cudaStream
   return GFB_OK;
 }
 
-int upload_cols(gfb_handle* h, PlanSlot& slot, const std::vector<DevObsCol>& cols, cudaStream_t stream) {
-  const size_t bytes = cols.size() * sizeof(DevObsCol);
-  if (!slot.cols_dev) CUDA_TRY(cudaMalloc(&slot.cols_dev, GFB_MAX_OBS_COLS * sizeof(DevObsCol)));
-  if (slot.cols_host.size() != cols.size() || (bytes && memcmp(slot.cols_host.data(), cols.data(), bytes) != 0)) {
-    slot.cols_host = cols;
-    if (bytes) CUDA_TRY(cudaMemcpyAsync(slot.cols_dev, slot.cols_host.data(), bytes, cudaMemcpyHostToDevice, stream));
+constexpr size_t kTableCapacityBytes =
+    GFB_MAX_OBS_COLS * sizeof(DevObsCol) + kMaxHeadCols * sizeof(HeadCol) + (GFB_MAX_OBS_COLS / 4) * 8 * 4 + 64;
+
+int upload_table(gfb_handle* h, PlanSlot& slot, const std::vector<int32_t>& table, cudaStream_t stream) {
+  const size_t bytes = table.size() * sizeof(int32_t);
+  if (bytes > kTableCapacityBytes) return fail(h, GFB_ERR_INVALID, "descriptor table too large");
+  if (!slot.table_dev) CUDA_TRY(cudaMalloc(&slot.table_dev, kTableCapacityBytes));
+  if (slot.table_host.size() != table.size() || (bytes && memcmp(slot.table_host.data(), table.data(), bytes) != 0)) {
+    slot.table_host = table;
+    if (bytes)
+      CUDA_TRY(cudaMemcpyAsync(slot.table_dev, slot.table_host.data(), bytes, cudaMemcpyHostToDevice, stream));
   }
   return GFB_OK;
 }
@@ -437,8 +524,8 @@ void gfb_destroy(gfb_handle* h) {
   cudaFree(h->scratch.report);
   if (h->report_host) cudaFreeHost(h->report_host);
   for (auto& s : h->slots)
-    if (s.cols_dev) cudaFree(s.cols_dev);
-  if (h->observe_slot.cols_dev) cudaFree(h->observe_slot.cols_dev);
+    if (s.table_dev) cudaFree(s.table_dev);
+  if (h->observe_slot.table_dev) cudaFree(h->observe_slot.table_dev);
   for (auto e : h->ev_post) cudaEventDestroy(e);
   for (auto e : h->ev_action) cudaEventDestroy(e);
   delete h;
@@ -592,9 +679,9 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
   // tile: shrink until the slab fits comfortably
   int tile = choose_tile(h);
   KParams kp{};
-  std::vector<DevObsCol> cols;
+  std::vector<int32_t> table;
   for (;;) {
-    int rc = build_plan(h, *b, phases, tile, kp.plan, cols);
+    int rc = build_plan(h, *b, phases, tile, kp.plan, table);
     if (rc != GFB_OK) return rc;
     if ((size_t)kp.plan.smem_words * 4 <= (size_t)kMaxSmemBytes / 2 || tile == 32) break;
     tile = tile / 2;
@@ -615,7 +702,7 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
   slot->used = true;
   slot->phases = phases;
   slot->tile = tile;
-  int rc = upload_cols(h, *slot, cols, stream);
+  int rc = upload_table(h, *slot, table, stream);
   if (rc != GFB_OK) return rc;
 
   const int n_tiles = (P.num_envs + tile - 1) / tile;
@@ -623,7 +710,7 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
   kp.b = *b;
   kp.s = h->scratch;
   kp.s.n_tiles = n_tiles;
-  kp.cols = slot->cols_dev;
+  kp.cols = reinterpret_cast<const DevObsCol*>(slot->table_dev);
   kp.phases = phases;
   kp.tma_ok = tma_eligible(h, *b, kp.plan, phases) ? 1 : 0;
 
@@ -675,22 +762,18 @@ int gfb_observe(gfb_handle* h, const gfb_buffers* b, const int64_t* idx, int32_t
   const gfb_program_head& P = h->prog.head;
   if (!b->buf[GFB_B_INV_BASE_QUAT]) return fail(h, GFB_ERR_INVALID, "INV_BASE_QUAT missing");
   ObserveParams op{};
-  std::vector<DevObsCol> cols;
-  // observe-only plan: nothing is staged, every staged-kind column falls back to its global buffer
+  std::vector<int32_t> table;
+  // observe-only plan: nothing is staged; the kernel reads staged-kind columns from their global buffer
   gfb_buffers probe = *b;
-  int rc = build_plan(h, probe, GFB_PHASE_OBSERVE, kObserveTile, op.plan, cols);
+  int rc = build_plan(h, probe, GFB_PHASE_OBSERVE, kObserveTile, op.plan, table);
   if (rc != GFB_OK) return rc;
-  for (auto& c : cols) {
-    if (c.kind == 1) c.kind = 2;
-    c.vec = 0;
-  }
   if ((op.plan.needs & NEED_LIN) && !b->buf[GFB_B_VEL]) return fail(h, GFB_ERR_INVALID, "VEL missing");
   if ((op.plan.needs & NEED_ANG) && !b->buf[GFB_B_ANG]) return fail(h, GFB_ERR_INVALID, "ANG missing");
-  rc = upload_cols(h, h->observe_slot, cols, stream);
+  rc = upload_table(h, h->observe_slot, table, stream);
   if (rc != GFB_OK) return rc;
   op.P = P;
   op.b = *b;
-  op.cols = h->observe_slot.cols_dev;
+  op.cols = reinterpret_cast<const DevObsCol*>(h->observe_slot.table_dev);
   op.idx = idx;
   op.n = n;
   const size_t smem = (size_t)op.plan.stash_stride * kObserveTile * 4;

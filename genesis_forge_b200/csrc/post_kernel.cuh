@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
   {
     const int32_t* src = reinterpret_cast<const int32_t*>(K.cols);
     int32_t* dst = reinterpret_cast<int32_t*>(S + plan.cols_off);
-    const int words = plan.n_cols_total * (int)(sizeof(DevObsCol) / 4);
+    const int words = plan.table_words;
     for (int w = tid; w < words; w += TILE) dst[w] = src[w];
   }
 
@@ -122,9 +122,7 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
   if ((ph & GFB_PHASE_REWARD) && K.b.buf[GFB_B_ACTION_RATE])
     action_rate = GFB_BUF(const float, GFB_B_ACTION_RATE)[e];
 
-  if (use_tma) {
-    mbar_wait(&bar, 0);
-  }
+  if (use_tma && warp == 0) mbar_wait(&bar, 0);  // one warp polls, the block barrier releases the rest
   __syncthreads();
 
   // slab copies that need no arithmetic (entity cache: base_pos / base_quat are copies of pos / quat)
@@ -612,6 +610,21 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
   }
   if (status) atomicOr(&s_status, status);
 
+  // head tile: the observation columns that are not part of a contiguous 16-byte run, evaluated by
+  // the env's own thread (after resample / reset so that command columns are current)
+  if ((ph & GFB_PHASE_OBSERVE) && plan.n_head > 0) {
+    const HeadCol* hd = reinterpret_cast<const HeadCol*>(S + plan.cols_off + plan.head_desc_off);
+    float* head = S + plan.head_tile_off + tid * plan.n_head;
+    for (int hcol = 0; hcol < plan.n_head; ++hcol) {
+      const HeadCol d = hd[hcol];
+      float v = 0.0f;
+      if (d.kind == 3) v = st[d.a];
+      else if (d.kind == 1) v = S[d.a + tid * d.row_words + d.col];
+      else if (d.kind == 2) v = reinterpret_cast<const float*>(K.b.buf[d.gbuf])[(size_t)e * d.row_words + d.col];
+      head[hcol] = mul(v, d.scale);
+    }
+  }
+
   if (use_tma) fence_async_smem();
   __syncthreads();
 
@@ -691,53 +704,54 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
       if (prev) prev += (size_t)e0 * OH;
       const float* noise = GFB_BUF(const float, GFB_B_OBS_NOISE0 + g);
       if (noise) noise += (size_t)e0 * O;
-      if ((O & 3) == 0) {
-        const int W = OH >> 2;
+      if (plan.grp_begin[g] >= 0) {
+        // 16-byte group path.  Group descriptors are a structure of arrays in shared memory, so the
+        // lanes of a warp (consecutive groups) read consecutive words: no bank conflicts.
+        const int32_t* tab = reinterpret_cast<const int32_t*>(S + plan.cols_off + plan.grp_off);
+        const int G = plan.n_groups, gb = plan.grp_begin[g];
+        const int32_t* g_base = tab + gb;
+        const int32_t* g_stride = tab + G + gb;
+        const int32_t* g_kindcol = tab + 2 * G + gb;
+        const float* g_scale = reinterpret_cast<const float*>(tab + 3 * G) + gb;
+        const float4* g_noise = reinterpret_cast<const float4*>(tab + 4 * G) + gb;
+        const int W = OH >> 2, W0 = O >> 2;
         const int total = valid * W;
         int row = tid / W, c4 = tid - row * W;
         const int drow = TILE / W, dc = TILE - drow * W;
+        float4* out4 = reinterpret_cast<float4*>(out);
+        const float4* prev4 = reinterpret_cast<const float4*>(prev);
+        const float4* noise4 = reinterpret_cast<const float4*>(noise);
         for (int f = tid; f < total; f += TILE) {
-          const int col = c4 << 2;
           float4 v;
-          if (col < O) {
-            const DevObsCol d0 = cols[col];
-            float s1 = d0.scale, s2 = d0.scale, s3 = d0.scale;
-            float n1 = d0.noise, n2 = d0.noise, n3 = d0.noise;
-            if (d0.vec) {
-              if (d0.kind == 1)
-                v = *reinterpret_cast<const float4*>(S + d0.a + row * d0.row_words + d0.col);
-              else
-                v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(K.b.buf[d0.gbuf]) +
-                                                      (size_t)(e0 + row) * d0.row_words + d0.col);
-            } else {
-              const DevObsCol d1 = cols[col + 1], d2 = cols[col + 2], d3 = cols[col + 3];
-              v.x = obs_fetch_post(d0, S, K.b, plan, row, e0 + row);
-              v.y = obs_fetch_post(d1, S, K.b, plan, row, e0 + row);
-              v.z = obs_fetch_post(d2, S, K.b, plan, row, e0 + row);
-              v.w = obs_fetch_post(d3, S, K.b, plan, row, e0 + row);
-              s1 = d1.scale; s2 = d2.scale; s3 = d3.scale;
-              n1 = d1.noise; n2 = d2.noise; n3 = d3.noise;
-            }
-            v.x = mul(v.x, d0.scale); v.y = mul(v.y, s1); v.z = mul(v.z, s2); v.w = mul(v.w, s3);
-            if (d0.noise != 0.f || n1 != 0.f || n2 != 0.f || n3 != 0.f) {
+          if (c4 < W0) {
+            const int base = g_base[c4], stride = g_stride[c4], kc = g_kindcol[c4];
+            const float sc = g_scale[c4];
+            const float4 nz = g_noise[c4];
+            if ((kc & 15) == 1)
+              v = *reinterpret_cast<const float4*>(S + base + row * stride);
+            else
+              v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(K.b.buf[base]) +
+                                                    (size_t)(e0 + row) * stride + (kc >> 4));
+            v.x = mul(v.x, sc); v.y = mul(v.y, sc); v.z = mul(v.z, sc); v.w = mul(v.w, sc);
+            if (nz.x != 0.f || nz.y != 0.f || nz.z != 0.f || nz.w != 0.f) {
               float4 u;
               if (P.rng_mode == 0) {
-                u = noise ? *reinterpret_cast<const float4*>(noise + (size_t)row * O + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                u = noise ? noise4[row * W0 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
               } else {
                 const uint4 x = rng((uint32_t)(e0 + row), (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32),
-                                    0x1000u + (uint32_t)(og.col_begin + col));
+                                    0x1000u + (uint32_t)(og.col_begin + (c4 << 2)));
                 u = make_float4(sub(mul(u01(x.x), 2.f), 1.f), sub(mul(u01(x.y), 2.f), 1.f),
                                 sub(mul(u01(x.z), 2.f), 1.f), sub(mul(u01(x.w), 2.f), 1.f));
               }
-              if (d0.noise != 0.f) v.x = add(v.x, mul(u.x, d0.noise));
-              if (n1 != 0.f) v.y = add(v.y, mul(u.y, n1));
-              if (n2 != 0.f) v.z = add(v.z, mul(u.z, n2));
-              if (n3 != 0.f) v.w = add(v.w, mul(u.w, n3));
+              if (nz.x != 0.f) v.x = add(v.x, mul(u.x, nz.x));
+              if (nz.y != 0.f) v.y = add(v.y, mul(u.y, nz.y));
+              if (nz.z != 0.f) v.z = add(v.z, mul(u.z, nz.z));
+              if (nz.w != 0.f) v.w = add(v.w, mul(u.w, nz.w));
             }
           } else {
-            v = *reinterpret_cast<const float4*>(prev + (size_t)row * OH + (col - O));
+            v = prev4[row * W + (c4 - W0)];
           }
-          *reinterpret_cast<float4*>(out + (size_t)row * OH + col) = v;
+          out4[f] = v;
           row += drow;
           c4 += dc;
           if (c4 >= W) { c4 -= W; ++row; }

@@ -355,26 +355,32 @@ class SyntheticRobot:
     del _noop_setter
 
     def set_dofs_position(self, position, dofs_idx_local=None, envs_idx=None, zero_velocity=True):
+        self._rec("set_dofs_position", position, envs_idx)
+        if not self._scene.apply_setters:
+            return
         st = self._scene.state
         st["dof_pos"][envs_idx] = position
         if zero_velocity:
             st["dof_vel"][envs_idx] = 0.0
-        self._rec("set_dofs_position", position, envs_idx)
 
     def _zero_base_velocity(self, envs_idx):
+        if not self._scene.apply_setters:
+            return
         st = self._scene.state
         st["vel"][envs_idx] = 0.0
         st["ang"][envs_idx] = 0.0
         st["dof_vel"][envs_idx] = 0.0
 
     def set_pos(self, pos, envs_idx=None, zero_velocity=True, relative=False):
-        self._scene.state["pos"][envs_idx] = pos
+        if self._scene.apply_setters:
+            self._scene.state["pos"][envs_idx] = pos
         if zero_velocity:
             self._zero_base_velocity(envs_idx)
         self._rec("set_pos", pos, envs_idx)
 
     def set_quat(self, quat, envs_idx=None, zero_velocity=True, relative=False):
-        self._scene.state["quat"][envs_idx] = quat
+        if self._scene.apply_setters:
+            self._scene.state["quat"][envs_idx] = quat
         if zero_velocity:
             self._zero_base_velocity(envs_idx)
         self._rec("set_quat", quat, envs_idx)
@@ -428,9 +434,15 @@ class SyntheticScene:
         copy_on_get: bool = False,
         pool: int = 0,
         source_kw: dict | None = None,
+        apply_setters: bool = True,
     ):
         self.dt = dt
         self._source_kw = source_kw or {}
+        # False: state setters are accepted but not applied.  Used by throughput benchmarks in pool
+        # mode, where the state sets are reused: applying resets would leave every env of every set in
+        # its reset pose after one cycle and no termination would ever fire again.  The manager path
+        # (index compaction, reset fan-out, setter calls, re-observation) still runs in full.
+        self.apply_setters = apply_setters
         self.n_contacts = n_contacts
         self.seed = seed
         self.device = torch.device(device) if device is not None else gs.device

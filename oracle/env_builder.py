@@ -58,10 +58,11 @@ def dropin_namespace():
     )
 
 
-def make_scene(spec: dict, device, source=None, copy_on_get=False, n_contacts=8, seed=1234, pool=0):
+def make_scene(spec: dict, device, source=None, copy_on_get=False, n_contacts=8, seed=1234, pool=0,
+               apply_setters=True):
     scene = SyntheticScene(
         dt=spec["dt"], n_contacts=n_contacts, seed=seed, device=device, source=source,
-        copy_on_get=copy_on_get, pool=pool,
+        copy_on_get=copy_on_get, pool=pool, apply_setters=apply_setters,
         source_kw={"xy_range": spec["xy_range"]} if "xy_range" in spec else None,
     )
     if "terrain" in spec:
