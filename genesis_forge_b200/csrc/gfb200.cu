@@ -196,6 +196,34 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, P
       if (!b.buf[GFB_B_COMMAND0 + k]) return fail(h, GFB_ERR_INVALID, "command buffer missing");
       plan.off_cmd[k] = stage(GFB_B_COMMAND0 + k, P.command[k].n_dims, -1);
     }
+  // arrays that only the observation rows read (dof velocity / force, targets, raw actions) are
+  // staged as well, so that the row assembly reads nothing but shared memory and every HBM read of
+  // the slab is issued up front by the TMA engine
+  int off_obs_src[GFB_B_COUNT];
+  for (int i = 0; i < GFB_B_COUNT; ++i) off_obs_src[i] = -1;
+  if (phases & GFB_PHASE_OBSERVE) {
+    for (int g = 0; g < P.n_obs_groups; ++g)
+      for (int c = 0; c < P.obs_group[g].n_cols; ++c) {
+        int buf = -1;
+        switch (prog.obs_cols[P.obs_group[g].col_begin + c].src) {
+          case GFB_O_DOF_VEL: buf = GFB_B_DOF_VEL; break;
+          case GFB_O_DOF_FORCE: buf = GFB_B_DOF_FORCE; break;
+          case GFB_O_TARGETS: buf = GFB_B_TARGETS; break;
+          case GFB_O_ENV_ACTIONS: buf = GFB_B_ENV_ACTIONS; break;
+          case GFB_O_DOF_POS: buf = GFB_B_DOF_POS; break;
+          default: break;
+        }
+        if (buf < 0 || off_obs_src[buf] >= 0 || !b.buf[buf]) continue;
+        if (buf == GFB_B_DOF_POS && plan.off_dof_pos >= 0) {
+          off_obs_src[buf] = plan.off_dof_pos;
+          continue;
+        }
+        // ENV_ACTIONS rows are zeroed for reset envs inside this kernel; staged copies would be stale
+        if (buf == GFB_B_ENV_ACTIONS && (phases & GFB_PHASE_RESET)) continue;
+        off_obs_src[buf] = stage(buf, P.num_dofs, -1);
+        if (buf == GFB_B_DOF_POS) plan.off_dof_pos = off_obs_src[buf];
+      }
+  }
   const bool contact = (phases & GFB_PHASE_CONTACT) && P.n_contact > 0;
   if (contact) {
     for (int id : {GFB_B_C_FORCE, GFB_B_C_POS, GFB_B_C_LINK_A, GFB_B_C_LINK_B, GFB_B_LINKS_QUAT})
@@ -243,6 +271,10 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, P
       d.kind = 2;
       d.gbuf = buf;
       d.row_words = row_words;
+      if (off_obs_src[buf] >= 0) {
+        d.kind = 1;
+        d.a = off_obs_src[buf];
+      }
     };
     switch (oc.src) {
       case GFB_O_COMMAND:

@@ -721,40 +721,58 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
         float4* out4 = reinterpret_cast<float4*>(out);
         const float4* prev4 = reinterpret_cast<const float4*>(prev);
         const float4* noise4 = reinterpret_cast<const float4*>(noise);
-        for (int f = tid; f < total; f += TILE) {
-          float4 v;
-          if (c4 < W0) {
-            const int base = g_base[c4], stride = g_stride[c4], kc = g_kindcol[c4];
-            const float sc = g_scale[c4];
-            const float4 nz = g_noise[c4];
-            if ((kc & 15) == 1)
-              v = *reinterpret_cast<const float4*>(S + base + row * stride);
-            else
-              v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(K.b.buf[base]) +
-                                                    (size_t)(e0 + row) * stride + (kc >> 4));
-            v.x = mul(v.x, sc); v.y = mul(v.y, sc); v.z = mul(v.z, sc); v.w = mul(v.w, sc);
-            if (nz.x != 0.f || nz.y != 0.f || nz.z != 0.f || nz.w != 0.f) {
-              float4 u;
-              if (P.rng_mode == 0) {
-                u = noise ? noise4[row * W0 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        constexpr int BATCH = 4;  // independent 16-byte pieces in flight per thread
+        for (int f0 = tid; f0 < total; f0 += BATCH * TILE) {
+          float4 v[BATCH];
+          int rows[BATCH], cs[BATCH];
+#pragma unroll
+          for (int j = 0; j < BATCH; ++j) {
+            rows[j] = row;
+            cs[j] = c4;
+            if (f0 + j * TILE < total) {
+              if (c4 < W0) {
+                const int base = g_base[c4], stride = g_stride[c4], kc = g_kindcol[c4];
+                if ((kc & 15) == 1)
+                  v[j] = *reinterpret_cast<const float4*>(S + base + row * stride);
+                else
+                  v[j] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(K.b.buf[base]) +
+                                                           (size_t)(e0 + row) * stride + (kc >> 4));
               } else {
-                const uint4 x = rng((uint32_t)(e0 + row), (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32),
-                                    0x1000u + (uint32_t)(og.col_begin + (c4 << 2)));
-                u = make_float4(sub(mul(u01(x.x), 2.f), 1.f), sub(mul(u01(x.y), 2.f), 1.f),
-                                sub(mul(u01(x.z), 2.f), 1.f), sub(mul(u01(x.w), 2.f), 1.f));
+                v[j] = prev4[row * W + (c4 - W0)];
               }
-              if (nz.x != 0.f) v.x = add(v.x, mul(u.x, nz.x));
-              if (nz.y != 0.f) v.y = add(v.y, mul(u.y, nz.y));
-              if (nz.z != 0.f) v.z = add(v.z, mul(u.z, nz.z));
-              if (nz.w != 0.f) v.w = add(v.w, mul(u.w, nz.w));
             }
-          } else {
-            v = prev4[row * W + (c4 - W0)];
+            row += drow;
+            c4 += dc;
+            if (c4 >= W) { c4 -= W; ++row; }
           }
-          out4[f] = v;
-          row += drow;
-          c4 += dc;
-          if (c4 >= W) { c4 -= W; ++row; }
+#pragma unroll
+          for (int j = 0; j < BATCH; ++j) {
+            const int f = f0 + j * TILE;
+            if (f >= total) break;
+            float4 x = v[j];
+            const int c = cs[j];
+            if (c < W0) {
+              const float sc = g_scale[c];
+              const float4 nz = g_noise[c];
+              x.x = mul(x.x, sc); x.y = mul(x.y, sc); x.z = mul(x.z, sc); x.w = mul(x.w, sc);
+              if (nz.x != 0.f || nz.y != 0.f || nz.z != 0.f || nz.w != 0.f) {
+                float4 u;
+                if (P.rng_mode == 0) {
+                  u = noise ? noise4[rows[j] * W0 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                  const uint4 r4 = rng((uint32_t)(e0 + rows[j]), (uint32_t)P.step_index,
+                                       (uint32_t)(P.step_index >> 32), 0x1000u + (uint32_t)(og.col_begin + (c << 2)));
+                  u = make_float4(sub(mul(u01(r4.x), 2.f), 1.f), sub(mul(u01(r4.y), 2.f), 1.f),
+                                  sub(mul(u01(r4.z), 2.f), 1.f), sub(mul(u01(r4.w), 2.f), 1.f));
+                }
+                if (nz.x != 0.f) x.x = add(x.x, mul(u.x, nz.x));
+                if (nz.y != 0.f) x.y = add(x.y, mul(u.y, nz.y));
+                if (nz.z != 0.f) x.z = add(x.z, mul(u.z, nz.z));
+                if (nz.w != 0.f) x.w = add(x.w, mul(u.w, nz.w));
+              }
+            }
+            out4[f] = x;
+          }
         }
       } else {
         const int total = valid * OH;
