@@ -346,85 +346,59 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, P
   }
   plan.n_cols_total = n_cols_total;
 
-  // 16-byte group path: every frame-0 group of 4 columns is either a contiguous run of a staged /
-  // global array, or 4 "head" columns that the owner thread evaluates into the head tile.
-  std::vector<HeadCol> head;
-  struct Group { int32_t base, stride, kindcol; float scale; float noise[4]; };
+  // 16-byte group path: each frame-0 group of 4 columns carries 4 shared-memory sources
+  // (offset, row stride, scale, noise).  A group whose 4 sources are one aligned contiguous run is
+  // flagged so that it moves with a single 16-byte shared load.
+  struct Group { int32_t off[4], stride[4]; float scale[4], noise[4]; int32_t flags; };
   std::vector<Group> groups;
   for (int g = 0; g < P.n_obs_groups; ++g) {
     const gfb_obs_group& og = P.obs_group[g];
     plan.grp_begin[g] = -1;
     if ((og.n_cols & 3) || !(phases & GFB_PHASE_OBSERVE)) continue;
-    // count the head columns this group would need
-    int need_head = 0;
-    for (int c = 0; c < og.n_cols; c += 4)
-      if (!cols[og.col_begin + c].vec) need_head += 4;
-    if ((int)head.size() + need_head > kMaxHeadCols) continue;  // falls back to the scalar path
+    bool all_shared = true;
+    for (int c = 0; c < og.n_cols; ++c) all_shared = all_shared && cols[og.col_begin + c].kind != 2;
+    if (!all_shared) continue;  // some source lives in global memory: per-element path
     plan.grp_begin[g] = (int)groups.size();
     for (int c = 0; c < og.n_cols; c += 4) {
       const DevObsCol* d = &cols[og.col_begin + c];
       Group G{};
-      if (d[0].vec) {
-        if (d[0].kind == 1) {
-          G.base = d[0].a + d[0].col;
-          G.kindcol = 1;
-        } else {
-          G.base = d[0].gbuf;
-          G.kindcol = 2 | (d[0].col << 4);
-        }
-        G.stride = d[0].row_words;
-        G.scale = d[0].scale;
-      } else {
-        G.base = (int)head.size();  // patched to a shared offset below
-        G.kindcol = 3;
-        G.stride = 0;
-        G.scale = 1.0f;
-        for (int j = 0; j < 4; ++j) {
-          HeadCol hc{};
-          hc.kind = d[j].kind;
-          hc.a = d[j].a;
-          hc.row_words = d[j].row_words;
-          hc.col = d[j].col;
-          hc.gbuf = d[j].gbuf;
-          hc.scale = d[j].scale;
-          head.push_back(hc);
+      for (int j = 0; j < 4; ++j) {
+        G.scale[j] = d[j].scale;
+        G.noise[j] = d[j].noise;
+        if (d[j].kind == 1) {
+          G.off[j] = d[j].a + d[j].col;
+          G.stride[j] = d[j].row_words;
+        } else if (d[j].kind == 3) {
+          G.off[j] = plan.stash_off + d[j].a;
+          G.stride[j] = plan.stash_stride;
+        } else {  // constant zero column
+          G.off[j] = plan.stash_off;
+          G.stride[j] = 0;
+          G.scale[j] = 0.0f;
         }
       }
-      for (int j = 0; j < 4; ++j) G.noise[j] = d[j].noise;
+      G.flags = d[0].vec ? 1 : 0;
       groups.push_back(G);
     }
   }
-  plan.n_head = (int)head.size();
   plan.n_groups = (int)groups.size();
-  plan.head_tile_off = cursor;
-  cursor = align4(cursor + plan.n_head * tile);
-  for (auto& G : groups)
-    if ((G.kindcol & 15) == 3) {
-      G.base = plan.head_tile_off + G.base;
-      G.stride = plan.n_head;
-      G.kindcol = 1;
-    }
 
-  // descriptor table: [DevObsCol x n_cols][HeadCol x n_head][group SoA]
+  // descriptor table: [DevObsCol x n_cols][group SoA], padded to 16 bytes
   table.clear();
   auto push_words = [&](const void* p, size_t bytes) {
     const int32_t* w = static_cast<const int32_t*>(p);
     table.insert(table.end(), w, w + bytes / 4);
   };
+  auto push_f = [&](float f) { int32_t w; memcpy(&w, &f, 4); table.push_back(w); };
   if (!cols.empty()) push_words(cols.data(), cols.size() * sizeof(DevObsCol));
-  plan.head_desc_off = (int)table.size();
-  if (!head.empty()) push_words(head.data(), head.size() * sizeof(HeadCol));
   while (table.size() & 3) table.push_back(0);
   plan.grp_off = (int)table.size();
-  const int G = plan.n_groups;
-  for (int i = 0; i < G; ++i) table.push_back(groups[i].base);
-  for (int i = 0; i < G; ++i) table.push_back(groups[i].stride);
-  for (int i = 0; i < G; ++i) table.push_back(groups[i].kindcol);
-  for (int i = 0; i < G; ++i) { int32_t w; memcpy(&w, &groups[i].scale, 4); table.push_back(w); }
+  for (const auto& G : groups) for (int j = 0; j < 4; ++j) table.push_back(G.off[j]);
+  for (const auto& G : groups) for (int j = 0; j < 4; ++j) table.push_back(G.stride[j]);
+  for (const auto& G : groups) for (int j = 0; j < 4; ++j) push_f(G.scale[j]);
+  for (const auto& G : groups) for (int j = 0; j < 4; ++j) push_f(G.noise[j]);
+  for (const auto& G : groups) table.push_back(G.flags);
   while (table.size() & 3) table.push_back(0);
-  for (int i = 0; i < G; ++i)
-    for (int j = 0; j < 4; ++j) { int32_t w; memcpy(&w, &groups[i].noise[j], 4); table.push_back(w); }
-  // (the noise block starts 16-byte aligned: grp_off and 4*G... are padded above)
   plan.table_words = (int)table.size();
   plan.cols_off = cursor;
   cursor = align4(cursor + plan.table_words);
@@ -478,8 +452,7 @@ int launch_action(gfb_handle* h, const ActionParams& ap, size_t smem, cudaStream
   return GFB_OK;
 }
 
-constexpr size_t kTableCapacityBytes =
-    GFB_MAX_OBS_COLS * sizeof(DevObsCol) + kMaxHeadCols * sizeof(HeadCol) + (GFB_MAX_OBS_COLS / 4) * 8 * 4 + 64;
+constexpr size_t kTableCapacityBytes = GFB_MAX_OBS_COLS * sizeof(DevObsCol) + (GFB_MAX_OBS_COLS / 4) * 17 * 4 + 64;
 
 int upload_table(gfb_handle* h, PlanSlot& slot, const std::vector<int32_t>& table, cudaStream_t stream) {
   const size_t bytes = table.size() * sizeof(int32_t);

@@ -27,20 +27,6 @@ struct DevObsCol {
   int32_t vec;
 };
 
-// A "head" column: an observation column that is not part of a 4-aligned contiguous run.  The env's
-// owner thread evaluates it (value * scale) into a per-slab head tile laid out in output order, so
-// that the cooperative row assembly only ever moves 16-byte pieces.
-struct HeadCol {
-  int32_t kind;       // 0 zero, 1 staged slab (shared), 2 global buffer, 3 stash
-  int32_t a;          // shared word offset (kind 1), stash offset (kind 3)
-  int32_t row_words;
-  int32_t col;
-  int32_t gbuf;
-  float scale;
-};
-
-constexpr int kMaxHeadCols = 64;
-
 // needs mask: which body-frame vectors the term table uses
 enum : uint32_t {
   NEED_LIN = 1u,
@@ -72,13 +58,11 @@ struct Plan {
   int32_t cols_off;                            // descriptor table copy (DevObsCol | HeadCol | group SoA)
   int32_t n_cols_total;
   int32_t table_words;                         // total words of the descriptor table
-  // 16-byte group path (observation groups whose frame width is a multiple of 4)
-  int32_t n_head;                              // head columns (multiple of 4)
-  int32_t head_desc_off;                       // word offset of HeadCol[n_head] inside the table
-  int32_t head_tile_off;                       // shared word offset of the (tile, n_head) head tile
-  int32_t n_groups;                            // 16-byte groups over all observation groups (frame 0)
-  int32_t grp_off;                             // word offset of the group SoA inside the table:
-                                               //   base[G] stride[G] kindcol[G] scale[G] noise[4G]
+  // 16-byte group path (observation groups whose frame width is a multiple of 4 and whose sources
+  // are all in shared memory).  Group table inside the descriptor table, structure of arrays:
+  //   off[4G] stride[4G] scale[4G] noise[4G] flags[G]     (G = n_groups, 4 columns per group)
+  int32_t n_groups;
+  int32_t grp_off;
   int32_t grp_begin[GFB_MAX_OBS_GROUPS];       // first group of each observation group, -1 = scalar path
   int32_t smem_words;
 };

@@ -64,30 +64,39 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
 
   if (tid < GFB_MAX_TERMINATION_TERMS) s_term_count[tid] = 0;
   if (tid == 0) s_status = 0;
+  for (int i = tid; i < GFB_MAX_REWARD_TERMS * (TILE / 32); i += TILE) (&s_rew_part[0][0])[i] = 0.0;
 
   // ------------------------------------------------------------------------------------------
-  // slab loads
+  // slab loads: every staged array, the episode-sum rows and the descriptor table are single
+  // cp.async.bulk transfers; the lanes of warp 0 issue them in parallel, all complete on one mbarrier
   // ------------------------------------------------------------------------------------------
+  const int n_sum_rows = stage_sums ? P.n_reward : 0;
   if (use_tma) {
     if (tid == 0) {
       mbar_init(&bar, 1);
       fence_mbar_init();
     }
     __syncthreads();
-    if (tid == 0) {
-      uint32_t total = 0;
-      for (int i = 0; i < plan.n_staged; ++i) total += (uint32_t)plan.staged_words[i] * TILE * 4u;
-      if (stage_sums) total += (uint32_t)P.n_reward * TILE * 4u;
-      mbar_expect_tx(&bar, total);
-      for (int i = 0; i < plan.n_staged; ++i) {
-        const float* src = reinterpret_cast<const float*>(K.b.buf[plan.staged_buf[i]]) +
-                           (size_t)e0 * plan.staged_words[i];
-        bulk_load(S + plan.staged_off[i], src, (uint32_t)plan.staged_words[i] * TILE * 4u, &bar);
+    if (warp == 0) {
+      if (lane == 0) {
+        uint32_t total = (uint32_t)plan.table_words * 4u + (uint32_t)n_sum_rows * TILE * 4u;
+        for (int i = 0; i < plan.n_staged; ++i) total += (uint32_t)plan.staged_words[i] * TILE * 4u;
+        mbar_expect_tx(&bar, total);
       }
-      if (stage_sums) {
-        const float* sums = GFB_BUF(const float, GFB_B_EP_SUMS);
-        for (int r = 0; r < P.n_reward; ++r)
-          bulk_load(S + plan.sums_off + r * TILE, sums + (size_t)r * N + e0, TILE * 4u, &bar);
+      __syncwarp();
+      const int n_ops = plan.n_staged + n_sum_rows + 1;
+      for (int i = lane; i < n_ops; i += 32) {
+        if (i < plan.n_staged) {
+          const float* src = reinterpret_cast<const float*>(K.b.buf[plan.staged_buf[i]]) +
+                             (size_t)e0 * plan.staged_words[i];
+          bulk_load(S + plan.staged_off[i], src, (uint32_t)plan.staged_words[i] * TILE * 4u, &bar);
+        } else if (i < plan.n_staged + n_sum_rows) {
+          const int r = i - plan.n_staged;
+          bulk_load(S + plan.sums_off + r * TILE, GFB_BUF(const float, GFB_B_EP_SUMS) + (size_t)r * N + e0,
+                    TILE * 4u, &bar);
+        } else {
+          bulk_load(S + plan.cols_off, K.cols, (uint32_t)plan.table_words * 4u, &bar);
+        }
       }
     }
   } else {
@@ -103,13 +112,9 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
       for (int r = 0; r < P.n_reward; ++r)
         if (active) S[plan.sums_off + r * TILE + tid] = sums[(size_t)r * N + e];
     }
-  }
-  // observation descriptor table -> shared memory (per-thread-varying index later on)
-  {
     const int32_t* src = reinterpret_cast<const int32_t*>(K.cols);
     int32_t* dst = reinterpret_cast<int32_t*>(S + plan.cols_off);
-    const int words = plan.table_words;
-    for (int w = tid; w < words; w += TILE) dst[w] = src[w];
+    for (int w = tid; w < plan.table_words; w += TILE) dst[w] = src[w];
   }
 
   // per-env scalars straight into registers while the slab is in flight
@@ -128,13 +133,13 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
   // slab copies that need no arithmetic (entity cache: base_pos / base_quat are copies of pos / quat)
   if (ph & GFB_PHASE_ENTITY) {
     if (use_tma) {
-      if (tid == 0) {
-        for (int i = 0; i < plan.n_staged; ++i)
-          if (plan.staged_store[i] >= 0 && K.b.buf[plan.staged_store[i]]) {
-            float* dst = reinterpret_cast<float*>(K.b.buf[plan.staged_store[i]]) + (size_t)e0 * plan.staged_words[i];
-            bulk_store(dst, S + plan.staged_off[i], (uint32_t)plan.staged_words[i] * TILE * 4u);
-          }
-        bulk_commit();
+      if (warp == 0 && lane < plan.n_staged) {
+        const int i = lane;
+        if (plan.staged_store[i] >= 0 && K.b.buf[plan.staged_store[i]]) {
+          float* dst = reinterpret_cast<float*>(K.b.buf[plan.staged_store[i]]) + (size_t)e0 * plan.staged_words[i];
+          bulk_store(dst, S + plan.staged_off[i], (uint32_t)plan.staged_words[i] * TILE * 4u);
+          bulk_commit();
+        }
       }
     } else {
       for (int i = 0; i < plan.n_staged; ++i)
@@ -561,22 +566,23 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
         if (P.contact[m].track_air_time)
           for (int k = 0; k < P.contact[m].n_links * 4; ++k) st[plan.st_air[m] + k] = 0.0f;
     }
-    // reward_manager.py:197-222: per-term episode mean over the reset envs, then clear
-    if (P.n_reward > 0) {
-      if (reset_votes) {
-        for (int r = 0; r < P.n_reward; ++r) {
-          float* sum = S + plan.sums_off + r * TILE + tid;
-          double q = 0.0;
-          if (reset) {
-            if (P.reward[r].weight != 0.0f) q = (double)fdiv(*sum, ep_secs);
-            *sum = 0.0f;
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-          if (lane == 0) s_rew_part[r][warp] = q;
+    // reward_manager.py:197-222: per-term episode mean over the reset envs, then clear.
+    // Resets are sparse: lane 0 visits the reset lanes of its warp in ascending order (fixed order,
+    // double accumulation -> deterministic logging).
+    if (P.n_reward > 0 && reset_votes) {
+      for (int r = 0; r < P.n_reward; ++r) {
+        float* sum = S + plan.sums_off + r * TILE + tid;
+        float q = 0.0f;
+        if (reset) {
+          if (P.reward[r].weight != 0.0f) q = fdiv(*sum, ep_secs);
+          *sum = 0.0f;
         }
-      } else if (lane == 0) {
-        for (int r = 0; r < P.n_reward; ++r) s_rew_part[r][warp] = 0.0;
+        double acc = 0.0;
+        for (uint32_t bits = reset_votes; bits; bits &= bits - 1) {
+          const float qb = __shfl_sync(0xffffffffu, q, __ffs(bits) - 1);
+          acc += (double)qb;
+        }
+        if (lane == 0) s_rew_part[r][warp] = acc;
       }
       if (reset) ep_secs = 1e-10f;
     }
@@ -610,21 +616,6 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
   }
   if (status) atomicOr(&s_status, status);
 
-  // head tile: the observation columns that are not part of a contiguous 16-byte run, evaluated by
-  // the env's own thread (after resample / reset so that command columns are current)
-  if ((ph & GFB_PHASE_OBSERVE) && plan.n_head > 0) {
-    const HeadCol* hd = reinterpret_cast<const HeadCol*>(S + plan.cols_off + plan.head_desc_off);
-    float* head = S + plan.head_tile_off + tid * plan.n_head;
-    for (int hcol = 0; hcol < plan.n_head; ++hcol) {
-      const HeadCol d = hd[hcol];
-      float v = 0.0f;
-      if (d.kind == 3) v = st[d.a];
-      else if (d.kind == 1) v = S[d.a + tid * d.row_words + d.col];
-      else if (d.kind == 2) v = reinterpret_cast<const float*>(K.b.buf[d.gbuf])[(size_t)e * d.row_words + d.col];
-      head[hcol] = mul(v, d.scale);
-    }
-  }
-
   if (use_tma) fence_async_smem();
   __syncthreads();
 
@@ -633,20 +624,24 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
   // ------------------------------------------------------------------------------------------
   const bool store_contacts = (ph & GFB_PHASE_CONTACT) && P.n_contact > 0;
   if (use_tma) {
-    if (tid == 0) {
-      if (stage_sums) {
-        float* sums = GFB_BUF(float, GFB_B_EP_SUMS);
-        for (int r = 0; r < P.n_reward; ++r)
-          bulk_store(sums + (size_t)r * N + e0, S + plan.sums_off + r * TILE, TILE * 4u);
-      }
-      if (store_contacts)
-        for (int m = 0; m < P.n_contact; ++m) {
+    if (warp == 0) {
+      const int n_c = store_contacts ? 2 * P.n_contact : 0;
+      bool issued = false;
+      for (int i = lane; i < n_sum_rows + n_c; i += 32) {
+        if (i < n_sum_rows) {
+          bulk_store(GFB_BUF(float, GFB_B_EP_SUMS) + (size_t)i * N + e0, S + plan.sums_off + i * TILE, TILE * 4u);
+        } else {
+          const int m = (i - n_sum_rows) >> 1;
           const uint32_t bytes = (uint32_t)P.contact[m].n_links * 3u * TILE * 4u;
           const size_t goff = (size_t)e0 * P.contact[m].n_links * 3;
-          bulk_store(GFB_BUF(float, GFB_B_CONTACTS0 + m) + goff, S + plan.cout_off[m], bytes);
-          bulk_store(GFB_BUF(float, GFB_B_CONTACT_POS0 + m) + goff, S + plan.cposout_off[m], bytes);
+          if ((i - n_sum_rows) & 1)
+            bulk_store(GFB_BUF(float, GFB_B_CONTACT_POS0 + m) + goff, S + plan.cposout_off[m], bytes);
+          else
+            bulk_store(GFB_BUF(float, GFB_B_CONTACTS0 + m) + goff, S + plan.cout_off[m], bytes);
         }
-      bulk_commit();
+        issued = true;
+      }
+      if (issued) bulk_commit();
     }
   } else {
     if (stage_sums && active) {
@@ -704,74 +699,58 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
       if (prev) prev += (size_t)e0 * OH;
       const float* noise = GFB_BUF(const float, GFB_B_OBS_NOISE0 + g);
       if (noise) noise += (size_t)e0 * O;
-      if (plan.grp_begin[g] >= 0) {
-        // 16-byte group path.  Group descriptors are a structure of arrays in shared memory, so the
-        // lanes of a warp (consecutive groups) read consecutive words: no bank conflicts.
-        const int32_t* tab = reinterpret_cast<const int32_t*>(S + plan.cols_off + plan.grp_off);
-        const int G = plan.n_groups, gb = plan.grp_begin[g];
-        const int32_t* g_base = tab + gb;
-        const int32_t* g_stride = tab + G + gb;
-        const int32_t* g_kindcol = tab + 2 * G + gb;
-        const float* g_scale = reinterpret_cast<const float*>(tab + 3 * G) + gb;
-        const float4* g_noise = reinterpret_cast<const float4*>(tab + 4 * G) + gb;
-        const int W = OH >> 2, W0 = O >> 2;
-        const int total = valid * W;
-        int row = tid / W, c4 = tid - row * W;
-        const int drow = TILE / W, dc = TILE - drow * W;
-        float4* out4 = reinterpret_cast<float4*>(out);
-        const float4* prev4 = reinterpret_cast<const float4*>(prev);
-        const float4* noise4 = reinterpret_cast<const float4*>(noise);
-        constexpr int BATCH = 4;  // independent 16-byte pieces in flight per thread
-        for (int f0 = tid; f0 < total; f0 += BATCH * TILE) {
-          float4 v[BATCH];
-          int rows[BATCH], cs[BATCH];
-#pragma unroll
-          for (int j = 0; j < BATCH; ++j) {
-            rows[j] = row;
-            cs[j] = c4;
-            if (f0 + j * TILE < total) {
-              if (c4 < W0) {
-                const int base = g_base[c4], stride = g_stride[c4], kc = g_kindcol[c4];
-                if ((kc & 15) == 1)
-                  v[j] = *reinterpret_cast<const float4*>(S + base + row * stride);
-                else
-                  v[j] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(K.b.buf[base]) +
-                                                           (size_t)(e0 + row) * stride + (kc >> 4));
+      const int W = OH >> 2, W0 = O >> 2;
+      if (plan.grp_begin[g] >= 0 && W <= TILE) {
+        // 16-byte path.  A thread owns one 16-byte column position c4 of the row and walks down the
+        // slab's rows, so its group descriptor is read once; consecutive threads cover consecutive
+        // 16-byte pieces of TILE/W whole rows -> fully coalesced stores.
+        const int rows_per_pass = TILE / W;
+        if (tid < rows_per_pass * W) {
+          const int r0 = tid / W, c4 = tid - r0 * W;
+          float4* out4 = reinterpret_cast<float4*>(out) + c4;
+          if (c4 < W0) {
+            const int32_t* tab = reinterpret_cast<const int32_t*>(S + plan.cols_off + plan.grp_off);
+            const int G = plan.n_groups, gi = plan.grp_begin[g] + c4;
+            const int4 off = reinterpret_cast<const int4*>(tab)[gi];
+            const int4 str = reinterpret_cast<const int4*>(tab + 4 * G)[gi];
+            const float4 sc = reinterpret_cast<const float4*>(tab + 8 * G)[gi];
+            const float4 nz = reinterpret_cast<const float4*>(tab + 12 * G)[gi];
+            const bool vec = (tab + 16 * G)[gi] & 1;
+            const bool noisy = nz.x != 0.f || nz.y != 0.f || nz.z != 0.f || nz.w != 0.f;
+            const float4* noise4 = reinterpret_cast<const float4*>(noise) + c4;
+#pragma unroll 4
+            for (int row = r0; row < valid; row += rows_per_pass) {
+              float4 v;
+              if (vec) {
+                v = *reinterpret_cast<const float4*>(S + off.x + row * str.x);
               } else {
-                v[j] = prev4[row * W + (c4 - W0)];
+                v.x = S[off.x + row * str.x];
+                v.y = S[off.y + row * str.y];
+                v.z = S[off.z + row * str.z];
+                v.w = S[off.w + row * str.w];
               }
-            }
-            row += drow;
-            c4 += dc;
-            if (c4 >= W) { c4 -= W; ++row; }
-          }
-#pragma unroll
-          for (int j = 0; j < BATCH; ++j) {
-            const int f = f0 + j * TILE;
-            if (f >= total) break;
-            float4 x = v[j];
-            const int c = cs[j];
-            if (c < W0) {
-              const float sc = g_scale[c];
-              const float4 nz = g_noise[c];
-              x.x = mul(x.x, sc); x.y = mul(x.y, sc); x.z = mul(x.z, sc); x.w = mul(x.w, sc);
-              if (nz.x != 0.f || nz.y != 0.f || nz.z != 0.f || nz.w != 0.f) {
+              v.x = mul(v.x, sc.x); v.y = mul(v.y, sc.y); v.z = mul(v.z, sc.z); v.w = mul(v.w, sc.w);
+              if (noisy) {
                 float4 u;
                 if (P.rng_mode == 0) {
-                  u = noise ? noise4[rows[j] * W0 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+                  u = noise ? noise4[row * W0] : make_float4(0.f, 0.f, 0.f, 0.f);
                 } else {
-                  const uint4 r4 = rng((uint32_t)(e0 + rows[j]), (uint32_t)P.step_index,
-                                       (uint32_t)(P.step_index >> 32), 0x1000u + (uint32_t)(og.col_begin + (c << 2)));
+                  const uint4 r4 = rng((uint32_t)(e0 + row), (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32),
+                                       0x1000u + (uint32_t)(og.col_begin + (c4 << 2)));
                   u = make_float4(sub(mul(u01(r4.x), 2.f), 1.f), sub(mul(u01(r4.y), 2.f), 1.f),
                                   sub(mul(u01(r4.z), 2.f), 1.f), sub(mul(u01(r4.w), 2.f), 1.f));
                 }
-                if (nz.x != 0.f) x.x = add(x.x, mul(u.x, nz.x));
-                if (nz.y != 0.f) x.y = add(x.y, mul(u.y, nz.y));
-                if (nz.z != 0.f) x.z = add(x.z, mul(u.z, nz.z));
-                if (nz.w != 0.f) x.w = add(x.w, mul(u.w, nz.w));
+                if (nz.x != 0.f) v.x = add(v.x, mul(u.x, nz.x));
+                if (nz.y != 0.f) v.y = add(v.y, mul(u.y, nz.y));
+                if (nz.z != 0.f) v.z = add(v.z, mul(u.z, nz.z));
+                if (nz.w != 0.f) v.w = add(v.w, mul(u.w, nz.w));
               }
+              out4[row * W] = v;
             }
-            out4[f] = x;
+          } else {
+            const float4* prev4 = reinterpret_cast<const float4*>(prev) + (c4 - W0);
+#pragma unroll 4
+            for (int row = r0; row < valid; row += rows_per_pass) out4[row * W] = prev4[row * W];
           }
         }
       } else {
@@ -804,7 +783,7 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
     }
   }
 
-  if (use_tma && tid == 0) bulk_wait_all();
+  if (use_tma && warp == 0) bulk_wait_all();
 }
 
 }  // namespace gfb
