@@ -1,6 +1,7 @@
 // libgfb200: C ABI + launch logic (see include/gfb200.h).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -46,6 +47,8 @@ struct gfb_handle {
   PlanSlot observe_slot;
   bool disable_tma = false;
   int force_tile = 0;
+  int force_stages = 0;
+  int num_sms = 0;
   int64_t launches = 0;
   // profiling
   bool profiling = false;
@@ -147,7 +150,7 @@ uint32_t compute_needs(const gfb_program& prog, uint32_t phases) {
 
 // Lay out the shared-memory slab for one (program, phases, tile) combination and lower the
 // observation columns to device descriptors.
-int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, Plan& plan,
+int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, int n_stages, Plan& plan,
                std::vector<int32_t>& table) {
   std::vector<DevObsCol> cols;
   const gfb_program& prog = h->prog;
@@ -400,9 +403,11 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, P
   for (const auto& G : groups) table.push_back(G.flags);
   while (table.size() & 3) table.push_back(0);
   plan.table_words = (int)table.size();
-  plan.cols_off = cursor;
-  cursor = align4(cursor + plan.table_words);
-  plan.smem_words = cursor;
+  // ring layout: [stage 0][stage 1][descriptor table]; offsets above are relative to a stage base
+  plan.stage_words = (cursor + 31) & ~31;
+  plan.n_stages = n_stages;
+  plan.cols_off = plan.stage_words * n_stages;
+  plan.smem_words = plan.cols_off + align4(plan.table_words);
   return GFB_OK;
 }
 
@@ -438,6 +443,18 @@ int launch_post(gfb_handle* h, const KParams& kp, size_t smem, cudaStream_t stre
   post_kernel<TILE><<<grid, TILE, smem, stream>>>(kp);
   CUDA_TRY(cudaGetLastError());
   return GFB_OK;
+}
+
+template <int TILE>
+int blocks_per_sm(gfb_handle* h, size_t smem) {
+  int& cur = h->smem_attr_post[tile_index(TILE)];
+  if ((int)smem > 48 * 1024 && (int)smem > cur) {
+    if (cudaFuncSetAttribute(post_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess)
+      cur = (int)smem;
+  }
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, post_kernel<TILE>, TILE, smem) != cudaSuccess) n = 0;
+  return n;
 }
 
 template <int TILE>
@@ -515,6 +532,9 @@ int gfb_create(int32_t num_envs, int32_t device, gfb_handle** out) {
   h->disable_tma = env && env[0] == '1';
   env = getenv("GFB_TILE");
   h->force_tile = env ? atoi(env) : 0;
+  env = getenv("GFB_STAGES");
+  h->force_stages = env ? atoi(env) : 0;
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   return GFB_OK;
 }
 
@@ -685,11 +705,16 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
   int tile = choose_tile(h);
   KParams kp{};
   std::vector<int32_t> table;
+  // prefer the two-stage prefetch ring with at least two resident blocks per SM; shrink the slab,
+  // then fall back to a single stage, until it fits
+  int n_stages = h->force_stages == 1 ? 1 : 2;
   for (;;) {
-    int rc = build_plan(h, *b, phases, tile, kp.plan, table);
+    int rc = build_plan(h, *b, phases, tile, n_stages, kp.plan, table);
     if (rc != GFB_OK) return rc;
-    if ((size_t)kp.plan.smem_words * 4 <= (size_t)kMaxSmemBytes / 2 || tile == 32) break;
-    tile = tile / 2;
+    if ((size_t)kp.plan.smem_words * 4 <= (size_t)kMaxSmemBytes / 2) break;
+    if (tile > 32) tile /= 2;
+    else if (n_stages == 2) n_stages = 1;
+    else break;
   }
   const size_t smem = (size_t)kp.plan.smem_words * 4;
   if (smem > (size_t)kMaxSmemBytes) return fail(h, GFB_ERR_UNSUPPORTED, "slab does not fit in shared memory");
@@ -725,9 +750,18 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
     e1 = h->ev_post[h->n_post++];
     cudaEventRecord(e0, stream);
   }
-  if (tile == 32) rc = launch_post<32>(h, kp, smem, stream, n_tiles);
-  else if (tile == 64) rc = launch_post<64>(h, kp, smem, stream, n_tiles);
-  else rc = launch_post<128>(h, kp, smem, stream, n_tiles);
+  // persistent grid: as many blocks as can be resident at once (or one per slab if fewer)
+  int grid = n_tiles;
+  {
+    int per_sm = 0;
+    if (tile == 32) per_sm = blocks_per_sm<32>(h, smem);
+    else if (tile == 64) per_sm = blocks_per_sm<64>(h, smem);
+    else per_sm = blocks_per_sm<128>(h, smem);
+    if (per_sm > 0 && h->num_sms > 0) grid = std::min(n_tiles, per_sm * h->num_sms);
+  }
+  if (tile == 32) rc = launch_post<32>(h, kp, smem, stream, grid);
+  else if (tile == 64) rc = launch_post<64>(h, kp, smem, stream, grid);
+  else rc = launch_post<128>(h, kp, smem, stream, grid);
   if (rc != GFB_OK) return rc;
   if (e1) cudaEventRecord(e1, stream);
 
@@ -770,7 +804,7 @@ int gfb_observe(gfb_handle* h, const gfb_buffers* b, const int64_t* idx, int32_t
   std::vector<int32_t> table;
   // observe-only plan: nothing is staged; the kernel reads staged-kind columns from their global buffer
   gfb_buffers probe = *b;
-  int rc = build_plan(h, probe, GFB_PHASE_OBSERVE, kObserveTile, op.plan, table);
+  int rc = build_plan(h, probe, GFB_PHASE_OBSERVE, kObserveTile, 1, op.plan, table);
   if (rc != GFB_OK) return rc;
   if ((op.plan.needs & NEED_LIN) && !b->buf[GFB_B_VEL]) return fail(h, GFB_ERR_INVALID, "VEL missing");
   if ((op.plan.needs & NEED_ANG) && !b->buf[GFB_B_ANG]) return fail(h, GFB_ERR_INVALID, "ANG missing");

@@ -64,6 +64,8 @@ struct Plan {
   int32_t n_groups;
   int32_t grp_off;
   int32_t grp_begin[GFB_MAX_OBS_GROUPS];       // first group of each observation group, -1 = scalar path
+  int32_t stage_words;                         // shared words of one ring stage
+  int32_t n_stages;                            // 2 = prefetch ring, 1 = single buffer
   int32_t smem_words;
 };
 

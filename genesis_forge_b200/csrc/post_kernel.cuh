@@ -39,10 +39,44 @@ __device__ __forceinline__ float obs_fetch_post(const DevObsCol& d, const float*
   }
 }
 
+// Issue the TMA loads of one slab (warp 0 only): staged arrays + episode-sum rows, optionally the
+// descriptor table.  All complete on `bar` (one arrival with the expected byte count by lane 0).
+template <int TILE>
+__device__ __forceinline__ void issue_slab_loads(const KParams& K, float* S, float* table_dst, uint64_t* bar,
+                                                 int tile, int n_sum_rows, bool with_table, int lane) {
+  const Plan& plan = K.plan;
+  const int N = K.P.num_envs;
+  const int e0 = tile * TILE;
+  const uint32_t valid = (uint32_t)min(TILE, N - e0);
+  if (lane == 0) {
+    uint32_t total = (with_table ? (uint32_t)plan.table_words * 4u : 0u) + (uint32_t)n_sum_rows * valid * 4u;
+    for (int i = 0; i < plan.n_staged; ++i) total += (uint32_t)plan.staged_words[i] * valid * 4u;
+    mbar_expect_tx(bar, total);
+  }
+  __syncwarp();
+  const int n_ops = plan.n_staged + n_sum_rows + (with_table ? 1 : 0);
+  for (int i = lane; i < n_ops; i += 32) {
+    if (i < plan.n_staged) {
+      const float* src = reinterpret_cast<const float*>(K.b.buf[plan.staged_buf[i]]) +
+                         (size_t)e0 * plan.staged_words[i];
+      bulk_load(S + plan.staged_off[i], src, (uint32_t)plan.staged_words[i] * valid * 4u, bar);
+    } else if (i < plan.n_staged + n_sum_rows) {
+      const int r = i - plan.n_staged;
+      bulk_load(S + plan.sums_off + r * TILE, GFB_BUF(const float, GFB_B_EP_SUMS) + (size_t)r * N + e0,
+                valid * 4u, bar);
+    } else {
+      bulk_load(table_dst, K.cols, (uint32_t)plan.table_words * 4u, bar);
+    }
+  }
+}
+
+// Persistent kernel: each block walks slabs blockIdx.x, blockIdx.x + gridDim.x, ... with a two-stage
+// shared-memory ring -- the TMA loads of the next slab are in flight while the current one is
+// processed, and the stores of the previous one drain in the background.
 template <int TILE>
 __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KParams K) {
-  extern __shared__ __align__(128) float S[];
-  __shared__ __align__(8) uint64_t bar;
+  extern __shared__ __align__(128) float Sbase[];
+  __shared__ __align__(8) uint64_t bars[2];
   __shared__ int32_t s_term_count[GFB_MAX_TERMINATION_TERMS];
   __shared__ double s_rew_part[GFB_MAX_REWARD_TERMS][TILE / 32];
   __shared__ uint32_t s_reset_bits[TILE / 32];
@@ -52,52 +86,54 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
   const Plan& plan = K.plan;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = P.num_envs;
-  const int tile = blockIdx.x;
+  const uint32_t ph = K.phases;
+  const bool use_tma = K.tma_ok != 0;
+  const int D = P.num_dofs;
+  const bool stage_sums = (ph & (GFB_PHASE_REWARD | GFB_PHASE_RESET)) != 0 && P.n_reward > 0;
+  const int n_sum_rows = stage_sums ? P.n_reward : 0;
+  const int n_tiles = K.s.n_tiles;
+  const int n_stages = plan.n_stages;
+  float* const Tbl = Sbase + plan.cols_off;  // descriptor table, loaded once per block
+  const Philox rng(P.rng_seed);
+
+  if (use_tma) {
+    if (tid == 0) {
+      mbar_init(&bars[0], 1);
+      mbar_init(&bars[1], 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (warp == 0 && (int)blockIdx.x < n_tiles)
+      issue_slab_loads<TILE>(K, Sbase, Tbl, &bars[0], blockIdx.x, n_sum_rows, true, lane);
+  } else {
+    const int32_t* src = reinterpret_cast<const int32_t*>(K.cols);
+    int32_t* dst = reinterpret_cast<int32_t*>(Tbl);
+    for (int w = tid; w < plan.table_words; w += TILE) dst[w] = src[w];
+  }
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+  const int stage = n_stages == 2 ? (it & 1) : 0;
+  float* const S = Sbase + stage * plan.stage_words;
   const int e0 = tile * TILE;
   const int valid = min(TILE, N - e0);
   const bool active = tid < valid;
   const int e = active ? e0 + tid : N - 1;  // inactive lanes shadow the last env and never write
-  const uint32_t ph = K.phases;
-  const bool use_tma = K.tma_ok && valid == TILE;
-  const int D = P.num_dofs;
-  const bool stage_sums = (ph & (GFB_PHASE_REWARD | GFB_PHASE_RESET)) != 0 && P.n_reward > 0;
+  const int next_tile = tile + gridDim.x;
 
   if (tid < GFB_MAX_TERMINATION_TERMS) s_term_count[tid] = 0;
   if (tid == 0) s_status = 0;
   for (int i = tid; i < GFB_MAX_REWARD_TERMS * (TILE / 32); i += TILE) (&s_rew_part[0][0])[i] = 0.0;
 
   // ------------------------------------------------------------------------------------------
-  // slab loads: every staged array, the episode-sum rows and the descriptor table are single
-  // cp.async.bulk transfers; the lanes of warp 0 issue them in parallel, all complete on one mbarrier
+  // slab loads: every staged array and the episode-sum rows are single cp.async.bulk transfers;
+  // the lanes of warp 0 issue them in parallel, all complete on the stage's mbarrier
   // ------------------------------------------------------------------------------------------
-  const int n_sum_rows = stage_sums ? P.n_reward : 0;
   if (use_tma) {
-    if (tid == 0) {
-      mbar_init(&bar, 1);
-      fence_mbar_init();
-    }
-    __syncthreads();
-    if (warp == 0) {
-      if (lane == 0) {
-        uint32_t total = (uint32_t)plan.table_words * 4u + (uint32_t)n_sum_rows * TILE * 4u;
-        for (int i = 0; i < plan.n_staged; ++i) total += (uint32_t)plan.staged_words[i] * TILE * 4u;
-        mbar_expect_tx(&bar, total);
-      }
-      __syncwarp();
-      const int n_ops = plan.n_staged + n_sum_rows + 1;
-      for (int i = lane; i < n_ops; i += 32) {
-        if (i < plan.n_staged) {
-          const float* src = reinterpret_cast<const float*>(K.b.buf[plan.staged_buf[i]]) +
-                             (size_t)e0 * plan.staged_words[i];
-          bulk_load(S + plan.staged_off[i], src, (uint32_t)plan.staged_words[i] * TILE * 4u, &bar);
-        } else if (i < plan.n_staged + n_sum_rows) {
-          const int r = i - plan.n_staged;
-          bulk_load(S + plan.sums_off + r * TILE, GFB_BUF(const float, GFB_B_EP_SUMS) + (size_t)r * N + e0,
-                    TILE * 4u, &bar);
-        } else {
-          bulk_load(S + plan.cols_off, K.cols, (uint32_t)plan.table_words * 4u, &bar);
-        }
-      }
+    if (warp == 0 && n_stages == 2 && next_tile < n_tiles) {
+      bulk_wait_all_read();  // the other stage's outgoing stores have left shared memory
+      issue_slab_loads<TILE>(K, Sbase + (stage ^ 1) * plan.stage_words, Tbl, &bars[stage ^ 1], next_tile,
+                             n_sum_rows, false, lane);
     }
   } else {
     for (int i = 0; i < plan.n_staged; ++i) {
@@ -112,9 +148,6 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
       for (int r = 0; r < P.n_reward; ++r)
         if (active) S[plan.sums_off + r * TILE + tid] = sums[(size_t)r * N + e];
     }
-    const int32_t* src = reinterpret_cast<const int32_t*>(K.cols);
-    int32_t* dst = reinterpret_cast<int32_t*>(S + plan.cols_off);
-    for (int w = tid; w < plan.table_words; w += TILE) dst[w] = src[w];
   }
 
   // per-env scalars straight into registers while the slab is in flight
@@ -127,7 +160,8 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
   if ((ph & GFB_PHASE_REWARD) && K.b.buf[GFB_B_ACTION_RATE])
     action_rate = GFB_BUF(const float, GFB_B_ACTION_RATE)[e];
 
-  if (use_tma && warp == 0) mbar_wait(&bar, 0);  // one warp polls, the block barrier releases the rest
+  // one warp polls the stage's mbarrier, the block barrier releases the rest
+  if (use_tma && warp == 0) mbar_wait(&bars[stage], (uint32_t)((n_stages == 2 ? (it >> 1) : it) & 1));
   __syncthreads();
 
   // slab copies that need no arithmetic (entity cache: base_pos / base_quat are copies of pos / quat)
@@ -137,7 +171,7 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
         const int i = lane;
         if (plan.staged_store[i] >= 0 && K.b.buf[plan.staged_store[i]]) {
           float* dst = reinterpret_cast<float*>(K.b.buf[plan.staged_store[i]]) + (size_t)e0 * plan.staged_words[i];
-          bulk_store(dst, S + plan.staged_off[i], (uint32_t)plan.staged_words[i] * TILE * 4u);
+          bulk_store(dst, S + plan.staged_off[i], (uint32_t)plan.staged_words[i] * (uint32_t)valid * 4u);
           bulk_commit();
         }
       }
@@ -491,7 +525,6 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
   // ------------------------------------------------------------------------------------------
   // command resample on the resample boundary (command_manager.py:152-162)
   // ------------------------------------------------------------------------------------------
-  const Philox rng(P.rng_seed);
   if (ph & GFB_PHASE_COMMAND) {
     for (int k = 0; k < P.n_command; ++k) {
       const gfb_command_manager& cm = P.command[k];
@@ -629,10 +662,11 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
       bool issued = false;
       for (int i = lane; i < n_sum_rows + n_c; i += 32) {
         if (i < n_sum_rows) {
-          bulk_store(GFB_BUF(float, GFB_B_EP_SUMS) + (size_t)i * N + e0, S + plan.sums_off + i * TILE, TILE * 4u);
+          bulk_store(GFB_BUF(float, GFB_B_EP_SUMS) + (size_t)i * N + e0, S + plan.sums_off + i * TILE,
+                     (uint32_t)valid * 4u);
         } else {
           const int m = (i - n_sum_rows) >> 1;
-          const uint32_t bytes = (uint32_t)P.contact[m].n_links * 3u * TILE * 4u;
+          const uint32_t bytes = (uint32_t)P.contact[m].n_links * 3u * (uint32_t)valid * 4u;
           const size_t goff = (size_t)e0 * P.contact[m].n_links * 3;
           if ((i - n_sum_rows) & 1)
             bulk_store(GFB_BUF(float, GFB_B_CONTACT_POS0 + m) + goff, S + plan.cposout_off[m], bytes);
@@ -689,7 +723,7 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
   //  frames 1..H-1 are the previous step's frames 0..H-2, observation_manager.py:223-226)
   // ------------------------------------------------------------------------------------------
   if (ph & GFB_PHASE_OBSERVE) {
-    const DevObsCol* cols_all = reinterpret_cast<const DevObsCol*>(S + plan.cols_off);
+    const DevObsCol* cols_all = reinterpret_cast<const DevObsCol*>(Tbl);
     for (int g = 0; g < P.n_obs_groups; ++g) {
       const gfb_obs_group& og = P.obs_group[g];
       const int O = og.n_cols, OH = og.n_cols * og.history;
@@ -709,7 +743,7 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
           const int r0 = tid / W, c4 = tid - r0 * W;
           float4* out4 = reinterpret_cast<float4*>(out) + c4;
           if (c4 < W0) {
-            const int32_t* tab = reinterpret_cast<const int32_t*>(S + plan.cols_off + plan.grp_off);
+            const int32_t* tab = reinterpret_cast<const int32_t*>(Tbl + plan.grp_off);
             const int G = plan.n_groups, gi = plan.grp_begin[g] + c4;
             const int4 off = reinterpret_cast<const int4*>(tab)[gi];
             const int4 str = reinterpret_cast<const int4*>(tab + 4 * G)[gi];
@@ -782,6 +816,14 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
       }
     }
   }
+
+  // everyone is done with this stage's shared memory before it is refilled
+  __syncthreads();
+  if (use_tma && n_stages == 1 && next_tile < n_tiles && warp == 0) {
+    bulk_wait_all_read();
+    issue_slab_loads<TILE>(K, Sbase, Tbl, &bars[0], next_tile, n_sum_rows, false, lane);
+  }
+  }  // slab loop
 
   if (use_tma && warp == 0) bulk_wait_all();
 }
