@@ -349,22 +349,25 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, i
   }
   plan.n_cols_total = n_cols_total;
 
-  // 16-byte group path: each frame-0 group of 4 columns carries 4 shared-memory sources
-  // (offset, row stride, scale, noise).  A group whose 4 sources are one aligned contiguous run is
-  // flagged so that it moves with a single 16-byte shared load.
-  struct Group { int32_t off[4], stride[4]; float scale[4], noise[4]; int32_t flags; };
-  std::vector<Group> groups;
+  // 16-byte group path.  Each frame-0 group of 4 columns is either an aligned contiguous run of one
+  // staged array ("run": one 16-byte shared load) or 4 independent shared sources ("mixed").  The
+  // two kinds are assembled in separate, warp-uniform passes; history pieces are a third pass.
+  struct Group { int32_t off[4], stride[4]; float scale[4], noise[4]; int32_t c4; };
+  std::vector<Group> runs, mixed;
   for (int g = 0; g < P.n_obs_groups; ++g) {
     const gfb_obs_group& og = P.obs_group[g];
-    plan.grp_begin[g] = -1;
+    plan.grp_run_begin[g] = plan.grp_mixed_begin[g] = -1;
+    plan.grp_run_count[g] = plan.grp_mixed_count[g] = 0;
     if ((og.n_cols & 3) || !(phases & GFB_PHASE_OBSERVE)) continue;
     bool all_shared = true;
     for (int c = 0; c < og.n_cols; ++c) all_shared = all_shared && cols[og.col_begin + c].kind != 2;
     if (!all_shared) continue;  // some source lives in global memory: per-element path
-    plan.grp_begin[g] = (int)groups.size();
+    plan.grp_run_begin[g] = (int)runs.size();
+    plan.grp_mixed_begin[g] = (int)mixed.size();
     for (int c = 0; c < og.n_cols; c += 4) {
       const DevObsCol* d = &cols[og.col_begin + c];
       Group G{};
+      G.c4 = c >> 2;
       for (int j = 0; j < 4; ++j) {
         G.scale[j] = d[j].scale;
         G.noise[j] = d[j].noise;
@@ -380,28 +383,45 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, i
           G.scale[j] = 0.0f;
         }
       }
-      G.flags = d[0].vec ? 1 : 0;
-      groups.push_back(G);
+      (d[0].vec ? runs : mixed).push_back(G);
     }
+    plan.grp_run_count[g] = (int)runs.size() - plan.grp_run_begin[g];
+    plan.grp_mixed_count[g] = (int)mixed.size() - plan.grp_mixed_begin[g];
   }
-  plan.n_groups = (int)groups.size();
 
-  // descriptor table: [DevObsCol x n_cols][group SoA], padded to 16 bytes
+  // descriptor table: [DevObsCol x n_cols][runs: off stride scale noise[4] c4][mixed SoA], 16-byte padded
   table.clear();
   auto push_words = [&](const void* p, size_t bytes) {
     const int32_t* w = static_cast<const int32_t*>(p);
     table.insert(table.end(), w, w + bytes / 4);
   };
   auto push_f = [&](float f) { int32_t w; memcpy(&w, &f, 4); table.push_back(w); };
-  if (!cols.empty()) push_words(cols.data(), cols.size() * sizeof(DevObsCol));
-  while (table.size() & 3) table.push_back(0);
-  plan.grp_off = (int)table.size();
-  for (const auto& G : groups) for (int j = 0; j < 4; ++j) table.push_back(G.off[j]);
-  for (const auto& G : groups) for (int j = 0; j < 4; ++j) table.push_back(G.stride[j]);
-  for (const auto& G : groups) for (int j = 0; j < 4; ++j) push_f(G.scale[j]);
-  for (const auto& G : groups) for (int j = 0; j < 4; ++j) push_f(G.noise[j]);
-  for (const auto& G : groups) table.push_back(G.flags);
-  while (table.size() & 3) table.push_back(0);
+  auto pad4 = [&]() { while (table.size() & 3) table.push_back(0); };
+  bool need_cols = false;  // the per-column table is only read by the per-element path
+  for (int g = 0; g < P.n_obs_groups; ++g) need_cols = need_cols || plan.grp_run_begin[g] < 0;
+  if (!(phases & GFB_PHASE_OBSERVE)) need_cols = false;
+  if (phases == GFB_PHASE_OBSERVE) need_cols = true;  // observe_kernel reads it
+  if (need_cols && !cols.empty()) push_words(cols.data(), cols.size() * sizeof(DevObsCol));
+  pad4();
+  // runs: per group {off, stride, c4, scale} as int4, then noise float4
+  plan.run_off = (int)table.size();
+  plan.n_runs = (int)runs.size();
+  for (const auto& G : runs) {
+    table.push_back(G.off[0]);
+    table.push_back(G.stride[0]);
+    table.push_back(G.c4);
+    push_f(G.scale[0]);
+  }
+  for (const auto& G : runs) for (int j = 0; j < 4; ++j) push_f(G.noise[j]);
+  // mixed: off int4, stride int4, scale float4, noise float4, c4
+  plan.mixed_off = (int)table.size();
+  plan.n_mixed = (int)mixed.size();
+  for (const auto& G : mixed) for (int j = 0; j < 4; ++j) table.push_back(G.off[j]);
+  for (const auto& G : mixed) for (int j = 0; j < 4; ++j) table.push_back(G.stride[j]);
+  for (const auto& G : mixed) for (int j = 0; j < 4; ++j) push_f(G.scale[j]);
+  for (const auto& G : mixed) for (int j = 0; j < 4; ++j) push_f(G.noise[j]);
+  for (const auto& G : mixed) table.push_back(G.c4);
+  pad4();
   plan.table_words = (int)table.size();
   // ring layout: [stage 0][stage 1][descriptor table]; offsets above are relative to a stage base
   plan.stage_words = (cursor + 31) & ~31;
@@ -707,7 +727,9 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
   std::vector<int32_t> table;
   // prefer the two-stage prefetch ring with at least two resident blocks per SM; shrink the slab,
   // then fall back to a single stage, until it fits
-  int n_stages = h->force_stages == 1 ? 1 : 2;
+  // (GFB_STAGES=2 selects the persistent two-stage ring; measured slower on B200 because only 3
+  //  blocks fit per SM and the per-env arithmetic becomes latency-bound -- see DESIGN.md)
+  int n_stages = h->force_stages == 2 ? 2 : 1;
   for (;;) {
     int rc = build_plan(h, *b, phases, tile, n_stages, kp.plan, table);
     if (rc != GFB_OK) return rc;
@@ -757,7 +779,7 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
     if (tile == 32) per_sm = blocks_per_sm<32>(h, smem);
     else if (tile == 64) per_sm = blocks_per_sm<64>(h, smem);
     else per_sm = blocks_per_sm<128>(h, smem);
-    if (per_sm > 0 && h->num_sms > 0) grid = std::min(n_tiles, per_sm * h->num_sms);
+    if (n_stages == 2 && per_sm > 0 && h->num_sms > 0) grid = std::min(n_tiles, per_sm * h->num_sms);
   }
   if (tile == 32) rc = launch_post<32>(h, kp, smem, stream, grid);
   else if (tile == 64) rc = launch_post<64>(h, kp, smem, stream, grid);

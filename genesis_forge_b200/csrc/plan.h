@@ -59,11 +59,17 @@ struct Plan {
   int32_t n_cols_total;
   int32_t table_words;                         // total words of the descriptor table
   // 16-byte group path (observation groups whose frame width is a multiple of 4 and whose sources
-  // are all in shared memory).  Group table inside the descriptor table, structure of arrays:
-  //   off[4G] stride[4G] scale[4G] noise[4G] flags[G]     (G = n_groups, 4 columns per group)
-  int32_t n_groups;
-  int32_t grp_off;
-  int32_t grp_begin[GFB_MAX_OBS_GROUPS];       // first group of each observation group, -1 = scalar path
+  // are all in shared memory).  Inside the descriptor table:
+  //   runs  (aligned contiguous run of one staged array):  int4 {off, stride, c4, scale}[n_runs],
+  //                                                         float4 noise[n_runs]
+  //   mixed (4 independent shared sources): int4 off[n_mixed], int4 stride[n_mixed],
+  //                                         float4 scale[n_mixed], float4 noise[n_mixed], int c4[n_mixed]
+  int32_t n_runs, run_off;
+  int32_t n_mixed, mixed_off;
+  int32_t grp_run_begin[GFB_MAX_OBS_GROUPS];   // -1 = per-element path for this observation group
+  int32_t grp_run_count[GFB_MAX_OBS_GROUPS];
+  int32_t grp_mixed_begin[GFB_MAX_OBS_GROUPS];
+  int32_t grp_mixed_count[GFB_MAX_OBS_GROUPS];
   int32_t stage_words;                         // shared words of one ring stage
   int32_t n_stages;                            // 2 = prefetch ring, 1 = single buffer
   int32_t smem_words;

@@ -39,6 +39,25 @@ __device__ __forceinline__ float obs_fetch_post(const DevObsCol& d, const float*
   }
 }
 
+// v += u * noise for one 16-byte piece; u from the injected U(-1,1) buffer or Philox
+__device__ __forceinline__ float4 add_noise(float4 v, const float4 nz, const float* noise, int row, int W0, int c4,
+                                            const gfb_program_head& P, const Philox& rng, int e0, int col_begin) {
+  float4 u;
+  if (P.rng_mode == 0) {
+    u = noise ? reinterpret_cast<const float4*>(noise)[row * W0 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    const uint4 r4 = rng((uint32_t)(e0 + row), (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32),
+                         0x1000u + (uint32_t)(col_begin + (c4 << 2)));
+    u = make_float4(sub(mul(u01(r4.x), 2.f), 1.f), sub(mul(u01(r4.y), 2.f), 1.f),
+                    sub(mul(u01(r4.z), 2.f), 1.f), sub(mul(u01(r4.w), 2.f), 1.f));
+  }
+  if (nz.x != 0.f) v.x = add(v.x, mul(u.x, nz.x));
+  if (nz.y != 0.f) v.y = add(v.y, mul(u.y, nz.y));
+  if (nz.z != 0.f) v.z = add(v.z, mul(u.z, nz.z));
+  if (nz.w != 0.f) v.w = add(v.w, mul(u.w, nz.w));
+  return v;
+}
+
 // Issue the TMA loads of one slab (warp 0 only): staged arrays + episode-sum rows, optionally the
 // descriptor table.  All complete on `bar` (one arrival with the expected byte count by lane 0).
 template <int TILE>
@@ -74,7 +93,7 @@ __device__ __forceinline__ void issue_slab_loads(const KParams& K, float* S, flo
 // shared-memory ring -- the TMA loads of the next slab are in flight while the current one is
 // processed, and the stores of the previous one drain in the background.
 template <int TILE>
-__global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KParams K) {
+__global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_constant__ KParams K) {
   extern __shared__ __align__(128) float Sbase[];
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ int32_t s_term_count[GFB_MAX_TERMINATION_TERMS];
@@ -734,57 +753,78 @@ __global__ void __launch_bounds__(TILE) post_kernel(const __grid_constant__ KPar
       const float* noise = GFB_BUF(const float, GFB_B_OBS_NOISE0 + g);
       if (noise) noise += (size_t)e0 * O;
       const int W = OH >> 2, W0 = O >> 2;
-      if (plan.grp_begin[g] >= 0 && W <= TILE) {
-        // 16-byte path.  A thread owns one 16-byte column position c4 of the row and walks down the
-        // slab's rows, so its group descriptor is read once; consecutive threads cover consecutive
-        // 16-byte pieces of TILE/W whole rows -> fully coalesced stores.
-        const int rows_per_pass = TILE / W;
-        if (tid < rows_per_pass * W) {
-          const int r0 = tid / W, c4 = tid - r0 * W;
-          float4* out4 = reinterpret_cast<float4*>(out) + c4;
-          if (c4 < W0) {
-            const int32_t* tab = reinterpret_cast<const int32_t*>(Tbl + plan.grp_off);
-            const int G = plan.n_groups, gi = plan.grp_begin[g] + c4;
-            const int4 off = reinterpret_cast<const int4*>(tab)[gi];
-            const int4 str = reinterpret_cast<const int4*>(tab + 4 * G)[gi];
-            const float4 sc = reinterpret_cast<const float4*>(tab + 8 * G)[gi];
-            const float4 nz = reinterpret_cast<const float4*>(tab + 12 * G)[gi];
-            const bool vec = (tab + 16 * G)[gi] & 1;
-            const bool noisy = nz.x != 0.f || nz.y != 0.f || nz.z != 0.f || nz.w != 0.f;
-            const float4* noise4 = reinterpret_cast<const float4*>(noise) + c4;
-#pragma unroll 4
-            for (int row = r0; row < valid; row += rows_per_pass) {
+      if (plan.grp_run_begin[g] >= 0) {
+        // 16-byte path, three warp-uniform passes over the slab's rows.  In each pass consecutive
+        // threads take consecutive pieces (piece-major within a row, then rows), so a warp's stores
+        // land in a few contiguous segments of neighbouring rows.
+        float4* out4 = reinterpret_cast<float4*>(out);
+        // pass 1: contiguous runs of a staged array (one 16-byte shared load per piece)
+        {
+          const int n = plan.grp_run_count[g];
+          const int4* desc = reinterpret_cast<const int4*>(Tbl + plan.run_off) + plan.grp_run_begin[g];
+          const float4* nzs = reinterpret_cast<const float4*>(Tbl + plan.run_off + 4 * plan.n_runs) + plan.grp_run_begin[g];
+          const int total = valid * n;
+          int row = tid / n, k = tid - row * n;
+          const int drow = TILE / n, dk = TILE - drow * n;
+#pragma unroll 2
+          for (int f = tid; f < total; f += TILE) {
+            const int4 d = desc[k];
+            float4 v = *reinterpret_cast<const float4*>(S + d.x + row * d.y);
+            const float sc = __int_as_float(d.w);
+            v.x = mul(v.x, sc); v.y = mul(v.y, sc); v.z = mul(v.z, sc); v.w = mul(v.w, sc);
+            const float4 nz = nzs[k];
+            if (nz.x != 0.f || nz.y != 0.f || nz.z != 0.f || nz.w != 0.f)
+              v = add_noise(v, nz, noise, row, W0, d.z, P, rng, e0, og.col_begin);
+            out4[row * W + d.z] = v;
+            row += drow;
+            k += dk;
+            if (k >= n) { k -= n; ++row; }
+          }
+        }
+        // pass 2: mixed groups (four independent shared sources: derived vectors, commands, ...)
+        {
+          const int n = plan.grp_mixed_count[g];
+          if (n > 0) {
+            const int NM = plan.n_mixed, mb = plan.grp_mixed_begin[g];
+            const int32_t* tab = reinterpret_cast<const int32_t*>(Tbl + plan.mixed_off);
+            const int4* offs = reinterpret_cast<const int4*>(tab) + mb;
+            const int4* strs = reinterpret_cast<const int4*>(tab + 4 * NM) + mb;
+            const float4* scs = reinterpret_cast<const float4*>(tab + 8 * NM) + mb;
+            const float4* nzs = reinterpret_cast<const float4*>(tab + 12 * NM) + mb;
+            const int32_t* c4s = tab + 16 * NM + mb;
+            const int total = valid * n;
+            int row = tid / n, k = tid - row * n;
+            const int drow = TILE / n, dk = TILE - drow * n;
+            for (int f = tid; f < total; f += TILE) {
+              const int4 off = offs[k], str = strs[k];
+              const float4 sc = scs[k], nz = nzs[k];
+              const int c4 = c4s[k];
               float4 v;
-              if (vec) {
-                v = *reinterpret_cast<const float4*>(S + off.x + row * str.x);
-              } else {
-                v.x = S[off.x + row * str.x];
-                v.y = S[off.y + row * str.y];
-                v.z = S[off.z + row * str.z];
-                v.w = S[off.w + row * str.w];
-              }
-              v.x = mul(v.x, sc.x); v.y = mul(v.y, sc.y); v.z = mul(v.z, sc.z); v.w = mul(v.w, sc.w);
-              if (noisy) {
-                float4 u;
-                if (P.rng_mode == 0) {
-                  u = noise ? noise4[row * W0] : make_float4(0.f, 0.f, 0.f, 0.f);
-                } else {
-                  const uint4 r4 = rng((uint32_t)(e0 + row), (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32),
-                                       0x1000u + (uint32_t)(og.col_begin + (c4 << 2)));
-                  u = make_float4(sub(mul(u01(r4.x), 2.f), 1.f), sub(mul(u01(r4.y), 2.f), 1.f),
-                                  sub(mul(u01(r4.z), 2.f), 1.f), sub(mul(u01(r4.w), 2.f), 1.f));
-                }
-                if (nz.x != 0.f) v.x = add(v.x, mul(u.x, nz.x));
-                if (nz.y != 0.f) v.y = add(v.y, mul(u.y, nz.y));
-                if (nz.z != 0.f) v.z = add(v.z, mul(u.z, nz.z));
-                if (nz.w != 0.f) v.w = add(v.w, mul(u.w, nz.w));
-              }
-              out4[row * W] = v;
+              v.x = mul(S[off.x + row * str.x], sc.x);
+              v.y = mul(S[off.y + row * str.y], sc.y);
+              v.z = mul(S[off.z + row * str.z], sc.z);
+              v.w = mul(S[off.w + row * str.w], sc.w);
+              if (nz.x != 0.f || nz.y != 0.f || nz.z != 0.f || nz.w != 0.f)
+                v = add_noise(v, nz, noise, row, W0, c4, P, rng, e0, og.col_begin);
+              out4[row * W + c4] = v;
+              row += drow;
+              k += dk;
+              if (k >= n) { k -= n; ++row; }
             }
-          } else {
-            const float4* prev4 = reinterpret_cast<const float4*>(prev) + (c4 - W0);
-#pragma unroll 4
-            for (int row = r0; row < valid; row += rows_per_pass) out4[row * W] = prev4[row * W];
+          }
+        }
+        // pass 3: history frames 1..H-1 are the previous step's frames 0..H-2
+        if (W > W0) {
+          const int n = W - W0;
+          const float4* prev4 = reinterpret_cast<const float4*>(prev);
+          const int total = valid * n;
+          int row = tid / n, k = tid - row * n;
+          const int drow = TILE / n, dk = TILE - drow * n;
+          for (int f = tid; f < total; f += TILE) {
+            out4[row * W + W0 + k] = prev4[row * W + k];
+            row += drow;
+            k += dk;
+            if (k >= n) { k -= n; ++row; }
           }
         }
       } else {
