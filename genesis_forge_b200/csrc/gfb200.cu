@@ -359,6 +359,7 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, i
     plan.grp_run_begin[g] = plan.grp_mixed_begin[g] = -1;
     plan.grp_run_count[g] = plan.grp_mixed_count[g] = 0;
     if ((og.n_cols & 3) || !(phases & GFB_PHASE_OBSERVE)) continue;
+    if ((og.n_cols >> 2) > tile) continue;  // a sweep needs at least one whole row per pass
     bool all_shared = true;
     for (int c = 0; c < og.n_cols; ++c) all_shared = all_shared && cols[og.col_begin + c].kind != 2;
     if (!all_shared) continue;  // some source lives in global memory: per-element path

@@ -754,62 +754,62 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
       if (noise) noise += (size_t)e0 * O;
       const int W = OH >> 2, W0 = O >> 2;
       if (plan.grp_run_begin[g] >= 0) {
-        // 16-byte path, three warp-uniform passes over the slab's rows.  In each pass consecutive
-        // threads take consecutive pieces (piece-major within a row, then rows), so a warp's stores
-        // land in a few contiguous segments of neighbouring rows.
+        // 16-byte path, three warp-uniform passes over the slab's rows.  Within a pass a thread
+        // owns ONE piece position k of the row (its descriptor is read once, outside the loop) and
+        // walks down the rows; consecutive threads hold consecutive pieces of TILE/n whole rows, so
+        // a warp's stores land in a few contiguous segments of neighbouring rows.
         float4* out4 = reinterpret_cast<float4*>(out);
         // pass 1: contiguous runs of a staged array (one 16-byte shared load per piece)
         {
           const int n = plan.grp_run_count[g];
-          const int4* desc = reinterpret_cast<const int4*>(Tbl + plan.run_off) + plan.grp_run_begin[g];
-          const float4* nzs = reinterpret_cast<const float4*>(Tbl + plan.run_off + 4 * plan.n_runs) + plan.grp_run_begin[g];
-          const int total = valid * n;
-          int row = tid / n, k = tid - row * n;
-          const int drow = TILE / n, dk = TILE - drow * n;
-#pragma unroll 2
-          for (int f = tid; f < total; f += TILE) {
-            const int4 d = desc[k];
-            float4 v = *reinterpret_cast<const float4*>(S + d.x + row * d.y);
+          const int rpp = n > 0 ? TILE / n : 0;  // rows per sweep
+          if (n > 0 && n <= TILE && tid < rpp * n) {
+            const int r0 = tid / n, k = tid - r0 * n;
+            const int4 d = (reinterpret_cast<const int4*>(Tbl + plan.run_off) + plan.grp_run_begin[g])[k];
+            const float4 nz =
+                (reinterpret_cast<const float4*>(Tbl + plan.run_off + 4 * plan.n_runs) + plan.grp_run_begin[g])[k];
             const float sc = __int_as_float(d.w);
-            v.x = mul(v.x, sc); v.y = mul(v.y, sc); v.z = mul(v.z, sc); v.w = mul(v.w, sc);
-            const float4 nz = nzs[k];
-            if (nz.x != 0.f || nz.y != 0.f || nz.z != 0.f || nz.w != 0.f)
-              v = add_noise(v, nz, noise, row, W0, d.z, P, rng, e0, og.col_begin);
-            out4[row * W + d.z] = v;
-            row += drow;
-            k += dk;
-            if (k >= n) { k -= n; ++row; }
+            const bool noisy = nz.x != 0.f || nz.y != 0.f || nz.z != 0.f || nz.w != 0.f;
+            const float* src = S + d.x + r0 * d.y;
+            float4* dst = out4 + r0 * W + d.z;
+            const int sstep = rpp * d.y, dstep = rpp * W;
+#pragma unroll 4
+            for (int row = r0; row < valid; row += rpp) {
+              float4 v = *reinterpret_cast<const float4*>(src);
+              v.x = mul(v.x, sc); v.y = mul(v.y, sc); v.z = mul(v.z, sc); v.w = mul(v.w, sc);
+              if (noisy) v = add_noise(v, nz, noise, row, W0, d.z, P, rng, e0, og.col_begin);
+              *dst = v;
+              src += sstep;
+              dst += dstep;
+            }
           }
         }
         // pass 2: mixed groups (four independent shared sources: derived vectors, commands, ...)
         {
           const int n = plan.grp_mixed_count[g];
-          if (n > 0) {
+          const int rpp = n > 0 ? TILE / n : 0;
+          if (n > 0 && n <= TILE && tid < rpp * n) {
+            const int r0 = tid / n, k = tid - r0 * n;
             const int NM = plan.n_mixed, mb = plan.grp_mixed_begin[g];
             const int32_t* tab = reinterpret_cast<const int32_t*>(Tbl + plan.mixed_off);
-            const int4* offs = reinterpret_cast<const int4*>(tab) + mb;
-            const int4* strs = reinterpret_cast<const int4*>(tab + 4 * NM) + mb;
-            const float4* scs = reinterpret_cast<const float4*>(tab + 8 * NM) + mb;
-            const float4* nzs = reinterpret_cast<const float4*>(tab + 12 * NM) + mb;
-            const int32_t* c4s = tab + 16 * NM + mb;
-            const int total = valid * n;
-            int row = tid / n, k = tid - row * n;
-            const int drow = TILE / n, dk = TILE - drow * n;
-            for (int f = tid; f < total; f += TILE) {
-              const int4 off = offs[k], str = strs[k];
-              const float4 sc = scs[k], nz = nzs[k];
-              const int c4 = c4s[k];
+            const int4 off = (reinterpret_cast<const int4*>(tab) + mb)[k];
+            const int4 str = (reinterpret_cast<const int4*>(tab + 4 * NM) + mb)[k];
+            const float4 sc = (reinterpret_cast<const float4*>(tab + 8 * NM) + mb)[k];
+            const float4 nz = (reinterpret_cast<const float4*>(tab + 12 * NM) + mb)[k];
+            const int c4 = (tab + 16 * NM + mb)[k];
+            const bool noisy = nz.x != 0.f || nz.y != 0.f || nz.z != 0.f || nz.w != 0.f;
+            const float *s0 = S + off.x + r0 * str.x, *s1 = S + off.y + r0 * str.y;
+            const float *s2 = S + off.z + r0 * str.z, *s3 = S + off.w + r0 * str.w;
+            float4* dst = out4 + r0 * W + c4;
+            const int dstep = rpp * W;
+#pragma unroll 2
+            for (int row = r0; row < valid; row += rpp) {
               float4 v;
-              v.x = mul(S[off.x + row * str.x], sc.x);
-              v.y = mul(S[off.y + row * str.y], sc.y);
-              v.z = mul(S[off.z + row * str.z], sc.z);
-              v.w = mul(S[off.w + row * str.w], sc.w);
-              if (nz.x != 0.f || nz.y != 0.f || nz.z != 0.f || nz.w != 0.f)
-                v = add_noise(v, nz, noise, row, W0, c4, P, rng, e0, og.col_begin);
-              out4[row * W + c4] = v;
-              row += drow;
-              k += dk;
-              if (k >= n) { k -= n; ++row; }
+              v.x = mul(*s0, sc.x); v.y = mul(*s1, sc.y); v.z = mul(*s2, sc.z); v.w = mul(*s3, sc.w);
+              if (noisy) v = add_noise(v, nz, noise, row, W0, c4, P, rng, e0, og.col_begin);
+              *dst = v;
+              s0 += rpp * str.x; s1 += rpp * str.y; s2 += rpp * str.z; s3 += rpp * str.w;
+              dst += dstep;
             }
           }
         }
@@ -858,7 +858,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   }
 
   // everyone is done with this stage's shared memory before it is refilled
-  __syncthreads();
+  if (next_tile < n_tiles) __syncthreads();
   if (use_tma && n_stages == 1 && next_tile < n_tiles && warp == 0) {
     bulk_wait_all_read();
     issue_slab_loads<TILE>(K, Sbase, Tbl, &bars[0], next_tile, n_sum_rows, false, lane);
