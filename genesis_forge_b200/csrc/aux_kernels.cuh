@@ -159,85 +159,106 @@ struct FinalizeParams {
   uint32_t reward_weight_mask;  // bit r set: term r has weight != 0 (mean is logged)
 };
 
-constexpr int FIN_THREADS = 1024;
+constexpr int FIN_THREADS = 256;
+constexpr int FIN_CHUNK_BLOCKS = 128;  // blocks that share the ordered compaction
 
-__global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinalizeParams F) {
-  __shared__ int s_warp_sum[FIN_THREADS / 32];
-  __shared__ int s_total;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// deterministic block-wide sum (fixed strided order per thread, shuffle tree, warps in order)
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* s_warp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) s_warp[warp] = v;
+  __syncthreads();
+  T total = 0;
+  for (int w = 0; w < FIN_THREADS / 32; ++w) total += s_warp[w];
+  return total;
+}
+
+// Grid layout: blocks [0, n_chunks) each own a contiguous range of slabs of the ordered compaction;
+// blocks [n_chunks, n_chunks + n_termination) reduce one termination counter each; the following
+// n_reward blocks reduce one reward term each; the last block writes n_reset / status.
+__global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinalizeParams F, int n_chunks) {
+  __shared__ int s_iwarp[FIN_THREADS / 32];
+  __shared__ double s_dwarp[FIN_THREADS / 32];
+  __shared__ int s_scan[FIN_THREADS];
+  const int tid = threadIdx.x;
   const int nt = F.s.n_tiles;
   const int words = F.tile / 32;
+  const int b = blockIdx.x;
+  gfb_report* rep = F.s.report;
 
-  // ---- ordered compaction ---------------------------------------------------------------------
-  const int per = (nt + FIN_THREADS - 1) / FIN_THREADS;
-  const int t0 = min(tid * per, nt), t1 = min(t0 + per, nt);
-  int local = 0;
-  for (int t = t0; t < t1; ++t) local += F.s.tile_reset_count[t];
-  int incl = local;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) s_warp_sum[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    int v = s_warp_sum[lane];
-    int inc2 = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, inc2, o);
-      if (lane >= o) inc2 += u;
-    }
-    s_warp_sum[lane] = inc2 - v;  // exclusive warp offsets
-    if (lane == 31) s_total = inc2;
-  }
-  __syncthreads();
-  int offset = s_warp_sum[warp] + incl - local;
-  if (F.reset_idx) {
-    for (int t = t0; t < t1; ++t) {
-      if (F.s.tile_reset_count[t] == 0) continue;
-      for (int w = 0; w < words; ++w) {
-        uint32_t bits = F.s.tile_reset_bits[(size_t)t * words + w];
-        while (bits) {
-          const int b = __ffs(bits) - 1;
-          bits &= bits - 1;
-          F.reset_idx[offset++] = (int64_t)t * F.tile + w * 32 + b;
+  if (b < n_chunks) {
+    // ---- ordered compaction of this block's slab range -------------------------------------------
+    const int per_block = (nt + n_chunks - 1) / n_chunks;
+    const int c0 = min(b * per_block, nt), c1 = min(c0 + per_block, nt);
+    // resets in all slabs before this range (every block re-reads the short count array: L2 hits)
+    int before = 0;
+    for (int t = tid; t < c0; t += FIN_THREADS) before += F.s.tile_reset_count[t];
+    before = block_sum<int>(before, s_iwarp);
+    if (!F.reset_idx) return;
+    // scan the range in sweeps of FIN_THREADS slabs
+    int base = before;
+    for (int t0 = c0; t0 < c1; t0 += FIN_THREADS) {
+      const int t = t0 + tid;
+      const int cnt = t < c1 ? F.s.tile_reset_count[t] : 0;
+      s_scan[tid] = cnt;
+      __syncthreads();
+      // Hillis-Steele inclusive scan over 256 entries
+      for (int o = 1; o < FIN_THREADS; o <<= 1) {
+        const int v = tid >= o ? s_scan[tid - o] : 0;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+      }
+      int offset = base + s_scan[tid] - cnt;
+      if (cnt > 0) {
+        for (int w = 0; w < words; ++w) {
+          uint32_t bits = F.s.tile_reset_bits[(size_t)t * words + w];
+          while (bits) {
+            const int bit = __ffs(bits) - 1;
+            bits &= bits - 1;
+            F.reset_idx[offset++] = (int64_t)t * F.tile + w * 32 + bit;
+          }
         }
       }
+      base += s_scan[FIN_THREADS - 1];
+      __syncthreads();
     }
+    return;
   }
-  const int n_reset = s_total;
 
-  // ---- logging reductions: one warp per term ----------------------------------------------------
-  gfb_report* rep = F.s.report;
-  if (warp < F.n_termination) {
+  // total reset count (needed for the means and the report)
+  int n_reset = 0;
+  for (int t = tid; t < nt; t += FIN_THREADS) n_reset += F.s.tile_reset_count[t];
+  n_reset = block_sum<int>(n_reset, s_iwarp);
+
+  const int k = b - n_chunks;
+  if (k < F.n_termination) {
     int acc = 0;
     if (F.phases & GFB_PHASE_TERMINATION)
-      for (int t = lane; t < nt; t += 32) acc += F.s.tile_term_count[(size_t)warp * nt + t];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      rep->termination_count[warp] = acc;
-      if (F.log_out) F.log_out[F.n_reward + warp] = fdiv((float)acc, (float)F.num_envs);
-      if (F.log_acc) F.log_acc[F.n_reward + warp] = (double)acc;
+      for (int t = tid; t < nt; t += FIN_THREADS) acc += F.s.tile_term_count[(size_t)k * nt + t];
+    acc = block_sum<int>(acc, s_iwarp);
+    if (tid == 0) {
+      rep->termination_count[k] = acc;
+      if (F.log_out) F.log_out[F.n_reward + k] = fdiv((float)acc, (float)F.num_envs);
+      if (F.log_acc) F.log_acc[F.n_reward + k] = (double)acc;
     }
-  }
-  for (int r = warp; r < F.n_reward; r += FIN_THREADS / 32) {
+  } else if (k < F.n_termination + F.n_reward) {
+    const int r = k - F.n_termination;
     double acc = 0.0;
     if (F.phases & GFB_PHASE_RESET)
-      for (int t = lane; t < nt; t += 32) acc += F.s.tile_rew_sum[(size_t)r * nt + t];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
+      for (int t = tid; t < nt; t += FIN_THREADS) acc += F.s.tile_rew_sum[(size_t)r * nt + t];
+    acc = block_sum<double>(acc, s_dwarp);
+    if (tid == 0) {
       const bool logged = (F.reward_weight_mask >> r) & 1u;
       const float mean = (n_reset > 0 && logged) ? (float)(acc / (double)n_reset) : 0.0f;
       rep->reward_episode_mean[r] = mean;
       if (F.log_out) F.log_out[r] = mean;
       if (F.log_acc) F.log_acc[r] = acc;
     }
-  }
-  if (tid == 0) {
+  } else if (tid == 0) {
     rep->n_reset = n_reset;
     rep->status = atomicExch(F.s.status, 0u);
     if (F.log_acc) F.log_acc[F.n_reward + F.n_termination] = (double)n_reset;
@@ -259,15 +280,24 @@ struct ObserveParams {
   int32_t n;
 };
 
-template <int TILE>
-__global__ void __launch_bounds__(TILE) observe_kernel(const __grid_constant__ ObserveParams K) {
-  extern __shared__ __align__(128) float S[];  // (TILE, stash_stride)
-  __shared__ long long s_env[TILE];
+constexpr int OBS_ENVS = 16;      // envs per block
+constexpr int OBS_THREADS = 128;  // 8 threads per env for the column gather
+
+__global__ void __launch_bounds__(OBS_THREADS) observe_kernel(const __grid_constant__ ObserveParams K) {
+  extern __shared__ __align__(128) float S[];  // (OBS_ENVS, stash_stride) stash, then the column table
+  __shared__ long long s_env[OBS_ENVS];
   const gfb_program_head& P = K.P;
   const Plan& plan = K.plan;
   const int tid = threadIdx.x;
-  const int i0 = blockIdx.x * TILE;
-  const int valid = min(TILE, K.n - i0);
+  const int i0 = blockIdx.x * OBS_ENVS;
+  const int valid = min(OBS_ENVS, K.n - i0);
+  DevObsCol* s_cols = reinterpret_cast<DevObsCol*>(S + OBS_ENVS * plan.stash_stride + 4 - ((OBS_ENVS * plan.stash_stride) & 3));
+  {
+    const int32_t* src = reinterpret_cast<const int32_t*>(K.cols);
+    int32_t* dst = reinterpret_cast<int32_t*>(s_cols);
+    const int words = plan.n_cols_total * (int)(sizeof(DevObsCol) / 4);
+    for (int w = tid; w < words; w += OBS_THREADS) dst[w] = src[w];
+  }
   if (tid < valid) {
     const long long e = K.idx ? (long long)K.idx[i0 + tid] : (long long)(i0 + tid);
     s_env[tid] = e;
@@ -301,11 +331,11 @@ __global__ void __launch_bounds__(TILE) observe_kernel(const __grid_constant__ O
   for (int g = 0; g < P.n_obs_groups; ++g) {
     const gfb_obs_group& og = P.obs_group[g];
     const int O = og.n_cols, OH = og.n_cols * og.history;
-    const DevObsCol* cols = K.cols + og.col_begin;
+    const DevObsCol* cols = s_cols + og.col_begin;
     float* out = GFB_BUF(float, GFB_B_OBS_OUT0 + g);
     const float* noise = GFB_BUF(const float, GFB_B_OBS_NOISE0 + g);
     const int total = valid * O;
-    for (int f = tid; f < total; f += TILE) {
+    for (int f = tid; f < total; f += OBS_THREADS) {
       const int row = f / O, col = f - row * O;
       const long long e = s_env[row];
       const DevObsCol d = cols[col];

@@ -20,7 +20,7 @@ namespace {
 constexpr int kMaxSmemBytes = 227 * 1024;
 constexpr int kPlanSlots = 6;
 constexpr int kEventPairs = 2048;
-constexpr int kObserveTile = 128;
+constexpr int kObserveTile = OBS_ENVS;
 
 inline int align4(int w) { return (w + 3) & ~3; }
 
@@ -801,7 +801,8 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
   fp.reward_weight_mask = 0;
   for (int r = 0; r < P.n_reward; ++r)
     if (P.reward[r].weight != 0.0f) fp.reward_weight_mask |= (1u << r);
-  finalize_kernel<<<1, FIN_THREADS, 0, stream>>>(fp);
+  const int n_chunks = std::max(1, std::min(FIN_CHUNK_BLOCKS, (n_tiles + 63) / 64));
+  finalize_kernel<<<n_chunks + P.n_termination + P.n_reward + 1, FIN_THREADS, 0, stream>>>(fp, n_chunks);
   CUDA_TRY(cudaGetLastError());
   h->launches += 2;
   return GFB_OK;
@@ -838,9 +839,10 @@ int gfb_observe(gfb_handle* h, const gfb_buffers* b, const int64_t* idx, int32_t
   op.cols = reinterpret_cast<const DevObsCol*>(h->observe_slot.table_dev);
   op.idx = idx;
   op.n = n;
-  const size_t smem = (size_t)op.plan.stash_stride * kObserveTile * 4;
-  const int grid = (n + kObserveTile - 1) / kObserveTile;
-  observe_kernel<kObserveTile><<<grid, kObserveTile, smem, stream>>>(op);
+  const size_t smem = (size_t)op.plan.stash_stride * OBS_ENVS * 4 + 16 +
+                      (size_t)op.plan.n_cols_total * sizeof(DevObsCol);
+  const int grid = (n + OBS_ENVS - 1) / OBS_ENVS;
+  observe_kernel<<<grid, OBS_THREADS, smem, stream>>>(op);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return GFB_OK;

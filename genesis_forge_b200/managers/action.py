@@ -250,7 +250,10 @@ class PositionActionManager(BaseActionManager):
             lower = self._add_random_noise("action_dr:force_lower", self._force_range[0], ns)
             upper = self._add_random_noise("action_dr:force_upper", self._force_range[1], ns)
             robot.set_dofs_force_range(lower, upper, self.dofs_idx, envs_idx)
-        position = self._add_random_noise("action_dr:position", self._default_dofs_pos[envs_idx], ns)
+        # every row of the default pose is the same vector: a stride-0 view instead of an index gather
+        n = envs_idx.numel() if torch.is_tensor(envs_idx) else len(envs_idx)
+        position = self._default_dofs_pos[0].unsqueeze(0).expand(n, -1)
+        position = self._add_random_noise("action_dr:position", position, ns)
         robot.set_dofs_position(position=position, dofs_idx_local=self.dofs_idx, envs_idx=envs_idx)
 
     # -- helpers ----------------------------------------------------------------------------------

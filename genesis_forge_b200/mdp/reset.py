@@ -34,16 +34,21 @@ class position(ResetMdpFnClass):
     def __init__(self, env, entity, position, quat=None, zero_velocity: bool = True):
         self.env = env
         self.zero_velocity = zero_velocity
+        n = env.num_envs
         self.reset_pos = torch.tensor(position, device=gs.device, dtype=gs.tc_float)
-        self.reset_quat = None if quat is None else torch.tensor(quat, device=gs.device, dtype=gs.tc_float)
+        # constant rows, filled once: a reset hands the engine the first n rows (a contiguous view)
+        self._pos_rows = self.reset_pos.unsqueeze(0).repeat(n, 1)
+        self.reset_quat = None
+        self._quat_rows = None
+        if quat is not None:
+            self.reset_quat = torch.tensor(quat, device=gs.device, dtype=gs.tc_float)
+            self._quat_rows = self.reset_quat.unsqueeze(0).repeat(n, 1)
 
     def __call__(self, env, entity, envs_idx, position, quat=None, zero_velocity: bool = True):
         n = len(envs_idx)
-        entity.set_pos(self.reset_pos.expand(n, 3).contiguous(), envs_idx=envs_idx, zero_velocity=self.zero_velocity)
-        if self.reset_quat is not None:
-            entity.set_quat(
-                self.reset_quat.expand(n, 4).contiguous(), envs_idx=envs_idx, zero_velocity=self.zero_velocity
-            )
+        entity.set_pos(self._pos_rows[:n], envs_idx=envs_idx, zero_velocity=self.zero_velocity)
+        if self._quat_rows is not None:
+            entity.set_quat(self._quat_rows[:n], envs_idx=envs_idx, zero_velocity=self.zero_velocity)
 
 
 class randomize_terrain_position(ResetMdpFnClass):
