@@ -80,6 +80,24 @@ class UnsupportedTermError(NotImplementedError):
     pass
 
 
+def combine_logging(acc: torch.Tensor, n_reward: int, n_termination: int, global_num_envs: int) -> torch.Tensor:
+    """
+    Logging vector from the (all-reduced) accumulator written by the finalize kernel.
+
+    acc = [sum over reset envs of (episode sum / episode seconds) per reward term,
+           fire count per termination term, number of reset envs]          (float64)
+    ->    [mean per reward term (reward_manager.py:211-216), fired fraction per termination term
+           (termination_manager.py:178-182)]                               (float32)
+    With envs sharded over ranks the accumulator is summed over ranks first, so the means are the
+    same numbers a single process over all envs would log.
+    """
+    out = torch.empty(n_reward + n_termination, device=acc.device, dtype=torch.float32)
+    n_reset = acc[n_reward + n_termination].clamp(min=1.0)
+    out[:n_reward] = (acc[:n_reward] / n_reset).float()
+    out[n_reward:] = (acc[n_reward:n_reward + n_termination] / float(global_num_envs)).float()
+    return out
+
+
 class FusedStep:
     def __init__(self, env, dry_run: bool = False):
         """`dry_run` compiles and packs the term table without a device (host-logic tests only)."""
@@ -109,6 +127,8 @@ class FusedStep:
         self.dist = None  # (process group) when envs are sharded over ranks
         self._contact_dims = None
         self._feet_slide_manager = None
+        self.global_acc = None
+        self.global_num_envs = self.N
         self._compile()
 
     # ------------------------------------------------------------------------------------------
@@ -633,6 +653,8 @@ class FusedStep:
         if self.dist is not None:
             self._allreduce_logging()
         self.handle.check(self.lib.gfb_read_report(self.handle.ptr, C.byref(self.report), stream), "gfb_read_report")
+        # global (all-rank) fire counts / reset count decide which logging keys exist on every rank
+        self.global_acc = self.log_acc.tolist() if self.dist is not None else None
         return self.report
 
     def observe(self, idx: torch.Tensor | None, n: int):

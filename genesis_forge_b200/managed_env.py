@@ -25,7 +25,7 @@ import torch
 
 from . import _native as nat
 from ._gs import gs
-from .fused import FusedStep, UnsupportedTermError, make_obs_dict
+from .fused import FusedStep, UnsupportedTermError, combine_logging, make_obs_dict
 from .genesis_env import GenesisEnv
 from .managers.base import BaseManager, ManagerType
 
@@ -225,16 +225,20 @@ class ManagedEnvironment(GenesisEnv):
                 print("Warning: Invalid contact forces detected (NaN/inf) and sanitized")
         snapshot = None
         n_r = fused.n_reward
+        # sharded over ranks: keys are published when ANY rank saw the event (global counts)
+        acc = fused.global_acc
+        term_count = (lambda i: acc[n_r + i]) if acc is not None else (lambda i: report.termination_count[i])
+        n_reset_logged = acc[-1] if acc is not None else report.n_reset
         if step and term is not None:
             self.extras["terminations"] = term._terminated_buf
             self.extras["time_outs"] = term._truncated_buf
             if term.logging_enabled:
                 for i, (name, _, _) in enumerate(fused.termination_terms):
-                    if report.termination_count[i] > 0:
+                    if term_count(i) > 0:
                         if snapshot is None:
                             snapshot = self._log_snapshot()
                         logging[f"{term.logging_tag} / {name}"] = snapshot[n_r + i]
-        if rew is not None and rew.enabled and rew.logging_enabled and report.n_reset > 0:
+        if rew is not None and rew.enabled and rew.logging_enabled and n_reset_logged > 0:
             index = {}
             for i, (name, item, _) in enumerate(fused.reward_terms):
                 if item.weight != 0:
@@ -250,13 +254,7 @@ class ManagedEnvironment(GenesisEnv):
         fused = self._fused
         if fused.dist is None:
             return fused.log_out.clone()
-        acc = fused.log_acc
-        n_r, n_t = fused.n_reward, fused.n_termination
-        out = torch.empty(n_r + n_t, device=acc.device, dtype=torch.float32)
-        n_reset = acc[n_r + n_t].clamp(min=1.0)
-        out[:n_r] = (acc[:n_r] / n_reset).float()
-        out[n_r:] = (acc[n_r:n_r + n_t] / float(fused.global_num_envs)).float()
-        return out
+        return combine_logging(fused.log_acc, fused.n_reward, fused.n_termination, fused.global_num_envs)
 
     def _host_reset(self, env_ids: torch.Tensor | None):
         """Engine-side part of reset(): action manager gains / joint positions, entity on_reset items."""

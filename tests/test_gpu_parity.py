@@ -38,3 +38,68 @@ def test_ragged_sizes(num_envs, cuda_device):
 
     run = ParityRun("contacts", num_envs=num_envs, device=cuda_device, seed=5)
     run.run(steps=40)
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_cuda_path_reproduces_reference_golden_trace(name, cuda_device):
+    """
+    The CUDA path against the committed traces of the UNMODIFIED reference (tests/golden/, generated
+    in the build container by oracle/make_golden.py): same seeded inputs, the reference's random draws
+    injected via the oracle port (which the CPU suite pins bit-exactly to the same traces).
+    """
+    import os
+
+    from oracle.make_golden import GOLDEN_DIR
+    from oracle.parity import ParityRun, _close
+
+    gold = torch.load(os.path.join(GOLDEN_DIR, f"{name}.pt"), weights_only=False)
+    run = ParityRun(name, num_envs=gold["num_envs"], device=cuda_device, seed=gold["seed"], sanitize=False)
+    run.reset()
+    for i, g in enumerate(gold["step"]):
+        out_e, out_p = run.step(nan_action=(i == gold["nan_step"]))
+        assert torch.equal(out_e[2].cpu(), g["terminated"]), f"step {i} terminated"
+        assert torch.equal(out_e[3].cpu(), g["truncated"]), f"step {i} truncated"
+        n = int(g["reset_idx"].numel())
+        assert torch.equal(run.env._fused.reset_idx[:n].cpu(), g["reset_idx"]), f"step {i} reset_idx"
+        ok, abs_err, _ = _close(out_e[1], g["rewards"])
+        assert ok, f"step {i} rewards err {abs_err}"
+        for group, want in g["obs"].items():
+            ok, abs_err, _ = _close(out_e[4]["observations"][group], want)
+            assert ok, f"step {i} obs[{group}] err {abs_err}"
+        for key, want in g["logging"].items():
+            ok, abs_err, _ = _close(torch.as_tensor(out_e[4]["episode"][key]).reshape(()), want)
+            assert ok, f"step {i} extras[{key}] err {abs_err}"
+
+
+def test_million_env_properties(cuda_device):
+    """
+    Full-size (1,048,576 envs) run checked through size-independent properties: reset indices are
+    exactly the ascending positions of (terminated | truncated); the logged termination fractions
+    equal the mask means; episode length is zero exactly on reset envs; observations are finite and
+    the command columns of the observation row equal the command buffer.
+    """
+    import genesis_forge_b200 as gfb
+    from oracle import specs
+    from oracle.env_builder import build_env, dropin_namespace
+
+    gfb.set_device(cuda_device)
+    n = 1 << 20
+    env = build_env(specs.get("command_direction"), dropin_namespace(), n, cuda_device, pool=2, seed=7, n_contacts=0,
+                    apply_setters=False)
+    env.build()
+    env.reset()
+    for step in range(3):
+        actions = torch.randn(n, 12, device=cuda_device)
+        obs, rew, term, trunc, extras = env.step(actions)
+        done = term | trunc
+        idx = done.nonzero().reshape(-1)
+        n_reset = env._fused.report.n_reset
+        assert n_reset == idx.numel() > 0
+        assert torch.equal(env._fused.reset_idx[:n_reset], idx)
+        assert torch.equal(env.episode_length == 0, done)
+        assert bool(torch.isfinite(obs).all()) and bool(torch.isfinite(rew).all())
+        assert torch.equal(obs[:, :3], env.velocity_command.command)
+        assert torch.equal(obs[:, 36:48], env.action_manager.get_actions())
+        frac = extras["episode"]["Terminations / fall_over"]
+        assert abs(float(frac) - float(term.float().mean())) < 1e-6
+        assert torch.equal(env.actions[idx], torch.zeros(n_reset, 12, device=cuda_device))
