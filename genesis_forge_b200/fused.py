@@ -128,6 +128,7 @@ class FusedStep:
         self._contact_dims = None
         self._feet_slide_manager = None
         self.global_acc = None
+        self._acc_host = None
         self.global_num_envs = self.N
         self._compile()
 
@@ -651,10 +652,14 @@ class FusedStep:
             self.lib.gfb_post_physics(self.handle.ptr, C.byref(self.buffers), phases, stream), "gfb_post_physics"
         )
         if self.dist is not None:
+            # global (all-rank) fire counts / reset count decide which logging keys exist on every rank;
+            # the copy rides on the same stream sync as the report read-back
             self._allreduce_logging()
+            if self._acc_host is None:
+                self._acc_host = torch.empty_like(self.log_acc, device="cpu").pin_memory()
+            self._acc_host.copy_(self.log_acc, non_blocking=True)
         self.handle.check(self.lib.gfb_read_report(self.handle.ptr, C.byref(self.report), stream), "gfb_read_report")
-        # global (all-rank) fire counts / reset count decide which logging keys exist on every rank
-        self.global_acc = self.log_acc.tolist() if self.dist is not None else None
+        self.global_acc = self._acc_host.tolist() if self.dist is not None else None
         return self.report
 
     def observe(self, idx: torch.Tensor | None, n: int):
