@@ -153,7 +153,8 @@ _LIB = None
 EXPORTS = [
     "gfb_abi_version", "gfb_abi_sizeof", "gfb_create", "gfb_destroy", "gfb_last_error", "gfb_set_program",
     "gfb_action_step", "gfb_post_physics", "gfb_read_report", "gfb_observe", "gfb_contact_forces",
-    "gfb_rotate", "gfb_profile_enable", "gfb_profile_read", "gfb_launch_count",
+    "gfb_rotate", "gfb_spec_describe", "gfb_spec_attach", "gfb_spec_stats",
+    "gfb_profile_enable", "gfb_profile_read", "gfb_launch_count",
 ]
 
 
@@ -201,6 +202,12 @@ def lib() -> C.CDLL:
     L.gfb_contact_forces.argtypes = [vp] + [vp] * 10 + [i32] * 6 + [vp]
     L.gfb_rotate.restype = C.c_int
     L.gfb_rotate.argtypes = [vp, vp, vp, vp, i32, i32, vp]
+    L.gfb_spec_describe.restype = C.c_int
+    L.gfb_spec_describe.argtypes = [vp, C.POINTER(Buffers), u32, vp, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(i32)]
+    L.gfb_spec_attach.restype = C.c_int
+    L.gfb_spec_attach.argtypes = [vp, C.c_char_p]
+    L.gfb_spec_stats.restype = C.c_int
+    L.gfb_spec_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     L.gfb_profile_enable.restype = C.c_int
     L.gfb_profile_enable.argtypes = [vp, i32]
     L.gfb_profile_read.restype = C.c_int

@@ -1,5 +1,6 @@
 // libgfb200: C ABI + launch logic (see include/gfb200.h).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -34,7 +35,19 @@ struct PlanSlot {
 
 }  // namespace
 
+struct AttachedSpec {
+  void* dl = nullptr;
+  int (*launch)(const KParams*, int, unsigned, void*) = nullptr;
+  int tile = 0;
+  uint32_t phases = 0;
+  gfb_program_head canon;
+  Plan plan;
+};
+
 struct gfb_handle {
+  std::vector<AttachedSpec> specs;
+  int64_t n_spec_launches = 0, n_generic_launches = 0;
+  bool host_only = false;
   int device = 0;
   int num_envs = 0;
   std::string err;
@@ -73,6 +86,37 @@ int fail(gfb_handle* h, int code, const std::string& msg) {
     if (_e != cudaSuccess)                                                                                 \
       return fail(h, GFB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
   } while (0)
+
+// The structural part of a program head: every live value zeroed (see gfb_spec_describe).
+void canonicalize(gfb_program_head& c) {
+  c.num_envs = 0;
+  c.env_dt = 0.f;
+  c.base_max_episode_length = 0;
+  c.max_len_random_span = 0.f;
+  c.rng_seed = 0;
+  c.step_index = 0;
+  c.height_field_rows = c.height_field_cols = 0;
+  memset(c.terrain_bounds, 0, sizeof(c.terrain_bounds));
+  memset(c.action_scale, 0, sizeof(c.action_scale));
+  memset(c.action_offset, 0, sizeof(c.action_offset));
+  memset(c.action_clip_lo, 0, sizeof(c.action_clip_lo));
+  memset(c.action_clip_hi, 0, sizeof(c.action_clip_hi));
+  memset(c.default_dof_pos, 0, sizeof(c.default_dof_pos));
+  for (auto& r : c.reward) {
+    r.weight = 0.f;
+    memset(r.p, 0, sizeof(r.p));
+  }
+  for (auto& t : c.termination) memset(t.p, 0, sizeof(t.p));
+  for (auto& k : c.command) {
+    k.resample_steps = 0;
+    memset(k.lo, 0, sizeof(k.lo));
+    memset(k.hi, 0, sizeof(k.hi));
+  }
+  for (auto& m : c.contact) {
+    m.air_time_threshold = 0.f;
+    m.scene_dt = 0.f;
+  }
+}
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -454,6 +498,26 @@ int choose_tile(const gfb_handle* h) {
   return h->num_envs >= 32768 ? 128 : 32;
 }
 
+// Slab size / ring depth for a launch: shrink the slab until it fits comfortably.
+// (GFB_STAGES=2 selects the persistent two-stage ring; measured slower on B200 because only 3
+//  blocks fit per SM and the per-env arithmetic becomes latency-bound -- see DESIGN.md)
+int plan_for_launch(gfb_handle* h, const gfb_buffers& b, uint32_t phases, Plan& plan, std::vector<int32_t>& table,
+                    int& tile, int& n_stages) {
+  tile = choose_tile(h);
+  n_stages = h->force_stages == 2 ? 2 : 1;
+  for (;;) {
+    int rc = build_plan(h, b, phases, tile, n_stages, plan, table);
+    if (rc != GFB_OK) return rc;
+    if ((size_t)plan.smem_words * 4 <= (size_t)kMaxSmemBytes / 2) break;
+    if (tile > 32) tile /= 2;
+    else if (n_stages == 2) n_stages = 1;
+    else break;
+  }
+  if ((size_t)plan.smem_words * 4 > (size_t)kMaxSmemBytes)
+    return fail(h, GFB_ERR_UNSUPPORTED, "slab does not fit in shared memory");
+  return GFB_OK;
+}
+
 template <int TILE>
 int launch_post(gfb_handle* h, const KParams& kp, size_t smem, cudaStream_t stream, int grid) {
   int& cur = h->smem_attr_post[tile_index(TILE)];
@@ -529,6 +593,16 @@ const char* gfb_last_error(const gfb_handle* h) { return h ? h->err.c_str() : "n
 int gfb_create(int32_t num_envs, int32_t device, gfb_handle** out) {
   if (!out || num_envs <= 0) return GFB_ERR_INVALID;
   *out = nullptr;
+  if (device < 0) {  // host-only handle: term-table packing and specialisation descriptions
+    gfb_handle* hh = new gfb_handle();
+    hh->host_only = true;
+    hh->device = -1;
+    hh->num_envs = num_envs;
+    const char* env_t = getenv("GFB_TILE");
+    hh->force_tile = env_t ? atoi(env_t) : 0;
+    *out = hh;
+    return GFB_OK;
+  }
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device >= count) return GFB_ERR_NO_DEVICE;
   gfb_handle* h = new gfb_handle();
@@ -561,6 +635,12 @@ int gfb_create(int32_t num_envs, int32_t device, gfb_handle** out) {
 
 void gfb_destroy(gfb_handle* h) {
   if (!h) return;
+  for (auto& sp : h->specs)
+    if (sp.dl) dlclose(sp.dl);
+  if (h->host_only) {
+    delete h;
+    return;
+  }
   cudaSetDevice(h->device);
   cudaFree(h->scratch.tile_reset_bits);
   cudaFree(h->scratch.tile_reset_count);
@@ -635,6 +715,7 @@ int gfb_set_program(gfb_handle* h, const gfb_program* program) {
 
 int gfb_action_step(gfb_handle* h, const gfb_buffers* b, const float* raw_env, const float* raw_mgr, void* stream_) {
   if (!h || !b || !raw_env) return GFB_ERR_INVALID;
+  if (h->host_only) return fail(h, GFB_ERR_NO_DEVICE, "host-only handle cannot launch kernels");
   if (!h->has_prog) return fail(h, GFB_ERR_INVALID, "gfb_set_program() first");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const gfb_program_head& P = h->prog.head;
@@ -676,6 +757,7 @@ int gfb_action_step(gfb_handle* h, const gfb_buffers* b, const float* raw_env, c
 
 int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void* stream_) {
   if (!h || !b) return GFB_ERR_INVALID;
+  if (h->host_only) return fail(h, GFB_ERR_NO_DEVICE, "host-only handle cannot launch kernels");
   if (!h->has_prog) return fail(h, GFB_ERR_INVALID, "gfb_set_program() first");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const gfb_program_head& P = h->prog.head;
@@ -722,25 +804,14 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
       return GFB_ERR_INVALID;
   }
 
-  // tile: shrink until the slab fits comfortably
-  int tile = choose_tile(h);
   KParams kp{};
   std::vector<int32_t> table;
-  // prefer the two-stage prefetch ring with at least two resident blocks per SM; shrink the slab,
-  // then fall back to a single stage, until it fits
-  // (GFB_STAGES=2 selects the persistent two-stage ring; measured slower on B200 because only 3
-  //  blocks fit per SM and the per-env arithmetic becomes latency-bound -- see DESIGN.md)
-  int n_stages = h->force_stages == 2 ? 2 : 1;
-  for (;;) {
-    int rc = build_plan(h, *b, phases, tile, n_stages, kp.plan, table);
-    if (rc != GFB_OK) return rc;
-    if ((size_t)kp.plan.smem_words * 4 <= (size_t)kMaxSmemBytes / 2) break;
-    if (tile > 32) tile /= 2;
-    else if (n_stages == 2) n_stages = 1;
-    else break;
+  int tile = 0, n_stages = 1;
+  {
+    int rc0 = plan_for_launch(h, *b, phases, kp.plan, table, tile, n_stages);
+    if (rc0 != GFB_OK) return rc0;
   }
   const size_t smem = (size_t)kp.plan.smem_words * 4;
-  if (smem > (size_t)kMaxSmemBytes) return fail(h, GFB_ERR_UNSUPPORTED, "slab does not fit in shared memory");
 
   PlanSlot* slot = nullptr;
   for (auto& s : h->slots)
@@ -782,9 +853,29 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
     else per_sm = blocks_per_sm<128>(h, smem);
     if (n_stages == 2 && per_sm > 0 && h->num_sms > 0) grid = std::min(n_tiles, per_sm * h->num_sms);
   }
-  if (tile == 32) rc = launch_post<32>(h, kp, smem, stream, grid);
-  else if (tile == 64) rc = launch_post<64>(h, kp, smem, stream, grid);
-  else rc = launch_post<128>(h, kp, smem, stream, grid);
+  // a specialised kernel whose compile-time structure equals this launch's, if one is attached
+  const AttachedSpec* spec = nullptr;
+  if (!h->specs.empty() && kp.tma_ok && n_stages == 1) {
+    gfb_program_head canon = P;
+    canonicalize(canon);
+    for (const auto& sp : h->specs)
+      if (sp.tile == tile && sp.phases == phases && memcmp(&sp.plan, &kp.plan, sizeof(Plan)) == 0 &&
+          memcmp(&sp.canon, &canon, sizeof(canon)) == 0) {
+        spec = &sp;
+        break;
+      }
+  }
+  if (spec) {
+    if (spec->launch(&kp, grid, (unsigned)smem, stream) != 0)
+      return fail(h, GFB_ERR_CUDA, std::string("specialised kernel launch: ") + cudaGetErrorString(cudaGetLastError()));
+    h->n_spec_launches += 1;
+    rc = GFB_OK;
+  } else {
+    if (tile == 32) rc = launch_post<32>(h, kp, smem, stream, grid);
+    else if (tile == 64) rc = launch_post<64>(h, kp, smem, stream, grid);
+    else rc = launch_post<128>(h, kp, smem, stream, grid);
+    h->n_generic_launches += 1;
+  }
   if (rc != GFB_OK) return rc;
   if (e1) cudaEventRecord(e1, stream);
 
@@ -810,6 +901,7 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
 
 int gfb_read_report(gfb_handle* h, gfb_report* out, void* stream_) {
   if (!h || !out) return GFB_ERR_INVALID;
+  if (h->host_only) return fail(h, GFB_ERR_NO_DEVICE, "host-only handle has no report");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CUDA_TRY(cudaMemcpyAsync(h->report_host, h->scratch.report, sizeof(gfb_report), cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
@@ -819,6 +911,7 @@ int gfb_read_report(gfb_handle* h, gfb_report* out, void* stream_) {
 
 int gfb_observe(gfb_handle* h, const gfb_buffers* b, const int64_t* idx, int32_t n, void* stream_) {
   if (!h || !b) return GFB_ERR_INVALID;
+  if (h->host_only) return fail(h, GFB_ERR_NO_DEVICE, "host-only handle cannot launch kernels");
   if (!h->has_prog) return fail(h, GFB_ERR_INVALID, "gfb_set_program() first");
   if (n <= 0) return GFB_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -875,6 +968,67 @@ int gfb_rotate(gfb_handle* h, const float* vec, const float* quat, float* out, i
   rotate_kernel<<<(n + 255) / 256, 256, 0, stream>>>(vec, reinterpret_cast<const float4*>(quat), out, n, conjugate);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
+  return GFB_OK;
+}
+
+int gfb_spec_describe(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void* canonical_head,
+                      int32_t* plan_out, int32_t plan_cap, int32_t* plan_words, int32_t* tile_out) {
+  if (!h || !b || !canonical_head || !plan_out || !plan_words || !tile_out) return GFB_ERR_INVALID;
+  if (!h->has_prog) return fail(h, GFB_ERR_INVALID, "gfb_set_program() first");
+  Plan plan;
+  std::vector<int32_t> table;
+  int tile = 0, n_stages = 1;
+  int rc = plan_for_launch(h, *b, phases, plan, table, tile, n_stages);
+  if (rc != GFB_OK) return rc;
+  const int words = (int)(sizeof(Plan) / 4);
+  *plan_words = words;
+  if (plan_cap < words) return fail(h, GFB_ERR_INVALID, "plan_out too small");
+  memcpy(plan_out, &plan, sizeof(Plan));
+  gfb_program_head canon = h->prog.head;
+  canonicalize(canon);
+  memcpy(canonical_head, &canon, sizeof(canon));
+  *tile_out = tile;
+  return GFB_OK;
+}
+
+int gfb_spec_attach(gfb_handle* h, const char* path) {
+  if (!h) return GFB_ERR_INVALID;
+  if (!path) {
+    for (auto& sp : h->specs)
+      if (sp.dl) dlclose(sp.dl);
+    h->specs.clear();
+    return GFB_OK;
+  }
+  void* dl = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!dl) return fail(h, GFB_ERR_INVALID, std::string("dlopen: ") + dlerror());
+  using InfoFn = int (*)(int*, unsigned*, const void**, const void**, int*, int*);
+  using LaunchFn = int (*)(const KParams*, int, unsigned, void*);
+  InfoFn info = reinterpret_cast<InfoFn>(dlsym(dl, "gfb_spec_info"));
+  LaunchFn launch = reinterpret_cast<LaunchFn>(dlsym(dl, "gfb_spec_launch"));
+  if (!info || !launch) {
+    dlclose(dl);
+    return fail(h, GFB_ERR_INVALID, "not a gfb200 specialised kernel library");
+  }
+  AttachedSpec sp;
+  const void *canon = nullptr, *plan = nullptr;
+  int head_bytes = 0, plan_bytes = 0;
+  info(&sp.tile, &sp.phases, &canon, &plan, &head_bytes, &plan_bytes);
+  if (head_bytes != (int)sizeof(gfb_program_head) || plan_bytes != (int)sizeof(Plan)) {
+    dlclose(dl);
+    return fail(h, GFB_ERR_INVALID, "specialised kernel library was built against other struct layouts");
+  }
+  memcpy(&sp.canon, canon, sizeof(sp.canon));
+  memcpy(&sp.plan, plan, sizeof(sp.plan));
+  sp.dl = dl;
+  sp.launch = launch;
+  h->specs.push_back(sp);
+  return GFB_OK;
+}
+
+int gfb_spec_stats(const gfb_handle* h, int64_t* specialised, int64_t* generic) {
+  if (!h) return GFB_ERR_INVALID;
+  if (specialised) *specialised = h->n_spec_launches;
+  if (generic) *generic = h->n_generic_launches;
   return GFB_OK;
 }
 

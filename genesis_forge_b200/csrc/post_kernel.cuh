@@ -22,6 +22,13 @@
 #include "device_utils.cuh"
 #include "plan.h"
 
+// In a specialised build the term loops have compile-time trip counts and are fully unrolled.
+#ifdef GFB_SPEC
+#define GFB_UNROLL_TERMS _Pragma("unroll")
+#else
+#define GFB_UNROLL_TERMS
+#endif
+
 namespace gfb {
 
 // fetch one observation value for slab row `row` (post kernel: staged arrays live in shared memory)
@@ -41,9 +48,10 @@ __device__ __forceinline__ float obs_fetch_post(const DevObsCol& d, const float*
 
 // v += u * noise for one 16-byte piece; u from the injected U(-1,1) buffer or Philox
 __device__ __forceinline__ float4 add_noise(float4 v, const float4 nz, const float* noise, int row, int W0, int c4,
-                                            const gfb_program_head& P, const Philox& rng, int e0, int col_begin) {
+                                            const gfb_program_head& P, const Philox& rng, int e0, int col_begin,
+                                            int rng_mode) {
   float4 u;
-  if (P.rng_mode == 0) {
+  if (rng_mode == 0) {
     u = noise ? reinterpret_cast<const float4*>(noise)[row * W0 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
   } else {
     const uint4 r4 = rng((uint32_t)(e0 + row), (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32),
@@ -61,9 +69,8 @@ __device__ __forceinline__ float4 add_noise(float4 v, const float4 nz, const flo
 // Issue the TMA loads of one slab (warp 0 only): staged arrays + episode-sum rows, optionally the
 // descriptor table.  All complete on `bar` (one arrival with the expected byte count by lane 0).
 template <int TILE>
-__device__ __forceinline__ void issue_slab_loads(const KParams& K, float* S, float* table_dst, uint64_t* bar,
-                                                 int tile, int n_sum_rows, bool with_table, int lane) {
-  const Plan& plan = K.plan;
+__device__ __forceinline__ void issue_slab_loads(const KParams& K, const Plan& plan, float* S, float* table_dst,
+                                                 uint64_t* bar, int tile, int n_sum_rows, bool with_table, int lane) {
   const int N = K.P.num_envs;
   const int e0 = tile * TILE;
   const uint32_t valid = (uint32_t)min(TILE, N - e0);
@@ -101,15 +108,28 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   __shared__ uint32_t s_reset_bits[TILE / 32];
   __shared__ uint32_t s_status;
 
+  // P: live values (weights, thresholds, ranges, dt, seeds) -- always the kernel parameters.
+  // SP / plan / ph: the STRUCTURE of the term table and of the slab.  In the generic build they are
+  // the kernel parameters too (an interpreter); in a specialised build (GFB_SPEC) they are
+  // compile-time constants, so the term loops unroll, every switch folds to its one case and all
+  // shared-memory offsets become immediates.
   const gfb_program_head& P = K.P;
+#ifdef GFB_SPEC
+  const gfb_program_head& SP = gfb_spec::kP;
+  const Plan& plan = gfb_spec::kPlan;
+  constexpr uint32_t ph = gfb_spec::PHASES;
+  constexpr bool use_tma = true;  // the host only selects a specialised kernel when TMA is usable
+#else
+  const gfb_program_head& SP = K.P;
   const Plan& plan = K.plan;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int N = P.num_envs;
   const uint32_t ph = K.phases;
   const bool use_tma = K.tma_ok != 0;
-  const int D = P.num_dofs;
-  const bool stage_sums = (ph & (GFB_PHASE_REWARD | GFB_PHASE_RESET)) != 0 && P.n_reward > 0;
-  const int n_sum_rows = stage_sums ? P.n_reward : 0;
+#endif
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = P.num_envs;
+  const int D = SP.num_dofs;
+  const bool stage_sums = (ph & (GFB_PHASE_REWARD | GFB_PHASE_RESET)) != 0 && SP.n_reward > 0;
+  const int n_sum_rows = stage_sums ? SP.n_reward : 0;
   const int n_tiles = K.s.n_tiles;
   const int n_stages = plan.n_stages;
   float* const Tbl = Sbase + plan.cols_off;  // descriptor table, loaded once per block
@@ -123,7 +143,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     }
     __syncthreads();
     if (warp == 0 && (int)blockIdx.x < n_tiles)
-      issue_slab_loads<TILE>(K, Sbase, Tbl, &bars[0], blockIdx.x, n_sum_rows, true, lane);
+      issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], blockIdx.x, n_sum_rows, true, lane);
   } else {
     const int32_t* src = reinterpret_cast<const int32_t*>(K.cols);
     int32_t* dst = reinterpret_cast<int32_t*>(Tbl);
@@ -151,7 +171,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   if (use_tma) {
     if (warp == 0 && n_stages == 2 && next_tile < n_tiles) {
       bulk_wait_all_read();  // the other stage's outgoing stores have left shared memory
-      issue_slab_loads<TILE>(K, Sbase + (stage ^ 1) * plan.stage_words, Tbl, &bars[stage ^ 1], next_tile,
+      issue_slab_loads<TILE>(K, plan, Sbase + (stage ^ 1) * plan.stage_words, Tbl, &bars[stage ^ 1], next_tile,
                              n_sum_rows, false, lane);
     }
   } else {
@@ -164,7 +184,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     }
     if (stage_sums) {
       const float* sums = GFB_BUF(const float, GFB_B_EP_SUMS);
-      for (int r = 0; r < P.n_reward; ++r)
+      for (int r = 0; r < SP.n_reward; ++r)
         if (active) S[plan.sums_off + r * TILE + tid] = sums[(size_t)r * N + e];
     }
   }
@@ -247,8 +267,8 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   // ------------------------------------------------------------------------------------------
   // contacts: ordered net force / mean position per tracked link, then air time
   // ------------------------------------------------------------------------------------------
-  if ((ph & GFB_PHASE_CONTACT) && P.n_contact > 0) {
-    const int C = P.n_contact_slots, L = P.n_links_total;
+  if ((ph & GFB_PHASE_CONTACT) && SP.n_contact > 0) {
+    const int C = SP.n_contact_slots, L = SP.n_links_total;
     const int32_t* la = reinterpret_cast<const int32_t*>(S + plan.off_cla) + tid * C;
     const int32_t* lb = reinterpret_cast<const int32_t*>(S + plan.off_clb) + tid * C;
     const float* cf = S + plan.off_cforce + tid * C * 3;
@@ -259,23 +279,24 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     if (bad && active) status |= GFB_STATUS_BAD_CONTACT;
     const float4* lq = GFB_BUF(const float4, GFB_B_LINKS_QUAT) + (size_t)e * L;
 
-    for (int m = 0; m < P.n_contact; ++m) {
+    for (int m = 0; m < SP.n_contact; ++m) {
       const gfb_contact_manager& cm = P.contact[m];
-      const int Lc = cm.n_links;
+      const gfb_contact_manager& cs_ = SP.contact[m];
+      const int Lc = cs_.n_links;
       float* fout = S + plan.cout_off[m] + tid * Lc * 3;
       float* pout = S + plan.cposout_off[m] + tid * Lc * 3;
       for (int t = 0; t < Lc; ++t) {
-        const int target = cm.link_ids[t];
+        const int target = cs_.link_ids[t];
         const float4 tq = lq[target];
         float fx = 0.f, fy = 0.f, fz = 0.f, px = 0.f, py = 0.f, pz = 0.f, cnt = 0.f;
         for (int c = 0; c < C; ++c) {
           const int a = la[c], b2 = lb[c];
           const bool is_a = a == target, is_b = b2 == target;
           bool hit = is_a | is_b;
-          if (hit && cm.has_with_filter) {
+          if (hit && cs_.has_with_filter) {
             bool keep = false;
-            for (int w = 0; w < cm.n_with; ++w) {
-              const int wl = cm.with_ids[w];
+            for (int w = 0; w < cs_.n_with; ++w) {
+              const int wl = cs_.with_ids[w];
               keep |= (is_a && b2 == wl) || (is_b && a == wl);
             }
             hit = keep;
@@ -302,7 +323,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
         const float nrm = norm3(fx, fy, fz);
         st[plan.st_cnorm[m] + t] = nrm;
 
-        if (cm.track_air_time) {  // contact_manager.py:434-477
+        if (cs_.track_air_time) {  // contact_manager.py:434-477
           const float* air = GFB_BUF(const float, GFB_B_AIR0 + m);
           const size_t base = (size_t)e * Lc + t, plane = (size_t)N * Lc;
           float last_air = air[base], cur_air = air[plane + base];
@@ -320,16 +341,17 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
         }
       }
     }
-  } else if (P.n_contact > 0 && (ph & (GFB_PHASE_REWARD | GFB_PHASE_TERMINATION | GFB_PHASE_OBSERVE))) {
+  } else if (SP.n_contact > 0 && (ph & (GFB_PHASE_REWARD | GFB_PHASE_TERMINATION | GFB_PHASE_OBSERVE))) {
     // split execution: contact results of an earlier launch come back from global memory
-    for (int m = 0; m < P.n_contact; ++m) {
+    for (int m = 0; m < SP.n_contact; ++m) {
       const gfb_contact_manager& cm = P.contact[m];
-      const float* cg = GFB_BUF(const float, GFB_B_CONTACTS0 + m) + (size_t)e * cm.n_links * 3;
-      for (int t = 0; t < cm.n_links; ++t) {
+      const gfb_contact_manager& cs_ = SP.contact[m];
+      const float* cg = GFB_BUF(const float, GFB_B_CONTACTS0 + m) + (size_t)e * cs_.n_links * 3;
+      for (int t = 0; t < cs_.n_links; ++t) {
         st[plan.st_cnorm[m] + t] = norm3(cg[t * 3], cg[t * 3 + 1], cg[t * 3 + 2]);
-        if (cm.track_air_time) {
+        if (cs_.track_air_time) {
           const float* air = GFB_BUF(const float, GFB_B_AIR0 + m);
-          const size_t base = (size_t)e * cm.n_links + t, plane = (size_t)N * cm.n_links;
+          const size_t base = (size_t)e * cs_.n_links + t, plane = (size_t)N * cs_.n_links;
           float* sa = st + plan.st_air[m] + t * 4;
           sa[0] = air[base]; sa[1] = air[plane + base]; sa[2] = air[2 * plane + base]; sa[3] = air[3 * plane + base];
         }
@@ -342,16 +364,18 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   // ------------------------------------------------------------------------------------------
   bool terminated = false, truncated = false;
   if (ph & GFB_PHASE_TERMINATION) {
-    for (int t = 0; t < P.n_termination; ++t) {
+    GFB_UNROLL_TERMS
+    for (int t = 0; t < SP.n_termination; ++t) {
       const gfb_termination_term& tt = P.termination[t];
+      const gfb_termination_term& ts = SP.termination[t];
       bool v = false;
-      switch (tt.op) {
+      switch (ts.op) {
         case GFB_T_TIMEOUT:
           v = P.base_max_episode_length > 0 && ep_len > max_len;
           break;
         case GFB_T_BAD_ORIENTATION: {
           const float tilt = fminf(norm2(grav_b.x, grav_b.y), 0.99f);
-          v = !(ep_len <= tt.i0) && (tilt >= tt.p[0]);
+          v = !(ep_len <= ts.i0) && (tilt >= tt.p[0]);
         } break;
         case GFB_T_BASE_HEIGHT_MIN:
           v = S[plan.off_pos + tid * 3 + 2] < tt.p[0];
@@ -362,20 +386,20 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
         } break;
         case GFB_T_HAS_CONTACT: {
           int n = 0;
-          for (int l = 0; l < P.contact[tt.mgr].n_links; ++l) n += st[plan.st_cnorm[tt.mgr] + l] > tt.p[0];
-          v = n >= tt.i0;
+          for (int l = 0; l < SP.contact[ts.mgr].n_links; ++l) n += st[plan.st_cnorm[ts.mgr] + l] > tt.p[0];
+          v = n >= ts.i0;
         } break;
         case GFB_T_CONTACT_FORCE:
         case GFB_T_CONTACT_FORCE_GRACE: {
           bool any = false;
-          for (int l = 0; l < P.contact[tt.mgr].n_links; ++l) any |= st[plan.st_cnorm[tt.mgr] + l] > tt.p[0];
-          v = any && (tt.op == GFB_T_CONTACT_FORCE || !(ep_len <= tt.i0));
+          for (int l = 0; l < SP.contact[ts.mgr].n_links; ++l) any |= st[plan.st_cnorm[ts.mgr] + l] > tt.p[0];
+          v = any && (ts.op == GFB_T_CONTACT_FORCE || !(ep_len <= ts.i0));
         } break;
         default:
           break;
       }
       v = v && active;
-      if (tt.time_out) truncated |= v; else terminated |= v;
+      if (ts.time_out) truncated |= v; else terminated |= v;
       const uint32_t votes = __ballot_sync(0xffffffffu, v);
       if (lane == 0 && votes) atomicAdd(&s_term_count[t], __popc(votes));
     }
@@ -403,11 +427,13 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     ep_secs = add(ep_secs, P.env_dt);  // reward_manager.py:178
     float dof_dev = 0.0f;
     bool have_dof_dev = false;
-    for (int r = 0; r < P.n_reward; ++r) {
+    GFB_UNROLL_TERMS
+    for (int r = 0; r < SP.n_reward; ++r) {
       const gfb_reward_term& rt = P.reward[r];
-      if (rt.weight == 0.0f || rt.op == GFB_R_NONE) continue;  // reward_manager.py:181-182
+      const gfb_reward_term& rs = SP.reward[r];
+      if (rt.weight == 0.0f || rs.op == GFB_R_NONE) continue;  // reward_manager.py:181-182
       float v = 0.0f;
-      switch (rt.op) {
+      switch (rs.op) {
         case GFB_R_IS_ALIVE:
           v = terminated ? 0.0f : 1.0f;
           break;
@@ -417,8 +443,8 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
         case GFB_R_BASE_HEIGHT: {
           float z = S[plan.off_pos + tid * 3 + 2];
           float off = 0.0f;
-          if (rt.flags & GFB_RF_TERRAIN_FLAT) off = rt.p[1];
-          if (rt.flags & GFB_RF_TERRAIN_HEIGHT) {
+          if (rs.flags & GFB_RF_TERRAIN_FLAT) off = rt.p[1];
+          if (rs.flags & GFB_RF_TERRAIN_HEIGHT) {
             // terrain_manager.py:100-166: normalise to [-1,1], bilinear grid_sample(align_corners, border)
             const float x = S[plan.off_pos + tid * 3], y = S[plan.off_pos + tid * 3 + 1];
             const float xmin = P.terrain_bounds[0], xmax = P.terrain_bounds[1];
@@ -442,8 +468,8 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
                       add(mul(h10, mul(wx0, ty)), mul(h11, mul(tx, ty))));
           }
           float target = rt.p[0];
-          if (rt.flags & GFB_RF_TARGET_FROM_COMMAND) target = S[plan.off_cmd[rt.mgr] + tid * P.command[rt.mgr].n_dims];
-          if (rt.flags & GFB_RF_TARGET_FROM_TENSOR) target = GFB_BUF(const float, GFB_B_TARGET_HEIGHT)[e];
+          if (rs.flags & GFB_RF_TARGET_FROM_COMMAND) target = S[plan.off_cmd[rs.mgr] + tid * SP.command[rs.mgr].n_dims];
+          if (rs.flags & GFB_RF_TARGET_FROM_TENSOR) target = GFB_BUF(const float, GFB_B_TARGET_HEIGHT)[e];
           v = sq(sub(sub(z, off), target));
         } break;
         case GFB_R_DOF_SIMILAR:
@@ -464,8 +490,8 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
             have_dof_dev = true;
           }
           v = dof_dev;
-          if (rt.op == GFB_R_STAND_STILL) {
-            const float* c = S + plan.off_cmd[rt.mgr] + tid * P.command[rt.mgr].n_dims;
+          if (rs.op == GFB_R_STAND_STILL) {
+            const float* c = S + plan.off_cmd[rs.mgr] + tid * SP.command[rs.mgr].n_dims;
             v = mul(dof_dev, norm2(c[0], c[1]) < rt.p[0] ? 1.0f : 0.0f);
           }
         } break;
@@ -484,15 +510,15 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
         case GFB_R_TRACK_LIN_VEL:
         case GFB_R_TRACK_ANG_VEL: {
           float c0, c1, c2;
-          if (rt.flags & GFB_RF_FIXED_COMMAND) {
+          if (rs.flags & GFB_RF_FIXED_COMMAND) {
             const float* c = GFB_BUF(const float, GFB_B_FIXED_COMMAND) + (size_t)e * 3;
             c0 = c[0]; c1 = c[1]; c2 = c[2];
           } else {
-            const float* c = S + plan.off_cmd[rt.mgr] + tid * P.command[rt.mgr].n_dims;
+            const float* c = S + plan.off_cmd[rs.mgr] + tid * SP.command[rs.mgr].n_dims;
             c0 = c[0]; c1 = c[1]; c2 = c[2];
           }
           float err;
-          if (rt.op == GFB_R_TRACK_LIN_VEL)
+          if (rs.op == GFB_R_TRACK_LIN_VEL)
             err = add(sq(sub(c0, lin_b.x)), sq(sub(c1, lin_b.y)));
           else
             err = sq(sub(c2, ang_b.z));
@@ -500,36 +526,36 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
         } break;
         case GFB_R_HAS_CONTACT: {
           int n = 0;
-          for (int l = 0; l < P.contact[rt.mgr].n_links; ++l) n += st[plan.st_cnorm[rt.mgr] + l] > rt.p[0];
-          v = n >= rt.i0 ? 1.0f : 0.0f;
+          for (int l = 0; l < SP.contact[rs.mgr].n_links; ++l) n += st[plan.st_cnorm[rs.mgr] + l] > rt.p[0];
+          v = n >= rs.i0 ? 1.0f : 0.0f;
         } break;
         case GFB_R_CONTACT_FORCE: {
-          for (int l = 0; l < P.contact[rt.mgr].n_links; ++l)
-            v = add(v, fmaxf(sub(st[plan.st_cnorm[rt.mgr] + l], rt.p[0]), 0.0f));
+          for (int l = 0; l < SP.contact[rs.mgr].n_links; ++l)
+            v = add(v, fmaxf(sub(st[plan.st_cnorm[rs.mgr] + l], rt.p[0]), 0.0f));
         } break;
         case GFB_R_FEET_AIR_TIME: {
-          for (int l = 0; l < P.contact[rt.mgr].n_links; ++l) {
-            const float* sa = st + plan.st_air[rt.mgr] + l * 4;
+          for (int l = 0; l < SP.contact[rs.mgr].n_links; ++l) {
+            const float* sa = st + plan.st_air[rs.mgr] + l * 4;
             const bool made = (sa[3] > 0.0f) && (sa[3] < rt.p[2]);  // contact_manager.py:198-224
             float a = mul(sub(sa[0], rt.p[0]), made ? 1.0f : 0.0f);
-            if (rt.flags & GFB_RF_HAS_MAX) a = fminf(a, rt.p[1]);
+            if (rs.flags & GFB_RF_HAS_MAX) a = fminf(a, rt.p[1]);
             v = add(v, a);
           }
-          if (rt.i0 >= 0) {
-            const float* c = S + plan.off_cmd[rt.i0] + tid * P.command[rt.i0].n_dims;
+          if (rs.i0 >= 0) {
+            const float* c = S + plan.off_cmd[rs.i0] + tid * SP.command[rs.i0].n_dims;
             v = mul(v, norm2(c[0], c[1]) > 0.1f ? 1.0f : 0.0f);
           }
         } break;
         case GFB_R_FEET_SLIDE: {
-          const int Lc = P.contact[rt.mgr].n_links;
+          const int Lc = SP.contact[rs.mgr].n_links;
           const float* lv = GFB_BUF(const float, GFB_B_LINKS_VEL) + (size_t)e * Lc * 3;
           for (int l = 0; l < Lc; ++l) {
             const float speed = norm3(lv[l * 3], lv[l * 3 + 1], lv[l * 3 + 2]);
-            v = add(v, mul(speed, st[plan.st_cnorm[rt.mgr] + l] > 1.0f ? 1.0f : 0.0f));
+            v = add(v, mul(speed, st[plan.st_cnorm[rs.mgr] + l] > 1.0f ? 1.0f : 0.0f));
           }
         } break;
         case GFB_R_EXTERNAL:
-          v = GFB_BUF(const float, GFB_B_OBS_EXT3)[(size_t)e * GFB_MAX_REWARD_TERMS + rt.ext_col];
+          v = GFB_BUF(const float, GFB_B_OBS_EXT3)[(size_t)e * GFB_MAX_REWARD_TERMS + rs.ext_col];
           break;
         default:
           break;
@@ -545,17 +571,18 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   // command resample on the resample boundary (command_manager.py:152-162)
   // ------------------------------------------------------------------------------------------
   if (ph & GFB_PHASE_COMMAND) {
-    for (int k = 0; k < P.n_command; ++k) {
+    for (int k = 0; k < SP.n_command; ++k) {
       const gfb_command_manager& cm = P.command[k];
-      if (!cm.enabled) continue;
+      const gfb_command_manager& ks = SP.command[k];
+      if (!ks.enabled) continue;
       if (active && (ep_len % cm.resample_steps) == 0) {
-        float* cs = S + plan.off_cmd[k] + tid * cm.n_dims;
-        float* cg = GFB_BUF(float, GFB_B_COMMAND0 + k) + (size_t)e * cm.n_dims;
+        float* cs = S + plan.off_cmd[k] + tid * ks.n_dims;
+        float* cg = GFB_BUF(float, GFB_B_COMMAND0 + k) + (size_t)e * ks.n_dims;
         const float* inj = GFB_BUF(const float, GFB_B_INJ_CMD_STEP0 + k);
-        for (int i = 0; i < cm.n_dims; ++i) {
+        for (int i = 0; i < ks.n_dims; ++i) {
           float val;
-          if (P.rng_mode == 0) {
-            val = inj ? inj[(size_t)e * cm.n_dims + i] : cs[i];
+          if (SP.rng_mode == 0) {
+            val = inj ? inj[(size_t)e * ks.n_dims + i] : cs[i];
           } else {
             const uint4 x = rng((uint32_t)e, (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32), 0x100u + k * 16 + i);
             val = add(mul(u01(x.x), sub(cm.hi[i], cm.lo[i])), cm.lo[i]);
@@ -583,7 +610,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
       ep_len = 0;
       if (P.max_len_random_span > 0.0f && P.base_max_episode_length > 0) {
         float u;
-        if (P.rng_mode == 0) {
+        if (SP.rng_mode == 0) {
           const float* inj = GFB_BUF(const float, GFB_B_INJ_MAX_LEN);
           u = inj ? inj[e] : 0.0f;
         } else {
@@ -595,16 +622,17 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
       }
       GFB_BUF(int32_t, GFB_B_EPISODE_LENGTH)[e] = 0;
       // command_manager.py:164-170
-      for (int k = 0; k < P.n_command; ++k) {
+      for (int k = 0; k < SP.n_command; ++k) {
         const gfb_command_manager& cm = P.command[k];
-        if (!cm.enabled) continue;
-        float* cs = S + plan.off_cmd[k] + tid * cm.n_dims;
-        float* cg = GFB_BUF(float, GFB_B_COMMAND0 + k) + (size_t)e * cm.n_dims;
+        const gfb_command_manager& ks = SP.command[k];
+        if (!ks.enabled) continue;
+        float* cs = S + plan.off_cmd[k] + tid * ks.n_dims;
+        float* cg = GFB_BUF(float, GFB_B_COMMAND0 + k) + (size_t)e * ks.n_dims;
         const float* inj = GFB_BUF(const float, GFB_B_INJ_CMD_RESET0 + k);
-        for (int i = 0; i < cm.n_dims; ++i) {
+        for (int i = 0; i < ks.n_dims; ++i) {
           float val;
-          if (P.rng_mode == 0) {
-            val = inj ? inj[(size_t)e * cm.n_dims + i] : cs[i];
+          if (SP.rng_mode == 0) {
+            val = inj ? inj[(size_t)e * ks.n_dims + i] : cs[i];
           } else {
             const uint4 x = rng((uint32_t)e, (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32), 0x300u + k * 16 + i);
             val = add(mul(u01(x.x), sub(cm.hi[i], cm.lo[i])), cm.lo[i]);
@@ -614,15 +642,15 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
         }
       }
       // contact_manager.py:316-329
-      for (int m = 0; m < P.n_contact; ++m)
-        if (P.contact[m].track_air_time)
-          for (int k = 0; k < P.contact[m].n_links * 4; ++k) st[plan.st_air[m] + k] = 0.0f;
+      for (int m = 0; m < SP.n_contact; ++m)
+        if (SP.contact[m].track_air_time)
+          for (int k = 0; k < SP.contact[m].n_links * 4; ++k) st[plan.st_air[m] + k] = 0.0f;
     }
     // reward_manager.py:197-222: per-term episode mean over the reset envs, then clear.
     // Resets are sparse: lane 0 visits the reset lanes of its warp in ascending order (fixed order,
     // double accumulation -> deterministic logging).
-    if (P.n_reward > 0 && reset_votes) {
-      for (int r = 0; r < P.n_reward; ++r) {
+    if (SP.n_reward > 0 && reset_votes) {
+      for (int r = 0; r < SP.n_reward; ++r) {
         float* sum = S + plan.sums_off + r * TILE + tid;
         float q = 0.0f;
         if (reset) {
@@ -652,15 +680,16 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     if ((ph & (GFB_PHASE_REWARD | GFB_PHASE_RESET)) && K.b.buf[GFB_B_EP_SECONDS])
       GFB_BUF(float, GFB_B_EP_SECONDS)[e] = ep_secs;
     if (ph & (GFB_PHASE_CONTACT | GFB_PHASE_RESET)) {
-      for (int m = 0; m < P.n_contact; ++m) {
+      for (int m = 0; m < SP.n_contact; ++m) {
         const gfb_contact_manager& cm = P.contact[m];
-        if (!cm.track_air_time) continue;
+        const gfb_contact_manager& cs_ = SP.contact[m];
+        if (!cs_.track_air_time) continue;
         if (!(ph & GFB_PHASE_CONTACT) && !reset) continue;
         float* air = GFB_BUF(float, GFB_B_AIR0 + m);
-        const size_t plane = (size_t)N * cm.n_links;
-        for (int t = 0; t < cm.n_links; ++t) {
+        const size_t plane = (size_t)N * cs_.n_links;
+        for (int t = 0; t < cs_.n_links; ++t) {
           const float* sa = st + plan.st_air[m] + t * 4;
-          const size_t base = (size_t)e * cm.n_links + t;
+          const size_t base = (size_t)e * cs_.n_links + t;
           air[base] = sa[0]; air[plane + base] = sa[1]; air[2 * plane + base] = sa[2]; air[3 * plane + base] = sa[3];
         }
       }
@@ -674,10 +703,10 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   // ------------------------------------------------------------------------------------------
   // slab outputs: episode sums, contact forces / positions
   // ------------------------------------------------------------------------------------------
-  const bool store_contacts = (ph & GFB_PHASE_CONTACT) && P.n_contact > 0;
+  const bool store_contacts = (ph & GFB_PHASE_CONTACT) && SP.n_contact > 0;
   if (use_tma) {
     if (warp == 0) {
-      const int n_c = store_contacts ? 2 * P.n_contact : 0;
+      const int n_c = store_contacts ? 2 * SP.n_contact : 0;
       bool issued = false;
       for (int i = lane; i < n_sum_rows + n_c; i += 32) {
         if (i < n_sum_rows) {
@@ -685,8 +714,8 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
                      (uint32_t)valid * 4u);
         } else {
           const int m = (i - n_sum_rows) >> 1;
-          const uint32_t bytes = (uint32_t)P.contact[m].n_links * 3u * (uint32_t)valid * 4u;
-          const size_t goff = (size_t)e0 * P.contact[m].n_links * 3;
+          const uint32_t bytes = (uint32_t)SP.contact[m].n_links * 3u * (uint32_t)valid * 4u;
+          const size_t goff = (size_t)e0 * SP.contact[m].n_links * 3;
           if ((i - n_sum_rows) & 1)
             bulk_store(GFB_BUF(float, GFB_B_CONTACT_POS0 + m) + goff, S + plan.cposout_off[m], bytes);
           else
@@ -699,12 +728,12 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   } else {
     if (stage_sums && active) {
       float* sums = GFB_BUF(float, GFB_B_EP_SUMS);
-      for (int r = 0; r < P.n_reward; ++r) sums[(size_t)r * N + e] = S[plan.sums_off + r * TILE + tid];
+      for (int r = 0; r < SP.n_reward; ++r) sums[(size_t)r * N + e] = S[plan.sums_off + r * TILE + tid];
     }
     if (store_contacts)
-      for (int m = 0; m < P.n_contact; ++m) {
-        const int words = P.contact[m].n_links * 3 * valid;
-        const size_t goff = (size_t)e0 * P.contact[m].n_links * 3;
+      for (int m = 0; m < SP.n_contact; ++m) {
+        const int words = SP.contact[m].n_links * 3 * valid;
+        const size_t goff = (size_t)e0 * SP.contact[m].n_links * 3;
         float* g1 = GFB_BUF(float, GFB_B_CONTACTS0 + m) + goff;
         float* g2 = GFB_BUF(float, GFB_B_CONTACT_POS0 + m) + goff;
         for (int w = tid; w < words; w += TILE) {
@@ -727,9 +756,9 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
       sc.tile_reset_count[tile] = n;
       if (s_status) atomicOr(sc.status, s_status);
     }
-    if ((ph & GFB_PHASE_TERMINATION) && tid < P.n_termination)
+    if ((ph & GFB_PHASE_TERMINATION) && tid < SP.n_termination)
       sc.tile_term_count[(size_t)tid * nt + tile] = s_term_count[tid];
-    if ((ph & GFB_PHASE_RESET) && tid < P.n_reward) {
+    if ((ph & GFB_PHASE_RESET) && tid < SP.n_reward) {
       double acc = 0.0;
       for (int w = 0; w < TILE / 32; ++w) acc += s_rew_part[tid][w];
       sc.tile_rew_sum[(size_t)tid * nt + tile] = acc;
@@ -743,8 +772,8 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   // ------------------------------------------------------------------------------------------
   if (ph & GFB_PHASE_OBSERVE) {
     const DevObsCol* cols_all = reinterpret_cast<const DevObsCol*>(Tbl);
-    for (int g = 0; g < P.n_obs_groups; ++g) {
-      const gfb_obs_group& og = P.obs_group[g];
+    for (int g = 0; g < SP.n_obs_groups; ++g) {
+      const gfb_obs_group& og = SP.obs_group[g];
       const int O = og.n_cols, OH = og.n_cols * og.history;
       const DevObsCol* cols = cols_all + og.col_begin;
       float* out = GFB_BUF(float, GFB_B_OBS_OUT0 + g) + (size_t)e0 * OH;
@@ -777,7 +806,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
             for (int row = r0; row < valid; row += rpp) {
               float4 v = *reinterpret_cast<const float4*>(src);
               v.x = mul(v.x, sc); v.y = mul(v.y, sc); v.z = mul(v.z, sc); v.w = mul(v.w, sc);
-              if (noisy) v = add_noise(v, nz, noise, row, W0, d.z, P, rng, e0, og.col_begin);
+              if (noisy) v = add_noise(v, nz, noise, row, W0, d.z, P, rng, e0, og.col_begin, SP.rng_mode);
               *dst = v;
               src += sstep;
               dst += dstep;
@@ -806,7 +835,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
             for (int row = r0; row < valid; row += rpp) {
               float4 v;
               v.x = mul(*s0, sc.x); v.y = mul(*s1, sc.y); v.z = mul(*s2, sc.z); v.w = mul(*s3, sc.w);
-              if (noisy) v = add_noise(v, nz, noise, row, W0, c4, P, rng, e0, og.col_begin);
+              if (noisy) v = add_noise(v, nz, noise, row, W0, c4, P, rng, e0, og.col_begin, SP.rng_mode);
               *dst = v;
               s0 += rpp * str.x; s1 += rpp * str.y; s2 += rpp * str.z; s3 += rpp * str.w;
               dst += dstep;
@@ -837,7 +866,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
             v = mul(obs_fetch_post(d, S, K.b, plan, row, e0 + row), d.scale);
             if (d.noise != 0.f) {
               float u;
-              if (P.rng_mode == 0) {
+              if (SP.rng_mode == 0) {
                 u = noise ? noise[(size_t)row * O + col] : 0.f;
               } else {
                 const uint4 x = rng((uint32_t)(e0 + row), (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32),
@@ -861,7 +890,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   if (next_tile < n_tiles) __syncthreads();
   if (use_tma && n_stages == 1 && next_tile < n_tiles && warp == 0) {
     bulk_wait_all_read();
-    issue_slab_loads<TILE>(K, Sbase, Tbl, &bars[0], next_tile, n_sum_rows, false, lane);
+    issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], next_tile, n_sum_rows, false, lane);
   }
   }  // slab loop
 

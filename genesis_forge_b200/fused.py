@@ -106,7 +106,9 @@ class FusedStep:
         self.N = env.num_envs
         self.dry_run = dry_run
         if dry_run:
-            self.lib = self.handle = None
+            # host-only handle: packs the term table and describes specialisations, cannot launch
+            self.lib = nat.lib()
+            self.handle = nat.Handle(self.N, -1)
         else:
             if self.device.type != "cuda":
                 raise nat.NativeLibraryError(
@@ -127,8 +129,14 @@ class FusedStep:
         self.dist = None  # (process group) when envs are sharded over ranks
         self._contact_dims = None
         self._feet_slide_manager = None
+        self._dof_force_used = None
         self.global_acc = None
         self._acc_host = None
+        self._stream_ptr = None
+        self._program_pushed = False
+        self._injected_bound = object()
+        self._spec_tried: set = set()
+        self.spec_paths: list = []
         self.global_num_envs = self.N
         self._compile()
 
@@ -213,6 +221,13 @@ class FusedStep:
             keep = True
         if keep:
             self._keepalive.append(tensor)
+        self.buffers.buf[buf_id] = tensor.data_ptr()
+
+    def _set_engine(self, buf_id: int, tensor: torch.Tensor, dtype):
+        """Pointer of an engine getter's tensor (kept alive until the next launch group)."""
+        if tensor.dtype is not dtype or not tensor.is_contiguous() or tensor.device != self.device:
+            tensor = tensor.to(self.device, dtype).contiguous()
+        self._keepalive.append(tensor)
         self.buffers.buf[buf_id] = tensor.data_ptr()
 
     def _static_buffers(self):
@@ -511,36 +526,40 @@ class FusedStep:
     # ------------------------------------------------------------------------------------------
     def _engine_buffers(self, post_reset: bool = False):
         """Pointers to the engine's state tensors (zero-copy; getters are called once per launch)."""
-        K, s = nat.K, self._set
+        K, s = nat.K, self._set_engine
         self._keepalive = []
         robot = self.primary_entity
         f32 = torch.float32
-        s(K["GFB_B_POS"], robot.get_pos(), f32, keep=True)
-        s(K["GFB_B_QUAT"], robot.get_quat(), f32, keep=True)
-        s(K["GFB_B_VEL"], robot.get_vel(), f32, keep=True)
-        s(K["GFB_B_ANG"], robot.get_ang(), f32, keep=True)
+        if not post_reset:  # the re-observation of reset envs reads the cached quaternion, not pos/quat
+            s(K["GFB_B_POS"], robot.get_pos(), f32)
+            s(K["GFB_B_QUAT"], robot.get_quat(), f32)
+        s(K["GFB_B_VEL"], robot.get_vel(), f32)
+        s(K["GFB_B_ANG"], robot.get_ang(), f32)
         if self.action is not None:
             idx = self.action.dofs_idx
-            s(K["GFB_B_DOF_POS"], robot.get_dofs_position(idx), f32, keep=True)
-            s(K["GFB_B_DOF_VEL"], robot.get_dofs_velocity(idx), f32, keep=True)
+            s(K["GFB_B_DOF_POS"], robot.get_dofs_position(idx), f32)
+            s(K["GFB_B_DOF_VEL"], robot.get_dofs_velocity(idx), f32)
             if self._uses_dof_force:
-                s(K["GFB_B_DOF_FORCE"], robot.get_dofs_force(idx), f32, keep=True)
+                s(K["GFB_B_DOF_FORCE"], robot.get_dofs_force(idx), f32)
         if self.contacts and not post_reset:
             solver = self.env.scene.rigid_solver
             c = solver.collider.get_contacts(as_tensor=True, to_torch=True)
-            s(K["GFB_B_C_FORCE"], c["force"], f32, keep=True)
-            s(K["GFB_B_C_POS"], c["position"], f32, keep=True)
-            s(K["GFB_B_C_LINK_A"], c["link_a"], torch.int32, keep=True)
-            s(K["GFB_B_C_LINK_B"], c["link_b"], torch.int32, keep=True)
+            s(K["GFB_B_C_FORCE"], c["force"], f32)
+            s(K["GFB_B_C_POS"], c["position"], f32)
+            s(K["GFB_B_C_LINK_A"], c["link_a"], torch.int32)
+            s(K["GFB_B_C_LINK_B"], c["link_b"], torch.int32)
             lq = solver.get_links_quat()
-            s(K["GFB_B_LINKS_QUAT"], lq, f32, keep=True)
-            self._contact_dims = (c["link_a"].shape[-1], lq.shape[1])
+            s(K["GFB_B_LINKS_QUAT"], lq, f32)
+            dims = (c["link_a"].shape[-1], lq.shape[1])
+            if dims != self._contact_dims:
+                self._contact_dims = dims
+                self._program_pushed = False
             if self._feet_slide_manager is not None:
                 mgr, attr = self._feet_slide_manager
                 vel = getattr(self.env, attr).get_links_vel(links_idx_local=mgr.local_link_ids)
-                s(K["GFB_B_LINKS_VEL"], vel, f32, keep=True)
+                s(K["GFB_B_LINKS_VEL"], vel, f32)
         if self._fixed_command_parts:
-            s(K["GFB_B_FIXED_COMMAND"], self._resolve_fixed_command(), f32, keep=True)
+            s(K["GFB_B_FIXED_COMMAND"], self._resolve_fixed_command(), f32)
 
     def _resolve_fixed_command(self) -> torch.Tensor:
         """(N,3) tensor [cmd_x, cmd_y, cmd_yaw] for tracking terms configured with fixed tensors."""
@@ -565,7 +584,9 @@ class FusedStep:
 
     @property
     def _uses_dof_force(self) -> bool:
-        return any(key == "dof_force" for om in self.observations for (_, key, _) in om._sources)
+        if self._dof_force_used is None:
+            self._dof_force_used = any(key == "dof_force" for om in self.observations for (_, key, _) in om._sources)
+        return self._dof_force_used
 
     def _obs_buffers(self):
         K, s = nat.K, self._set
@@ -575,6 +596,9 @@ class FusedStep:
             s(K["GFB_B_OBS_OUT0"] + g, om._buffers[1 - cur])
 
     def _injection_buffers(self):
+        if self._injected_bound is self.injected:
+            return
+        self._injected_bound = self.injected
         K, s = nat.K, self._set
         inj = self.injected or {}
         for k in range(len(self.commands)):
@@ -593,14 +617,25 @@ class FusedStep:
         None returns to in-kernel Philox.
         """
         self.injected = draws
+        self._program_pushed = False  # rng_mode is part of the packed table
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if self._stream_ptr is None:
+            self._stream_ptr = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return self._stream_ptr
+
+    def begin_step(self):
+        """Per-step caches: the caller's current stream, one live-config check."""
+        self._stream_ptr = None
+        self._program_pushed = False
 
     # ------------------------------------------------------------------------------------------
     # launches
     # ------------------------------------------------------------------------------------------
-    def _set_program(self):
+    def _set_program(self, force: bool = False):
+        """Pack (if a live value changed) and hand the term table to the library; once per step."""
+        if self._program_pushed and not force:
+            return
         self.pack()
         P = self.program.head
         P.step_index = self.env.step_count
@@ -610,9 +645,8 @@ class FusedStep:
                 c = solver.collider.get_contacts(as_tensor=True, to_torch=True)
                 self._contact_dims = (c["link_a"].shape[-1], solver.get_links_quat().shape[1])
             P.n_contact_slots, P.n_links_total = self._contact_dims
-        if self.dry_run:
-            return
         self.handle.check(self.lib.gfb_set_program(self.handle.ptr, C.byref(self.program)), "gfb_set_program")
+        self._program_pushed = not self.dry_run
 
     def cache_entity(self):
         """Entity phase alone (EntityManager.build() caches the pose before the first reset)."""
@@ -642,11 +676,66 @@ class FusedStep:
         if self.action is not None:
             env.robot.control_dofs_position(self.action._actions, self.action.dofs_idx)
 
+    # ------------------------------------------------------------------------------------------
+    # specialised kernels (spec.py)
+    # ------------------------------------------------------------------------------------------
+    def prepare_describe(self, injected: bool):
+        """Bind every buffer the way a real step does, so that the slab plan can be described."""
+        if injected:
+            draws = {"max_len": torch.zeros(self.N, device=self.device)}
+            for k, mgr in enumerate(self.commands):
+                draws[f"cmd_step{k}"] = torch.zeros_like(mgr._command)
+                draws[f"cmd_reset{k}"] = torch.zeros_like(mgr._command)
+            for g, om in enumerate(self.observations):
+                draws[f"obs_noise{g}"] = torch.zeros((self.N, om.frame_size), device=self.device)
+            self.inject(draws)
+        else:
+            self.inject(None)
+        self._engine_buffers()
+        self._obs_buffers()
+        self._injection_buffers()
+        self._set_program(force=True)
+
+    def _maybe_specialise(self, phases: int):
+        """Attach the specialised kernel for the current table structure (once per structure)."""
+        from . import spec
+
+        if spec.disabled() or self.dry_run:
+            return
+        tag = (self._fingerprint_structure(), self.injected is not None, phases)
+        if tag in self._spec_tried:
+            return
+        self._spec_tried.add(tag)
+        try:
+            path = spec.ensure(self, phases)
+            if path is not None:
+                spec.attach(self, path)
+                self.spec_paths.append(path)
+        except Exception as e:  # a failed specialisation is not fatal: the generic kernel runs
+            print(f"[genesis_forge_b200] kernel specialisation skipped: {e}")
+
+    def _fingerprint_structure(self):
+        """Cheap proxy for 'the table structure may have changed' (exact matching is done in C)."""
+        return (
+            tuple(item.weight == 0 for _, item, _ in self.reward_terms),
+            tuple(item.version for _, item, _ in self.reward_terms),
+            tuple(item.version for _, item, _ in self.termination_terms),
+            tuple(m._external_controller is None for m in self.commands),
+            self._contact_dims,
+        )
+
+    def spec_stats(self) -> dict:
+        a, b = C.c_int64(), C.c_int64()
+        self.lib.gfb_spec_stats(self.handle.ptr, C.byref(a), C.byref(b))
+        return {"specialised_launches": a.value, "generic_launches": b.value, "libraries": [p.name for p in self.spec_paths]}
+
     def post_physics(self, phases: int) -> nat.Report:
         self._engine_buffers()
         self._obs_buffers()
         self._injection_buffers()
         self._set_program()
+        if phases == nat.K["GFB_PHASE_ALL"]:
+            self._maybe_specialise(phases)
         stream = self._stream()
         self.handle.check(
             self.lib.gfb_post_physics(self.handle.ptr, C.byref(self.buffers), phases, stream), "gfb_post_physics"

@@ -179,6 +179,7 @@ class ManagedEnvironment(GenesisEnv):
         if fused is None:
             raise RuntimeError("build() the environment before stepping it")
         self._begin_step()
+        fused.begin_step()
         if self._actions is None:
             self._allocate_action_buffers(actions.shape[1])
             fused.bind_action_buffers()
@@ -277,6 +278,7 @@ class ManagedEnvironment(GenesisEnv):
             self._allocate_action_buffers(self.action_space.shape[0])
             fused.bind_action_buffers()
         K = nat.K
+        fused.begin_step()
         mask = None
         if env_ids is not None:
             env_ids = torch.as_tensor(env_ids, device=gs.device, dtype=torch.int64)
@@ -303,6 +305,7 @@ class ManagedEnvironment(GenesisEnv):
         if "observations" not in self.extras:
             self.extras["observations"] = make_obs_dict(gs.device)
         fused = self._fused
+        fused.begin_step()
         # shift history (observation_manager.py:223-226), then frame 0 for every env
         for om in self.managers["observation"]:
             cur, nxt = om._buffers[om._current], om._buffers[1 - om._current]

@@ -301,7 +301,8 @@ typedef struct {
 
 typedef struct gfb_handle gfb_handle;
 
-/* Create a handle for `num_envs` environments on CUDA device `device`. */
+/* Create a handle for `num_envs` environments on CUDA device `device`.  device < 0 creates a
+ * host-only handle (no CUDA calls): it accepts gfb_set_program / gfb_spec_describe only.        */
 int gfb_create(int32_t num_envs, int32_t device, gfb_handle** out);
 void gfb_destroy(gfb_handle* h);
 const char* gfb_last_error(const gfb_handle* h);
@@ -355,6 +356,25 @@ int gfb_contact_forces(gfb_handle* h, const float* force, const float* position,
  * vec (n,3), quat (n,4) w-first, out (n,3).                                                     */
 int gfb_rotate(gfb_handle* h, const float* vec, const float* quat, float* out, int32_t n, int32_t conjugate,
                void* stream);
+
+/* ---- compile-time specialisation of the fused kernel -------------------------------------------
+ * The fused post-physics kernel is an interpreter over the packed term table.  For a given table
+ * STRUCTURE (opcodes, manager indices, flags, widths, link ids, observation layout -- everything
+ * except live values such as weights, thresholds, ranges, dt) and slab plan, the same source can be
+ * compiled with the structure as compile-time constants (genesis_forge_b200/spec.py generates the
+ * header and runs nvcc; results are cached as genesis_forge_b200/_spec/spec_<hash>.so).
+ *   gfb_spec_describe  structure of the CURRENT program for `phases`: the program head with every
+ *                      live value zeroed (sizeof(gfb_program_head) bytes), the slab plan as int32
+ *                      words (returns their count via *plan_words; capacity in plan_cap), the slab
+ *                      size.  Works on a host-only handle (gfb_create with device < 0).
+ *   gfb_spec_attach    load a specialised kernel library; it is used by gfb_post_physics whenever
+ *                      its structure, plan, slab size and phases match the launch, otherwise the
+ *                      generic kernel runs.  path == NULL detaches everything.                  */
+int gfb_spec_describe(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void* canonical_head,
+                      int32_t* plan_out, int32_t plan_cap, int32_t* plan_words, int32_t* tile);
+int gfb_spec_attach(gfb_handle* h, const char* path);
+/* number of gfb_post_physics launches so far that ran a specialised / the generic kernel */
+int gfb_spec_stats(const gfb_handle* h, int64_t* specialised, int64_t* generic);
 
 /* Timing instrumentation: when enabled, each launch of gfb_post_physics' fused kernel is bracketed
  * by CUDA events on its stream; gfb_profile_read returns the accumulated device time.          */

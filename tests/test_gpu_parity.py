@@ -13,13 +13,50 @@ CONFIGS = ["simple", "command_direction", "contacts", "rough_terrain", "berkeley
 
 @pytest.mark.parametrize("name", CONFIGS)
 def test_step_parity(name, cuda_device):
+    """Default path: the specialised kernel for the config's table structure."""
     from oracle.parity import ParityRun
 
     run = ParityRun(name, num_envs=256, device=cuda_device, seed=1234)
     stats = run.run(steps=120, nan_step=7)
     assert stats["steps"] == 120
     assert stats["resets"] > 0
-    print(name, stats)
+    spec_stats = run.env._fused.spec_stats()
+    assert spec_stats["specialised_launches"] == 120 and spec_stats["generic_launches"] == 0, spec_stats
+    print(name, stats, spec_stats)
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_step_parity_generic_interpreter(name, cuda_device, monkeypatch):
+    """Same run through the generic (interpreting) kernel: what runs when no specialisation exists."""
+    from oracle.parity import ParityRun
+
+    monkeypatch.setenv("GFB_NO_SPEC", "1")
+    run = ParityRun(name, num_envs=256, device=cuda_device, seed=1234)
+    stats = run.run(steps=60, nan_step=7)
+    assert stats["resets"] > 0
+    spec_stats = run.env._fused.spec_stats()
+    assert spec_stats["specialised_launches"] == 0 and spec_stats["generic_launches"] == 60
+
+
+def test_live_mutation_keeps_the_specialised_kernel(cuda_device):
+    """Weights / params / ranges are live values: mutating them must not need a new specialisation."""
+    from oracle.parity import ParityRun
+
+    run = ParityRun("command_direction", num_envs=64, device=cuda_device, seed=3)
+    run.reset()
+    for i in range(10):
+        run.step()
+    for env_like in (run.env,):
+        env_like.reward_manager.cfg["lin_vel_z"].weight = -4.0
+        env_like.reward_manager.cfg["base_height_target"].params["target_height"] = 0.33
+        env_like.velocity_command.range = {"lin_vel_x": [0.0, 2.0], "lin_vel_y": [-0.5, 0.5], "ang_vel_z": [-1.0, 1.0]}
+    run.port.spec["rewards"]["lin_vel_z"]["weight"] = -4.0
+    run.port.spec["rewards"]["base_height_target"]["params"]["target_height"] = 0.33
+    run.port.command["velocity_command"]["range"] = {"lin_vel_x": [0.0, 2.0], "lin_vel_y": [-0.5, 0.5], "ang_vel_z": [-1.0, 1.0]}
+    for i in range(20):
+        run.step()
+    stats = run.env._fused.spec_stats()
+    assert stats["generic_launches"] == 0 and len(stats["libraries"]) == 1, stats
 
 
 @pytest.mark.parametrize("name", ["command_direction", "berkeley_humanoid"])
