@@ -134,17 +134,20 @@ def time_dropin(env, actions, steps, warmup, dist_on):
     for i in range(warmup):
         env.step(actions[i % len(actions)])
     torch.cuda.synchronize(dev)
+    env._fused.profile(True)  # per-kernel CUDA events only inside the timed region
     if dist_on:
         dist.barrier()
     torch.cuda.synchronize(dev)
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_reset = 0
+    launches0 = env._fused.launch_count()
     start.record()
     for i in range(steps):
         env.step(actions[i % len(actions)])
         n_reset += env._fused.report.n_reset
     end.record()
     torch.cuda.synchronize(dev)
+    env.timed_launches = env._fused.launch_count() - launches0
     if dist_on:
         dist.barrier()
     ms = start.elapsed_time(end) / steps
@@ -305,12 +308,10 @@ def run_b200(args, rank, local_rank, world):
     actions = [a.to(dev) for a in actions_host]
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    launches0 = fused.launch_count()
-    fused.profile(True)
     ms, resets_per_step = time_dropin(env, actions, args.steps, args.warmup, dist_on)
     prof = fused.profile_read()
     fused.profile(False)
-    launches = fused.launch_count() - launches0
+    launches = env.timed_launches
     clocks = sampler.stop() if sampler else None
 
     value = N * world / (ms / 1e3)
@@ -335,7 +336,6 @@ def run_b200(args, rank, local_rank, world):
                 continue
             small = make_dropin_env(spec, n_small, dev, max(args.pool, 4), seed)
             acts = [torch.randn(n_small, fused.D, device=dev) for _ in range(4)]
-            small._fused.profile(True)
             ms_s, _ = time_dropin(small, acts, max(args.steps, 100), max(args.warmup, 10), False)
             p = small._fused.profile_read()
             sweep[str(n_small)] = {
@@ -376,6 +376,7 @@ def run_b200(args, rank, local_rank, world):
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": launches,
+            "kernel_variant": fused.spec_stats(),
             "clocks": clocks,
             "sweep": sweep,
         }

@@ -21,7 +21,8 @@ def test_step_parity(name, cuda_device):
     assert stats["steps"] == 120
     assert stats["resets"] > 0
     spec_stats = run.env._fused.spec_stats()
-    assert spec_stats["specialised_launches"] == 120 and spec_stats["generic_launches"] == 0, spec_stats
+    # (the two generic launches are the build-time entity phase and the initial reset phase)
+    assert spec_stats["specialised_launches"] == 120 and spec_stats["generic_launches"] == 2, spec_stats
     print(name, stats, spec_stats)
 
 
@@ -35,7 +36,7 @@ def test_step_parity_generic_interpreter(name, cuda_device, monkeypatch):
     stats = run.run(steps=60, nan_step=7)
     assert stats["resets"] > 0
     spec_stats = run.env._fused.spec_stats()
-    assert spec_stats["specialised_launches"] == 0 and spec_stats["generic_launches"] == 60
+    assert spec_stats["specialised_launches"] == 0 and spec_stats["generic_launches"] == 62
 
 
 def test_live_mutation_keeps_the_specialised_kernel(cuda_device):
@@ -56,7 +57,7 @@ def test_live_mutation_keeps_the_specialised_kernel(cuda_device):
     for i in range(20):
         run.step()
     stats = run.env._fused.spec_stats()
-    assert stats["generic_launches"] == 0 and len(stats["libraries"]) == 1, stats
+    assert stats["generic_launches"] == 2 and stats["specialised_launches"] == 30 and len(stats["libraries"]) == 1, stats
 
 
 @pytest.mark.parametrize("name", ["command_direction", "berkeley_humanoid"])
