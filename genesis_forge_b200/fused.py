@@ -708,7 +708,7 @@ class FusedStep:
         self._spec_tried.add(tag)
         try:
             path = spec.ensure(self, phases)
-            if path is not None:
+            if path is not None and path not in self.spec_paths:
                 spec.attach(self, path)
                 self.spec_paths.append(path)
         except Exception as e:  # a failed specialisation is not fatal: the generic kernel runs
