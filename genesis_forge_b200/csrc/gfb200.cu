@@ -699,8 +699,7 @@ int gfb_set_program(gfb_handle* h, const gfb_program* program) {
                         (t.op == GFB_R_BASE_HEIGHT && (t.flags & GFB_RF_TARGET_FROM_COMMAND));
     if (cmd_op && (t.mgr < 0 || t.mgr >= P.n_command)) return fail(h, GFB_ERR_INVALID, "reward: bad command manager");
     if (t.op == GFB_R_FEET_AIR_TIME && t.i0 >= P.n_command) return fail(h, GFB_ERR_INVALID, "feet_air_time: bad command manager");
-    if (t.op == GFB_R_BODY_ACC_EXP || t.op == GFB_R_EXTERNAL)
-      return fail(h, GFB_ERR_UNSUPPORTED, "reward op not implemented in this build");
+    if (t.op == GFB_R_EXTERNAL) return fail(h, GFB_ERR_UNSUPPORTED, "reward op not implemented in this build");
   }
   for (int t = 0; t < P.n_termination; ++t) {
     const gfb_termination_term& tt = P.termination[t];
@@ -795,6 +794,7 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
     const gfb_reward_term& t = P.reward[r];
     if (t.op == GFB_R_ACTION_RATE && !need(GFB_B_ACTION_RATE, "ACTION_RATE")) return GFB_ERR_INVALID;
     if (t.op == GFB_R_FEET_SLIDE && !need(GFB_B_LINKS_VEL, "LINKS_VEL")) return GFB_ERR_INVALID;
+    if (t.op == GFB_R_BODY_ACC_EXP && !need(GFB_B_BODY_ACC_PREV, "BODY_ACC_PREV")) return GFB_ERR_INVALID;
     if ((t.flags & GFB_RF_FIXED_COMMAND) && (t.op == GFB_R_TRACK_LIN_VEL || t.op == GFB_R_TRACK_ANG_VEL) &&
         !need(GFB_B_FIXED_COMMAND, "FIXED_COMMAND"))
       return GFB_ERR_INVALID;

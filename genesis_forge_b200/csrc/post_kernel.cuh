@@ -507,6 +507,24 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
         case GFB_R_ACTION_RATE:
           v = action_rate;
           break;
+        case GFB_R_BODY_ACC_EXP: {
+          // rewards.py:196-249: 1 - exp(-s * (|d lin_b / dt| + |d ang_b / dt|)); previous body-frame
+          // velocities are term state that is NOT cleared on reset; the first evaluation sees zeros
+          float* prev = GFB_BUF(float, GFB_B_BODY_ACC_PREV) + (size_t)e * 6;
+          float ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+          if (rt.p[1] != 0.0f) {
+            ax = fdiv(sub(lin_b.x, prev[0]), P.env_dt); ay = fdiv(sub(lin_b.y, prev[1]), P.env_dt);
+            az = fdiv(sub(lin_b.z, prev[2]), P.env_dt);
+            bx = fdiv(sub(ang_b.x, prev[3]), P.env_dt); by = fdiv(sub(ang_b.y, prev[4]), P.env_dt);
+            bz = fdiv(sub(ang_b.z, prev[5]), P.env_dt);
+          }
+          if (active) {
+            prev[0] = lin_b.x; prev[1] = lin_b.y; prev[2] = lin_b.z;
+            prev[3] = ang_b.x; prev[4] = ang_b.y; prev[5] = ang_b.z;
+          }
+          const float motion = add(norm3(ax, ay, az), norm3(bx, by, bz));
+          v = sub(1.0f, expf(mul(-rt.p[0], motion)));
+        } break;
         case GFB_R_TRACK_LIN_VEL:
         case GFB_R_TRACK_ANG_VEL: {
           float c0, c1, c2;

@@ -132,11 +132,17 @@ class FusedStep:
         self._dof_force_used = None
         self.global_acc = None
         self._acc_host = None
+        self._log_stream = None
+        self._log_event = None
+        self._log_pending = False
         self._stream_ptr = None
         self._program_pushed = False
         self._injected_bound = object()
         self._spec_tried: set = set()
         self.spec_paths: list = []
+        self._body_acc_prev = None
+        self._body_acc_started: dict[str, bool] = {}
+        self._body_acc_terms: set = set()
         self.global_num_envs = self.N
         self._compile()
 
@@ -197,6 +203,8 @@ class FusedStep:
     @staticmethod
     def _opcode_of(fn, kind: str, name: str) -> int:
         target = getattr(fn, "__func__", fn)
+        if not hasattr(target, "gfb_opcode") and hasattr(type(target), "gfb_opcode"):
+            target = type(target)  # instance of a class-style term (MdpFnClass)
         opcode = getattr(target, "gfb_opcode", None)
         if opcode is None or getattr(target, "gfb_kind", None) != kind:
             mod = getattr(target, "__module__", "?")
@@ -281,7 +289,7 @@ class FusedStep:
     # ------------------------------------------------------------------------------------------
     def _live_fingerprint(self):
         fp = [self.env.dt, self.env._base_max_episode_length, self.env._max_episode_random_scaling,
-              self.injected is not None, self.rng_seed]
+              self.injected is not None, self.rng_seed, tuple(sorted(self._body_acc_started.items()))]
         for _, item, _ in self.reward_terms:
             fp.append(item.weight)
             fp.append(item.version)
@@ -403,6 +411,14 @@ class FusedStep:
             sig = getattr(item.fn, "gfb_signature", None) or item.fn.__func__.gfb_signature
             p = sig(env, **item.params)
             what = f"reward '{name}'"
+            if opcode == K["GFB_R_BODY_ACC_EXP"]:
+                self._entity_ok(p, what)
+                t.p[0] = p["sensitivity"]
+                t.p[1] = 1.0 if self._body_acc_started.get(name, False) else 0.0
+                if self._body_acc_prev is None:
+                    self._body_acc_prev = torch.zeros((self.N, 6), device=self.device)
+                self._set(K["GFB_B_BODY_ACC_PREV"], self._body_acc_prev)
+                self._body_acc_terms.add(name)
             if opcode in (K["GFB_R_LIN_VEL_Z"], K["GFB_R_ANG_VEL_XY"], K["GFB_R_FLAT_ORIENTATION"],
                           K["GFB_R_TRACK_LIN_VEL"], K["GFB_R_TRACK_ANG_VEL"], K["GFB_R_BASE_HEIGHT"]):
                 self._entity_ok(p, what)
@@ -736,19 +752,21 @@ class FusedStep:
         self._set_program()
         if phases == nat.K["GFB_PHASE_ALL"]:
             self._maybe_specialise(phases)
+            self._after_launch_started = [
+                name for name in self._body_acc_terms
+                if not self._body_acc_started.get(name, False) and self.reward.cfg[name].weight != 0
+            ]
         stream = self._stream()
         self.handle.check(
             self.lib.gfb_post_physics(self.handle.ptr, C.byref(self.buffers), phases, stream), "gfb_post_physics"
         )
         if self.dist is not None:
-            # global (all-rank) fire counts / reset count decide which logging keys exist on every rank;
-            # the copy rides on the same stream sync as the report read-back
             self._allreduce_logging()
-            if self._acc_host is None:
-                self._acc_host = torch.empty_like(self.log_acc, device="cpu").pin_memory()
-            self._acc_host.copy_(self.log_acc, non_blocking=True)
         self.handle.check(self.lib.gfb_read_report(self.handle.ptr, C.byref(self.report), stream), "gfb_read_report")
-        self.global_acc = self._acc_host.tolist() if self.dist is not None else None
+        self.global_acc = None
+        if phases == nat.K["GFB_PHASE_ALL"]:
+            for name in self._after_launch_started:  # the term now has a previous velocity to difference
+                self._body_acc_started[name] = True
         return self.report
 
     def observe(self, idx: torch.Tensor | None, n: int):
@@ -792,10 +810,33 @@ class FusedStep:
     # multi-GPU logging
     # ------------------------------------------------------------------------------------------
     def _allreduce_logging(self):
-        """Sum per-term partials over ranks so that logged means are global."""
+        """
+        Sum per-term partials over ranks so that logged means are global.  The
+        collective and its read-back run on a side stream: nothing on the step's critical path (the
+        local reset count, the reset fan-out, the re-observation) depends on them, so their latency
+        overlaps that work; `finish_logging()` joins before the extras are published.
+        """
         import torch.distributed as dist
 
-        dist.all_reduce(self.log_acc, op=dist.ReduceOp.SUM, group=self.dist)
+        main = torch.cuda.current_stream(self.device)
+        if self._log_stream is None:
+            self._log_stream = torch.cuda.Stream(self.device)
+            self._log_event = torch.cuda.Event()
+            self._acc_host = torch.empty_like(self.log_acc, device="cpu").pin_memory()
+        self._log_stream.wait_stream(main)
+        with torch.cuda.stream(self._log_stream):
+            dist.all_reduce(self.log_acc, op=dist.ReduceOp.SUM, group=self.dist)
+            self._acc_host.copy_(self.log_acc, non_blocking=True)
+            self._log_event.record(self._log_stream)
+        self._log_pending = True
+
+    def finish_logging(self):
+        """Join the side-stream all-reduce of this step (no-op when envs are not sharded)."""
+        if self._log_pending:
+            self._log_event.synchronize()
+            torch.cuda.current_stream(self.device).wait_stream(self._log_stream)  # log_acc is rewritten next step
+            self.global_acc = self._acc_host.tolist()
+            self._log_pending = False
 
     def launch_count(self) -> int:
         return int(self.lib.gfb_launch_count(self.handle.ptr))

@@ -188,13 +188,14 @@ class ManagedEnvironment(GenesisEnv):
         fused.action_step(actions)
         self.scene.step()
         report = fused.post_physics(nat.K["GFB_PHASE_ALL"])
-        self._publish(report, step=True)
 
         n_reset = report.n_reset
         if n_reset > 0:
             reset_idx = fused.reset_idx[:n_reset]
             self._host_reset(reset_idx)
             fused.observe(reset_idx, n_reset)
+        fused.finish_logging()  # sharded envs: joins the logging all-reduce issued on a side stream
+        self._publish(report, step=True)
 
         obs = None
         for om in self.managers["observation"]:
@@ -288,6 +289,7 @@ class ManagedEnvironment(GenesisEnv):
         self._reset_mask_keep = mask
         if env_ids is None or env_ids.numel() > 0:
             report = fused.post_physics(K["GFB_PHASE_RESET"] | K["GFB_PHASE_FORCED_RESET"])
+            fused.finish_logging()
             self._publish(report, step=False)
             self._host_reset(env_ids)
         obs = None

@@ -5,6 +5,7 @@ lives in csrc/post_kernel.cuh under the opcode named in the decorator.
 """
 from __future__ import annotations
 
+from ..managers.config import MdpFnClass
 from ._term import term
 
 
@@ -109,3 +110,30 @@ def feet_air_time(env, contact_manager, time_threshold, time_threshold_max=None,
 def feet_slide(env, contact_manager, entity_attr="robot"):
     """Speed of tracked links while they are in contact (rewards.py:472-504)."""
     return dict(contact_manager=contact_manager, entity_attr=entity_attr)
+
+
+class body_acceleration_exp(MdpFnClass):
+    """
+    Penalise jerky body motion: 1 - exp(-sensitivity * (|d v_body / dt| + |d w_body / dt|))
+    (rewards.py:196-249).  A class-style term: it keeps the previous step's body-frame velocities,
+    which are not cleared on reset; its first evaluation sees zero acceleration.  Evaluated by the
+    kernel (opcode GFB_R_BODY_ACC_EXP); the state lives in a (N,6) tensor owned by the fused step.
+    As in the reference an `entity_manager` is required (the reference's `entity_attr` path reads an
+    attribute it never sets).
+    """
+
+    gfb_kind = "reward"
+    gfb_opcode = "GFB_R_BODY_ACC_EXP"
+
+    def __init__(self, env, entity_attr="robot", entity_manager=None, sensitivity=0.10):
+        super().__init__(env)
+        self.evaluations = 0
+
+    @staticmethod
+    def gfb_signature(env, entity_attr="robot", entity_manager=None, sensitivity=0.10):
+        if entity_manager is None:
+            raise AttributeError("'body_acceleration_exp' object has no attribute '_entity_attr'")
+        return dict(entity_attr=entity_attr, entity_manager=entity_manager, sensitivity=sensitivity)
+
+    def __call__(self, env, entity_attr="robot", entity_manager=None, sensitivity=0.10):
+        return env._fused.evaluate_single_term("reward", self, self.gfb_signature(env, entity_attr, entity_manager, sensitivity))

@@ -40,6 +40,7 @@ class PortEnv:
         self.margins: list[tuple[str, torch.Tensor, float]] = []  # (what, value, threshold)
         self.record_margins = record_margins
         self.printed: list[str] = []
+        self.body_acc_state: dict[str, dict] = {}
 
         # genesis_env.py:60-93
         self.extras = {"episode": {}}
@@ -514,7 +515,7 @@ class PortEnv:
     def _resolve_cmd(self, ref: str) -> torch.Tensor:
         return self.command[ref[1:]]["command"]
 
-    def _reward_value(self, fn: str, p: dict) -> torch.Tensor:
+    def _reward_value(self, fn: str, p: dict, name: str = "") -> torch.Tensor:
         if fn == "is_alive":  # :31-37
             return (~self.extras["terminations"]).float().detach()
         if fn == "terminated":  # :40-46
@@ -537,6 +538,20 @@ class PortEnv:
             return torch.sum(torch.square(self._ang_vel(self._cached(p))[:, :2]), dim=1)
         if fn == "flat_orientation_l2":  # :164-193
             return torch.sum(torch.square(self._gravity(self._cached(p))[:, :2]), dim=1)
+        if fn == "body_acceleration_exp":  # :196-249 (class-style term with state, not cleared on reset)
+            state = self.body_acc_state.setdefault(name, {})
+            curr_lin = self._lin_vel(True)
+            curr_ang = self._ang_vel(True)
+            if "prev_lin" in state:
+                lin_acc = (curr_lin - state["prev_lin"]) / self.dt
+                ang_acc = (curr_ang - state["prev_ang"]) / self.dt
+            else:
+                lin_acc = torch.zeros_like(curr_lin)
+                ang_acc = torch.zeros_like(curr_ang)
+            state["prev_lin"] = curr_lin.clone()
+            state["prev_ang"] = curr_ang.clone()
+            pelvis_motion = torch.norm(lin_acc, dim=-1) + torch.norm(ang_acc, dim=-1)
+            return 1 - torch.exp(-p.get("sensitivity", 0.10) * pelvis_motion)
         if fn == "action_rate_l2":  # :257-271
             return torch.sum(torch.square(self.last_actions - self.actions), dim=1)
         if fn == "command_tracking_lin_vel":  # :279-317
@@ -600,7 +615,7 @@ class PortEnv:
             if item["weight"] == 0:
                 continue
             weight = item["weight"] * dt
-            value = self._reward_value(item["fn"], item.get("params") or {}) * weight
+            value = self._reward_value(item["fn"], item.get("params") or {}, name) * weight
             self.reward_buf += value
             self.episode_data[name] += value
         return self.reward_buf

@@ -330,6 +330,10 @@ def kitchen_sink() -> dict:
         },
         "feet_slide": {"fn": "feet_slide", "weight": -0.1, "params": {"contact_manager": "@foot_contact_manager"}},
         "zero_weight": {"fn": "lin_vel_z_l2", "weight": 0.0, "params": {"entity_manager": _EM}},
+        "body_acceleration": {
+            "fn": "body_acceleration_exp", "weight": -0.1,
+            "params": {"entity_manager": _EM, "sensitivity": 0.15},
+        },
     })
     s["terminations"].update({
         "too_low": {"fn": "base_height_below_minimum", "params": {"minimum_height": 0.24, "entity_manager": _EM}},
