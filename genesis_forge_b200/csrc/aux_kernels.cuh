@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinalizePar
     if (F.phases & GFB_PHASE_TERMINATION)
       for (int t = tid; t < nt; t += FIN_THREADS) acc += F.s.tile_term_count[(size_t)k * nt + t];
     acc = block_sum<int>(acc, s_iwarp);
-    if (tid == 0) {
+    if (tid == 0 && (F.phases & GFB_PHASE_TERMINATION)) {  // split execution: later launches keep the counts
       rep->termination_count[k] = acc;
       if (F.log_out) F.log_out[F.n_reward + k] = fdiv((float)acc, (float)F.num_envs);
       if (F.log_acc) F.log_acc[F.n_reward + k] = (double)acc;
@@ -251,14 +251,14 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinalizePar
     if (F.phases & GFB_PHASE_RESET)
       for (int t = tid; t < nt; t += FIN_THREADS) acc += F.s.tile_rew_sum[(size_t)r * nt + t];
     acc = block_sum<double>(acc, s_dwarp);
-    if (tid == 0) {
+    if (tid == 0 && (F.phases & GFB_PHASE_RESET)) {
       const bool logged = (F.reward_weight_mask >> r) & 1u;
       const float mean = (n_reset > 0 && logged) ? (float)(acc / (double)n_reset) : 0.0f;
       rep->reward_episode_mean[r] = mean;
       if (F.log_out) F.log_out[r] = mean;
       if (F.log_acc) F.log_acc[r] = acc;
     }
-  } else if (tid == 0) {
+  } else if (tid == 0 && (F.phases & GFB_PHASE_RESET)) {
     rep->n_reset = n_reset;
     rep->status = atomicExch(F.s.status, 0u);
     if (F.log_acc) F.log_acc[F.n_reward + F.n_termination] = (double)n_reset;

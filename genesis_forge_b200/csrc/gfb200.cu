@@ -258,6 +258,7 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, i
           case GFB_O_TARGETS: buf = GFB_B_TARGETS; break;
           case GFB_O_ENV_ACTIONS: buf = GFB_B_ENV_ACTIONS; break;
           case GFB_O_DOF_POS: buf = GFB_B_DOF_POS; break;
+          case GFB_O_EXTERNAL: buf = GFB_B_OBS_EXT0; break;
           default: break;
         }
         if (buf < 0 || off_obs_src[buf] >= 0 || !b.buf[buf]) continue;
@@ -267,7 +268,8 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, i
         }
         // ENV_ACTIONS rows are zeroed for reset envs inside this kernel; staged copies would be stale
         if (buf == GFB_B_ENV_ACTIONS && (phases & GFB_PHASE_RESET)) continue;
-        off_obs_src[buf] = stage(buf, P.num_dofs, -1);
+        const int row_words = buf == GFB_B_OBS_EXT0 ? prog.obs_cols[P.obs_group[g].col_begin + c].mgr : P.num_dofs;
+        off_obs_src[buf] = stage(buf, row_words, -1);
         if (buf == GFB_B_DOF_POS) plan.off_dof_pos = off_obs_src[buf];
       }
   }
@@ -364,6 +366,10 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, i
         if (oc.mgr < 0 || oc.mgr >= P.n_contact) return fail(h, GFB_ERR_INVALID, "obs: bad contact manager");
         d.kind = 3;
         d.a = plan.st_cnorm[oc.mgr] + oc.col;
+        break;
+      case GFB_O_EXTERNAL:
+        if (oc.mgr <= 0) return fail(h, GFB_ERR_INVALID, "obs: external column needs its array width in mgr");
+        global_src(GFB_B_OBS_EXT0, oc.mgr);
         break;
       case GFB_O_ZERO:
         d.kind = 0;
@@ -699,13 +705,13 @@ int gfb_set_program(gfb_handle* h, const gfb_program* program) {
                         (t.op == GFB_R_BASE_HEIGHT && (t.flags & GFB_RF_TARGET_FROM_COMMAND));
     if (cmd_op && (t.mgr < 0 || t.mgr >= P.n_command)) return fail(h, GFB_ERR_INVALID, "reward: bad command manager");
     if (t.op == GFB_R_FEET_AIR_TIME && t.i0 >= P.n_command) return fail(h, GFB_ERR_INVALID, "feet_air_time: bad command manager");
-    if (t.op == GFB_R_EXTERNAL) return fail(h, GFB_ERR_UNSUPPORTED, "reward op not implemented in this build");
+
   }
   for (int t = 0; t < P.n_termination; ++t) {
     const gfb_termination_term& tt = P.termination[t];
     const bool contact_op = tt.op == GFB_T_HAS_CONTACT || tt.op == GFB_T_CONTACT_FORCE || tt.op == GFB_T_CONTACT_FORCE_GRACE;
     if (contact_op && (tt.mgr < 0 || tt.mgr >= P.n_contact)) return fail(h, GFB_ERR_INVALID, "termination: bad contact manager");
-    if (tt.op == GFB_T_EXTERNAL) return fail(h, GFB_ERR_UNSUPPORTED, "termination op not implemented in this build");
+
   }
   h->prog = *program;
   h->has_prog = true;
@@ -795,6 +801,7 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
     if (t.op == GFB_R_ACTION_RATE && !need(GFB_B_ACTION_RATE, "ACTION_RATE")) return GFB_ERR_INVALID;
     if (t.op == GFB_R_FEET_SLIDE && !need(GFB_B_LINKS_VEL, "LINKS_VEL")) return GFB_ERR_INVALID;
     if (t.op == GFB_R_BODY_ACC_EXP && !need(GFB_B_BODY_ACC_PREV, "BODY_ACC_PREV")) return GFB_ERR_INVALID;
+    if (t.op == GFB_R_EXTERNAL && !need(GFB_B_EXT_VALUES, "EXT_VALUES")) return GFB_ERR_INVALID;
     if ((t.flags & GFB_RF_FIXED_COMMAND) && (t.op == GFB_R_TRACK_LIN_VEL || t.op == GFB_R_TRACK_ANG_VEL) &&
         !need(GFB_B_FIXED_COMMAND, "FIXED_COMMAND"))
       return GFB_ERR_INVALID;

@@ -395,6 +395,9 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
           for (int l = 0; l < SP.contact[ts.mgr].n_links; ++l) any |= st[plan.st_cnorm[ts.mgr] + l] > tt.p[0];
           v = any && (ts.op == GFB_T_CONTACT_FORCE || !(ep_len <= ts.i0));
         } break;
+        case GFB_T_EXTERNAL:  // user-defined term evaluated on the host before this launch
+          v = GFB_BUF(const float, GFB_B_EXT_VALUES)[(size_t)ts.i0 * N + e] != 0.0f;
+          break;
         default:
           break;
       }
@@ -572,8 +575,8 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
             v = add(v, mul(speed, st[plan.st_cnorm[rs.mgr] + l] > 1.0f ? 1.0f : 0.0f));
           }
         } break;
-        case GFB_R_EXTERNAL:
-          v = GFB_BUF(const float, GFB_B_OBS_EXT3)[(size_t)e * GFB_MAX_REWARD_TERMS + rs.ext_col];
+        case GFB_R_EXTERNAL:  // user-defined term evaluated on the host before this launch
+          v = GFB_BUF(const float, GFB_B_EXT_VALUES)[(size_t)rs.ext_col * N + e];
           break;
         default:
           break;

@@ -76,8 +76,7 @@ def asin_tilt_threshold(limit_angle_deg: float) -> float:
     return float(np.array([hi], dtype=np.int32).view(np.float32)[0])
 
 
-class UnsupportedTermError(NotImplementedError):
-    pass
+from .managers.observation import UnsupportedTermError  # noqa: E402  (one class, importable from here too)
 
 
 def combine_logging(acc: torch.Tensor, n_reward: int, n_termination: int, global_num_envs: int) -> torch.Tensor:
@@ -99,7 +98,7 @@ def combine_logging(acc: torch.Tensor, n_reward: int, n_termination: int, global
 
 
 class FusedStep:
-    def __init__(self, env, dry_run: bool = False):
+    def __init__(self, env, dry_run: bool = False, compile_now: bool = True):
         """`dry_run` compiles and packs the term table without a device (host-logic tests only)."""
         self.env = env
         self.device = torch.device(gs.device)
@@ -143,8 +142,13 @@ class FusedStep:
         self._body_acc_prev = None
         self._body_acc_started: dict[str, bool] = {}
         self._body_acc_terms: set = set()
+        self.entities = list(env.managers["entity"])
+        self.entity_manager = self.entities[0] if self.entities else None
+        if self.entity_manager is None:
+            self._inv_base_quat = torch.zeros((self.N, 4), device=self.device)
         self.global_num_envs = self.N
-        self._compile()
+        if compile_now:
+            self._compile()
 
     # ------------------------------------------------------------------------------------------
     # compile: static structure
@@ -184,35 +188,66 @@ class FusedStep:
         self.n_reward, self.n_termination = n_r, n_t
         self.log_out = torch.zeros(max(n_r + n_t, 1), device=dev)
         self.log_acc = torch.zeros(n_r + n_t + 1, device=dev, dtype=torch.float64)
-        # entity cache tensors when there is no EntityManager to own them
-        if self.entity_manager is None:
-            self._inv_base_quat = torch.zeros((N, 4), device=dev)
         self._fixed_command = None
         self._fixed_command_parts = None
-        # terms
+        # terms.  Functions that are not mdp descriptors are user-defined: they stay Python callbacks
+        # whose (N,) result is handed to the kernel as a row of the external-values buffer, and the step
+        # runs in split mode (see ManagedEnvironment._step_split).
         self.reward_terms = []
+        self.external_rows: list[tuple[str, str, object]] = []  # (kind, name, config item)
         if self.reward is not None:
             for name, item in self.reward.cfg.items():
-                self.reward_terms.append((name, item, self._opcode_of(item.fn, "reward", name)))
+                opcode = self._opcode_of(item.fn, "reward")
+                if opcode is None:
+                    opcode = nat.K["GFB_R_EXTERNAL"]
+                    self.external_rows.append(("reward", name, item))
+                self.reward_terms.append((name, item, opcode))
         self.termination_terms = []
         if self.termination is not None:
             for name, item in self.termination.term_cfg.items():
-                self.termination_terms.append((name, item, self._opcode_of(item.fn, "termination", name)))
+                opcode = self._opcode_of(item.fn, "termination")
+                if opcode is None:
+                    opcode = nat.K["GFB_T_EXTERNAL"]
+                    self.external_rows.append(("termination", name, item))
+                self.termination_terms.append((name, item, opcode))
+        self.ext_values = None
+        if self.external_rows:
+            self.ext_values = torch.zeros((len(self.external_rows), N), device=dev)
+        self.ext_row = {(kind, name): j for j, (kind, name, _) in enumerate(self.external_rows)}
+        # command managers with overridden behaviour are stepped / reset in Python
+        from .managers.command import CommandManager, VelocityCommandManager
+
+        def stock(mgr) -> bool:
+            cls = type(mgr)
+            for attr in ("step", "reset", "resample_command"):
+                if getattr(cls, attr) is not getattr(CommandManager, attr) and getattr(cls, attr) is not getattr(VelocityCommandManager, attr):
+                    return False
+            return True
+
+        self.python_commands = [m for m in self.commands if not stock(m)]
+        # user-defined observation terms: one (N, W) array filled on the host
+        self.external_obs: list[tuple[object, str, object, int, int]] = []  # (manager, name, item, col0, width)
+        width = 0
+        for om in self.observations:
+            for name, key, w in om._sources:
+                if isinstance(key, tuple) and key[0] == "external":
+                    self.external_obs.append((om, name, om.cfg[name], width, w))
+                    om._external_col0[name] = width
+                    width += w
+        self.ext_obs_width = width
+        self.ext_obs = torch.zeros((N, width), device=dev) if width else None
+        self.split_mode = bool(self.external_rows or self.python_commands or self.external_obs)
         self._static_buffers()
 
     @staticmethod
-    def _opcode_of(fn, kind: str, name: str) -> int:
+    def _opcode_of(fn, kind: str) -> int | None:
+        """Kernel opcode of an mdp descriptor, None for a user-defined function."""
         target = getattr(fn, "__func__", fn)
         if not hasattr(target, "gfb_opcode") and hasattr(type(target), "gfb_opcode"):
             target = type(target)  # instance of a class-style term (MdpFnClass)
         opcode = getattr(target, "gfb_opcode", None)
         if opcode is None or getattr(target, "gfb_kind", None) != kind:
-            mod = getattr(target, "__module__", "?")
-            raise UnsupportedTermError(
-                f"{kind} term '{name}': function {mod}.{getattr(target, '__name__', target)} is not one of the "
-                f"mdp.{kind}s functions of genesis_forge_b200; user-defined terms are not supported by the "
-                "fused step yet"
-            )
+            return None
         return nat.K[opcode]
 
     def _set(self, buf_id: int, tensor: torch.Tensor | None, dtype=None, keep: bool = False):
@@ -276,6 +311,8 @@ class FusedStep:
         for t in self.terrains:
             if t.height_field is not None:
                 s(K["GFB_B_HEIGHT_FIELD"], t.height_field)
+        s(K["GFB_B_EXT_VALUES"], self.ext_values)
+        s(K["GFB_B_OBS_EXT0"], self.ext_obs)
 
     def bind_action_buffers(self):
         K = nat.K
@@ -371,7 +408,7 @@ class FusedStep:
                 raise UnsupportedTermError("command manager with too many ranges")
             cm.n_dims = len(ranges)
             cm.resample_steps = mgr._resample_steps
-            cm.enabled = 1 if (mgr.enabled and mgr._external_controller is None) else 0
+            cm.enabled = 1 if (mgr.enabled and mgr._external_controller is None and mgr not in self.python_commands) else 0
             for i, (lo, hi) in enumerate(ranges):
                 cm.lo[i], cm.hi[i] = lo, hi
 
@@ -408,6 +445,9 @@ class FusedStep:
             t.weight = item.weight * env.dt  # reward_manager.py:184
             if not self.reward.enabled:
                 t.weight = 0.0
+            if opcode == K["GFB_R_EXTERNAL"]:
+                t.ext_col = self.ext_row[("reward", name)]
+                continue
             sig = getattr(item.fn, "gfb_signature", None) or item.fn.__func__.gfb_signature
             p = sig(env, **item.params)
             what = f"reward '{name}'"
@@ -482,6 +522,9 @@ class FusedStep:
         for i, (name, item, opcode) in enumerate(self.termination_terms):
             t = P.termination[i]
             t.op, t.mgr, t.time_out = opcode, -1, 1 if item.time_out else 0
+            if opcode == K["GFB_T_EXTERNAL"]:
+                t.i0 = self.ext_row[("termination", name)]
+                continue
             sig = getattr(item.fn, "gfb_signature", None) or item.fn.__func__.gfb_signature
             p = sig(env, **item.params)
             what = f"termination '{name}'"
@@ -530,6 +573,9 @@ class FusedStep:
                     oc.src, oc.mgr = K["GFB_O_COMMAND"], self._command_index(key[1], "observation")
                 elif isinstance(key, tuple) and key[0] == "contact_norm":
                     oc.src, oc.mgr = K["GFB_O_CONTACT_NORM"], self._contact_index(key[1], "observation")
+                elif isinstance(key, tuple) and key[0] == "external":
+                    oc.src, oc.mgr = K["GFB_O_EXTERNAL"], self.ext_obs_width
+                    oc.col = om._external_col0[key[1]] + c["col"]
                 elif key in src_of:
                     oc.src = src_of[key]
                 else:
@@ -745,7 +791,22 @@ class FusedStep:
         self.lib.gfb_spec_stats(self.handle.ptr, C.byref(a), C.byref(b))
         return {"specialised_launches": a.value, "generic_launches": b.value, "libraries": [p.name for p in self.spec_paths]}
 
-    def post_physics(self, phases: int) -> nat.Report:
+    def evaluate_external(self, kind: str):
+        """Run the user-defined reward / termination functions; their values become kernel inputs."""
+        for j, (k, name, item) in enumerate(self.external_rows):
+            if k != kind:
+                continue
+            if kind == "reward" and item.weight == 0:
+                continue  # reward_manager.py:181-182: zero-weight terms are not evaluated
+            value = item.fn(self.env, **item.params)
+            self.ext_values[j].copy_(value.reshape(self.N))
+
+    def evaluate_external_obs(self):
+        for om, name, item, col0, width in self.external_obs:
+            value = item.fn(env=self.env, **item.params)
+            self.ext_obs[:, col0:col0 + width].copy_(value.reshape(self.N, width))
+
+    def post_physics(self, phases: int, read_report: bool = True) -> nat.Report | None:
         self._engine_buffers()
         self._obs_buffers()
         self._injection_buffers()
@@ -760,6 +821,8 @@ class FusedStep:
         self.handle.check(
             self.lib.gfb_post_physics(self.handle.ptr, C.byref(self.buffers), phases, stream), "gfb_post_physics"
         )
+        if not read_report:
+            return None
         if self.dist is not None:
             self._allreduce_logging()
         self.handle.check(self.lib.gfb_read_report(self.handle.ptr, C.byref(self.report), stream), "gfb_read_report")

@@ -128,10 +128,11 @@ class ManagedEnvironment(GenesisEnv):
             for key, sentinel in self._tracing.items():
                 if result is sentinel:
                     if isinstance(key, str) and key.endswith("_uncached"):
-                        raise UnsupportedTermError(
-                            f"{what}: body-frame observations without an entity_manager are not supported by "
-                            "the fused step (pass entity_manager=...)"
-                        )
+                        # without an entity_manager the term inverts the CURRENT (post-reset) quaternion
+                        # (utils.py:13-55); it runs as a host-evaluated term through the rotation kernel
+                        err = UnsupportedTermError(f"{what}: body-frame term without an entity_manager")
+                        err.width = 3
+                        raise err
                     return key, sentinel.shape[1]
         finally:
             self._tracing = None
@@ -168,7 +169,10 @@ class ManagedEnvironment(GenesisEnv):
             entity_manager.build()
         for obs in M["observation"]:
             obs.build()
-        self._fused = FusedStep(self, dry_run=getattr(self, "_dry_run", False))
+        self._fused = FusedStep(self, dry_run=getattr(self, "_dry_run", False), compile_now=False)
+        for obs in M["observation"]:
+            obs.resolve_external()  # user-defined terms are evaluated once for their width (may use the library)
+        self._fused._compile()
         # EntityManager.build() caches the base pose once (entity_manager.py:157-167)
         if not self._fused.dry_run:
             self._fused.cache_entity()
@@ -187,6 +191,8 @@ class ManagedEnvironment(GenesisEnv):
 
         fused.action_step(actions)
         self.scene.step()
+        if fused.split_mode:
+            return self._finish_step_split()
         report = fused.post_physics(nat.K["GFB_PHASE_ALL"])
 
         n_reset = report.n_reset
@@ -197,6 +203,42 @@ class ManagedEnvironment(GenesisEnv):
         fused.finish_logging()  # sharded envs: joins the logging all-reduce issued on a side stream
         self._publish(report, step=True)
 
+        return self._step_outputs()
+
+    def _finish_step_split(self):
+        """
+        Post-physics part of a step when the configuration contains user-defined (Python) terms or
+        command managers with overridden behaviour.  The kernel phases run as separate launches with
+        the Python callbacks in between, in the reference's order (managed_env.py:294-326):
+            entity + contacts | user terminations | terminations | user rewards |
+            rewards + command resample + in-library reset | python command managers, engine reset |
+            user observation terms | observations of every env (taken after the reset, so no patch).
+        """
+        fused, K = self._fused, nat.K
+        term, rew = self.managers["termination"], self.managers["reward"]
+        fused.post_physics(K["GFB_PHASE_ENTITY"] | K["GFB_PHASE_CONTACT"], read_report=False)
+        fused.evaluate_external("termination")
+        fused.post_physics(K["GFB_PHASE_TERMINATION"], read_report=False)
+        if term is not None:
+            self.extras["terminations"] = term._terminated_buf
+            self.extras["time_outs"] = term._truncated_buf
+        fused.evaluate_external("reward")
+        report = fused.post_physics(K["GFB_PHASE_REWARD"] | K["GFB_PHASE_COMMAND"] | K["GFB_PHASE_RESET"])
+        for mgr in fused.python_commands:
+            mgr.step()
+        n_reset = report.n_reset
+        if n_reset > 0:
+            reset_idx = fused.reset_idx[:n_reset]
+            self._host_reset(reset_idx)
+            for mgr in fused.python_commands:
+                mgr.reset(reset_idx)
+        fused.evaluate_external_obs()
+        fused.post_physics(K["GFB_PHASE_OBSERVE"], read_report=False)
+        fused.finish_logging()
+        self._publish(report, step=True)
+        return self._step_outputs()
+
+    def _step_outputs(self):
         obs = None
         for om in self.managers["observation"]:
             om._current = 1 - om._current
@@ -292,6 +334,8 @@ class ManagedEnvironment(GenesisEnv):
             fused.finish_logging()
             self._publish(report, step=False)
             self._host_reset(env_ids)
+            for mgr in fused.python_commands:
+                mgr.reset(env_ids)
         obs = None
         if env_ids is None:
             self.extras.pop("observations", None)
@@ -314,6 +358,7 @@ class ManagedEnvironment(GenesisEnv):
             single = om.frame_size
             if om._history_len > 1:
                 nxt[:, single:] = cur[:, : single * (om._history_len - 1)]
+        fused.evaluate_external_obs()
         fused.observe(None, self.num_envs)
         policy = None
         for om in self.managers["observation"]:

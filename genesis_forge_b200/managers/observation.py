@@ -22,6 +22,10 @@ from .base import BaseManager
 from .config import ObservationConfigItem
 
 
+class UnsupportedTermError(NotImplementedError):
+    """A term configuration the fused step cannot execute."""
+
+
 class ObservationManager(BaseManager):
     def __init__(self, env, cfg: dict[str, dict], name: str = "policy", history_len: int | None = None, noise=None):
         super().__init__(env, "observation")
@@ -36,6 +40,7 @@ class ObservationManager(BaseManager):
         self._sources: list[tuple[str, tuple, int]] = []  # per term: (name, source key, width)
         self._buffers: list[torch.Tensor] = []            # ping-pong (N, O*H) rows
         self._current = 0
+        self._external_col0: dict[str, int] = {}          # user-defined terms: first column in the host-filled array
 
     @property
     def name(self) -> str:
@@ -51,11 +56,34 @@ class ObservationManager(BaseManager):
 
     def build(self):
         self._sources = []
+        self._pending: list[str] = []
         for name, cfg in self.cfg.items():
             cfg.build()
             assert callable(cfg.fn), f"Observation function {name} is not callable"
-            key, width = self.env._trace_term(cfg.fn, dict(cfg.params), what=f"observation '{name}'")
+            try:
+                key, width = self.env._trace_term(cfg.fn, dict(cfg.params), what=f"observation '{name}'")
+            except UnsupportedTermError as e:
+                # user-defined term: stays a Python callback, handed to the kernel as extra columns
+                key, width = ("external", name), getattr(e, "width", None)
+                if width is None:
+                    self._pending.append(name)
             self._sources.append((name, key, width))
+        if not self._pending:
+            self._allocate()
+
+    def resolve_external(self):
+        """Evaluate pending user-defined terms once for their width (the reference's dry run,
+        observation_manager.py:202-210), after the fused step's library handle exists."""
+        if not self._pending:
+            return
+        for i, (name, key, width) in enumerate(self._sources):
+            if name in self._pending:
+                value = self.cfg[name].fn(env=self.env, **self.cfg[name].params)
+                self._sources[i] = (name, key, int(value.reshape(self.env.num_envs, -1).shape[1]))
+        self._pending = []
+        self._allocate()
+
+    def _allocate(self):
         single = self.frame_size
         self._observation_size = single * self._history_len
         self._observation_space = Box(low=-np.inf, high=np.inf, shape=(self._observation_size,), dtype=np.float32)

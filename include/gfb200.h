@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GFB_ABI_VERSION 3
+#define GFB_ABI_VERSION 4
 
 /* ---- limits ------------------------------------------------------------------------------- */
 #define GFB_MAX_DOFS 32
@@ -112,6 +112,8 @@ typedef enum {
   GFB_B_INJ_CMD_STEP0, GFB_B_INJ_CMD_STEP1, GFB_B_INJ_CMD_STEP2, GFB_B_INJ_CMD_STEP3,     /* (N,K_k) */
   GFB_B_INJ_CMD_RESET0, GFB_B_INJ_CMD_RESET1, GFB_B_INJ_CMD_RESET2, GFB_B_INJ_CMD_RESET3, /* (N,K_k) */
   GFB_B_INJ_MAX_LEN,  /* (N,) fp32 U(-1,1) draws for max_episode_length */
+  /* values of user-defined (host-evaluated) reward / termination terms: (J, N) fp32, one row per term */
+  GFB_B_EXT_VALUES,
   GFB_B_COUNT
 } gfb_buf;
 
@@ -147,7 +149,7 @@ typedef enum {
   GFB_T_HAS_CONTACT,         /* terminations.py:139-155 p0=threshold, i0=min_contacts */
   GFB_T_CONTACT_FORCE,       /* terminations.py:158-172 p0=threshold */
   GFB_T_CONTACT_FORCE_GRACE, /* terminations.py:175-205 p0=threshold, i0=grace */
-  GFB_T_EXTERNAL
+  GFB_T_EXTERNAL             /* host-evaluated term: fires where row i0 of GFB_B_EXT_VALUES is non-zero */
 } gfb_termination_op;
 
 /* observation column sources (mdp/observations.py:16-193 and the manager getters they wrap) */
@@ -163,7 +165,7 @@ typedef enum {
   GFB_O_TARGETS,       /* action_manager.get_actions(): processed targets                  */
   GFB_O_ENV_ACTIONS,   /* env.actions (raw)                                                */
   GFB_O_CONTACT_NORM,  /* |contacts[mgr][:, col]|  observations.py:181-193                 */
-  GFB_O_EXTERNAL       /* column `col` of GFB_B_OBS_EXT<mgr>                               */
+  GFB_O_EXTERNAL       /* column `col` of GFB_B_OBS_EXT0, a (N, mgr) array of host-evaluated terms */
 } gfb_obs_src;
 
 /* reward-term flag bits */
@@ -181,7 +183,7 @@ typedef struct {
   int32_t i0;
   float weight;   /* fp32(weight * dt) (reward_manager.py:184-185); 0 = skipped  */
   float p[4];
-  int32_t ext_col; /* GFB_R_EXTERNAL: column of GFB_B_OBS_EXT3 holding the value */
+  int32_t ext_col; /* GFB_R_EXTERNAL: row of GFB_B_EXT_VALUES holding the value */
 } gfb_reward_term;
 
 typedef struct {

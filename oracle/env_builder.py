@@ -110,6 +110,10 @@ def build_env(spec: dict, ns, num_envs: int, device, **scene_kw):
 
         def _obs_fn(self, term):
             kind = term["fn"]
+            if callable(kind):  # user-defined observation term
+                return kind, {}
+            if kind == "ang_vel_uncached":  # mdp.observations without an entity manager (utils path)
+                return ns.observations.entity_angular_velocity, {}
             if kind == "command":
                 return getattr(self, term["mgr"]).observation, {}
             if kind == "ang_vel":
@@ -151,7 +155,18 @@ def build_env(spec: dict, ns, num_envs: int, device, **scene_kw):
             for name, c in spec["commands"].items():
                 c = dict(c)
                 ctype = c.pop("type")
-                if ctype == "velocity":
+                if ctype == "python":  # user-level subclass with its own step()/reset()
+                    env_self, step_fn, reset_fn = self, c["step"], c["reset"]
+
+                    class PythonCommand(M.CommandManager):
+                        def step(mgr, _fn=step_fn):
+                            _fn(mgr, env_self)
+
+                        def reset(mgr, env_ids=None, _fn=reset_fn):
+                            _fn(mgr, env_self, env_ids)
+
+                    mgr = PythonCommand(self, range=c["range"], resample_time_sec=c["resample_time_sec"])
+                elif ctype == "velocity":
                     mgr = M.VelocityCommandManager(
                         self, range=c["range"], resample_time_sec=c["resample_time_sec"],
                         standing_probability=c.get("standing_probability", 0.0),
@@ -167,7 +182,7 @@ def build_env(spec: dict, ns, num_envs: int, device, **scene_kw):
             for name, item in spec["rewards"].items():
                 cfg[name] = {
                     "weight": item["weight"],
-                    "fn": getattr(ns.rewards, item["fn"]),
+                    "fn": item["fn"] if callable(item["fn"]) else getattr(ns.rewards, item["fn"]),
                     "params": self._params(item.get("params")),
                 }
             self.reward_manager = M.RewardManager(self, logging_enabled=True, cfg=cfg)
@@ -175,7 +190,7 @@ def build_env(spec: dict, ns, num_envs: int, device, **scene_kw):
             term_cfg = {}
             for name, item in spec["terminations"].items():
                 term_cfg[name] = {
-                    "fn": getattr(ns.terminations, item["fn"]),
+                    "fn": item["fn"] if callable(item["fn"]) else getattr(ns.terminations, item["fn"]),
                     "time_out": item.get("time_out", False),
                     "params": self._params(item.get("params")),
                 }

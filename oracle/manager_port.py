@@ -27,6 +27,28 @@ from .contact_kernel import kernel_get_contact_forces
 from .geom import inv_quat, transform_by_quat, xyz_to_quat
 
 
+class _ContactView:
+    """What user-defined terms may read of a contact manager (same attribute names as the reference)."""
+
+    def __init__(self, m):
+        self._m = m
+
+    contacts = property(lambda self: self._m["contacts"])
+    contact_positions = property(lambda self: self._m["positions"])
+    last_air_time = property(lambda self: self._m.get("last_air"))
+    current_air_time = property(lambda self: self._m.get("cur_air"))
+    last_contact_time = property(lambda self: self._m.get("last_contact"))
+    current_contact_time = property(lambda self: self._m.get("cur_contact"))
+
+
+class _CommandView:
+    def __init__(self, c):
+        self._c = c
+
+    _command = property(lambda self: self._c["command"])
+    command = property(lambda self: self._c["command"])
+
+
 class PortEnv:
     """Spec-driven restatement of ManagedEnvironment + all managers.  CPU tensors only."""
 
@@ -219,6 +241,7 @@ class PortEnv:
                 for k in ("last_air", "cur_air", "last_contact", "cur_contact"):
                     m[k] = torch.zeros((N, Lc))
             self.contact[name] = m
+            setattr(self, name, _ContactView(m))
 
         # --- termination_manager.py:116-119
         self.terminated = torch.zeros(N, dtype=torch.bool)
@@ -238,7 +261,9 @@ class PortEnv:
             self.command[name] = {
                 "range": rng, "command": torch.zeros(N, k),
                 "resample_steps": int(c["resample_time_sec"] / self.dt),
+                "python": c if c.get("type") == "python" else None,
             }
+            setattr(self, name, _CommandView(self.command[name]))
 
         # --- entity_manager.py:87-99, 157-167
         self.global_gravity = torch.tensor([0.0, 0.0, -1.0]).repeat(N, 1)
@@ -393,6 +418,9 @@ class PortEnv:
 
         self.resample_idx = {}
         for name, c in self.command.items():                  # command_manager.py:152-162
+            if c["python"] is not None:  # user-level subclass overriding step()
+                c["python"]["step"](getattr(self, name), self)
+                continue
             idx = (self.episode_length % c["resample_steps"] == 0).nonzero(as_tuple=False).reshape((-1,))
             self.resample_idx[name] = idx
             self._resample(name, c, idx, "cmd_step")
@@ -452,7 +480,9 @@ class PortEnv:
         m["cur_contact"] = torch.where(is_contact, m["cur_contact"] + dt, 0.0)
 
     # -- terminations (mdp/terminations.py) ------------------------------------------------------
-    def _termination_value(self, fn: str, p: dict) -> torch.Tensor:
+    def _termination_value(self, fn, p: dict) -> torch.Tensor:
+        if callable(fn):  # user-defined term
+            return fn(self, **p)
         if fn == "timeout":  # :17-23
             if self.max_episode_length is None:
                 return torch.zeros(self.num_envs, dtype=torch.bool)
@@ -515,7 +545,9 @@ class PortEnv:
     def _resolve_cmd(self, ref: str) -> torch.Tensor:
         return self.command[ref[1:]]["command"]
 
-    def _reward_value(self, fn: str, p: dict, name: str = "") -> torch.Tensor:
+    def _reward_value(self, fn, p: dict, name: str = "") -> torch.Tensor:
+        if callable(fn):  # user-defined term
+            return fn(self, **p)
         if fn == "is_alive":  # :31-37
             return (~self.extras["terminations"]).float().detach()
         if fn == "terminated":  # :40-46
@@ -728,6 +760,9 @@ class PortEnv:
 
         # -- command_manager.py:164-170
         for name, c in self.command.items():
+            if c["python"] is not None:
+                c["python"]["reset"](getattr(self, name), self, env_ids)
+                continue
             kidx = torch.arange(N) if env_ids is None else env_ids
             self._resample(name, c, kidx, "cmd_reset")
 
@@ -741,6 +776,10 @@ class PortEnv:
     # ------------------------------------------------------------------------------------------
     def _obs_value(self, term: dict) -> torch.Tensor:
         kind = term["fn"]
+        if callable(kind):  # user-defined term
+            return kind(env=self)
+        if kind == "ang_vel_uncached":
+            return self._ang_vel(False)
         if kind == "command":
             return self.command[term["mgr"]]["command"]
         if kind == "ang_vel":

@@ -129,6 +129,10 @@ class ParityRun:
 
     def _term_width(self, term: dict) -> int:
         kind = term["fn"]
+        if callable(kind):
+            return int(kind(env=self.port).reshape(self.N, -1).shape[1])
+        if kind == "ang_vel_uncached":
+            return 3
         if kind == "command":
             return self.port.command[term["mgr"]]["command"].shape[1]
         if kind in ("ang_vel", "lin_vel", "gravity"):

@@ -366,6 +366,55 @@ def kitchen_sink() -> dict:
     return s
 
 
+def custom_terms() -> dict:
+    """
+    Not a BASELINE config: user-defined (Python) reward / termination / observation terms and a
+    command manager with overridden step()/reset(), the way examples/gait_trainer extends the
+    library (gait_command_manager.py).  The callables only use API that the reference and the
+    drop-in share, so the same objects drive the reference, the port and the CUDA path (which runs
+    them as host callbacks between kernel phases).
+    """
+    import torch
+
+    s = contacts()
+    s["name"] = "custom_terms"
+
+    def speed_reward(env):
+        return env.robot.get_vel()[:, 0].abs()
+
+    def contact_reward(env, gain=0.01):
+        return env.foot_contact_manager.contacts[:, :, 2].sum(dim=1) * gain + env.extras["terminations"].float()
+
+    def wandered_off(env, limit=9.5):
+        return env.robot.get_pos()[:, 0] > limit
+
+    def clock_obs(env):
+        return torch.stack([env.episode_length.float() * 0.001, env.robot.get_pos()[:, 2]], dim=1)
+
+    def wave_step(mgr, env):
+        mgr._command[:, 0] = 0.5 + 0.001 * float(env.step_count % 7)
+
+    def wave_reset(mgr, env, env_ids):
+        if env_ids is None:
+            mgr._command[:, 0] = -1.0
+        else:
+            mgr._command[env_ids, 0] = -1.0
+
+    s["commands"]["wave"] = {"type": "python", "range": (-1.0, 1.0), "resample_time_sec": 5.0,
+                             "step": wave_step, "reset": wave_reset}
+    s["rewards"]["speed"] = {"fn": speed_reward, "weight": 0.3}
+    s["rewards"]["contact_z"] = {"fn": contact_reward, "weight": -0.2, "params": {"gain": 0.02}}
+    s["rewards"]["body_acceleration"] = {
+        "fn": "body_acceleration_exp", "weight": -0.1, "params": {"entity_manager": _EM},
+    }
+    s["terminations"]["wandered_off"] = {"fn": wandered_off, "params": {"limit": 9.6}}
+    terms = s["observations"]["policy"]["terms"]
+    terms["clock"] = {"fn": clock_obs, "scale": 2.0}
+    terms["wave"] = {"fn": "command", "mgr": "wave"}
+    terms["ang_vel_fresh"] = {"fn": "ang_vel_uncached", "noise": 0.05}
+    return s
+
+
 ALL = {
     "simple": simple,
     "command_direction": command_direction,
@@ -373,6 +422,7 @@ ALL = {
     "rough_terrain": rough_terrain,
     "berkeley_humanoid": berkeley_humanoid,
     "kitchen_sink": kitchen_sink,
+    "custom_terms": custom_terms,
 }
 
 

@@ -8,7 +8,9 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-CONFIGS = ["simple", "command_direction", "contacts", "rough_terrain", "berkeley_humanoid", "kitchen_sink"]
+CONFIGS = ["simple", "command_direction", "contacts", "rough_terrain", "berkeley_humanoid", "kitchen_sink",
+           "custom_terms"]
+SPLIT = {"custom_terms"}  # user-defined Python terms: kernel phases run as separate (generic) launches
 
 
 @pytest.mark.parametrize("name", CONFIGS)
@@ -21,8 +23,11 @@ def test_step_parity(name, cuda_device):
     assert stats["steps"] == 120
     assert stats["resets"] > 0
     spec_stats = run.env._fused.spec_stats()
-    # (the two generic launches are the build-time entity phase and the initial reset phase)
-    assert spec_stats["specialised_launches"] == 120 and spec_stats["generic_launches"] == 2, spec_stats
+    if name in SPLIT:
+        assert run.env._fused.split_mode and spec_stats["generic_launches"] == 2 + 4 * 120, spec_stats
+    else:
+        # (the two generic launches are the build-time entity phase and the initial reset phase)
+        assert spec_stats["specialised_launches"] == 120 and spec_stats["generic_launches"] == 2, spec_stats
     print(name, stats, spec_stats)
 
 
@@ -36,7 +41,8 @@ def test_step_parity_generic_interpreter(name, cuda_device, monkeypatch):
     stats = run.run(steps=60, nan_step=7)
     assert stats["resets"] > 0
     spec_stats = run.env._fused.spec_stats()
-    assert spec_stats["specialised_launches"] == 0 and spec_stats["generic_launches"] == 62
+    assert spec_stats["specialised_launches"] == 0
+    assert spec_stats["generic_launches"] == (2 + 4 * 60 if name in SPLIT else 62)
 
 
 def test_live_mutation_keeps_the_specialised_kernel(cuda_device):

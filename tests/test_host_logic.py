@@ -108,36 +108,25 @@ def test_tilt_threshold_is_the_exact_decision_boundary():
     assert asin_tilt_threshold(85.0) == float("inf")  # asin(0.99) = 81.9 deg never exceeds 85
 
 
-def test_user_defined_terms_fail_loudly(cpu_device):
-    spec = specs.get("command_direction")
-    env = build_env(spec, dropin_namespace(), 8, torch.device("cpu"))
-    env._dry_run = True
-    orig_config = env.config
-
-    def config_with_custom_reward():
-        orig_config()
-        env.reward_manager.cfg["custom"] = type(env.reward_manager.cfg["lin_vel_z"])(
-            {"fn": lambda env: torch.zeros(env.num_envs), "weight": 1.0}, env
-        )
-
-    env.config = config_with_custom_reward
-    with pytest.raises(UnsupportedTermError, match="custom"):
-        env.build()
-
-
-def test_unrecognised_observation_term_fails_loudly(cpu_device):
-    spec = specs.get("simple")
-    env = build_env(spec, dropin_namespace(), 8, torch.device("cpu"))
-    env._dry_run = True
-    orig = env.config
-
-    def config():
-        orig()
-        ObservationManager(env, name="extra", cfg={"twice": {"fn": lambda env: env.robot_manager.get_linear_velocity() * 2}})
-
-    env.config = config
-    with pytest.raises(UnsupportedTermError, match="twice"):
-        env.build()
+def test_user_defined_terms_select_split_execution(cpu_device):
+    """Python reward / termination / observation terms and overridden command managers are kept as
+    host callbacks (opcode EXTERNAL), and the step runs its kernel phases around them."""
+    env = dry_env("custom_terms")
+    fused, P, K = env._fused, env._fused.program.head, nat.K
+    assert fused.split_mode
+    names = [n for n, _, _ in fused.reward_terms]
+    assert P.reward[names.index("speed")].op == K["GFB_R_EXTERNAL"]
+    assert P.reward[names.index("contact_z")].ext_col == fused.ext_row[("reward", "contact_z")]
+    tnames = [n for n, _, _ in fused.termination_terms]
+    assert P.termination[tnames.index("wandered_off")].op == K["GFB_T_EXTERNAL"]
+    assert [type(m).__name__ for m in fused.python_commands] == ["PythonCommand"]
+    wave = fused.commands.index(fused.python_commands[0])
+    assert P.command[wave].enabled == 0 and P.command[0].enabled == 1
+    # external observation columns: 'clock' (2 wide) and the uncached angular velocity (3 wide)
+    assert fused.ext_obs_width == 5 and fused.ext_obs.shape == (32, 5)
+    srcs = [fused.program.obs_cols[c].src for c in range(P.obs_group[0].n_cols)]
+    assert srcs.count(K["GFB_O_EXTERNAL"]) == 5
+    assert not dry_env("contacts")._fused.split_mode
 
 
 def test_no_cpu_fallback(cpu_device):
