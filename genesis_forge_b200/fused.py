@@ -813,6 +813,7 @@ class FusedStep:
         self._set_program()
         if phases == nat.K["GFB_PHASE_ALL"]:
             self._maybe_specialise(phases)
+        if phases & nat.K["GFB_PHASE_REWARD"]:
             self._after_launch_started = [
                 name for name in self._body_acc_terms
                 if not self._body_acc_started.get(name, False) and self.reward.cfg[name].weight != 0
@@ -827,7 +828,7 @@ class FusedStep:
             self._allreduce_logging()
         self.handle.check(self.lib.gfb_read_report(self.handle.ptr, C.byref(self.report), stream), "gfb_read_report")
         self.global_acc = None
-        if phases == nat.K["GFB_PHASE_ALL"]:
+        if phases & nat.K["GFB_PHASE_REWARD"]:
             for name in self._after_launch_started:  # the term now has a previous velocity to difference
                 self._body_acc_started[name] = True
         return self.report
