@@ -272,67 +272,14 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     const int32_t* la = reinterpret_cast<const int32_t*>(S + plan.off_cla) + tid * C;
     const int32_t* lb = reinterpret_cast<const int32_t*>(S + plan.off_clb) + tid * C;
     const float* cf = S + plan.off_cforce + tid * C * 3;
-    const float* cp = GFB_BUF(const float, GFB_B_C_POS) + (size_t)e * C * 3;  // read on demand (L1/L2)
-    const float4* lq = GFB_BUF(const float4, GFB_B_LINKS_QUAT) + (size_t)e * L;
-    // accumulators live in the per-slab output tiles (force, position) and the stash (count)
-    for (int m = 0; m < SP.n_contact; ++m) {
-      const int Lc = SP.contact[m].n_links;
-      float* fout = S + plan.cout_off[m] + tid * Lc * 3;
-      float* pout = S + plan.cposout_off[m] + tid * Lc * 3;
-      float* cnt = st + plan.st_cnorm[m];
-      for (int k = 0; k < Lc * 3; ++k) { fout[k] = 0.f; pout[k] = 0.f; }
-      for (int t = 0; t < Lc; ++t) cnt[t] = 0.f;
-    }
+    // contact positions are only touched on a hit: read them on demand (L1/L2) instead of holding
+    // another 12*C bytes per env in shared memory, which is what limits resident blocks here
+    const float* cp = GFB_BUF(const float, GFB_B_C_POS) + (size_t)e * C * 3;
+    // contact_manager.py:401-403: any NaN/Inf force is zeroed (and reported)
     bool bad = false;
-    // Slot-major: the force of slot c rotated into link_b's frame (and its reaction into link_a's
-    // frame) does not depend on which manager tracks the link, so each slot is rotated once per side
-    // and then handed to every tracked link that matches -- no divergent per-(target, slot) bodies.
-    // Per target the contributions still arrive in slot order, i.e. the oracle's summation order;
-    // a non-matching slot adds +0.0, which is exact.
-    for (int c = 0; c < C; ++c) {
-      const int a = la[c], b2 = lb[c];
-      float x = cf[c * 3 + 0], y = cf[c * 3 + 1], z = cf[c * 3 + 2];
-      // contact_manager.py:401-403: NaN/Inf forces are zeroed (and reported)
-      if (!finite_f(x)) { x = 0.f; bad = true; }
-      if (!finite_f(y)) { y = 0.f; bad = true; }
-      if (!finite_f(z)) { z = 0.f; bad = true; }
-      const float4 qb = lq[b2], qa = lq[a];
-      const V3 fb = inv_rotate_ti(V3{x, y, z}, qb.x, V3{qb.y, qb.z, qb.w});      // kernel.py:75-76
-      const V3 fa = inv_rotate_ti(V3{-x, -y, -z}, qa.x, V3{qa.y, qa.z, qa.w});   // kernel.py:77-78
-      const float px = cp[c * 3 + 0], py = cp[c * 3 + 1], pz = cp[c * 3 + 2];
-      for (int m = 0; m < SP.n_contact; ++m) {
-        const gfb_contact_manager& cs_ = SP.contact[m];
-        const int Lc = cs_.n_links;
-        float* fout = S + plan.cout_off[m] + tid * Lc * 3;
-        float* pout = S + plan.cposout_off[m] + tid * Lc * 3;
-        float* cnt = st + plan.st_cnorm[m];
-        // with-filter: the OTHER link of the contact must be in the with-list (kernel.py:48-57)
-        bool a_in_with = true, b_in_with = true;
-        if (cs_.has_with_filter) {
-          a_in_with = b_in_with = false;
-          for (int w = 0; w < cs_.n_with; ++w) {
-            a_in_with |= a == cs_.with_ids[w];
-            b_in_with |= b2 == cs_.with_ids[w];
-          }
-        }
-        for (int t = 0; t < Lc; ++t) {
-          const int target = cs_.link_ids[t];
-          const bool is_a = a == target, is_b = b2 == target;
-          const bool hit = (is_a && b_in_with) || (is_b && a_in_with);
-          const float gx = hit ? (is_b ? fb.x : fa.x) : 0.f;
-          const float gy = hit ? (is_b ? fb.y : fa.y) : 0.f;
-          const float gz = hit ? (is_b ? fb.z : fa.z) : 0.f;
-          fout[t * 3 + 0] = add(fout[t * 3 + 0], gx);
-          fout[t * 3 + 1] = add(fout[t * 3 + 1], gy);
-          fout[t * 3 + 2] = add(fout[t * 3 + 2], gz);
-          pout[t * 3 + 0] = add(pout[t * 3 + 0], hit ? px : 0.f);
-          pout[t * 3 + 1] = add(pout[t * 3 + 1], hit ? py : 0.f);
-          pout[t * 3 + 2] = add(pout[t * 3 + 2], hit ? pz : 0.f);
-          cnt[t] = add(cnt[t], hit ? 1.0f : 0.f);
-        }
-      }
-    }
+    for (int k = 0; k < C * 3; ++k) bad |= !finite_f(cf[k]);
     if (bad && active) status |= GFB_STATUS_BAD_CONTACT;
+    const float4* lq = GFB_BUF(const float4, GFB_B_LINKS_QUAT) + (size_t)e * L;
 
     for (int m = 0; m < SP.n_contact; ++m) {
       const gfb_contact_manager& cm = P.contact[m];
@@ -341,13 +288,41 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
       float* fout = S + plan.cout_off[m] + tid * Lc * 3;
       float* pout = S + plan.cposout_off[m] + tid * Lc * 3;
       for (int t = 0; t < Lc; ++t) {
-        const float n_hits = st[plan.st_cnorm[m] + t];
-        if (n_hits > 0.f) {  // kernel.py:85-90: mean contact position
-          pout[t * 3 + 0] = fdiv(pout[t * 3 + 0], n_hits);
-          pout[t * 3 + 1] = fdiv(pout[t * 3 + 1], n_hits);
-          pout[t * 3 + 2] = fdiv(pout[t * 3 + 2], n_hits);
+        const int target = cs_.link_ids[t];
+        const float4 tq = lq[target];
+        float fx = 0.f, fy = 0.f, fz = 0.f, px = 0.f, py = 0.f, pz = 0.f, cnt = 0.f;
+        for (int c = 0; c < C; ++c) {
+          const int a = la[c], b2 = lb[c];
+          const bool is_a = a == target, is_b = b2 == target;
+          bool hit = is_a | is_b;
+          if (hit && cs_.has_with_filter) {
+            bool keep = false;
+            for (int w = 0; w < cs_.n_with; ++w) {
+              const int wl = cs_.with_ids[w];
+              keep |= (is_a && b2 == wl) || (is_b && a == wl);
+            }
+            hit = keep;
+          }
+          if (hit) {
+            float x = cf[c * 3 + 0], y = cf[c * 3 + 1], z = cf[c * 3 + 2];
+            if (bad) {
+              x = finite_f(x) ? x : 0.f;
+              y = finite_f(y) ? y : 0.f;
+              z = finite_f(z) ? z : 0.f;
+            }
+            V3 f = is_b ? V3{x, y, z} : V3{-x, -y, -z};  // kernel.py:75-78
+            f = inv_rotate_ti(f, tq.x, V3{tq.y, tq.z, tq.w});
+            fx = add(fx, f.x); fy = add(fy, f.y); fz = add(fz, f.z);
+            px = add(px, cp[c * 3 + 0]); py = add(py, cp[c * 3 + 1]); pz = add(pz, cp[c * 3 + 2]);
+            cnt = add(cnt, 1.0f);
+          }
         }
-        const float nrm = norm3(fout[t * 3 + 0], fout[t * 3 + 1], fout[t * 3 + 2]);
+        if (cnt > 0.f) {  // kernel.py:85-90
+          px = fdiv(px, cnt); py = fdiv(py, cnt); pz = fdiv(pz, cnt);
+        }
+        fout[t * 3 + 0] = fx; fout[t * 3 + 1] = fy; fout[t * 3 + 2] = fz;
+        pout[t * 3 + 0] = px; pout[t * 3 + 1] = py; pout[t * 3 + 2] = pz;
+        const float nrm = norm3(fx, fy, fz);
         st[plan.st_cnorm[m] + t] = nrm;
 
         if (cs_.track_air_time) {  // contact_manager.py:434-477
