@@ -279,8 +279,7 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, i
       if (!b.buf[id]) return fail(h, GFB_ERR_INVALID, "contact input buffer missing");
     const int C = P.n_contact_slots;
     plan.off_cforce = stage(GFB_B_C_FORCE, 3 * C, -1);
-    // contact positions are only needed per slot while it is being accumulated: read from global on
-    // demand instead of holding another 12*C bytes per env in shared memory
+    plan.off_cpos = stage(GFB_B_C_POS, 3 * C, -1);
     plan.off_cla = stage(GFB_B_C_LINK_A, C, -1);
     plan.off_clb = stage(GFB_B_C_LINK_B, C, -1);
   }

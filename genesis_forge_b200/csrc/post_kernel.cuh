@@ -272,9 +272,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     const int32_t* la = reinterpret_cast<const int32_t*>(S + plan.off_cla) + tid * C;
     const int32_t* lb = reinterpret_cast<const int32_t*>(S + plan.off_clb) + tid * C;
     const float* cf = S + plan.off_cforce + tid * C * 3;
-    // contact positions are only touched on a hit: read them on demand (L1/L2) instead of holding
-    // another 12*C bytes per env in shared memory, which is what limits resident blocks here
-    const float* cp = GFB_BUF(const float, GFB_B_C_POS) + (size_t)e * C * 3;
+    const float* cp = S + plan.off_cpos + tid * C * 3;
     // contact_manager.py:401-403: any NaN/Inf force is zeroed (and reported)
     bool bad = false;
     for (int k = 0; k < C * 3; ++k) bad |= !finite_f(cf[k]);
