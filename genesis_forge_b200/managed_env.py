@@ -298,7 +298,7 @@ class ManagedEnvironment(GenesisEnv):
         fused = self._fused
         if fused.dist is None:
             return fused.log_out.clone()
-        return combine_logging(fused.log_acc, fused.n_reward, fused.n_termination, fused.global_num_envs)
+        return fused.global_log_snapshot()
 
     def _host_reset(self, env_ids: torch.Tensor | None):
         """Engine-side part of reset(): action manager gains / joint positions, entity on_reset items."""
