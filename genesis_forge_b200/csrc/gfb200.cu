@@ -511,6 +511,25 @@ int plan_for_launch(gfb_handle* h, const gfb_buffers& b, uint32_t phases, Plan& 
                     int& tile, int& n_stages) {
   tile = choose_tile(h);
   n_stages = h->force_stages == 2 ? 2 : 1;
+  if (h->force_tile == 0 && tile == 128 && n_stages == 1) {
+    // big slabs (contact slots staged): pick the slab size that keeps the most warps resident
+    // (shared memory per block vs. the 80-register limit of 6 x 128 threads); ties go to the larger slab
+    int best_tile = 128, best_warps = -1;
+    for (int t : {128, 64, 32}) {
+      int rc = build_plan(h, b, phases, t, 1, plan, table);
+      if (rc != GFB_OK) return rc;
+      const size_t bytes = (size_t)plan.smem_words * 4 + 2048;
+      if (bytes > (size_t)kMaxSmemBytes) continue;
+      const int by_smem = (int)((size_t)(228 * 1024) / bytes);
+      const int by_regs = 768 / t;
+      const int warps = std::min(std::min(by_smem, by_regs), 32) * (t / 32);
+      if (warps > best_warps) {
+        best_warps = warps;
+        best_tile = t;
+      }
+    }
+    tile = best_tile;
+  }
   for (;;) {
     int rc = build_plan(h, b, phases, tile, n_stages, plan, table);
     if (rc != GFB_OK) return rc;

@@ -289,19 +289,34 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
         const int target = cs_.link_ids[t];
         const float4 tq = lq[target];
         float fx = 0.f, fy = 0.f, fz = 0.f, px = 0.f, py = 0.f, pz = 0.f, cnt = 0.f;
-        for (int c = 0; c < C; ++c) {
-          const int a = la[c], b2 = lb[c];
-          const bool is_a = a == target, is_b = b2 == target;
-          bool hit = is_a | is_b;
-          if (hit && cs_.has_with_filter) {
-            bool keep = false;
-            for (int w = 0; w < cs_.n_with; ++w) {
-              const int wl = cs_.with_ids[w];
-              keep |= (is_a && b2 == wl) || (is_b && a == wl);
+        // Which contact slots involve this link: a cheap compare pass builds a per-lane bit mask
+        // (one word of hits, one of "the target is link_b"), then only the hits are
+        // visited, in ascending slot order (= the oracle's summation order).  A warp iterates
+        // max-over-lanes(#hits) times -- typically 1-2 -- instead of paying the rotate body for every
+        // one of the C slots under divergence.
+        for (int c0 = 0; c0 < C; c0 += 32) {  // 32 slots per mask word
+          const int cn = min(32, C - c0);
+          uint32_t hits = 0, hit_is_b = 0;
+          for (int j = 0; j < cn; ++j) {
+            const int a = la[c0 + j], b2 = lb[c0 + j];
+            const bool is_a = a == target, is_b = b2 == target;
+            bool hit = is_a | is_b;
+            if (cs_.has_with_filter) {
+              bool keep = false;
+              for (int w = 0; w < cs_.n_with; ++w) {
+                const int wl = cs_.with_ids[w];
+                keep |= (is_a && b2 == wl) || (is_b && a == wl);
+              }
+              hit = hit && keep;
             }
-            hit = keep;
+            hits |= (hit ? 1u : 0u) << j;
+            hit_is_b |= ((hit && is_b) ? 1u : 0u) << j;
           }
-          if (hit) {
+          while (hits) {
+            const int j = __ffs(hits) - 1;
+            const int c = c0 + j;
+            const bool is_b = (hit_is_b >> j) & 1u;
+            hits &= hits - 1;
             float x = cf[c * 3 + 0], y = cf[c * 3 + 1], z = cf[c * 3 + 2];
             if (bad) {
               x = finite_f(x) ? x : 0.f;
