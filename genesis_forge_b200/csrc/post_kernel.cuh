@@ -278,16 +278,48 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     for (int k = 0; k < C * 3; ++k) bad |= !finite_f(cf[k]);
     if (bad && active) status |= GFB_STATUS_BAD_CONTACT;
     const float4* lq = GFB_BUF(const float4, GFB_B_LINKS_QUAT) + (size_t)e * L;
+#ifdef GFB_SPEC
+    // specialised build: the tracked links are compile-time constants, so every link quaternion and
+    // every air-time word of this env is requested up front (independent loads, one latency) instead
+    // of one dependent global load per target inside the loops below
+    float4 tq_all[gfb_spec::N_TARGETS];
+    float air_all[gfb_spec::N_TARGETS][4];
+    {
+      int k = 0;
+      GFB_UNROLL_TERMS
+      for (int m = 0; m < SP.n_contact; ++m) {
+        const int Lc = SP.contact[m].n_links;
+        GFB_UNROLL_TERMS
+        for (int t = 0; t < Lc; ++t, ++k) {
+          tq_all[k] = lq[SP.contact[m].link_ids[t]];
+          if (SP.contact[m].track_air_time) {
+            const float* air = GFB_BUF(const float, GFB_B_AIR0 + m);
+            const size_t base = (size_t)e * Lc + t, plane = (size_t)N * Lc;
+            air_all[k][0] = air[base]; air_all[k][1] = air[plane + base];
+            air_all[k][2] = air[2 * plane + base]; air_all[k][3] = air[3 * plane + base];
+          }
+        }
+      }
+    }
+    int k_target = 0;
+#endif
 
+    GFB_UNROLL_TERMS
     for (int m = 0; m < SP.n_contact; ++m) {
       const gfb_contact_manager& cm = P.contact[m];
       const gfb_contact_manager& cs_ = SP.contact[m];
       const int Lc = cs_.n_links;
       float* fout = S + plan.cout_off[m] + tid * Lc * 3;
       float* pout = S + plan.cposout_off[m] + tid * Lc * 3;
+      GFB_UNROLL_TERMS
       for (int t = 0; t < Lc; ++t) {
         const int target = cs_.link_ids[t];
+#ifdef GFB_SPEC
+        const int kt = k_target++;
+        const float4 tq = tq_all[kt];
+#else
         const float4 tq = lq[target];
+#endif
         float fx = 0.f, fy = 0.f, fz = 0.f, px = 0.f, py = 0.f, pz = 0.f, cnt = 0.f;
         // Which contact slots involve this link: a cheap compare pass builds a per-lane bit mask
         // (one word of hits, one of "the target is link_b"), then only the hits are
@@ -339,10 +371,15 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
         st[plan.st_cnorm[m] + t] = nrm;
 
         if (cs_.track_air_time) {  // contact_manager.py:434-477
+#ifdef GFB_SPEC
+          float last_air = air_all[kt][0], cur_air = air_all[kt][1];
+          float last_con = air_all[kt][2], cur_con = air_all[kt][3];
+#else
           const float* air = GFB_BUF(const float, GFB_B_AIR0 + m);
           const size_t base = (size_t)e * Lc + t, plane = (size_t)N * Lc;
           float last_air = air[base], cur_air = air[plane + base];
           float last_con = air[2 * plane + base], cur_con = air[3 * plane + base];
+#endif
           const float dt = cm.scene_dt;
           const bool is_contact = nrm > cm.air_time_threshold;
           const bool new_contact = (cur_air > 0.f) && is_contact;

@@ -15,9 +15,9 @@ run berkeley_humanoid 4096 200
 run berkeley_humanoid 65536 100
 run berkeley_humanoid 262144 50
 run berkeley_humanoid 1048576 30 3
-python - <<'PY'
-import json
-for line in open("gpurun_out/matrix_TAG.jsonl".replace("TAG", "$TAG")):
+TAG=$TAG python - <<'PY'
+import json, os
+for line in open(f"gpurun_out/matrix_{os.environ['TAG']}.jsonl"):
     d = json.loads(line)
     r = d["roofline"]
     print(f'{d["config"]["workload"][:60]:60s} {d["ms_per_step"]*1e3:8.1f} us/step {d["value"]/1e9:6.2f} G/s  post {r["kernel_us"]:7.1f} us {r["frac"]*100:5.1f}%  bytes/env {r["bytes_per_env"]}  spec {d["kernel_variant"]["specialised_launches"]}')
