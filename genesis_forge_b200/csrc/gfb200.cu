@@ -35,6 +35,37 @@ struct PlanSlot {
 
 }  // namespace
 
+// Host-side result of planning one launch.  The plan is a pure function of the term table, the
+// phase set and, per buffer, whether it is present and 16-byte aligned -- so it is computed once
+// and looked up by that key on every later step (planning costs 10-20 us, a launch 3-4 us).
+struct BufferKey {
+  uint64_t w[(2 * GFB_B_COUNT + 63) / 64];
+  bool operator==(const BufferKey& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
+};
+
+inline BufferKey buffer_key(const gfb_buffers& b) {
+  BufferKey k{};
+  for (int i = 0; i < GFB_B_COUNT; ++i) {
+    const uintptr_t p = reinterpret_cast<uintptr_t>(b.buf[i]);
+    const uint64_t bits = (p ? 1u : 0u) | ((p & 15) == 0 ? 2u : 0u);
+    k.w[(2 * i) >> 6] |= bits << ((2 * i) & 63);
+  }
+  return k;
+}
+
+struct LaunchCache {
+  bool valid = false;
+  uint64_t prog_epoch = 0, spec_gen = 0;
+  uint32_t phases = 0;
+  BufferKey key{};
+  Plan plan;
+  std::vector<int32_t> table;
+  int tile = 0, n_stages = 1;
+  int tma_ok = 0;
+  int spec_index = -1;  // index into gfb_handle::specs, -1 = generic kernel
+};
+constexpr int kLaunchCaches = 8;
+
 struct AttachedSpec {
   void* dl = nullptr;
   int (*launch)(const KParams*, int, unsigned, void*) = nullptr;
@@ -58,6 +89,11 @@ struct gfb_handle {
   gfb_report* report_host = nullptr;  // pinned
   PlanSlot slots[kPlanSlots];
   PlanSlot observe_slot;
+  uint64_t prog_epoch = 0;  // bumped when anything but the step index of the term table changes
+  uint64_t spec_gen = 0;    // bumped by gfb_spec_attach
+  LaunchCache post_cache[kLaunchCaches];
+  int post_cache_next = 0;
+  LaunchCache observe_cache;
   bool disable_tma = false;
   int force_tile = 0;
   int force_stages = 0;
@@ -685,6 +721,11 @@ void gfb_destroy(gfb_handle* h) {
 int gfb_set_program(gfb_handle* h, const gfb_program* program) {
   if (!h || !program) return GFB_ERR_INVALID;
   const gfb_program_head& P = program->head;
+  if (h->has_prog) {
+    // the usual per-step call: nothing but the step index moved -> no validation, plans stay cached
+    h->prog.head.step_index = P.step_index;
+    if (memcmp(&h->prog, program, sizeof(gfb_program)) == 0) return GFB_OK;
+  }
   if (P.num_envs != h->num_envs) return fail(h, GFB_ERR_INVALID, "program.num_envs differs from the handle's");
   if (P.num_dofs < 0 || P.num_dofs > GFB_MAX_DOFS) return fail(h, GFB_ERR_INVALID, "num_dofs out of range");
   if (P.n_reward < 0 || P.n_reward > GFB_MAX_REWARD_TERMS) return fail(h, GFB_ERR_INVALID, "n_reward out of range");
@@ -734,6 +775,7 @@ int gfb_set_program(gfb_handle* h, const gfb_program* program) {
   }
   h->prog = *program;
   h->has_prog = true;
+  h->prog_epoch += 1;
   return GFB_OK;
 }
 
@@ -831,12 +873,44 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
   }
 
   KParams kp{};
-  std::vector<int32_t> table;
-  int tile = 0, n_stages = 1;
-  {
-    int rc0 = plan_for_launch(h, *b, phases, kp.plan, table, tile, n_stages);
+  const BufferKey key = buffer_key(*b);
+  LaunchCache* lc = nullptr;
+  for (auto& c : h->post_cache)
+    if (c.valid && c.prog_epoch == h->prog_epoch && c.spec_gen == h->spec_gen && c.phases == phases && c.key == key) {
+      lc = &c;
+      break;
+    }
+  if (!lc) {
+    LaunchCache& c = h->post_cache[h->post_cache_next];
+    h->post_cache_next = (h->post_cache_next + 1) % kLaunchCaches;
+    c.valid = false;
+    int rc0 = plan_for_launch(h, *b, phases, c.plan, c.table, c.tile, c.n_stages);
     if (rc0 != GFB_OK) return rc0;
+    c.tma_ok = tma_eligible(h, *b, c.plan, phases) ? 1 : 0;
+    // a specialised kernel whose compile-time structure equals this launch's, if one is attached
+    c.spec_index = -1;
+    if (!h->specs.empty() && c.tma_ok && c.n_stages == 1) {
+      gfb_program_head canon = P;
+      canonicalize(canon);
+      for (size_t i = 0; i < h->specs.size(); ++i) {
+        const AttachedSpec& sp = h->specs[i];
+        if (sp.tile == c.tile && sp.phases == phases && memcmp(&sp.plan, &c.plan, sizeof(Plan)) == 0 &&
+            memcmp(&sp.canon, &canon, sizeof(canon)) == 0) {
+          c.spec_index = (int)i;
+          break;
+        }
+      }
+    }
+    c.prog_epoch = h->prog_epoch;
+    c.spec_gen = h->spec_gen;
+    c.phases = phases;
+    c.key = key;
+    c.valid = true;
+    lc = &c;
   }
+  kp.plan = lc->plan;
+  const std::vector<int32_t>& table = lc->table;
+  const int tile = lc->tile, n_stages = lc->n_stages;
   const size_t smem = (size_t)kp.plan.smem_words * 4;
 
   PlanSlot* slot = nullptr;
@@ -862,7 +936,7 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
   kp.s.n_tiles = n_tiles;
   kp.cols = reinterpret_cast<const DevObsCol*>(slot->table_dev);
   kp.phases = phases;
-  kp.tma_ok = tma_eligible(h, *b, kp.plan, phases) ? 1 : 0;
+  kp.tma_ok = lc->tma_ok;
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->profiling && h->n_post + 2 <= (int)h->ev_post.size()) {
@@ -872,25 +946,14 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
   }
   // persistent grid: as many blocks as can be resident at once (or one per slab if fewer)
   int grid = n_tiles;
-  {
+  if (n_stages == 2) {
     int per_sm = 0;
     if (tile == 32) per_sm = blocks_per_sm<32>(h, smem);
     else if (tile == 64) per_sm = blocks_per_sm<64>(h, smem);
     else per_sm = blocks_per_sm<128>(h, smem);
-    if (n_stages == 2 && per_sm > 0 && h->num_sms > 0) grid = std::min(n_tiles, per_sm * h->num_sms);
+    if (per_sm > 0 && h->num_sms > 0) grid = std::min(n_tiles, per_sm * h->num_sms);
   }
-  // a specialised kernel whose compile-time structure equals this launch's, if one is attached
-  const AttachedSpec* spec = nullptr;
-  if (!h->specs.empty() && kp.tma_ok && n_stages == 1) {
-    gfb_program_head canon = P;
-    canonicalize(canon);
-    for (const auto& sp : h->specs)
-      if (sp.tile == tile && sp.phases == phases && memcmp(&sp.plan, &kp.plan, sizeof(Plan)) == 0 &&
-          memcmp(&sp.canon, &canon, sizeof(canon)) == 0) {
-        spec = &sp;
-        break;
-      }
-  }
+  const AttachedSpec* spec = lc->spec_index >= 0 ? &h->specs[lc->spec_index] : nullptr;
   if (spec) {
     if (spec->launch(&kp, grid, (unsigned)smem, stream) != 0)
       return fail(h, GFB_ERR_CUDA, std::string("specialised kernel launch: ") + cudaGetErrorString(cudaGetLastError()));
@@ -944,11 +1007,20 @@ int gfb_observe(gfb_handle* h, const gfb_buffers* b, const int64_t* idx, int32_t
   const gfb_program_head& P = h->prog.head;
   if (!b->buf[GFB_B_INV_BASE_QUAT]) return fail(h, GFB_ERR_INVALID, "INV_BASE_QUAT missing");
   ObserveParams op{};
-  std::vector<int32_t> table;
   // observe-only plan: nothing is staged; the kernel reads staged-kind columns from their global buffer
-  gfb_buffers probe = *b;
-  int rc = build_plan(h, probe, GFB_PHASE_OBSERVE, kObserveTile, 1, op.plan, table);
-  if (rc != GFB_OK) return rc;
+  LaunchCache& oc = h->observe_cache;
+  const BufferKey key = buffer_key(*b);
+  int rc = GFB_OK;
+  if (!(oc.valid && oc.prog_epoch == h->prog_epoch && oc.key == key)) {
+    oc.valid = false;
+    rc = build_plan(h, *b, GFB_PHASE_OBSERVE, kObserveTile, 1, oc.plan, oc.table);
+    if (rc != GFB_OK) return rc;
+    oc.prog_epoch = h->prog_epoch;
+    oc.key = key;
+    oc.valid = true;
+  }
+  op.plan = oc.plan;
+  const std::vector<int32_t>& table = oc.table;
   if ((op.plan.needs & NEED_LIN) && !b->buf[GFB_B_VEL]) return fail(h, GFB_ERR_INVALID, "VEL missing");
   if ((op.plan.needs & NEED_ANG) && !b->buf[GFB_B_ANG]) return fail(h, GFB_ERR_INVALID, "ANG missing");
   rc = upload_table(h, h->observe_slot, table, stream);
@@ -1023,6 +1095,7 @@ int gfb_spec_attach(gfb_handle* h, const char* path) {
     for (auto& sp : h->specs)
       if (sp.dl) dlclose(sp.dl);
     h->specs.clear();
+    h->spec_gen += 1;
     return GFB_OK;
   }
   void* dl = dlopen(path, RTLD_NOW | RTLD_LOCAL);
@@ -1048,6 +1121,7 @@ int gfb_spec_attach(gfb_handle* h, const char* path) {
   sp.dl = dl;
   sp.launch = launch;
   h->specs.push_back(sp);
+  h->spec_gen += 1;
   return GFB_OK;
 }
 

@@ -108,6 +108,7 @@ class FusedStep:
             # host-only handle: packs the term table and describes specialisations, cannot launch
             self.lib = nat.lib()
             self.handle = nat.Handle(self.N, -1)
+            self.index = -1  # Tensor.get_device() of host tensors
         else:
             if self.device.type != "cuda":
                 raise nat.NativeLibraryError(
@@ -139,6 +140,9 @@ class FusedStep:
         self._program_pushed = False
         self._injected_bound = object()
         self._spec_tried: set = set()
+        self._spec_checked = False
+        self._obs_ptrs = None
+        self._log_out_handed_out = False
         self.spec_paths: list = []
         self._body_acc_prev = None
         self._body_acc_started: dict[str, bool] = {}
@@ -269,7 +273,7 @@ class FusedStep:
 
     def _set_engine(self, buf_id: int, tensor: torch.Tensor, dtype):
         """Pointer of an engine getter's tensor (kept alive until the next launch group)."""
-        if tensor.dtype is not dtype or not tensor.is_contiguous() or tensor.device != self.device:
+        if tensor.dtype is not dtype or not tensor.is_contiguous() or tensor.get_device() != self.index:
             tensor = tensor.to(self.device, dtype).contiguous()
         self._keepalive.append(tensor)
         self.buffers.buf[buf_id] = tensor.data_ptr()
@@ -283,6 +287,7 @@ class FusedStep:
         s(K["GFB_B_ACTION_RATE"], self.action_rate)
         s(K["GFB_B_RESET_IDX"], self.reset_idx)
         s(K["GFB_B_LOG_OUT"], self.log_out)
+        self._log_out_id = K["GFB_B_LOG_OUT"]
         s(K["GFB_B_LOG_ACC"], self.log_acc)
         for k, mgr in enumerate(self.commands):
             s(K["GFB_B_COMMAND0"] + k, mgr._command)
@@ -379,6 +384,7 @@ class FusedStep:
         fp = self._live_fingerprint()
         if fp == self._fingerprint:
             return
+        self._spec_checked = False  # the structure may have changed with the values
         env, K, P = self.env, nat.K, self.program.head
         C.memset(C.byref(self.program), 0, C.sizeof(self.program))
         P.num_envs, P.num_dofs = self.N, self.D
@@ -617,6 +623,7 @@ class FusedStep:
             if dims != self._contact_dims:
                 self._contact_dims = dims
                 self._program_pushed = False
+                self._spec_checked = False
             if self._feet_slide_manager is not None:
                 mgr, attr = self._feet_slide_manager
                 vel = getattr(self.env, attr).get_links_vel(links_idx_local=mgr.local_link_ids)
@@ -652,11 +659,20 @@ class FusedStep:
         return self._dof_force_used
 
     def _obs_buffers(self):
-        K, s = nat.K, self._set
-        for g, om in enumerate(self.observations):
+        """The two frame buffers of every observation group swap roles each step (fixed storage)."""
+        table = self._obs_ptrs
+        if table is None:
+            K = nat.K
+            table = self._obs_ptrs = [
+                (om, K["GFB_B_OBS_PREV0"] + g, K["GFB_B_OBS_OUT0"] + g,
+                 (om._buffers[0].data_ptr(), om._buffers[1].data_ptr()), (om._buffers[0], om._buffers[1]))
+                for g, om in enumerate(self.observations)
+            ]
+        buf = self.buffers.buf
+        for om, prev_id, out_id, ptrs, _ in table:
             cur = om._current
-            s(K["GFB_B_OBS_PREV0"] + g, om._buffers[cur])
-            s(K["GFB_B_OBS_OUT0"] + g, om._buffers[1 - cur])
+            buf[prev_id] = ptrs[cur]
+            buf[out_id] = ptrs[1 - cur]
 
     def _injection_buffers(self):
         if self._injected_bound is self.injected:
@@ -684,13 +700,20 @@ class FusedStep:
 
     def _stream(self):
         if self._stream_ptr is None:
-            self._stream_ptr = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            self._stream_ptr = C.c_void_p(torch._C._cuda_getCurrentRawStream(self.index))
         return self._stream_ptr
 
     def begin_step(self):
         """Per-step caches: the caller's current stream, one live-config check."""
         self._stream_ptr = None
         self._program_pushed = False
+        # logged means are handed out as views of this vector and may be kept by the caller (rsl_rl
+        # collects extras["episode"] over a whole iteration): once views were handed out, the next
+        # step writes into fresh storage
+        if self._log_out_handed_out:
+            self.log_out = torch.empty_like(self.log_out)
+            self.buffers.buf[self._log_out_id] = self.log_out.data_ptr()
+            self._log_out_handed_out = False
 
     # ------------------------------------------------------------------------------------------
     # launches
@@ -761,6 +784,9 @@ class FusedStep:
 
     def _maybe_specialise(self, phases: int):
         """Attach the specialised kernel for the current table structure (once per structure)."""
+        if self._spec_checked:  # nothing was re-packed since the last look
+            return
+        self._spec_checked = True
         from . import spec
 
         if spec.disabled() or self.dry_run:

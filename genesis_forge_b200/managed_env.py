@@ -57,6 +57,7 @@ class ManagedEnvironment(GenesisEnv):
         self._truncated_buf = torch.zeros((num_envs,), device=gs.device, dtype=gs.tc_bool)
         self._fused: FusedStep | None = None
         self._tracing: dict | None = None
+        self._log_key_cache: dict = {}
 
     # -- spaces ---------------------------------------------------------------------------------
     @property
@@ -267,7 +268,7 @@ class ManagedEnvironment(GenesisEnv):
                 print("ERROR: Infinite actions received!")
             if status & nat.K["GFB_STATUS_BAD_CONTACT"]:
                 print("Warning: Invalid contact forces detected (NaN/inf) and sanitized")
-        snapshot = None
+        snapshot = None  # tuple of 0-dim views of this step's logging vector
         n_r = fused.n_reward
         # sharded over ranks: keys are published when ANY rank saw the event (global counts)
         acc = fused.global_acc
@@ -277,28 +278,37 @@ class ManagedEnvironment(GenesisEnv):
             self.extras["terminations"] = term._terminated_buf
             self.extras["time_outs"] = term._truncated_buf
             if term.logging_enabled:
-                for i, (name, _, _) in enumerate(fused.termination_terms):
+                for i, key in self._log_keys(term, fused.termination_terms):
                     if term_count(i) > 0:
                         if snapshot is None:
                             snapshot = self._log_snapshot()
-                        logging[f"{term.logging_tag} / {name}"] = snapshot[n_r + i]
+                        logging[key] = snapshot[n_r + i]
         if rew is not None and rew.enabled and rew.logging_enabled and n_reset_logged > 0:
             index = {}
-            for i, (name, item, _) in enumerate(fused.reward_terms):
+            for (i, key), (name, item, _) in zip(self._log_keys(rew, fused.reward_terms), fused.reward_terms):
                 if item.weight != 0:
                     if snapshot is None:
                         snapshot = self._log_snapshot()
-                    logging[f"{rew.logging_tag} / {name}"] = snapshot[i]
+                    logging[key] = snapshot[i]
                     index[name] = i
             if index:
-                rew._last_log = (snapshot, index)
+                rew._last_log = (fused.log_out if fused.dist is None else snapshot[0]._base, index)
 
-    def _log_snapshot(self) -> torch.Tensor:
-        """Copy of the kernel's logging vector (entries are handed out as 0-dim views)."""
+    def _log_keys(self, manager, terms) -> list:
+        """[(row, "<tag> / <term>")] of one manager's logged entries (built once per logging tag)."""
+        cached = self._log_key_cache.get(manager.type)
+        if cached is None or cached[0] != manager.logging_tag or len(cached[1]) != len(terms):
+            cached = (manager.logging_tag, [(i, f"{manager.logging_tag} / {name}") for i, (name, _, _) in enumerate(terms)])
+            self._log_key_cache[manager.type] = cached
+        return cached[1]
+
+    def _log_snapshot(self) -> tuple:
+        """The kernel's logging vector of this step as 0-dim views."""
         fused = self._fused
         if fused.dist is None:
-            return fused.log_out.clone()
-        return fused.global_log_snapshot()
+            fused._log_out_handed_out = True  # the next step gets fresh storage (FusedStep.begin_step)
+            return fused.log_out.unbind(0)
+        return fused.global_log_snapshot().unbind(0)
 
     def _host_reset(self, env_ids: torch.Tensor | None):
         """Engine-side part of reset(): action manager gains / joint positions, entity on_reset items."""

@@ -116,6 +116,7 @@ class PositionActionManager(BaseActionManager):
         self._quiet_action_errors = quiet_action_errors
         self._enabled_dof = None
         self._noise_scale = noise_scale
+        self._reset_plan = None  # (robot, [(gain key, draw tag, engine setter)], default pose row), built on first reset
         self._use_default_offset = use_default_offset
         self._default_dofs_pos: torch.Tensor = None
         if use_default_offset and offset != 0.0:
@@ -209,6 +210,7 @@ class PositionActionManager(BaseActionManager):
             )
         self._actions = torch.zeros((N, n), device=gs.device, dtype=gs.tc_float)
         self._has_stepped = False
+        self._reset_plan = None
 
     def kernel_params(self) -> dict[str, torch.Tensor]:
         """Per-DOF fp32 vectors for the action kernel: scale, offset, clip bounds, default pose."""
@@ -237,24 +239,28 @@ class PositionActionManager(BaseActionManager):
             envs_idx = torch.arange(self.env.num_envs, device=gs.device)
         robot = self.env.robot
         ns = self._noise_scale
-        setters = {
-            "kp": robot.set_dofs_kp, "kv": robot.set_dofs_kv, "damping": robot.set_dofs_damping,
-            "stiffness": robot.set_dofs_stiffness, "frictionloss": robot.set_dofs_frictionloss,
-        }
-        tags = {"kp": "pd_kp", "kv": "pd_kv"}
-        for key, setter in setters.items():
-            if key in self._gain_values:
-                value = self._add_random_noise(f"action_dr:{tags.get(key, key)}", self._gain_values[key], ns)
-                setter(value, self.dofs_idx, envs_idx)
+        dofs_idx = self.dofs_idx
+        plan = self._reset_plan
+        if plan is None or plan[0] is not robot:
+            names = {"kp": "set_dofs_kp", "kv": "set_dofs_kv", "damping": "set_dofs_damping",
+                     "stiffness": "set_dofs_stiffness", "frictionloss": "set_dofs_frictionloss"}
+            tags = {"kp": "pd_kp", "kv": "pd_kv"}
+            plan = self._reset_plan = (
+                robot,
+                [(key, f"action_dr:{tags.get(key, key)}", getattr(robot, attr))
+                 for key, attr in names.items() if key in self._gain_values],
+                self._default_dofs_pos[0].unsqueeze(0),
+            )
+        for key, tag, setter in plan[1]:
+            setter(self._add_random_noise(tag, self._gain_values[key], ns), dofs_idx, envs_idx)
         if self._force_range is not None:
             lower = self._add_random_noise("action_dr:force_lower", self._force_range[0], ns)
             upper = self._add_random_noise("action_dr:force_upper", self._force_range[1], ns)
-            robot.set_dofs_force_range(lower, upper, self.dofs_idx, envs_idx)
+            robot.set_dofs_force_range(lower, upper, dofs_idx, envs_idx)
         # every row of the default pose is the same vector: a stride-0 view instead of an index gather
         n = envs_idx.numel() if torch.is_tensor(envs_idx) else len(envs_idx)
-        position = self._default_dofs_pos[0].unsqueeze(0).expand(n, -1)
-        position = self._add_random_noise("action_dr:position", position, ns)
-        robot.set_dofs_position(position=position, dofs_idx_local=self.dofs_idx, envs_idx=envs_idx)
+        position = self._add_random_noise("action_dr:position", plan[2].expand(n, -1), ns)
+        robot.set_dofs_position(position=position, dofs_idx_local=dofs_idx, envs_idx=envs_idx)
 
     # -- helpers ----------------------------------------------------------------------------------
     def _dof_values(self, values: dict, default_value=0.0, output=None):
