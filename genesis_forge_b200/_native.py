@@ -137,6 +137,16 @@ class Buffers(C.Structure):
     _fields_ = [("buf", C.c_void_p * B_COUNT)]
 
 
+class Spawn(C.Structure):
+    _fields_ = [
+        ("x_lo", C.c_float), ("x_span", C.c_float), ("y_lo", C.c_float), ("y_span", C.c_float),
+        ("height_offset", C.c_float), ("flat_height", C.c_float), ("terrain_bounds", C.c_float * 4),
+        ("height_field_rows", C.c_int32), ("height_field_cols", C.c_int32), ("with_rotation", C.c_int32),
+        ("rot_mode", C.c_int32 * 3), ("rot_lo", C.c_float * 3), ("rot_hi", C.c_float * 3),
+        ("rng_seed", C.c_uint64), ("rng_counter", C.c_uint64),
+    ]
+
+
 class Report(C.Structure):
     _fields_ = [
         ("n_reset", C.c_int32), ("status", C.c_uint32),
@@ -153,7 +163,7 @@ _LIB = None
 EXPORTS = [
     "gfb_abi_version", "gfb_abi_sizeof", "gfb_create", "gfb_destroy", "gfb_last_error", "gfb_set_program",
     "gfb_action_step", "gfb_post_physics", "gfb_read_report", "gfb_observe", "gfb_contact_forces",
-    "gfb_rotate", "gfb_spec_describe", "gfb_spec_attach", "gfb_spec_stats",
+    "gfb_rotate", "gfb_spawn_pose", "gfb_spec_describe", "gfb_spec_attach", "gfb_spec_stats",
     "gfb_profile_enable", "gfb_profile_read", "gfb_launch_count",
 ]
 
@@ -202,6 +212,8 @@ def lib() -> C.CDLL:
     L.gfb_contact_forces.argtypes = [vp] + [vp] * 10 + [i32] * 6 + [vp]
     L.gfb_rotate.restype = C.c_int
     L.gfb_rotate.argtypes = [vp, vp, vp, vp, i32, i32, vp]
+    L.gfb_spawn_pose.restype = C.c_int
+    L.gfb_spawn_pose.argtypes = [vp, C.POINTER(Spawn), vp, i32, i32] + [vp] * 11 + [vp]
     L.gfb_spec_describe.restype = C.c_int
     L.gfb_spec_describe.argtypes = [vp, C.POINTER(Buffers), u32, vp, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(i32)]
     L.gfb_spec_attach.restype = C.c_int
@@ -220,7 +232,7 @@ def lib() -> C.CDLL:
             f"{LIB_PATH} has ABI version {L.gfb_abi_version()}, header says {K['GFB_ABI_VERSION']}; "
             f"rebuild with `{build_command()}`"
         )
-    checks = [(0, Program), (1, Buffers), (2, Report), (3, ProgramHead)]
+    checks = [(0, Program), (1, Buffers), (2, Report), (3, ProgramHead), (5, Spawn)]
     for which, struct in checks:
         if L.gfb_abi_sizeof(which) != C.sizeof(struct):
             raise NativeLibraryError(

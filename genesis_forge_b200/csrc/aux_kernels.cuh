@@ -428,4 +428,95 @@ __global__ void rotate_kernel(const float* __restrict__ vec, const float4* __res
   out[i * 3 + 2] = r.z;
 }
 
+// ---------------------------------------------------------------------------------------------
+// spawn_kernel: spawn pose of the reset envs in one launch (gfb_spawn_pose, include/gfb200.h).
+// One thread per reset env; every scattered row belongs to exactly one thread.
+// ---------------------------------------------------------------------------------------------
+struct SpawnParams {
+  gfb_spawn cfg;
+  const int64_t* idx;
+  int32_t n;
+  const float* height_field;
+  const float* u_x;
+  const float* u_y;
+  const float* u_rot[3];
+  float* position_buffer;
+  float* rot_buffer;
+  float* quat_buffer;
+  float* pos_out;
+  float* quat_out;
+};
+
+__global__ void __launch_bounds__(128) spawn_kernel(const SpawnParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  const gfb_spawn& c = p.cfg;
+  const int64_t e = p.idx ? p.idx[i] : (int64_t)i;
+  const Philox rng(c.rng_seed);
+  const uint32_t e_lo = (uint32_t)e, e_hi = (uint32_t)((uint64_t)e >> 32);
+  const uint32_t k_lo = (uint32_t)c.rng_counter, k_hi = (uint32_t)(c.rng_counter >> 32);
+
+  float ux, uy;
+  if (p.u_x && p.u_y) {
+    ux = p.u_x[i];
+    uy = p.u_y[i];
+  } else {
+    const uint4 r = rng(e_lo, e_hi ^ 0x53504157u, k_lo, k_hi);  // stream tag 'SPAW'
+    ux = p.u_x ? p.u_x[i] : u01(r.x);
+    uy = p.u_y ? p.u_y[i] : u01(r.y);
+  }
+  const float x = add(mul(ux, c.x_span), c.x_lo);
+  const float y = add(mul(uy, c.y_span), c.y_lo);
+  const float ground = p.height_field
+                           ? terrain_height(x, y, c.terrain_bounds, c.height_field_rows, c.height_field_cols, p.height_field)
+                           : c.flat_height;
+  const float z = add(ground, c.height_offset);
+  float* row = p.position_buffer + e * 3;
+  row[0] = x;
+  row[1] = y;
+  row[2] = z;
+  if (p.pos_out) {
+    p.pos_out[(size_t)i * 3] = x;
+    p.pos_out[(size_t)i * 3 + 1] = y;
+    p.pos_out[(size_t)i * 3 + 2] = z;
+  }
+  if (!c.with_rotation) return;
+
+  float ang[3];
+  uint4 r{};
+  bool drawn = false;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float* cell = p.rot_buffer + e * 3 + a;
+    if (c.rot_mode[a] == GFB_SPAWN_ROT_DRAW) {
+      float v;
+      if (p.u_rot[a]) {
+        v = p.u_rot[a][i];
+      } else {
+        if (!drawn) {
+          r = rng(e_lo, e_hi ^ 0x53505254u, k_lo, k_hi);  // stream tag 'SPRT'
+          drawn = true;
+        }
+        const uint32_t bits = a == 0 ? r.x : (a == 1 ? r.y : r.z);
+        v = add(mul(u01(bits), sub(c.rot_hi[a], c.rot_lo[a])), c.rot_lo[a]);
+      }
+      *cell = v;
+      ang[a] = v;
+    } else {
+      ang[a] = *cell;
+    }
+  }
+  // xyz_to_quat (genesis.utils.geom; mdp/reset.py:63,194): extrinsic x-y-z, w first
+  const float hx = mul(ang[0], 0.5f), hy = mul(ang[1], 0.5f), hz = mul(ang[2], 0.5f);
+  const float cx = cosf(hx), cy = cosf(hy), cz = cosf(hz);
+  const float sx = sinf(hx), sy = sinf(hy), sz = sinf(hz);
+  const float qw = sub(mul(mul(cx, cy), cz), mul(mul(sx, sy), sz));
+  const float qx = add(mul(mul(sx, cy), cz), mul(mul(cx, sy), sz));
+  const float qy = sub(mul(mul(cx, sy), cz), mul(mul(sx, cy), sz));
+  const float qz = add(mul(mul(cx, cy), sz), mul(mul(sx, sy), cz));
+  const float4 q = make_float4(qw, qx, qy, qz);
+  reinterpret_cast<float4*>(p.quat_buffer)[e] = q;
+  if (p.quat_out) reinterpret_cast<float4*>(p.quat_out)[i] = q;
+}
+
 }  // namespace gfb

@@ -124,6 +124,32 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
+// TerrainManager.get_terrain_height (terrain_manager.py:100-166): normalise (x, y) to [-1, 1] by the
+// terrain bounds with the reference's op sequence (sub, div, mul 2, sub 1), then bilinear
+// grid_sample(padding=border, align_corners=True) on the (Hf, Wf) height field.
+// bounds = {x_min, x_max, y_min, y_max}.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float terrain_height(float x, float y, const float* bounds, int Hf, int Wf,
+                                                const float* __restrict__ hf) {
+  const float xmin = bounds[0], xmax = bounds[1], ymin = bounds[2], ymax = bounds[3];
+  const float gx = sub(mul(fdiv(sub(x, xmin), sub(xmax, xmin)), 2.0f), 1.0f);
+  const float gy = sub(mul(fdiv(sub(y, ymin), sub(ymax, ymin)), 2.0f), 1.0f);
+  float ix = mul(fdiv(add(gx, 1.0f), 2.0f), (float)(Wf - 1));
+  float iy = mul(fdiv(add(gy, 1.0f), 2.0f), (float)(Hf - 1));
+  ix = fminf(fmaxf(ix, 0.0f), (float)(Wf - 1));
+  iy = fminf(fmaxf(iy, 0.0f), (float)(Hf - 1));
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const int x0 = (int)fx0, y0 = (int)fy0;
+  const int x1 = min(x0 + 1, Wf - 1), y1 = min(y0 + 1, Hf - 1);
+  const float tx = sub(ix, fx0), ty = sub(iy, fy0);
+  const float h00 = hf[y0 * Wf + x0], h01 = hf[y0 * Wf + x1];
+  const float h10 = hf[y1 * Wf + x0], h11 = hf[y1 * Wf + x1];
+  const float wx0 = sub(1.0f, tx), wy0 = sub(1.0f, ty);
+  return add(add(mul(h00, mul(wx0, wy0)), mul(h01, mul(tx, wy0))),
+             add(mul(h10, mul(wx0, ty)), mul(h11, mul(tx, ty))));
+}
+
+// ---------------------------------------------------------------------------------------------
 // Philox4x32-10
 // ---------------------------------------------------------------------------------------------
 struct Philox {

@@ -645,6 +645,7 @@ int64_t gfb_abi_sizeof(int32_t which) {
     case 2: return (int64_t)sizeof(gfb_report);
     case 3: return (int64_t)sizeof(gfb_program_head);
     case 4: return (int64_t)GFB_B_COUNT;
+    case 5: return (int64_t)sizeof(gfb_spawn);
     default: return -1;
   }
 }
@@ -1064,6 +1065,47 @@ int gfb_rotate(gfb_handle* h, const float* vec, const float* quat, float* out, i
   if (n <= 0) return GFB_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   rotate_kernel<<<(n + 255) / 256, 256, 0, stream>>>(vec, reinterpret_cast<const float4*>(quat), out, n, conjugate);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GFB_OK;
+}
+
+int gfb_spawn_pose(gfb_handle* h, const gfb_spawn* cfg, const int64_t* idx, int32_t n, int32_t n_rows,
+                   const float* height_field, const float* u_x, const float* u_y, const float* u_rot_x,
+                   const float* u_rot_y, const float* u_rot_z, float* position_buffer, float* rot_buffer,
+                   float* quat_buffer, float* pos_out, float* quat_out, void* stream_) {
+  if (!h || !cfg) return GFB_ERR_INVALID;
+  if (h->host_only) return fail(h, GFB_ERR_NO_DEVICE, "host-only handle cannot launch kernels");
+  if (n < 0 || n_rows < 0) return fail(h, GFB_ERR_INVALID, "gfb_spawn_pose: negative size");
+  if (n == 0) return GFB_OK;
+  if (!position_buffer) return fail(h, GFB_ERR_INVALID, "gfb_spawn_pose: position_buffer is NULL");
+  if (!idx && n > n_rows) return fail(h, GFB_ERR_INVALID, "gfb_spawn_pose: n exceeds the buffer rows");
+  if (height_field && (cfg->height_field_rows < 1 || cfg->height_field_cols < 1))
+    return fail(h, GFB_ERR_INVALID, "gfb_spawn_pose: height field dimensions missing");
+  if (cfg->with_rotation) {
+    if (!rot_buffer || !quat_buffer) return fail(h, GFB_ERR_INVALID, "gfb_spawn_pose: rotation buffers missing");
+    if (!aligned16(quat_buffer) || (quat_out && !aligned16(quat_out)))
+      return fail(h, GFB_ERR_INVALID, "gfb_spawn_pose: quaternion buffers must be 16-byte aligned");
+    for (int a = 0; a < 3; ++a)
+      if (cfg->rot_mode[a] != GFB_SPAWN_ROT_KEEP && cfg->rot_mode[a] != GFB_SPAWN_ROT_DRAW)
+        return fail(h, GFB_ERR_INVALID, "gfb_spawn_pose: bad rot_mode");
+  }
+  SpawnParams sp{};
+  sp.cfg = *cfg;
+  sp.idx = idx;
+  sp.n = n;
+  sp.height_field = height_field;
+  sp.u_x = u_x;
+  sp.u_y = u_y;
+  sp.u_rot[0] = u_rot_x;
+  sp.u_rot[1] = u_rot_y;
+  sp.u_rot[2] = u_rot_z;
+  sp.position_buffer = position_buffer;
+  sp.rot_buffer = rot_buffer;
+  sp.quat_buffer = quat_buffer;
+  sp.pos_out = pos_out;
+  sp.quat_out = quat_out;
+  spawn_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream_)>>>(sp);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return GFB_OK;

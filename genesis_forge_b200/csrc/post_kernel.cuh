@@ -500,27 +500,9 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
           float off = 0.0f;
           if (rs.flags & GFB_RF_TERRAIN_FLAT) off = rt.p[1];
           if (rs.flags & GFB_RF_TERRAIN_HEIGHT) {
-            // terrain_manager.py:100-166: normalise to [-1,1], bilinear grid_sample(align_corners, border)
             const float x = S[plan.off_pos + tid * 3], y = S[plan.off_pos + tid * 3 + 1];
-            const float xmin = P.terrain_bounds[0], xmax = P.terrain_bounds[1];
-            const float ymin = P.terrain_bounds[2], ymax = P.terrain_bounds[3];
-            const float gx = sub(mul(fdiv(sub(x, xmin), sub(xmax, xmin)), 2.0f), 1.0f);
-            const float gy = sub(mul(fdiv(sub(y, ymin), sub(ymax, ymin)), 2.0f), 1.0f);
-            const int Hf = P.height_field_rows, Wf = P.height_field_cols;
-            float ix = mul(fdiv(add(gx, 1.0f), 2.0f), (float)(Wf - 1));
-            float iy = mul(fdiv(add(gy, 1.0f), 2.0f), (float)(Hf - 1));
-            ix = fminf(fmaxf(ix, 0.0f), (float)(Wf - 1));
-            iy = fminf(fmaxf(iy, 0.0f), (float)(Hf - 1));
-            const float fx0 = floorf(ix), fy0 = floorf(iy);
-            const int x0 = (int)fx0, y0 = (int)fy0;
-            const int x1 = min(x0 + 1, Wf - 1), y1 = min(y0 + 1, Hf - 1);
-            const float tx = sub(ix, fx0), ty = sub(iy, fy0);
-            const float* hf = GFB_BUF(const float, GFB_B_HEIGHT_FIELD);
-            const float h00 = hf[y0 * Wf + x0], h01 = hf[y0 * Wf + x1];
-            const float h10 = hf[y1 * Wf + x0], h11 = hf[y1 * Wf + x1];
-            const float wx0 = sub(1.0f, tx), wy0 = sub(1.0f, ty);
-            off = add(add(mul(h00, mul(wx0, wy0)), mul(h01, mul(tx, wy0))),
-                      add(mul(h10, mul(wx0, ty)), mul(h11, mul(tx, ty))));
+            off = terrain_height(x, y, P.terrain_bounds, P.height_field_rows, P.height_field_cols,
+                                 GFB_BUF(const float, GFB_B_HEIGHT_FIELD));
           }
           float target = rt.p[0];
           if (rs.flags & GFB_RF_TARGET_FROM_COMMAND) target = S[plan.off_cmd[rs.mgr] + tid * SP.command[rs.mgr].n_dims];

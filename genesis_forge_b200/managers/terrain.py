@@ -4,14 +4,19 @@ TerrainManager: terrain / sub-terrain bounds, cached height field, height lookup
 API of genesis_forge/managers/terrain_manager.py.  `get_bounds` feeds the out_of_bounds
 termination and the height field feeds `rewards.base_height(terrain_manager=...)`, both evaluated
 in the fused kernel from the values cached here (:285-359).  Spawn-position sampling
-(:168-279) is reset-side work on the compacted reset indices and runs on the host.
+(:168-279) is reset-side work on the compacted reset indices: one launch of the library's spawn
+kernel (gfb_spawn_pose) instead of the reference's chain of indexed torch ops.
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import torch
 import torch.nn.functional as F
 
+from .. import _native as nat
 from .._gs import gs
+from ..rng import HostRng
 from .base import BaseManager
 
 
@@ -27,6 +32,8 @@ class TerrainManager(BaseManager):
         self._subterrain_size = None
         self._height_field: torch.Tensor | None = None
         self._env_pos_buffer = torch.zeros((env.num_envs, 3), device=gs.device, dtype=gs.tc_float)
+        self._own_handle = None
+        self._spawn_calls = 0
 
     def build(self):
         self._terrain = getattr(self.env, self._terrain_attr)
@@ -63,8 +70,54 @@ class TerrainManager(BaseManager):
         assert output is not None or num is not None, "Either output or num must be provided"
         if output is None:
             output = torch.zeros(num, 3, device=gs.device)
-        if out_idx is None:
-            out_idx = torch.arange(output.shape[0], device=gs.device)
+        self._spawn(output, out_idx, usable_ratio, subterrain, height_offset)
+        return output
+
+    def generate_random_env_pos(
+        self, envs_idx=None, usable_ratio: float = 0.5, subterrain: str | None = None, height_offset: float = 0.1e-3,
+    ) -> torch.Tensor:
+        pos, _ = self._spawn(self._env_pos_buffer, envs_idx, usable_ratio, subterrain, height_offset, compact=True)
+        return pos
+
+    # -- the spawn kernel -------------------------------------------------------------------------
+    def _handle(self):
+        fused = getattr(self.env, "_fused", None)
+        if fused is not None and not fused.dry_run:
+            return fused.handle, fused.lib
+        if self._own_handle is None:  # used before env.build(): a minimal handle of its own
+            device = torch.device(gs.device)
+            if device.type != "cuda":
+                raise nat.NativeLibraryError(
+                    f"spawn positions are sampled by the CUDA library (gs.device is {device}); "
+                    "there is no CPU implementation in this package"
+                )
+            index = device.index if device.index is not None else torch.cuda.current_device()
+            self._own_handle = nat.Handle(1, index)
+        return self._own_handle, nat.lib()
+
+    def _spawn(self, output: torch.Tensor, out_idx, usable_ratio, subterrain, height_offset, compact: bool = False,
+               rotation: dict | None = None, rot_buffer: torch.Tensor | None = None,
+               quat_buffer: torch.Tensor | None = None):
+        """
+        One launch of gfb_spawn_pose: positions (terrain_manager.py:168-279) for rows `out_idx` of
+        `output`, and -- when `rotation` is given -- the Euler draws and quaternions of
+        randomize_terrain_position.define_quat (mdp/reset.py:172-195).  Returns the compact
+        (n,3) / (n,4) copies when `compact`.  Draws come from the kernel's Philox stream unless the
+        environment carries a custom `rng` (parity harness), whose values are passed through.
+        """
+        handle, lib = self._handle()
+        dev = output.device
+        if output.dtype != torch.float32 or not output.is_contiguous() or output.dim() != 2 or output.shape[1] != 3:
+            raise ValueError("spawn positions need a contiguous float32 (rows, 3) output tensor")
+        if out_idx is not None:
+            out_idx = torch.as_tensor(out_idx, device=dev)
+            if out_idx.dtype == torch.bool:
+                out_idx = out_idx.nonzero().reshape(-1)
+            if out_idx.dtype != torch.int64 or not out_idx.is_contiguous():
+                out_idx = out_idx.to(torch.int64).contiguous()
+            n = out_idx.numel()
+        else:
+            n = output.shape[0]
         bounds, size = self._bounds, self._size
         if subterrain is not None and subterrain in self._subterrain_bounds:
             size, bounds = self._subterrain_size, self._subterrain_bounds[subterrain]
@@ -74,23 +127,53 @@ class TerrainManager(BaseManager):
         margin_y = (y_size - y_size * usable_ratio) / 2
         x_lo, x_hi = x_origin + margin_x, x_origin + x_size - margin_x
         y_lo, y_hi = y_origin + margin_y, y_origin + y_size - margin_y
-        like = output[out_idx, 0]
-        output[out_idx, 0] = self.env.rng.uniform("spawn_x", like, 0.0, 1.0) * (x_hi - x_lo) + x_lo
-        output[out_idx, 1] = self.env.rng.uniform("spawn_y", like, 0.0, 1.0) * (y_hi - y_lo) + y_lo
-        heights = self.get_terrain_height(output[out_idx, 0], output[out_idx, 1])
-        output[out_idx, 2] = heights + height_offset
-        return output
 
-    def generate_random_env_pos(
-        self, envs_idx=None, usable_ratio: float = 0.5, subterrain: str | None = None, height_offset: float = 0.1e-3,
-    ) -> torch.Tensor:
-        if envs_idx is None:
-            envs_idx = torch.arange(self.env.num_envs, device=gs.device)
-        self.generate_random_positions(
-            output=self._env_pos_buffer, out_idx=envs_idx, usable_ratio=usable_ratio,
-            subterrain=subterrain, height_offset=height_offset,
+        cfg = nat.Spawn()
+        cfg.x_lo, cfg.x_span, cfg.y_lo, cfg.y_span = float(x_lo), float(x_hi - x_lo), float(y_lo), float(y_hi - y_lo)
+        cfg.height_offset = float(height_offset)
+        cfg.flat_height = float(self._origin[2])
+        field = self._height_field
+        if field is not None:
+            cfg.height_field_rows, cfg.height_field_cols = field.shape
+            for k in range(4):
+                cfg.terrain_bounds[k] = float(self._bounds[k])
+        rng = getattr(self.env, "rng", None)
+        in_kernel = rng is None or type(rng) is HostRng
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+        u_x = u_y = None
+        if not in_kernel:
+            like = torch.empty(n, device=dev)
+            u_x = rng.uniform("spawn_x", like, 0.0, 1.0).to(dev, torch.float32).contiguous()
+            u_y = rng.uniform("spawn_y", like, 0.0, 1.0).to(dev, torch.float32).contiguous()
+        u_rot = [None, None, None]
+        if rotation is not None:
+            cfg.with_rotation = 1
+            for col, axis in enumerate(("x", "y", "z")):
+                value = rotation.get(axis, 0)
+                if isinstance(value, tuple):  # fixed values are ignored by the reference as well (reset.py:176-190)
+                    cfg.rot_mode[col] = nat.K["GFB_SPAWN_ROT_DRAW"]
+                    cfg.rot_lo[col], cfg.rot_hi[col] = float(value[0]), float(value[1])
+                    if not in_kernel:
+                        like = torch.empty(n, device=dev)
+                        u_rot[col] = rng.uniform(f"spawn_rot_{axis}", like, *value).to(dev, torch.float32).contiguous()
+        self._spawn_calls += 1
+        fused = getattr(self.env, "_fused", None)
+        cfg.rng_seed = (getattr(fused, "rng_seed", 0x5EED) << 8) ^ 0x7E44A1  # per-rank seed, own stream
+        cfg.rng_counter = (int(getattr(self.env, "step_count", 0)) << 20) ^ self._spawn_calls
+        pos_out = torch.empty((n, 3), device=dev) if compact else None
+        quat_out = torch.empty((n, 4), device=dev) if (compact and rotation is not None) else None
+        stream = C.c_void_p(torch._C._cuda_getCurrentRawStream(dev.index if dev.index is not None else torch.cuda.current_device()))
+        handle.check(
+            lib.gfb_spawn_pose(
+                handle.ptr, C.byref(cfg), ptr(out_idx), n, output.shape[0], ptr(field), ptr(u_x), ptr(u_y),
+                ptr(u_rot[0]), ptr(u_rot[1]), ptr(u_rot[2]), ptr(output),
+                ptr(rot_buffer) if rotation is not None else None,
+                ptr(quat_buffer) if rotation is not None else None, ptr(pos_out), ptr(quat_out), stream,
+            ),
+            "gfb_spawn_pose",
         )
-        return self._env_pos_buffer[envs_idx]
+        # (temporaries handed to the launch may be released now: same-stream reuse is ordered after it)
+        return pos_out, quat_out
 
     def _map_terrain(self):
         (geom,) = self._terrain.geoms

@@ -52,7 +52,11 @@ class position(ResetMdpFnClass):
 
 
 class randomize_terrain_position(ResetMdpFnClass):
-    """Random spot on the terrain with a random yaw by default (reset.py:127-226)."""
+    """
+    Random spot on the terrain with a random yaw by default (reset.py:127-226).  Position, Euler
+    draws and quaternion of all reset envs come from ONE launch of the library's spawn kernel
+    (TerrainManager._spawn -> gfb_spawn_pose); the engine setters follow.
+    """
 
     def __init__(self, env, entity, terrain_manager, height_offset: float = 0.1e-3,
                  subterrain: str | Callable[[], str] | None = None,
@@ -60,25 +64,22 @@ class randomize_terrain_position(ResetMdpFnClass):
         self.env = env
         self.rotation = rotation
         self._rotation_buffer = None
+        self._quat_buffer = None
 
     def build(self):
         self._rotation_buffer = torch.zeros((self.env.num_envs, 3), device=gs.device, dtype=gs.tc_float)
+        self._quat_buffer = torch.zeros((self.env.num_envs, 4), device=gs.device, dtype=gs.tc_float)
 
     def __call__(self, env, entity, envs_idx, terrain_manager, height_offset: float = 0.1e-3, subterrain=None,
                  rotation: dict | None = {"z": (0, 2 * math.pi)}, zero_velocity: bool = True):
         if subterrain is not None and callable(subterrain):
             subterrain = subterrain()
-        pos = terrain_manager.generate_random_env_pos(
-            envs_idx=envs_idx, subterrain=subterrain, height_offset=height_offset
+        pos, quat = terrain_manager._spawn(
+            terrain_manager._env_pos_buffer, envs_idx, 0.5, subterrain, height_offset, compact=True,
+            rotation=rotation, rot_buffer=self._rotation_buffer, quat_buffer=self._quat_buffer,
         )
         entity.set_pos(pos, envs_idx=envs_idx, zero_velocity=zero_velocity)
         if rotation is not None:
-            for col, axis in enumerate(("x", "y", "z")):
-                value = rotation.get(axis, 0)
-                if isinstance(value, tuple):
-                    like = torch.empty(len(envs_idx), device=gs.device)
-                    self._rotation_buffer[envs_idx, col] = env.rng.uniform(f"spawn_rot_{axis}", like, *value)
-            quat = xyz_to_quat(self._rotation_buffer[envs_idx])
             entity.set_quat(quat, envs_idx=envs_idx, zero_velocity=zero_velocity)
 
 

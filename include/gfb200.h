@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GFB_ABI_VERSION 4
+#define GFB_ABI_VERSION 5
 
 /* ---- limits ------------------------------------------------------------------------------- */
 #define GFB_MAX_DOFS 32
@@ -310,8 +310,8 @@ void gfb_destroy(gfb_handle* h);
 const char* gfb_last_error(const gfb_handle* h);
 int gfb_abi_version(void);
 /* Binding self-check: size in bytes of gfb_program (0), gfb_buffers (1), gfb_report (2),
- * gfb_program_head (3); GFB_B_COUNT (4).  A foreign-language binding compares these with its own
- * struct layouts at load time.                                                                 */
+ * gfb_program_head (3); GFB_B_COUNT (4); gfb_spawn (5).  A foreign-language binding compares these
+ * with its own struct layouts at load time.                                                     */
 int64_t gfb_abi_sizeof(int32_t which);
 
 /* Install the packed term table used by subsequent launches (host memcpy; cheap, call every step). */
@@ -358,6 +358,40 @@ int gfb_contact_forces(gfb_handle* h, const float* force, const float* position,
  * vec (n,3), quat (n,4) w-first, out (n,3).                                                     */
 int gfb_rotate(gfb_handle* h, const float* vec, const float* quat, float* out, int32_t n, int32_t conjugate,
                void* stream);
+
+/* ---- reset-side writer: spawn pose of the reset envs ---------------------
+ * One launch for what the reference does with ~35 indexed torch ops per reset:
+ *   TerrainManager.generate_random_positions / generate_random_env_pos (terrain_manager.py:168-279):
+ *     x = u_x * x_span + x_lo, y = u_y * y_span + y_lo (u in [0,1)), z = terrain height(x, y) +
+ *     height_offset (bilinear height-field lookup of terrain_manager.py:100-166, or flat_height);
+ *     written to row idx[i] of the manager's (n_rows,3) position buffer and to row i of pos_out.
+ *   randomize_terrain_position.define_quat (mdp/reset.py:172-195): axes with rot_mode DRAW get
+ *     rot_buffer[idx[i], axis] = U(rot_lo, rot_hi); the quaternion of the WHOLE buffer row
+ *     (extrinsic x-y-z Euler -> w-first quaternion) goes to quat_buffer[idx[i]] and quat_out[i].     */
+#define GFB_SPAWN_ROT_KEEP 0 /* leave the buffer column as it is (fixed / absent axis)            */
+#define GFB_SPAWN_ROT_DRAW 1 /* draw U(rot_lo, rot_hi) for the reset envs                         */
+
+typedef struct gfb_spawn {
+  float x_lo, x_span, y_lo, y_span;
+  float height_offset;
+  float flat_height;              /* terrain height when there is no height field                */
+  float terrain_bounds[4];        /* x_min, x_max, y_min, y_max of the height field              */
+  int32_t height_field_rows, height_field_cols;
+  int32_t with_rotation;          /* 0: positions only                                           */
+  int32_t rot_mode[3];
+  float rot_lo[3], rot_hi[3];
+  uint64_t rng_seed, rng_counter; /* Philox key / counter for draws not supplied by the caller   */
+} gfb_spawn;
+
+/* idx: n int64 row indices (NULL = rows 0..n-1).  height_field: (rows, cols) fp32 or NULL (flat).
+ * u_x, u_y: n draws in [0,1) each, or NULL = drawn in the kernel (Philox).  u_rot_{x,y,z}: n FINAL
+ * angles for DRAW axes (already in [rot_lo, rot_hi)), or NULL = drawn in the kernel.
+ * position_buffer (n_rows,3) in/out; rot_buffer (n_rows,3) in/out and quat_buffer (n_rows,4) out are
+ * required when with_rotation; pos_out (n,3) and quat_out (n,4) are optional compact copies.        */
+int gfb_spawn_pose(gfb_handle* h, const gfb_spawn* cfg, const int64_t* idx, int32_t n, int32_t n_rows,
+                   const float* height_field, const float* u_x, const float* u_y, const float* u_rot_x,
+                   const float* u_rot_y, const float* u_rot_z, float* position_buffer, float* rot_buffer,
+                   float* quat_buffer, float* pos_out, float* quat_out, void* stream);
 
 /* ---- compile-time specialisation of the fused kernel -------------------------------------------
  * The fused post-physics kernel is an interpreter over the packed term table.  For a given table

@@ -44,6 +44,7 @@ def test_abi_version_and_struct_layouts():
     assert lib.gfb_abi_sizeof(2) == ctypes.sizeof(_native.Report)
     assert lib.gfb_abi_sizeof(3) == ctypes.sizeof(_native.ProgramHead)
     assert lib.gfb_abi_sizeof(4) == _native.B_COUNT
+    assert lib.gfb_abi_sizeof(5) == ctypes.sizeof(_native.Spawn)
     assert lib.gfb_abi_sizeof(99) == -1
 
 
@@ -60,6 +61,11 @@ def test_invalid_arguments_are_reported_not_crashed():
     assert lib.gfb_create(0, 0, ctypes.byref(ctypes.c_void_p())) == _native.K["GFB_ERR_INVALID"] % (1 << 32) - (1 << 32)
     assert lib.gfb_set_program(None, None) < 0
     assert lib.gfb_launch_count(None) == 0
+    assert lib.gfb_spawn_pose(None, None, None, 0, 0, *([None] * 12)) < 0
+    host = _native.Handle(8, -1)  # host-only handle: launches are refused with a message, not a crash
+    assert lib.gfb_spawn_pose(host.ptr, ctypes.byref(_native.Spawn()), None, 4, 8, *([None] * 12)) == \
+        _native.K["GFB_ERR_NO_DEVICE"] % (1 << 32) - (1 << 32)
+    assert b"host-only" in lib.gfb_last_error(host.ptr)
     lib.gfb_destroy(None)  # no-op
 
 

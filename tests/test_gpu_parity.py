@@ -147,3 +147,74 @@ def test_million_env_properties(cuda_device):
         frac = extras["episode"]["Terminations / fall_over"]
         assert abs(float(frac) - float(term.float().mean())) < 1e-6
         assert torch.equal(env.actions[idx], torch.zeros(n_reset, 12, device=cuda_device))
+
+
+def test_spawn_pose_matches_the_oracle(cuda_device):
+    """
+    Reset-side writer (gfb_spawn_pose): positions / quaternions handed to the engine setters and the
+    managers' persistent spawn buffers, against the oracle's restatement of
+    terrain_manager.py:168-279 and mdp/reset.py:172-195 fed with the same draws.  x / y are
+    specified op by op (bit-exact); z goes through the bilinear height lookup (1e-5 relative, as for
+    the base_height reward); the quaternion goes through cos/sin (1e-6 absolute).
+    """
+    from oracle.parity import ParityRun
+
+    run = ParityRun("rough_terrain", num_envs=512, device=cuda_device, seed=4321)
+    run.port.robot.record_calls = True
+    run.env.robot.record_calls = True
+    stats = run.run(steps=60)
+    assert stats["resets"] > 40
+
+    def poses(robot, name):
+        return [(c[1].cpu(), c[2].cpu()) for c in robot.calls if c[0] == name]
+
+    for name, exact in (("set_pos", True), ("set_quat", False)):
+        want, got = poses(run.port.robot, name), poses(run.env.robot, name)
+        assert len(want) == len(got) > 10
+        for (w_val, w_idx), (g_val, g_idx) in zip(want, got):
+            assert torch.equal(w_idx, g_idx)
+            if exact:  # x, y: two specified roundings; z: bilinear lookup, the package's fp32 tolerance
+                assert torch.equal(w_val[:, :2], g_val[:, :2])
+                assert torch.allclose(w_val[:, 2], g_val[:, 2], rtol=1e-5, atol=1e-6)
+            else:
+                assert torch.allclose(w_val, g_val, rtol=0.0, atol=1e-6)
+    terrain = run.env.managers["terrain"][0]
+    assert torch.equal(terrain._env_pos_buffer.cpu()[:, :2], run.port.t_env_pos[:, :2])
+    assert torch.allclose(terrain._env_pos_buffer.cpu()[:, 2], run.port.t_env_pos[:, 2], rtol=1e-5, atol=1e-6)
+    item = next(i for i in run.port.reset_items if i["fn"] == "randomize_terrain_position")
+    (cfg,) = [c for c in run.env.managers["entity"][0].on_reset.values() if hasattr(c.fn, "_rotation_buffer")]
+    assert torch.equal(cfg.fn._rotation_buffer.cpu(), item["rotation_buffer"])
+    assert torch.allclose(cfg.fn._quat_buffer.cpu(), item["quat_buffer"], rtol=0.0, atol=1e-6)
+
+
+def test_spawn_pose_in_kernel_draws(cuda_device):
+    """Production mode (no injected draws): Philox in the kernel; statistical and geometric properties."""
+    import genesis_forge_b200 as gfb
+    from oracle import specs
+    from oracle.env_builder import build_env, dropin_namespace
+
+    gfb.set_device(cuda_device)
+    n = 1 << 16
+    env = build_env(specs.get("rough_terrain"), dropin_namespace(), n, cuda_device, pool=2, seed=5, n_contacts=8)
+    env.build()
+    env.reset()
+    terrain = env.managers["terrain"][0]
+    launches = env._fused.launch_count()
+    pos = terrain.generate_random_env_pos()
+    assert env._fused.launch_count() == launches + 1  # one kernel, no torch op chain
+    x_min, x_max, y_min, y_max = terrain.get_bounds()
+    cx, cy, hx, hy = (x_min + x_max) / 2, (y_min + y_max) / 2, (x_max - x_min) / 4, (y_max - y_min) / 4
+    assert bool(((pos[:, 0] >= cx - hx) & (pos[:, 0] <= cx + hx)).all())
+    assert bool(((pos[:, 1] >= cy - hy) & (pos[:, 1] <= cy + hy)).all())
+    assert abs(float(pos[:, 0].mean()) - cx) < 0.05 * hx and abs(float(pos[:, 1].mean()) - cy) < 0.05 * hy
+    assert abs(float(pos[:, 0].std()) - 2 * hx / 12 ** 0.5) < 0.02 * hx
+    height = terrain.get_terrain_height(pos[:, 0], pos[:, 1])  # torch grid_sample on the same field
+    assert torch.allclose(pos[:, 2], height + 0.1e-3, rtol=1e-5, atol=1e-6)
+    assert torch.equal(terrain._env_pos_buffer, pos)
+    again = terrain.generate_random_env_pos()
+    assert not torch.equal(again, pos)  # a new counter per call
+    some = torch.tensor([5, 17, 4000], device=cuda_device)
+    before = terrain._env_pos_buffer.clone()
+    sub = terrain.generate_random_env_pos(envs_idx=some)
+    changed = (terrain._env_pos_buffer != before).any(dim=1).nonzero().reshape(-1)
+    assert torch.equal(changed, some) and torch.equal(terrain._env_pos_buffer[some], sub)
