@@ -141,6 +141,7 @@ class FusedStep:
         self._injected_bound = object()
         self._spec_tried: set = set()
         self._spec_checked = False
+        self._eval_handle = None  # second library handle for directly called mdp terms
         self._obs_ptrs = None
         self._log_out_handed_out = False
         self.spec_paths: list = []
@@ -893,9 +894,93 @@ class FusedStep:
         return out
 
     def evaluate_single_term(self, kind, fn, params):
-        raise NotImplementedError(
-            f"direct evaluation of mdp {kind} terms outside the fused step is not available in this build"
-        )
+        """
+        A stock mdp term called directly -- `rewards.lin_vel_z_l2(env, ...)` inside a user-defined term
+        or from curriculum code -- is evaluated by the SAME kernel code as in the fused step: a
+        one-term table goes to a second library handle and the reward (or termination) phase runs
+        alone, with every array that phase writes redirected to scratch.  The value is the
+        unweighted term, as in the reference (reward_manager.py:185, termination_manager.py:168);
+        terms given an `entity_manager` use the base pose cached by the last step, the others the
+        entity's current pose; contact terms read the last step's net forces.
+        """
+        if self.dry_run:
+            raise nat.NativeLibraryError("direct evaluation of mdp terms needs a CUDA device (dry-run handle)")
+        K = nat.K
+        opcode = K[fn.gfb_opcode]
+        if kind == "reward" and opcode == K["GFB_R_BODY_ACC_EXP"]:
+            raise UnsupportedTermError("body_acceleration_exp keeps per-term state and cannot be evaluated on its own")
+        if self._eval_handle is None:
+            self._eval_handle = nat.Handle(self.N, self.index)
+
+        class _Item:  # what pack() reads from a config item
+            weight, time_out, version = 1.0, False, 0
+
+        item = _Item()
+        item.fn, item.params = fn, params
+        saved = {k: getattr(self, k) for k in (
+            "program", "buffers", "handle", "_fingerprint", "_program_pushed", "reward_terms", "termination_terms",
+            "_feet_slide_manager", "_fixed_command_parts", "_keepalive", "_body_acc_terms", "_spec_checked",
+        )}
+        N, dev = self.N, self.device
+        try:
+            self.program = nat.Program()
+            self.buffers = nat.Buffers.from_buffer_copy(saved["buffers"])
+            self.handle = self._eval_handle
+            self._fingerprint = None
+            self._program_pushed = False
+            self._keepalive = []
+            if kind == "reward":
+                self.reward_terms, self.termination_terms = [("direct", item, opcode)], []
+                phase = K["GFB_PHASE_REWARD"]
+                out = torch.empty(N, device=dev)
+                scratch = [out, torch.zeros((1, N), device=dev), torch.zeros(N, device=dev)]
+                self._set(K["GFB_B_REWARD"], out)
+                self._set(K["GFB_B_EP_SUMS"], scratch[1])
+                self._set(K["GFB_B_EP_SECONDS"], scratch[2])
+            else:
+                self.reward_terms, self.termination_terms = [], [("direct", item, opcode)]
+                phase = K["GFB_PHASE_TERMINATION"]
+                out = torch.empty(N, device=dev, dtype=torch.bool)
+                scratch = [out, torch.empty(N, device=dev, dtype=torch.bool)]
+                self._set(K["GFB_B_TERMINATED"], out)
+                self._set(K["GFB_B_TRUNCATED"], scratch[1])
+            if params.get("entity_manager") is None and "entity_attr" in params:
+                # the uncached variant (utils.py:13-55) rotates by the entity's CURRENT quaternion: run the
+                # entity phase as well, its cache outputs going to scratch
+                phase |= K["GFB_PHASE_ENTITY"]
+                scratch += [torch.empty((N, 3), device=dev), torch.empty((N, 4), device=dev), torch.empty((N, 4), device=dev)]
+                self._set(K["GFB_B_BASE_POS"], scratch[-3])
+                self._set(K["GFB_B_BASE_QUAT"], scratch[-2])
+                self._set(K["GFB_B_INV_BASE_QUAT"], scratch[-1])
+            if kind == "reward" and opcode == K["GFB_R_ACTION_RATE"]:
+                # in the step this sum is produced by the action kernel before the reset; a direct call
+                # sees the env's current action buffers (rewards.py:257-271)
+                env = self.env
+                scratch.append(torch.square(env.last_actions - env.actions).sum(dim=1).contiguous())
+                self._set(K["GFB_B_ACTION_RATE"], scratch[-1])
+            self._set(K["GFB_B_RESET_IDX"], None)  # nothing of the step's bookkeeping is touched
+            self._set(K["GFB_B_LOG_OUT"], None)
+            self._set(K["GFB_B_LOG_ACC"], None)
+            self.pack()
+            if kind == "reward":
+                self.program.head.reward[0].weight = 1.0  # value * fp32(1.0): the unweighted term
+            self._engine_buffers()
+            em = params.get("entity_manager")
+            if kind == "termination" and opcode == K["GFB_T_BASE_HEIGHT_MIN"] and em is not None:
+                self._set(K["GFB_B_POS"], em._base_pos)  # the cached position (terminations.py:74-99)
+            P = self.program.head
+            P.step_index = self.env.step_count
+            if self.contacts and self._contact_dims is not None:
+                P.n_contact_slots, P.n_links_total = self._contact_dims
+            self.handle.check(self.lib.gfb_set_program(self.handle.ptr, C.byref(self.program)), "gfb_set_program")
+            self.handle.check(
+                self.lib.gfb_post_physics(self.handle.ptr, C.byref(self.buffers), phase, self._stream()),
+                f"gfb_post_physics({kind} term)",
+            )
+        finally:
+            for k, v in saved.items():
+                setattr(self, k, v)
+        return out
 
     # ------------------------------------------------------------------------------------------
     # multi-GPU logging

@@ -34,6 +34,7 @@ class TerrainManager(BaseManager):
         self._env_pos_buffer = torch.zeros((env.num_envs, 3), device=gs.device, dtype=gs.tc_float)
         self._own_handle = None
         self._spawn_calls = 0
+        self._spawn_cfgs: dict = {}
 
     def build(self):
         self._terrain = getattr(self.env, self._terrain_attr)
@@ -118,6 +119,50 @@ class TerrainManager(BaseManager):
             n = out_idx.numel()
         else:
             n = output.shape[0]
+        rng = getattr(self.env, "rng", None)
+        in_kernel = rng is None or type(rng) is HostRng
+        cfg = self._spawn_config(usable_ratio, subterrain, height_offset, rotation)
+        field = self._height_field
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+        u_x = u_y = None
+        u_rot = [None, None, None]
+        if not in_kernel:
+            like = torch.empty(n, device=dev)
+            u_x = rng.uniform("spawn_x", like, 0.0, 1.0).to(dev, torch.float32).contiguous()
+            u_y = rng.uniform("spawn_y", like, 0.0, 1.0).to(dev, torch.float32).contiguous()
+            if rotation is not None:
+                for col, axis in enumerate(("x", "y", "z")):
+                    value = rotation.get(axis, 0)
+                    if isinstance(value, tuple):
+                        u_rot[col] = rng.uniform(f"spawn_rot_{axis}", like, *value).to(dev, torch.float32).contiguous()
+        self._spawn_calls += 1
+        cfg.rng_counter = (int(getattr(self.env, "step_count", 0)) << 20) ^ self._spawn_calls
+        pos_out = torch.empty((n, 3), device=dev) if compact else None
+        quat_out = torch.empty((n, 4), device=dev) if (compact and rotation is not None) else None
+        stream = C.c_void_p(torch._C._cuda_getCurrentRawStream(dev.index if dev.index is not None else torch.cuda.current_device()))
+        handle.check(
+            lib.gfb_spawn_pose(
+                handle.ptr, C.byref(cfg), ptr(out_idx), n, output.shape[0], ptr(field), ptr(u_x), ptr(u_y),
+                ptr(u_rot[0]), ptr(u_rot[1]), ptr(u_rot[2]), ptr(output),
+                ptr(rot_buffer) if rotation is not None else None,
+                ptr(quat_buffer) if rotation is not None else None, ptr(pos_out), ptr(quat_out), stream,
+            ),
+            "gfb_spawn_pose",
+        )
+        # (temporaries handed to the launch may be released now: same-stream reuse is ordered after it)
+        return pos_out, quat_out
+
+    def _spawn_config(self, usable_ratio, subterrain, height_offset, rotation) -> "nat.Spawn":
+        """The gfb_spawn block for one (area, offset, rotation) request; built once per distinct request."""
+        rot_key = None if rotation is None else tuple(
+            (axis, value) for axis in ("x", "y", "z") if isinstance(value := rotation.get(axis, 0), tuple)
+        )
+        fused = getattr(self.env, "_fused", None)
+        key = (usable_ratio, subterrain, height_offset, rot_key, self._bounds, self._size,
+               None if self._height_field is None else self._height_field.data_ptr(), getattr(fused, "rng_seed", None))
+        cfg = self._spawn_cfgs.get(key)
+        if cfg is not None:
+            return cfg
         bounds, size = self._bounds, self._size
         if subterrain is not None and subterrain in self._subterrain_bounds:
             size, bounds = self._subterrain_size, self._subterrain_bounds[subterrain]
@@ -137,15 +182,6 @@ class TerrainManager(BaseManager):
             cfg.height_field_rows, cfg.height_field_cols = field.shape
             for k in range(4):
                 cfg.terrain_bounds[k] = float(self._bounds[k])
-        rng = getattr(self.env, "rng", None)
-        in_kernel = rng is None or type(rng) is HostRng
-        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
-        u_x = u_y = None
-        if not in_kernel:
-            like = torch.empty(n, device=dev)
-            u_x = rng.uniform("spawn_x", like, 0.0, 1.0).to(dev, torch.float32).contiguous()
-            u_y = rng.uniform("spawn_y", like, 0.0, 1.0).to(dev, torch.float32).contiguous()
-        u_rot = [None, None, None]
         if rotation is not None:
             cfg.with_rotation = 1
             for col, axis in enumerate(("x", "y", "z")):
@@ -153,27 +189,11 @@ class TerrainManager(BaseManager):
                 if isinstance(value, tuple):  # fixed values are ignored by the reference as well (reset.py:176-190)
                     cfg.rot_mode[col] = nat.K["GFB_SPAWN_ROT_DRAW"]
                     cfg.rot_lo[col], cfg.rot_hi[col] = float(value[0]), float(value[1])
-                    if not in_kernel:
-                        like = torch.empty(n, device=dev)
-                        u_rot[col] = rng.uniform(f"spawn_rot_{axis}", like, *value).to(dev, torch.float32).contiguous()
-        self._spawn_calls += 1
-        fused = getattr(self.env, "_fused", None)
         cfg.rng_seed = (getattr(fused, "rng_seed", 0x5EED) << 8) ^ 0x7E44A1  # per-rank seed, own stream
-        cfg.rng_counter = (int(getattr(self.env, "step_count", 0)) << 20) ^ self._spawn_calls
-        pos_out = torch.empty((n, 3), device=dev) if compact else None
-        quat_out = torch.empty((n, 4), device=dev) if (compact and rotation is not None) else None
-        stream = C.c_void_p(torch._C._cuda_getCurrentRawStream(dev.index if dev.index is not None else torch.cuda.current_device()))
-        handle.check(
-            lib.gfb_spawn_pose(
-                handle.ptr, C.byref(cfg), ptr(out_idx), n, output.shape[0], ptr(field), ptr(u_x), ptr(u_y),
-                ptr(u_rot[0]), ptr(u_rot[1]), ptr(u_rot[2]), ptr(output),
-                ptr(rot_buffer) if rotation is not None else None,
-                ptr(quat_buffer) if rotation is not None else None, ptr(pos_out), ptr(quat_out), stream,
-            ),
-            "gfb_spawn_pose",
-        )
-        # (temporaries handed to the launch may be released now: same-stream reuse is ordered after it)
-        return pos_out, quat_out
+        if len(self._spawn_cfgs) > 64:
+            self._spawn_cfgs.clear()
+        self._spawn_cfgs[key] = cfg
+        return cfg
 
     def _map_terrain(self):
         (geom,) = self._terrain.geoms

@@ -218,3 +218,40 @@ def test_spawn_pose_in_kernel_draws(cuda_device):
     sub = terrain.generate_random_env_pos(envs_idx=some)
     changed = (terrain._env_pos_buffer != before).any(dim=1).nonzero().reshape(-1)
     assert torch.equal(changed, some) and torch.equal(terrain._env_pos_buffer[some], sub)
+
+
+@pytest.mark.parametrize("name", ["kitchen_sink", "rough_terrain", "berkeley_humanoid"])
+def test_direct_term_calls_match_the_oracle(name, cuda_device):
+    """
+    Stock mdp terms called directly (`rewards.x(env, **params)`, as user-defined terms and curricula
+    do) return the unweighted per-env value, evaluated by the kernel on a one-term table, and leave
+    no trace: the step-by-step parity run continues unchanged afterwards.
+    """
+    from oracle.parity import ParityRun, _close
+
+    run = ParityRun(name, num_envs=200, device=cuda_device, seed=77)
+    run.reset()
+    for _ in range(12):
+        run.step()
+    env, port = run.env, run.port
+    checked = 0
+    for kind, cfg, spec_terms, oracle in (
+        ("reward", env.reward_manager.cfg, port.spec["rewards"], port._reward_value),
+        ("termination", env.termination_manager.term_cfg, port.spec["terminations"], port._termination_value),
+    ):
+        for tname, item in cfg.items():
+            spec_item = spec_terms[tname]
+            if callable(spec_item["fn"]) or spec_item["fn"] == "body_acceleration_exp":
+                continue
+            got = item.fn(env, **item.params)
+            want = oracle(spec_item["fn"], spec_item.get("params") or {})
+            assert got.shape == want.shape == (200,), (tname, got.shape)
+            if kind == "termination":
+                assert got.dtype == torch.bool and torch.equal(got.cpu(), want), tname
+            else:
+                ok, abs_err, rel_err = _close(got, want)
+                assert ok, (tname, abs_err, rel_err)
+            checked += 1
+    assert checked >= 6
+    for _ in range(5):
+        run.step()
