@@ -152,6 +152,7 @@ class Report(C.Structure):
         ("n_reset", C.c_int32), ("status", C.c_uint32),
         ("termination_count", C.c_int32 * MAX_TERMINATION),
         ("reward_episode_mean", C.c_float * MAX_REWARD),
+        ("global_n_reset", C.c_int64), ("global_termination_count", C.c_int64 * MAX_TERMINATION),
     ]
 
 
@@ -163,7 +164,7 @@ _LIB = None
 EXPORTS = [
     "gfb_abi_version", "gfb_abi_sizeof", "gfb_create", "gfb_destroy", "gfb_last_error", "gfb_set_program",
     "gfb_action_step", "gfb_post_physics", "gfb_read_report", "gfb_observe", "gfb_contact_forces",
-    "gfb_rotate", "gfb_spawn_pose", "gfb_spec_describe", "gfb_spec_attach", "gfb_spec_stats",
+    "gfb_rotate", "gfb_spawn_pose", "gfb_peer_export", "gfb_peer_connect", "gfb_peer_disconnect", "gfb_spec_describe", "gfb_spec_attach", "gfb_spec_stats",
     "gfb_profile_enable", "gfb_profile_read", "gfb_launch_count",
 ]
 
@@ -214,6 +215,12 @@ def lib() -> C.CDLL:
     L.gfb_rotate.argtypes = [vp, vp, vp, vp, i32, i32, vp]
     L.gfb_spawn_pose.restype = C.c_int
     L.gfb_spawn_pose.argtypes = [vp, C.POINTER(Spawn), vp, i32, i32] + [vp] * 11 + [vp]
+    L.gfb_peer_export.restype = C.c_int
+    L.gfb_peer_export.argtypes = [vp, vp]
+    L.gfb_peer_connect.restype = C.c_int
+    L.gfb_peer_connect.argtypes = [vp, i32, i32, vp, i64]
+    L.gfb_peer_disconnect.restype = C.c_int
+    L.gfb_peer_disconnect.argtypes = [vp]
     L.gfb_spec_describe.restype = C.c_int
     L.gfb_spec_describe.argtypes = [vp, C.POINTER(Buffers), u32, vp, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(i32)]
     L.gfb_spec_attach.restype = C.c_int

@@ -146,8 +146,44 @@ __global__ void __launch_bounds__(TILE) action_kernel(const __grid_constant__ Ac
 // Reductions are fixed-order (lane-strided partial sums in double, then a shuffle tree), so the
 // logged values are run-to-run deterministic.
 // ---------------------------------------------------------------------------------------------
+// Logging exchange between the ranks of one NVLink domain (gfb_peer_connect): every rank owns an
+// inbox with one slot per sender and step parity; senders store their partials straight into the
+// peers' inboxes and publish them with a release store of the exchange sequence number.
+constexpr int PEER_VALS = GFB_MAX_REWARD_TERMS + GFB_MAX_TERMINATION_TERMS + 1;
+struct PeerSlot {
+  double vals[PEER_VALS];
+  unsigned long long seq;
+  unsigned long long _pad[64 - PEER_VALS - 1];
+};
+static_assert(sizeof(PeerSlot) == 512, "PeerSlot is padded to 512 bytes");
+struct PeerInbox {
+  PeerSlot slot[2][GFB_MAX_PEERS];
+};
+struct PeerParams {
+  PeerInbox* inbox[GFB_MAX_PEERS];  // [r] = rank r's inbox (own one for r == rank)
+  int32_t rank, world;              // world <= 1: single rank, no exchange
+  unsigned long long seq;           // sequence number of this exchange (same on every rank)
+  int64_t global_num_envs;
+  uint32_t* done_counter;           // blocks of this launch that have written their results
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 struct FinalizeParams {
   Scratch s;
+  PeerParams peer;
   int64_t* reset_idx;
   float* log_out;
   double* log_acc;
@@ -262,6 +298,75 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinalizePar
     rep->n_reset = n_reset;
     rep->status = atomicExch(F.s.status, 0u);
     if (F.log_acc) F.log_acc[F.n_reward + F.n_termination] = (double)n_reset;
+  }
+  if (!(F.phases & GFB_PHASE_RESET)) return;
+
+  // ---- global view: the LAST of the result blocks publishes counts over all ranks ----------------
+  __shared__ int s_last;
+  __shared__ double s_global[PEER_VALS];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t participants = (uint32_t)(F.n_termination + F.n_reward + 1);
+    s_last = (atomicAdd(F.peer.done_counter, 1u) == participants - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (tid == 0) *F.peer.done_counter = 0u;
+  __threadfence();
+  const int n_vals = F.n_reward + F.n_termination + 1;
+  if (F.peer.world <= 1 || !F.log_acc) {
+    if (tid == 0) rep->global_n_reset = rep->n_reset;
+    if (tid < F.n_termination) rep->global_termination_count[tid] = rep->termination_count[tid];
+    return;
+  }
+  // exchange over peer memory: my partials into every rank's inbox, then wait for everyone's
+  const int parity = (int)(F.peer.seq & 1ull);
+  const int me = F.peer.rank, W = F.peer.world;
+  if (tid < n_vals) {
+    const double mine = __ldcg(F.log_acc + tid);
+    for (int p = 0; p < W; ++p) F.peer.inbox[p]->slot[parity][me].vals[tid] = mine;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < W) st_release_sys(&F.peer.inbox[tid]->slot[parity][me].seq, F.peer.seq);
+  int timed_out = 0;
+  if (tid < W) {
+    const unsigned long long* flag = &F.peer.inbox[me]->slot[parity][tid].seq;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys(flag) != F.peer.seq) {
+      if (global_timer_ns() - t0 > 2000000000ull) {  // ~2 s: a peer never issued this exchange
+        timed_out = 1;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  timed_out = __syncthreads_or(timed_out);
+  __threadfence_system();
+  if (timed_out) {
+    if (tid == 0) {
+      atomicOr(&rep->status, GFB_STATUS_PEER_TIMEOUT);
+      rep->global_n_reset = rep->n_reset;
+    }
+    if (tid < F.n_termination) rep->global_termination_count[tid] = rep->termination_count[tid];
+    return;
+  }
+  if (tid < n_vals) {
+    double g = 0.0;
+    for (int r = 0; r < W; ++r) g += __ldcv(&F.peer.inbox[me]->slot[parity][r].vals[tid]);  // rank order
+    s_global[tid] = g;
+  }
+  __syncthreads();
+  const double g_reset = s_global[n_vals - 1];
+  if (tid == 0) rep->global_n_reset = (int64_t)g_reset;
+  if (tid < F.n_reward) {
+    const bool logged = (F.reward_weight_mask >> tid) & 1u;
+    if (F.log_out) F.log_out[tid] = (g_reset > 0.0 && logged) ? (float)(s_global[tid] / g_reset) : 0.0f;
+  } else if (tid < F.n_reward + F.n_termination) {
+    const int k = tid - F.n_reward;
+    rep->global_termination_count[k] = (int64_t)s_global[tid];
+    if (F.log_out) F.log_out[tid] = fdiv((float)s_global[tid], (float)F.peer.global_num_envs);
   }
 }
 

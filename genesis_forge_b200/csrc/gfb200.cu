@@ -94,6 +94,13 @@ struct gfb_handle {
   LaunchCache post_cache[kLaunchCaches];
   int post_cache_next = 0;
   LaunchCache observe_cache;
+  // logging exchange over peer memory (gfb_peer_*)
+  uint32_t* done_counter = nullptr;
+  PeerInbox* inbox_own = nullptr;
+  PeerInbox* inbox[GFB_MAX_PEERS] = {};
+  int peer_rank = 0, peer_world = 0;
+  uint64_t peer_seq = 0;
+  int64_t global_num_envs = 0;
   bool disable_tma = false;
   int force_tile = 0;
   int force_stages = 0;
@@ -685,6 +692,8 @@ int gfb_create(int32_t num_envs, int32_t device, gfb_handle** out) {
   CUDA_TRY(cudaMemset(h->scratch.tile_reset_count, 0, (size_t)nt * sizeof(int32_t)));
   CUDA_TRY(cudaMemset(h->scratch.tile_reset_bits, 0, (size_t)nt * sizeof(uint32_t)));
   CUDA_TRY(cudaMallocHost(&h->report_host, sizeof(gfb_report)));
+  CUDA_TRY(cudaMalloc(&h->done_counter, sizeof(uint32_t)));
+  CUDA_TRY(cudaMemset(h->done_counter, 0, sizeof(uint32_t)));
   const char* env = getenv("GFB_DISABLE_TMA");
   h->disable_tma = env && env[0] == '1';
   env = getenv("GFB_TILE");
@@ -711,6 +720,9 @@ void gfb_destroy(gfb_handle* h) {
   cudaFree(h->scratch.status);
   cudaFree(h->scratch.report);
   if (h->report_host) cudaFreeHost(h->report_host);
+  gfb_peer_disconnect(h);
+  if (h->inbox_own) cudaFree(h->inbox_own);
+  cudaFree(h->done_counter);
   for (auto& s : h->slots)
     if (s.table_dev) cudaFree(s.table_dev);
   if (h->observe_slot.table_dev) cudaFree(h->observe_slot.table_dev);
@@ -979,6 +991,16 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
   fp.n_reward = P.n_reward;
   fp.n_termination = P.n_termination;
   fp.phases = phases;
+  fp.peer.done_counter = h->done_counter;
+  fp.peer.world = 0;
+  if (h->peer_world > 1 && (phases & GFB_PHASE_RESET)) {
+    if (!fp.log_acc) return fail(h, GFB_ERR_INVALID, "sharded logging needs GFB_B_LOG_ACC");
+    for (int r = 0; r < h->peer_world; ++r) fp.peer.inbox[r] = h->inbox[r];
+    fp.peer.rank = h->peer_rank;
+    fp.peer.world = h->peer_world;
+    fp.peer.seq = ++h->peer_seq;
+    fp.peer.global_num_envs = h->global_num_envs;
+  }
   fp.reward_weight_mask = 0;
   for (int r = 0; r < P.n_reward; ++r)
     if (P.reward[r].weight != 0.0f) fp.reward_weight_mask |= (1u << r);
@@ -996,6 +1018,65 @@ int gfb_read_report(gfb_handle* h, gfb_report* out, void* stream_) {
   CUDA_TRY(cudaMemcpyAsync(h->report_host, h->scratch.report, sizeof(gfb_report), cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
   *out = *h->report_host;
+  return GFB_OK;
+}
+
+int gfb_peer_export(gfb_handle* h, void* ipc_handle_out) {
+  if (!h || !ipc_handle_out) return GFB_ERR_INVALID;
+  if (h->host_only) return fail(h, GFB_ERR_NO_DEVICE, "host-only handle has no device memory to share");
+  static_assert(sizeof(cudaIpcMemHandle_t) == GFB_IPC_HANDLE_BYTES, "IPC handle size");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->inbox_own) CUDA_TRY(cudaMalloc(&h->inbox_own, sizeof(PeerInbox)));
+  // (re)connecting restarts the sequence numbers: no stale flag may survive.  Peers write here only
+  // after their gfb_peer_connect, i.e. after the handle exchange that follows this call.
+  CUDA_TRY(cudaMemset(h->inbox_own, 0, sizeof(PeerInbox)));
+  CUDA_TRY(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t ipc;
+  CUDA_TRY(cudaIpcGetMemHandle(&ipc, h->inbox_own));
+  memcpy(ipc_handle_out, &ipc, sizeof(ipc));
+  return GFB_OK;
+}
+
+int gfb_peer_connect(gfb_handle* h, int32_t rank, int32_t world, const void* ipc_handles, int64_t global_num_envs) {
+  if (!h || !ipc_handles) return GFB_ERR_INVALID;
+  if (h->host_only) return fail(h, GFB_ERR_NO_DEVICE, "host-only handle cannot connect to peers");
+  if (world < 1 || world > GFB_MAX_PEERS || rank < 0 || rank >= world)
+    return fail(h, GFB_ERR_INVALID, "gfb_peer_connect: rank / world out of range");
+  if (!h->inbox_own) return fail(h, GFB_ERR_INVALID, "gfb_peer_connect: call gfb_peer_export first");
+  if (global_num_envs < h->num_envs) return fail(h, GFB_ERR_INVALID, "gfb_peer_connect: global_num_envs too small");
+  gfb_peer_disconnect(h);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const cudaIpcMemHandle_t* handles = static_cast<const cudaIpcMemHandle_t*>(ipc_handles);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      h->inbox[r] = h->inbox_own;
+      continue;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, handles[r], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int q = 0; q < r; ++q)
+        if (q != rank && h->inbox[q]) cudaIpcCloseMemHandle(h->inbox[q]);
+      for (auto& q : h->inbox) q = nullptr;
+      return fail(h, GFB_ERR_CUDA, std::string("cudaIpcOpenMemHandle (peer inbox): ") + cudaGetErrorString(e));
+    }
+    h->inbox[r] = static_cast<PeerInbox*>(p);
+  }
+  h->peer_rank = rank;
+  h->peer_world = world;
+  h->peer_seq = 0;
+  h->global_num_envs = global_num_envs;
+  return GFB_OK;
+}
+
+int gfb_peer_disconnect(gfb_handle* h) {
+  if (!h) return GFB_ERR_INVALID;
+  if (h->host_only) return GFB_OK;
+  for (int r = 0; r < h->peer_world; ++r)
+    if (r != h->peer_rank && h->inbox[r]) cudaIpcCloseMemHandle(h->inbox[r]);
+  for (auto& q : h->inbox) q = nullptr;
+  h->peer_world = 0;
+  h->peer_rank = 0;
   return GFB_OK;
 }
 

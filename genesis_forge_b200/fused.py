@@ -127,6 +127,7 @@ class FusedStep:
         self.injected: dict[str, torch.Tensor] | None = None
         self.rng_seed = 0x5EED
         self.dist = None  # (process group) when envs are sharded over ranks
+        self.peer_mode = False  # True: the logging exchange runs inside the finalize kernel (peer memory)
         self._contact_dims = None
         self._feet_slide_manager = None
         self._dof_force_used = None
@@ -852,10 +853,15 @@ class FusedStep:
         )
         if not read_report:
             return None
-        if self.dist is not None:
+        if self.dist is not None and not self.peer_mode:
             self._allreduce_logging()
         self.handle.check(self.lib.gfb_read_report(self.handle.ptr, C.byref(self.report), stream), "gfb_read_report")
         self.global_acc = None
+        if self.report.status & nat.K["GFB_STATUS_PEER_TIMEOUT"]:
+            raise nat.NativeLibraryError(
+                "sharded logging: a peer rank did not take part in this step's exchange within 2 s "
+                "(every rank must issue the same sequence of env.step / env.reset calls)"
+            )
         if phases & nat.K["GFB_PHASE_REWARD"]:
             for name in self._after_launch_started:  # the term now has a previous velocity to difference
                 self._body_acc_started[name] = True
@@ -985,6 +991,38 @@ class FusedStep:
     # ------------------------------------------------------------------------------------------
     # multi-GPU logging
     # ------------------------------------------------------------------------------------------
+    def shard(self, group, global_num_envs: int, peer: bool | None = None):
+        """
+        Envs sharded over the ranks of `group` (this object holds one shard): logged means and
+        publish decisions become global.  With `peer` (default on for NCCL groups, GFB_PEER_LOGGING=0
+        turns it off) the exchange of the per-term partials runs INSIDE the finalize kernel over
+        NVLink peer memory (gfb_peer_connect) and the step keeps its single host sync; otherwise one
+        NCCL all-reduce per step runs on a side stream.
+        """
+        import os
+
+        import torch.distributed as dist
+
+        self.dist = group
+        self.global_num_envs = int(global_num_envs)
+        if peer is None:
+            peer = os.environ.get("GFB_PEER_LOGGING", "1") != "0" and dist.get_backend(group) == "nccl"
+        self.peer_mode = False
+        if not peer or self.dry_run:
+            return
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        mine = (C.c_ubyte * nat.K["GFB_IPC_HANDLE_BYTES"])()
+        self.handle.check(self.lib.gfb_peer_export(self.handle.ptr, mine), "gfb_peer_export")
+        local = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=self.device)
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local, group=group)
+        handles = b"".join(bytes(g.cpu().tolist()) for g in gathered)
+        self.handle.check(
+            self.lib.gfb_peer_connect(self.handle.ptr, rank, world, handles, self.global_num_envs), "gfb_peer_connect"
+        )
+        dist.barrier(group)
+        self.peer_mode = True
+
     def _allreduce_logging(self):
         """
         Sum per-term partials over ranks so that logged means are global.  The

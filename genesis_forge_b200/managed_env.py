@@ -271,9 +271,10 @@ class ManagedEnvironment(GenesisEnv):
         snapshot = None  # tuple of 0-dim views of this step's logging vector
         n_r = fused.n_reward
         # sharded over ranks: keys are published when ANY rank saw the event (global counts)
+        # (single rank / peer-memory exchange: the kernel's report carries the global counts)
         acc = fused.global_acc
-        term_count = (lambda i: acc[n_r + i]) if acc is not None else (lambda i: report.termination_count[i])
-        n_reset_logged = acc[-1] if acc is not None else report.n_reset
+        term_count = (lambda i: acc[n_r + i]) if acc is not None else (lambda i: report.global_termination_count[i])
+        n_reset_logged = acc[-1] if acc is not None else report.global_n_reset
         if step and term is not None:
             self.extras["terminations"] = term._terminated_buf
             self.extras["time_outs"] = term._truncated_buf
@@ -292,7 +293,7 @@ class ManagedEnvironment(GenesisEnv):
                     logging[key] = snapshot[i]
                     index[name] = i
             if index:
-                rew._last_log = (fused.log_out if fused.dist is None else snapshot[0]._base, index)
+                rew._last_log = (snapshot[0]._base, index)
 
     def _log_keys(self, manager, terms) -> list:
         """[(row, "<tag> / <term>")] of one manager's logged entries (built once per logging tag)."""
@@ -305,7 +306,7 @@ class ManagedEnvironment(GenesisEnv):
     def _log_snapshot(self) -> tuple:
         """The kernel's logging vector of this step as 0-dim views."""
         fused = self._fused
-        if fused.dist is None:
+        if fused.dist is None or fused.peer_mode:
             fused._log_out_handed_out = True  # the next step gets fresh storage (FusedStep.begin_step)
             return fused.log_out.unbind(0)
         return fused.global_log_snapshot().unbind(0)

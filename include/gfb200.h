@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GFB_ABI_VERSION 5
+#define GFB_ABI_VERSION 6
 
 /* ---- limits ------------------------------------------------------------------------------- */
 #define GFB_MAX_DOFS 32
@@ -293,12 +293,20 @@ typedef struct {
 #define GFB_STATUS_NAN_ACTION 1u   /* position_action_manager.py:403-404 */
 #define GFB_STATUS_INF_ACTION 2u   /* position_action_manager.py:405-406 */
 #define GFB_STATUS_BAD_CONTACT 4u  /* contact_manager.py:401-403         */
+#define GFB_STATUS_PEER_TIMEOUT 8u /* a peer rank did not deliver its logging partials in time */
+
+#define GFB_MAX_PEERS 16           /* ranks of one NVLink domain sharing the logging exchange   */
+#define GFB_IPC_HANDLE_BYTES 64    /* sizeof(cudaIpcMemHandle_t)                                */
 
 typedef struct {
   int32_t n_reset;   /* number of valid entries in GFB_B_RESET_IDX */
   uint32_t status;   /* GFB_STATUS_* seen since the last report    */
   int32_t termination_count[GFB_MAX_TERMINATION_TERMS]; /* envs that fired each term this step */
   float reward_episode_mean[GFB_MAX_REWARD_TERMS];       /* reward_manager.py:211-216 (n_reset>0) */
+  /* envs sharded over ranks (gfb_peer_connect): the same quantities over ALL ranks; on a
+   * single-rank handle they repeat the local values                                            */
+  int64_t global_n_reset;
+  int64_t global_termination_count[GFB_MAX_TERMINATION_TERMS];
 } gfb_report;
 
 typedef struct gfb_handle gfb_handle;
@@ -336,6 +344,23 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
 /* Copy the step report to the host and wait for it (the one blocking point of a step; the
  * reference blocks at the same place, managed_env.py:309,322).                                 */
 int gfb_read_report(gfb_handle* h, gfb_report* out, void* stream);
+
+/* ---- envs sharded over the GPUs of one node ------------------------------------
+ * The only exchange between ranks is the logging vector [sum of episode quotients per reward term,
+ * fire count per termination term, n_reset].  Instead of a collective call after the kernel, the
+ * finalize kernel itself does the exchange over NVLink peer memory: its last block stores the
+ * rank's partials into every peer's inbox (P2P stores + a release flag), waits for the peers'
+ * partials in its own inbox, sums them in rank order (bit-identical on all ranks) and writes the
+ * GLOBAL logged means to GFB_B_LOG_OUT and the global counts to the report -- so the step keeps its
+ * single host synchronisation.  Every rank must issue the same sequence of launches that contain
+ * GFB_PHASE_RESET (step / reset calls); a missing peer raises GFB_STATUS_PEER_TIMEOUT after ~2 s.
+ *   gfb_peer_export:  allocate this rank's inbox and return its CUDA IPC handle (64 bytes)
+ *   gfb_peer_connect: open all `world` inboxes (handles = world x 64 bytes, in rank order)
+ *   gfb_peer_disconnect: back to single-rank behaviour                                          */
+int gfb_peer_export(gfb_handle* h, void* ipc_handle_out);
+int gfb_peer_connect(gfb_handle* h, int32_t rank, int32_t world, const void* ipc_handles,
+                     int64_t global_num_envs);
+int gfb_peer_disconnect(gfb_handle* h);
 
 /* Observation rows for a list of envs (idx == NULL: all envs) from the CURRENT engine state and
  * the cached inverse base quaternion.  Used after the engine-side reset writes for the envs in

@@ -12,7 +12,7 @@ n = 1 << 20
 env = make_dropin_env(specs.get("command_direction"), n, dev, 4, 1234 + rank)
 fused = env._fused
 if world > 1:
-    fused.dist = dist.group.WORLD; fused.global_num_envs = n * world
+    fused.shard(dist.group.WORLD, n * world)
 acts = [torch.randn(n, 12, device=dev) for _ in range(4)]
 T = {}
 def wrap(obj, name):
