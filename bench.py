@@ -64,49 +64,98 @@ def peaks():
 # --------------------------------------------------------------------------------------------------
 # clocks sampler
 # --------------------------------------------------------------------------------------------------
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml as N
+N.nvmlInit()
+key = sys.argv[1]
+if key.startswith('GPU-'):
+    try:
+        h = N.nvmlDeviceGetHandleByUUID(key)
+    except Exception:
+        h = N.nvmlDeviceGetHandleByUUID(key.encode())
+else:
+    h = N.nvmlDeviceGetHandleByIndex(int(key))
+reasons_fn = getattr(N, 'nvmlDeviceGetCurrentClocksEventReasons', None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+print('ready', flush=True)
+while True:
+    print(time.time(), N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), mx, int(reasons_fn(h)), flush=True)
+    time.sleep(0.002)
+"""
+
+
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """
+    SM clock + throttle reasons every ~2 ms from a side process (NVML), time-stamped so that the
+    samples INSIDE the timed region can be picked out afterwards (`window`); the step loop itself
+    is host-bound at small env counts, so nothing is sampled from this process.
+    """
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, index: int):
         self.proc = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
-            )
+            key = str(index)
+            uuid = getattr(torch.cuda.get_device_properties(index), "uuid", None)
+            if uuid is not None:
+                key = f"GPU-{uuid}"
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, key], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            if self.proc.stdout.readline().strip() != "ready":  # NVML is up: samples flow from here on
+                raise RuntimeError("sampler did not start")
         except Exception:
+            if self.proc is not None:
+                self.proc.kill()
             self.proc = None
 
-    def stop(self) -> dict:
+    def stop(self, window: tuple[float, float] | None = None) -> dict:
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["NVML sampler unavailable"]}
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in out.strip().splitlines():
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, flag in zip(names, parts[2:6]):
-                if flag.lower().startswith("active"):
-                    reasons.add(name)
+            parts = line.split()
+            if len(parts) == 4:
+                try:
+                    rows.append((float(parts[0]), float(parts[1]), float(parts[2]), int(parts[3])))
+                except ValueError:
+                    pass
+        inside = [r for r in rows if window is None or window[0] <= r[0] <= window[1]]
+        where = "timed region"
+        if not inside and rows and window is not None:  # region shorter than the sampling period: nearest samples
+            mid = 0.5 * (window[0] + window[1])
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+            where = "nearest to the timed region"
+        bits = 0
+        for r in inside:
+            bits |= r[3]
         return {
-            "sm_mhz": statistics.median(sm) if sm else None,
-            "sm_max_mhz": max(mx) if mx else None,
-            "samples": len(sm),
-            "reasons": sorted(reasons),
+            "sm_mhz": statistics.median(r[1] for r in inside) if inside else None,
+            "sm_max_mhz": max(r[2] for r in inside) if inside else None,
+            "samples": len(inside),
+            "sampled": where,
+            "reasons": sorted(name for bit, name in self.REASONS.items() if bits & bit),
         }
+
+
+def measured_traffic(config: str, num_envs: int):
+    """
+    DRAM bytes (read + write) of ONE post_kernel launch of this workload from the committed
+    `ncu --set full` capture (profiles/traffic.json, written by tools/summarize_profile.py), or None.
+    """
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            entry = json.load(f).get(f"{config}:{num_envs}")
+        return None if entry is None else entry["dram_bytes"]
+    except (OSError, ValueError):
+        return None
 
 
 # --------------------------------------------------------------------------------------------------
@@ -141,12 +190,14 @@ def time_dropin(env, actions, steps, warmup, dist_on):
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_reset = 0
     launches0 = env._fused.launch_count()
+    wall0 = time.time()
     start.record()
     for i in range(steps):
         env.step(actions[i % len(actions)])
         n_reset += env._fused.report.n_reset
     end.record()
     torch.cuda.synchronize(dev)
+    env.timed_window = (wall0, time.time())
     env.timed_launches = env._fused.launch_count() - launches0
     if dist_on:
         dist.barrier()
@@ -311,7 +362,7 @@ def run_b200(args, rank, local_rank, world):
     prof = fused.profile_read()
     fused.profile(False)
     launches = env.timed_launches
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(env.timed_window) if sampler else None
 
     value = N * world / (ms / 1e3)
     peak, peak_src = peaks()
@@ -366,7 +417,8 @@ def run_b200(args, rank, local_rank, world):
             },
             "roofline": {
                 "kernel": "post_kernel (gfb_post_physics)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args.config, N),
+                "peak_source": peak_src,
                 "bytes_per_env": post_bytes, "kernel_us": post_ms * 1e3,
                 "action_kernel": {"bytes_per_env": roofline.action_kernel_bytes(fused), "kernel_us": act_ms * 1e3,
                                   "achieved": roofline.action_kernel_bytes(fused) * N / max(act_ms, 1e-9) / 1e6,

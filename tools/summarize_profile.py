@@ -1,7 +1,7 @@
 """
 Turn the artefacts of tools/gpu_profile.sh (gpurun_out/) into the text summaries kept under profiles/.
 
-    python tools/summarize_profile.py <tag> [<out-name>]
+    python tools/summarize_profile.py <tag> [<out-name> [<config>]]
 
 Reads gpurun_out/post_<tag>.ncu-rep (one `ncu --set full` capture of post_kernel),
 gpurun_out/launches_<tag>.csv (the `--metrics gpu__time_duration.sum` launch list of a short bench
@@ -50,6 +50,25 @@ if rep.exists():
                 except ValueError:
                     pass
         out.append("  warps stalled per issue-active cycle: " + ", ".join(f"{n} {v:.2f}" for v, n in sorted(stalls, reverse=True)[:8]))
+        # measured DRAM traffic of this launch -> profiles/traffic.json (bench.py reports it as roofline.traffic)
+        try:
+            def _bytes(metric):
+                v, u = float(r[hdr.index(metric)].replace(",", "")), units[hdr.index(metric)].lower()
+                return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
+
+            traffic = _bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum")
+            grid = int(r[hdr.index("launch__grid_size")].replace(",", ""))
+            block = int(r[hdr.index("launch__block_size")].replace(",", ""))
+            tpath = ROOT / "profiles" / "traffic.json"
+            table = json.loads(tpath.read_text()) if tpath.exists() else {}
+            key = sys.argv[3] if len(sys.argv) > 3 else "command_direction"
+            table[f"{key}:{grid * block}"] = {
+                "dram_bytes": traffic, "kernel": r[hdr.index("Kernel Name")][:60], "capture": f"{out_name} (post_{tag}.ncu-rep)",
+            }
+            tpath.write_text(json.dumps(table, indent=1, sort_keys=True) + "\n")
+            out.append(f"  DRAM traffic of the launch (read + write): {traffic / 1e6:.1f} MB -> profiles/traffic.json[{key}:{grid * block}]")
+        except (ValueError, KeyError) as e:
+            out.append(f"  (traffic not recorded: {e})")
     cs = subprocess.run(["ncu", "-i", str(rep), "--page", "source", "--csv", "--print-source", "cuda,sass"],
                         capture_output=True, text=True).stdout
     rows = list(csv.reader(cs.splitlines()))
