@@ -211,18 +211,33 @@ def time_dropin(env, actions, steps, warmup, dist_on):
 
 def time_e2e(env, actions_host, steps, warmup, dist_on):
     """
-    Same step with HOST buffers: every step copies that step's engine state and actions from pinned
-    host memory to the device (inside scene.step(), i.e. where the physics engine would produce
-    them) and reads obs / reward / masks back to pinned host memory.
+    Same step with HOST buffers: every step copies that step's engine state (the arrays the step
+    reads) and actions from pinned host memory to the device (inside scene.step(), i.e. where the
+    physics engine would produce them) and reads obs / reward / masks back to pinned host memory.
+    The observation read-back (the bulk of the D2H bytes) runs on a copy stream so that it overlaps
+    the next step's H2D copies (PCIe is full duplex); the host waits for step i-1's read-back before
+    it starts step i+1, and the timed region ends when the last read-back has landed.
     """
     import torch.distributed as dist
 
     fused = env._fused
     dev = fused.device
     scene = env.scene
-    host_pool = [{k: v.cpu().pin_memory() for k, v in st.items()} for st in scene._pool]
-    dev_state = {k: torch.empty_like(v) for k, v in scene._pool[0].items()}
-    h2d_state = sum(v.numel() * v.element_size() for v in dev_state.values())
+    # which state arrays does one step read?
+    used: set[str] = set()
+    original_get = scene._get
+
+    def recording_get(key):
+        used.add(key)
+        return original_get(key)
+
+    scene._get = recording_get
+    env.step(actions_host[0].to(dev))
+    scene._get = original_get
+    keys = sorted(used)
+    host_pool = [{k: st[k].cpu().pin_memory() for k in keys} for st in scene._pool]
+    dev_state = {k: (torch.empty_like(v) if k in used else v) for k, v in scene._pool[0].items()}
+    h2d_state = sum(dev_state[k].numel() * dev_state[k].element_size() for k in keys)
     counter = {"i": 0}
 
     def host_fed_step():
@@ -236,23 +251,32 @@ def time_e2e(env, actions_host, steps, warmup, dist_on):
     scene.step = host_fed_step
     obs_dev = env.managers["observation"][0]._buffers[0]
     out_host = {
-        "obs": torch.empty_like(obs_dev, device="cpu").pin_memory(),
+        "obs": [torch.empty_like(obs_dev, device="cpu").pin_memory() for _ in range(2)],
         "rew": torch.empty(env.num_envs, dtype=torch.float32).pin_memory(),
         "term": torch.empty(env.num_envs, dtype=torch.bool).pin_memory(),
         "trunc": torch.empty(env.num_envs, dtype=torch.bool).pin_memory(),
     }
     act_dev = torch.empty((env.num_envs, fused.D), device=dev)
     h2d = h2d_state + act_dev.numel() * 4
-    d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+    d2h = out_host["obs"][0].numel() * 4 + sum(v.numel() * v.element_size() for k, v in out_host.items() if k != "obs")
+    main = torch.cuda.current_stream(dev)
+    copy_out = torch.cuda.Stream(dev)
+    stepped = [torch.cuda.Event() for _ in range(2)]
+    landed = [torch.cuda.Event() for _ in range(2)]
 
     def one(i):
         act_dev.copy_(actions_host[i % len(actions_host)], non_blocking=True)
         obs, rew, term, trunc, _ = env.step(act_dev)
-        out_host["obs"].copy_(obs, non_blocking=True)
-        out_host["rew"].copy_(rew, non_blocking=True)
+        out_host["rew"].copy_(rew, non_blocking=True)      # small, rewritten by the next step: in order
         out_host["term"].copy_(term, non_blocking=True)
         out_host["trunc"].copy_(trunc, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        stepped[i % 2].record(main)
+        with torch.cuda.stream(copy_out):                   # ping-pong observation buffer: safe to overlap
+            copy_out.wait_event(stepped[i % 2])
+            out_host["obs"][i % 2].copy_(obs, non_blocking=True)
+            landed[i % 2].record(copy_out)
+        if i > 0:
+            landed[(i - 1) % 2].synchronize()               # step i-1's results are on the host
 
     try:
         for i in range(warmup):
@@ -261,10 +285,11 @@ def time_e2e(env, actions_host, steps, warmup, dist_on):
         if dist_on:
             dist.barrier()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        start.record()
+        start.record(main)
         for i in range(steps):
             one(i)
-        end.record()
+        main.wait_stream(copy_out)
+        end.record(main)
         torch.cuda.synchronize(dev)
         ms = start.elapsed_time(end) / steps
         if dist_on:
@@ -377,7 +402,8 @@ def run_b200(args, rank, local_rank, world):
         e2e_steps = max(3, min(args.steps, 10))
         e2e_ms, h2d, d2h = time_e2e(env, actions_host, e2e_steps, 3, dist_on)
         e2e = {"value": N * world / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps}
+               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "overlap": "observation read-back of step i on a copy stream, overlapping step i+1's H2D copies"}
 
     sweep = {}
     if not args.no_sweep and not dist_on:
