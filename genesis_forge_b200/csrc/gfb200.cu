@@ -102,6 +102,7 @@ struct gfb_handle {
   uint64_t peer_seq = 0;
   int64_t global_num_envs = 0;
   bool disable_tma = false;
+  bool disable_overlay = false;  // GFB_NO_OVERLAY=1: load every staged array up front
   int force_tile = 0;
   int force_stages = 0;
   int num_sms = 0;
@@ -261,6 +262,8 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, i
     return off;
   };
   const bool entity = phases & GFB_PHASE_ENTITY;
+  const bool contact = (phases & GFB_PHASE_CONTACT) && P.n_contact > 0;
+  // ---- early group: what the entity and contact phases read ---------------------------------------
   if (entity) {
     if (!b.buf[GFB_B_QUAT]) return fail(h, GFB_ERR_INVALID, "GFB_B_QUAT is required for the entity phase");
     plan.off_quat = stage(GFB_B_QUAT, 4, GFB_B_BASE_QUAT);
@@ -277,6 +280,23 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, i
     if (!b.buf[GFB_B_ANG]) return fail(h, GFB_ERR_INVALID, "GFB_B_ANG missing");
     plan.off_ang = stage(GFB_B_ANG, 3, -1);
   }
+  int contact_begin = cursor, contact_end = cursor;
+  if (contact) {
+    for (int id : {GFB_B_C_FORCE, GFB_B_C_POS, GFB_B_C_LINK_A, GFB_B_C_LINK_B, GFB_B_LINKS_QUAT})
+      if (!b.buf[id]) return fail(h, GFB_ERR_INVALID, "contact input buffer missing");
+    const int C = P.n_contact_slots;
+    plan.off_cforce = stage(GFB_B_C_FORCE, 3 * C, -1);
+    plan.off_cpos = stage(GFB_B_C_POS, 3 * C, -1);
+    plan.off_cla = stage(GFB_B_C_LINK_A, C, -1);
+    plan.off_clb = stage(GFB_B_C_LINK_B, C, -1);
+    contact_end = cursor;
+  }
+  // ---- late group: read by rewards / command resample / reset / observations only.  With contact
+  // slots staged (single-stage kernel) these arrays are loaded after the contact phase into the
+  // contact slots' shared memory; otherwise they simply follow the early arrays.
+  const bool overlay = contact && n_stages == 1 && !h->disable_overlay;
+  plan.n_early = plan.n_staged;
+  if (overlay) cursor = contact_begin;
   if (plan.needs & NEED_DOF_POS) {
     if (!b.buf[GFB_B_DOF_POS]) return fail(h, GFB_ERR_INVALID, "GFB_B_DOF_POS missing");
     plan.off_dof_pos = stage(GFB_B_DOF_POS, P.num_dofs, -1);
@@ -288,7 +308,7 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, i
     }
   // arrays that only the observation rows read (dof velocity / force, targets, raw actions) are
   // staged as well, so that the row assembly reads nothing but shared memory and every HBM read of
-  // the slab is issued up front by the TMA engine
+  // the slab is issued by the TMA engine
   int off_obs_src[GFB_B_COUNT];
   for (int i = 0; i < GFB_B_COUNT; ++i) off_obs_src[i] = -1;
   if (phases & GFB_PHASE_OBSERVE) {
@@ -316,15 +336,15 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, i
         if (buf == GFB_B_DOF_POS) plan.off_dof_pos = off_obs_src[buf];
       }
   }
-  const bool contact = (phases & GFB_PHASE_CONTACT) && P.n_contact > 0;
-  if (contact) {
-    for (int id : {GFB_B_C_FORCE, GFB_B_C_POS, GFB_B_C_LINK_A, GFB_B_C_LINK_B, GFB_B_LINKS_QUAT})
-      if (!b.buf[id]) return fail(h, GFB_ERR_INVALID, "contact input buffer missing");
-    const int C = P.n_contact_slots;
-    plan.off_cforce = stage(GFB_B_C_FORCE, 3 * C, -1);
-    plan.off_cpos = stage(GFB_B_C_POS, 3 * C, -1);
-    plan.off_cla = stage(GFB_B_C_LINK_A, C, -1);
-    plan.off_clb = stage(GFB_B_C_LINK_B, C, -1);
+  const bool stage_sums = (phases & (GFB_PHASE_REWARD | GFB_PHASE_RESET)) && P.n_reward > 0;
+  if (overlay) {
+    plan.sums_off = cursor;
+    if (stage_sums) cursor = align4(cursor + P.n_reward * tile);
+    plan.sums_late = stage_sums ? 1 : 0;
+    if (plan.n_early == plan.n_staged && !stage_sums) plan.sums_late = 0;  // nothing is late
+    cursor = std::max(cursor, contact_end);
+  } else {
+    plan.n_early = plan.n_staged;  // one group
   }
   // stash
   int stride = 9;
@@ -338,8 +358,10 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, i
   plan.stash_stride = stride;
   plan.stash_off = cursor;
   cursor = align4(cursor + stride * tile);
-  plan.sums_off = cursor;
-  if ((phases & (GFB_PHASE_REWARD | GFB_PHASE_RESET)) && P.n_reward > 0) cursor = align4(cursor + P.n_reward * tile);
+  if (!overlay) {
+    plan.sums_off = cursor;
+    if (stage_sums) cursor = align4(cursor + P.n_reward * tile);
+  }
   for (int m = 0; m < P.n_contact; ++m) {
     plan.cout_off[m] = cursor;
     if (contact) cursor = align4(cursor + 3 * P.contact[m].n_links * tile);
@@ -669,6 +691,8 @@ int gfb_create(int32_t num_envs, int32_t device, gfb_handle** out) {
     hh->num_envs = num_envs;
     const char* env_t = getenv("GFB_TILE");
     hh->force_tile = env_t ? atoi(env_t) : 0;
+    const char* env_o = getenv("GFB_NO_OVERLAY");
+    hh->disable_overlay = env_o && env_o[0] == '1';
     *out = hh;
     return GFB_OK;
   }
@@ -696,6 +720,8 @@ int gfb_create(int32_t num_envs, int32_t device, gfb_handle** out) {
   CUDA_TRY(cudaMemset(h->done_counter, 0, sizeof(uint32_t)));
   const char* env = getenv("GFB_DISABLE_TMA");
   h->disable_tma = env && env[0] == '1';
+  env = getenv("GFB_NO_OVERLAY");
+  h->disable_overlay = env && env[0] == '1';
   env = getenv("GFB_TILE");
   h->force_tile = env ? atoi(env) : 0;
   env = getenv("GFB_STAGES");

@@ -42,6 +42,13 @@ struct Plan {
   int32_t tile;          // envs per thread block
   uint32_t needs;
   int32_t n_staged;
+  // Two load groups.  Arrays [0, n_early) are loaded before the entity / contact phases.  Arrays
+  // [n_early, n_staged) and (sums_late) the episode-sum rows are only read after the contact phase
+  // and are loaded THEN, into the shared memory that held the contact slots -- the slab of a
+  // contact-bearing table needs ~1/3 less shared memory, so more warps stay resident.
+  // n_early == n_staged && !sums_late: everything is loaded up front (no contact slots staged).
+  int32_t n_early;
+  int32_t sums_late;
   int32_t staged_buf[GFB_MAX_STAGED];
   int32_t staged_words[GFB_MAX_STAGED];
   int32_t staged_off[GFB_MAX_STAGED];

@@ -68,26 +68,30 @@ __device__ __forceinline__ float4 add_noise(float4 v, const float4 nz, const flo
 
 // Issue the TMA loads of one slab (warp 0 only): staged arrays + episode-sum rows, optionally the
 // descriptor table.  All complete on `bar` (one arrival with the expected byte count by lane 0).
+// Staged arrays [a_begin, a_end) of the plan take part (the early or the late load group).
 template <int TILE>
 __device__ __forceinline__ void issue_slab_loads(const KParams& K, const Plan& plan, float* S, float* table_dst,
-                                                 uint64_t* bar, int tile, int n_sum_rows, bool with_table, int lane) {
+                                                 uint64_t* bar, int tile, int a_begin, int a_end, int n_sum_rows,
+                                                 bool with_table, int lane) {
   const int N = K.P.num_envs;
   const int e0 = tile * TILE;
   const uint32_t valid = (uint32_t)min(TILE, N - e0);
+  const int n_arrays = a_end - a_begin;
   if (lane == 0) {
     uint32_t total = (with_table ? (uint32_t)plan.table_words * 4u : 0u) + (uint32_t)n_sum_rows * valid * 4u;
-    for (int i = 0; i < plan.n_staged; ++i) total += (uint32_t)plan.staged_words[i] * valid * 4u;
+    for (int i = a_begin; i < a_end; ++i) total += (uint32_t)plan.staged_words[i] * valid * 4u;
     mbar_expect_tx(bar, total);
   }
   __syncwarp();
-  const int n_ops = plan.n_staged + n_sum_rows + (with_table ? 1 : 0);
-  for (int i = lane; i < n_ops; i += 32) {
-    if (i < plan.n_staged) {
+  const int n_ops = n_arrays + n_sum_rows + (with_table ? 1 : 0);
+  for (int op = lane; op < n_ops; op += 32) {
+    if (op < n_arrays) {
+      const int i = a_begin + op;
       const float* src = reinterpret_cast<const float*>(K.b.buf[plan.staged_buf[i]]) +
                          (size_t)e0 * plan.staged_words[i];
       bulk_load(S + plan.staged_off[i], src, (uint32_t)plan.staged_words[i] * valid * 4u, bar);
-    } else if (i < plan.n_staged + n_sum_rows) {
-      const int r = i - plan.n_staged;
+    } else if (op < n_arrays + n_sum_rows) {
+      const int r = op - n_arrays;
       bulk_load(S + plan.sums_off + r * TILE, GFB_BUF(const float, GFB_B_EP_SUMS) + (size_t)r * N + e0,
                 valid * 4u, bar);
     } else {
@@ -132,6 +136,9 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   const int n_sum_rows = stage_sums ? SP.n_reward : 0;
   const int n_tiles = K.s.n_tiles;
   const int n_stages = plan.n_stages;
+  // two load groups (plan.h): the late one follows the contact phase into the contact slots' memory
+  const bool two_groups = plan.n_early < plan.n_staged || plan.sums_late != 0;
+  const int n_sum_rows_early = plan.sums_late ? 0 : n_sum_rows;
   float* const Tbl = Sbase + plan.cols_off;  // descriptor table, loaded once per block
   const Philox rng(P.rng_seed);
 
@@ -143,7 +150,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     }
     __syncthreads();
     if (warp == 0 && (int)blockIdx.x < n_tiles)
-      issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], blockIdx.x, n_sum_rows, true, lane);
+      issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], blockIdx.x, 0, plan.n_early, n_sum_rows_early, true, lane);
   } else {
     const int32_t* src = reinterpret_cast<const int32_t*>(K.cols);
     int32_t* dst = reinterpret_cast<int32_t*>(Tbl);
@@ -172,17 +179,17 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     if (warp == 0 && n_stages == 2 && next_tile < n_tiles) {
       bulk_wait_all_read();  // the other stage's outgoing stores have left shared memory
       issue_slab_loads<TILE>(K, plan, Sbase + (stage ^ 1) * plan.stage_words, Tbl, &bars[stage ^ 1], next_tile,
-                             n_sum_rows, false, lane);
+                             0, plan.n_early, n_sum_rows_early, false, lane);
     }
   } else {
-    for (int i = 0; i < plan.n_staged; ++i) {
+    for (int i = 0; i < plan.n_early; ++i) {
       const int words = plan.staged_words[i] * valid;
       const float* src = reinterpret_cast<const float*>(K.b.buf[plan.staged_buf[i]]) +
                          (size_t)e0 * plan.staged_words[i];
       float* dst = S + plan.staged_off[i];
       for (int w = tid; w < words; w += TILE) dst[w] = src[w];
     }
-    if (stage_sums) {
+    if (stage_sums && !plan.sums_late) {
       const float* sums = GFB_BUF(const float, GFB_B_EP_SUMS);
       for (int r = 0; r < SP.n_reward; ++r)
         if (active) S[plan.sums_off + r * TILE + tid] = sums[(size_t)r * N + e];
@@ -412,6 +419,35 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   }
 
   // ------------------------------------------------------------------------------------------
+  // late load group: the arrays that only rewards / resample / reset / observations read (joint
+  // state, targets, commands, episode-sum rows) now replace the contact slots in shared memory;
+  // the terminations below run while they are in flight
+  // ------------------------------------------------------------------------------------------
+  if (two_groups) {
+    __syncthreads();  // every thread is done with the contact slots
+    if (use_tma) {
+      if (warp == 0) {
+        fence_async_smem();  // generic-proxy reads above, async-proxy writes below
+        issue_slab_loads<TILE>(K, plan, S, Tbl, &bars[1], tile, plan.n_early, plan.n_staged,
+                               plan.sums_late ? n_sum_rows : 0, false, lane);
+      }
+    } else {
+      for (int i = plan.n_early; i < plan.n_staged; ++i) {
+        const int words = plan.staged_words[i] * valid;
+        const float* src = reinterpret_cast<const float*>(K.b.buf[plan.staged_buf[i]]) +
+                           (size_t)e0 * plan.staged_words[i];
+        float* dst = S + plan.staged_off[i];
+        for (int w = tid; w < words; w += TILE) dst[w] = src[w];
+      }
+      if (stage_sums && plan.sums_late) {
+        const float* sums = GFB_BUF(const float, GFB_B_EP_SUMS);
+        for (int r = 0; r < SP.n_reward; ++r)
+          if (active) S[plan.sums_off + r * TILE + tid] = sums[(size_t)r * N + e];
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
   // terminations
   // ------------------------------------------------------------------------------------------
   bool terminated = false, truncated = false;
@@ -472,6 +508,11 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
       reset = terminated | truncated;  // managed_env.py:308-310
     }
     reset = reset && active;
+  }
+
+  if (two_groups) {  // the late group has landed
+    if (use_tma && warp == 0) mbar_wait(&bars[1], (uint32_t)(it & 1));
+    __syncthreads();
   }
 
   // ------------------------------------------------------------------------------------------
@@ -945,7 +986,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   if (next_tile < n_tiles) __syncthreads();
   if (use_tma && n_stages == 1 && next_tile < n_tiles && warp == 0) {
     bulk_wait_all_read();
-    issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], next_tile, n_sum_rows, false, lane);
+    issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], next_tile, 0, plan.n_early, n_sum_rows_early, false, lane);
   }
   }  // slab loop
 
