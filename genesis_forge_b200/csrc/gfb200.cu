@@ -110,9 +110,11 @@ struct gfb_handle {
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> ev_post, ev_action;
+  std::vector<uint8_t> ev_post_obs_only;  // per event pair: the launch ran the observation phase alone
   int n_post = 0, n_action = 0;
-  float post_ms = 0.f, action_ms = 0.f;
-  int post_count = 0, action_count = 0;
+  float post_ms = 0.f, action_ms = 0.f, post_obs_ms = 0.f;
+  int post_count = 0, action_count = 0, post_obs_count = 0;
+  cudaEvent_t report_event = nullptr;  // gfb_request_report / gfb_wait_report
   int smem_attr_post[3] = {0, 0, 0};
   int smem_attr_action[3] = {0, 0, 0};
 };
@@ -716,6 +718,7 @@ int gfb_create(int32_t num_envs, int32_t device, gfb_handle** out) {
   CUDA_TRY(cudaMemset(h->scratch.tile_reset_count, 0, (size_t)nt * sizeof(int32_t)));
   CUDA_TRY(cudaMemset(h->scratch.tile_reset_bits, 0, (size_t)nt * sizeof(uint32_t)));
   CUDA_TRY(cudaMallocHost(&h->report_host, sizeof(gfb_report)));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->report_event, cudaEventDisableTiming));
   CUDA_TRY(cudaMalloc(&h->done_counter, sizeof(uint32_t)));
   CUDA_TRY(cudaMemset(h->done_counter, 0, sizeof(uint32_t)));
   const char* env = getenv("GFB_DISABLE_TMA");
@@ -752,6 +755,7 @@ void gfb_destroy(gfb_handle* h) {
   for (auto& s : h->slots)
     if (s.table_dev) cudaFree(s.table_dev);
   if (h->observe_slot.table_dev) cudaFree(h->observe_slot.table_dev);
+  if (h->report_event) cudaEventDestroy(h->report_event);
   for (auto e : h->ev_post) cudaEventDestroy(e);
   for (auto e : h->ev_action) cudaEventDestroy(e);
   delete h;
@@ -979,6 +983,7 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->profiling && h->n_post + 2 <= (int)h->ev_post.size()) {
+    h->ev_post_obs_only[h->n_post / 2] = phases == GFB_PHASE_OBSERVE ? 1 : 0;
     e0 = h->ev_post[h->n_post++];
     e1 = h->ev_post[h->n_post++];
     cudaEventRecord(e0, stream);
@@ -1007,6 +1012,10 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
   if (rc != GFB_OK) return rc;
   if (e1) cudaEventRecord(e1, stream);
 
+  if (!(phases & (GFB_PHASE_TERMINATION | GFB_PHASE_REWARD | GFB_PHASE_RESET))) {
+    h->launches += 1;  // entity / contact / observation phases alone leave nothing to finalize
+    return GFB_OK;
+  }
   FinalizeParams fp{};
   fp.s = kp.s;
   fp.reset_idx = static_cast<int64_t*>(b->buf[GFB_B_RESET_IDX]);
@@ -1043,6 +1052,23 @@ int gfb_read_report(gfb_handle* h, gfb_report* out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CUDA_TRY(cudaMemcpyAsync(h->report_host, h->scratch.report, sizeof(gfb_report), cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
+  *out = *h->report_host;
+  return GFB_OK;
+}
+
+int gfb_request_report(gfb_handle* h, void* stream_) {
+  if (!h) return GFB_ERR_INVALID;
+  if (h->host_only) return fail(h, GFB_ERR_NO_DEVICE, "host-only handle has no report");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CUDA_TRY(cudaMemcpyAsync(h->report_host, h->scratch.report, sizeof(gfb_report), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaEventRecord(h->report_event, stream));
+  return GFB_OK;
+}
+
+int gfb_wait_report(gfb_handle* h, gfb_report* out) {
+  if (!h || !out) return GFB_ERR_INVALID;
+  if (h->host_only) return fail(h, GFB_ERR_NO_DEVICE, "host-only handle has no report");
+  CUDA_TRY(cudaEventSynchronize(h->report_event));
   *out = *h->report_host;
   return GFB_OK;
 }
@@ -1285,14 +1311,15 @@ int gfb_profile_enable(gfb_handle* h, int32_t enabled) {
   if (!h) return GFB_ERR_INVALID;
   if (enabled && h->ev_post.empty()) {
     h->ev_post.resize(kEventPairs * 2);
+    h->ev_post_obs_only.assign(kEventPairs, 0);
     h->ev_action.resize(kEventPairs * 2);
     for (auto& e : h->ev_post) CUDA_TRY(cudaEventCreate(&e));
     for (auto& e : h->ev_action) CUDA_TRY(cudaEventCreate(&e));
   }
   h->profiling = enabled != 0;
   h->n_post = h->n_action = 0;
-  h->post_ms = h->action_ms = 0.f;
-  h->post_count = h->action_count = 0;
+  h->post_ms = h->action_ms = h->post_obs_ms = 0.f;
+  h->post_count = h->action_count = h->post_obs_count = 0;
   return GFB_OK;
 }
 
@@ -1303,8 +1330,13 @@ int gfb_profile_read(gfb_handle* h, float* post_ms_total, int32_t* post_launches
   for (int i = 0; i + 1 < h->n_post; i += 2) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->ev_post[i], h->ev_post[i + 1]) == cudaSuccess) {
-      h->post_ms += ms;
-      h->post_count += 1;
+      if (h->ev_post_obs_only[i / 2]) {
+        h->post_obs_ms += ms;
+        h->post_obs_count += 1;
+      } else {
+        h->post_ms += ms;
+        h->post_count += 1;
+      }
     }
   }
   for (int i = 0; i + 1 < h->n_action; i += 2) {
@@ -1319,6 +1351,15 @@ int gfb_profile_read(gfb_handle* h, float* post_ms_total, int32_t* post_launches
   if (post_launches) *post_launches = h->post_count;
   if (action_ms_total) *action_ms_total = h->action_ms;
   if (action_launches) *action_launches = h->action_count;
+  return GFB_OK;
+}
+
+int gfb_profile_read_observation_pass(gfb_handle* h, float* ms_total, int32_t* launches) {
+  if (!h) return GFB_ERR_INVALID;
+  int rc = gfb_profile_read(h, nullptr, nullptr, nullptr, nullptr);  // folds pending event pairs
+  if (rc != GFB_OK) return rc;
+  if (ms_total) *ms_total = h->post_obs_ms;
+  if (launches) *launches = h->post_obs_count;
   return GFB_OK;
 }
 

@@ -194,7 +194,10 @@ class ManagedEnvironment(GenesisEnv):
         self.scene.step()
         if fused.split_mode:
             return self._finish_step_split()
-        report = fused.post_physics(nat.K["GFB_PHASE_ALL"])
+        if fused.overlap_obs:  # large batch: observation rows by a second launch behind the report copy
+            report = fused.post_physics_overlapped()
+        else:
+            report = fused.post_physics(nat.K["GFB_PHASE_ALL"])
 
         n_reset = report.n_reset
         if n_reset > 0:

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GFB_ABI_VERSION 6
+#define GFB_ABI_VERSION 7
 
 /* ---- limits ------------------------------------------------------------------------------- */
 #define GFB_MAX_DOFS 32
@@ -345,6 +345,12 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
  * reference blocks at the same place, managed_env.py:309,322).                                 */
 int gfb_read_report(gfb_handle* h, gfb_report* out, void* stream);
 
+/* The same in two halves: gfb_request_report enqueues the copy and marks the stream position,
+ * gfb_wait_report blocks until that position is reached.  Work enqueued in between (the separate
+ * observation pass of a large batch) runs while the host handles the report.    */
+int gfb_request_report(gfb_handle* h, void* stream);
+int gfb_wait_report(gfb_handle* h, gfb_report* out);
+
 /* ---- envs sharded over the GPUs of one node ------------------------------------
  * The only exchange between ranks is the logging vector [sum of episode quotients per reward term,
  * fire count per termination term, n_reset].  Instead of a collective call after the kernel, the
@@ -442,7 +448,10 @@ int gfb_spec_stats(const gfb_handle* h, int64_t* specialised, int64_t* generic);
 int gfb_profile_enable(gfb_handle* h, int32_t enabled);
 int gfb_profile_read(gfb_handle* h, float* post_ms_total, int32_t* post_launches, float* action_ms_total,
                      int32_t* action_launches);
-/* kernels launched by this handle since creation (gfb_action_step: 1, gfb_post_physics: 2, ...) */
+/* Same for the launches of gfb_post_physics that ran GFB_PHASE_OBSERVE alone (they are excluded
+ * from the post_* totals of gfb_profile_read).                                                  */
+int gfb_profile_read_observation_pass(gfb_handle* h, float* ms_total, int32_t* launches);
+/* kernels launched by this handle since creation (gfb_action_step: 1, gfb_post_physics: 1-2, ...) */
 int64_t gfb_launch_count(const gfb_handle* h);
 
 #ifdef __cplusplus

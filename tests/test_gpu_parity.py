@@ -24,7 +24,9 @@ def test_step_parity(name, cuda_device):
     assert stats["resets"] > 0
     spec_stats = run.env._fused.spec_stats()
     if name in SPLIT:
-        assert run.env._fused.split_mode and spec_stats["generic_launches"] == 2 + 4 * 120, spec_stats
+        # four launches per step with the Python callbacks in between; the observation pass is specialised
+        assert run.env._fused.split_mode, spec_stats
+        assert spec_stats["generic_launches"] == 2 + 3 * 120 and spec_stats["specialised_launches"] == 120, spec_stats
     else:
         # (the two generic launches are the build-time entity phase and the initial reset phase)
         assert spec_stats["specialised_launches"] == 120 and spec_stats["generic_launches"] == 2, spec_stats
@@ -255,3 +257,36 @@ def test_direct_term_calls_match_the_oracle(name, cuda_device):
     assert checked >= 6
     for _ in range(5):
         run.step()
+
+
+@pytest.mark.parametrize("name", ["command_direction", "contacts", "rough_terrain", "kitchen_sink"])
+def test_two_launch_step_parity(name, cuda_device, monkeypatch):
+    """
+    Optional large-batch mode (GFB_OVERLAP_OBS=1): the step as main launch + report copy + separate
+    observation pass (FusedStep.post_physics_overlapped) must reproduce the oracle like the single
+    fused launch does.  (No specialisations are pre-built for this slab size: generic kernels.)
+    """
+    from oracle.parity import ParityRun
+
+    monkeypatch.setenv("GFB_OVERLAP_OBS", "1")
+    monkeypatch.setenv("GFB_SPEC_JIT", "0")
+    run = ParityRun(name, num_envs=200, device=cuda_device, seed=2024)
+    assert run.env._fused.overlap_obs
+    stats = run.run(steps=60, nan_step=5)
+    assert stats["resets"] > 0
+    spec_stats = run.env._fused.spec_stats()
+    assert spec_stats["generic_launches"] + spec_stats["specialised_launches"] == 2 + 2 * 60, spec_stats
+
+
+@pytest.mark.parametrize("name", ["command_direction", "berkeley_humanoid"])
+def test_two_launch_step_parity_specialised(name, cuda_device, monkeypatch):
+    """The same at a large-slab batch size, where both launches have pre-built specialisations."""
+    from oracle.parity import ParityRun
+
+    monkeypatch.setenv("GFB_OVERLAP_OBS", "1")
+    run = ParityRun(name, num_envs=131072, device=cuda_device, seed=8)
+    assert run.env._fused.overlap_obs
+    stats = run.run(steps=4)
+    assert stats["resets"] > 0
+    spec_stats = run.env._fused.spec_stats()
+    assert spec_stats["specialised_launches"] == 2 * 4 and spec_stats["generic_launches"] == 2, spec_stats

@@ -63,7 +63,8 @@ wrap(env, "_begin_step", "_begin_step")
 wrap(fused, "begin_step", "begin_step")
 wrap(fused, "action_step", "action_step (launch)")
 wrap(env.scene, "step", "scene.step")
-wrap(fused, "post_physics", "post_physics (launch + report sync)")
+wrap(fused, "post_physics", "post_physics (launch + report sync)" if not fused.overlap_obs else "    post_physics main (launch)")
+wrap(fused, "post_physics_overlapped", "post_physics_overlapped (2 launches + report wait)")
 wrap(env, "_host_reset", "host reset handlers")
 wrap(fused, "observe", "observe (launch)")
 wrap(fused, "finish_logging", "finish_logging")
@@ -73,6 +74,7 @@ for i in range(20):
     env.step(acts[i % 4])
 torch.cuda.synchronize()
 T.clear()
+fused.profile(True)
 K = 100
 t0 = time.perf_counter()
 for i in range(K):
@@ -86,3 +88,7 @@ for k, v in T.items():
     if not k.startswith("    "):
         acc += v / K * 1e6
 print(f"  {'(other python in step)':40s} {total - acc:8.1f} us")
+prof = fused.profile_read(); obs = fused.profile_read_observation_pass()
+print(f"  kernels: action {prof['action_ms'] / max(prof['action_launches'], 1) * 1e3:.1f} us, post(main) "
+      f"{prof['post_ms'] / max(prof['post_launches'], 1) * 1e3:.1f} us, observation pass "
+      f"{obs['obs_ms'] / max(obs['obs_launches'], 1) * 1e3:.1f} us ({obs['obs_launches']} launches)")
