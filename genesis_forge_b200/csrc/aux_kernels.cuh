@@ -17,7 +17,10 @@ namespace gfb {
 // last_actions / actions are pure copies -> TMA out of the very same shared-memory slabs.
 // ---------------------------------------------------------------------------------------------
 struct ActionParams {
-  gfb_program_head P;
+  // the action part of the term table only (a launch copies its parameter block: 4 KB -> 0.6 KB)
+  int32_t num_envs, num_dofs, action_mode, _pad;
+  float action_scale[GFB_MAX_DOFS], action_offset[GFB_MAX_DOFS];
+  float action_clip_lo[GFB_MAX_DOFS], action_clip_hi[GFB_MAX_DOFS];
   const float* raw_env;
   const float* raw_mgr;  // == raw_env unless a delay FIFO is active
   float* env_actions;
@@ -34,7 +37,7 @@ template <int TILE>
 __global__ void __launch_bounds__(TILE) action_kernel(const __grid_constant__ ActionParams A) {
   extern __shared__ __align__(128) float S[];
   __shared__ __align__(8) uint64_t bar;
-  const gfb_program_head& P = A.P;
+  const ActionParams& P = A;
   const int tid = threadIdx.x;
   const int N = P.num_envs, D = P.num_dofs;
   const int e0 = blockIdx.x * TILE;
@@ -393,8 +396,15 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinalizePar
 // reset (managed_env.py:322-326) with post-reset engine getters but the pre-reset cached
 // quaternion (entity_manager.py:134-146 vs :189-195; EntityManager.reset does not refresh it).
 // ---------------------------------------------------------------------------------------------
+struct ObserveHead {  // the observation part of the term table (instead of the whole 4 KB head)
+  int32_t n_contact, n_obs_groups, rng_mode, _pad;
+  uint64_t rng_seed, step_index;
+  int32_t contact_links[GFB_MAX_CONTACT_MANAGERS];
+  gfb_obs_group obs_group[GFB_MAX_OBS_GROUPS];
+};
+
 struct ObserveParams {
-  gfb_program_head P;
+  ObserveHead P;
   gfb_buffers b;
   Plan plan;
   const DevObsCol* cols;
@@ -408,7 +418,7 @@ constexpr int OBS_THREADS = 128;  // 8 threads per env for the column gather
 __global__ void __launch_bounds__(OBS_THREADS) observe_kernel(const __grid_constant__ ObserveParams K) {
   extern __shared__ __align__(128) float S[];  // (OBS_ENVS, stash_stride) stash, then the column table
   __shared__ long long s_env[OBS_ENVS];
-  const gfb_program_head& P = K.P;
+  const ObserveHead& P = K.P;
   const Plan& plan = K.plan;
   const int tid = threadIdx.x;
   const int i0 = blockIdx.x * OBS_ENVS;
@@ -443,8 +453,8 @@ __global__ void __launch_bounds__(OBS_THREADS) observe_kernel(const __grid_const
     for (int m = 0; m < P.n_contact; ++m) {
       const float* cg = GFB_BUF(const float, GFB_B_CONTACTS0 + m);
       if (!cg) continue;
-      cg += e * P.contact[m].n_links * 3;
-      for (int t = 0; t < P.contact[m].n_links; ++t)
+      cg += e * P.contact_links[m] * 3;
+      for (int t = 0; t < P.contact_links[m]; ++t)
         st[plan.st_cnorm[m] + t] = norm3(cg[t * 3], cg[t * 3 + 1], cg[t * 3 + 2]);
     }
   }

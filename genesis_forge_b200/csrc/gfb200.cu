@@ -830,7 +830,13 @@ int gfb_action_step(gfb_handle* h, const gfb_buffers* b, const float* raw_env, c
   const gfb_program_head& P = h->prog.head;
   if (!raw_mgr) raw_mgr = raw_env;
   ActionParams ap{};
-  ap.P = P;
+  ap.num_envs = P.num_envs;
+  ap.num_dofs = P.num_dofs;
+  ap.action_mode = P.action_mode;
+  memcpy(ap.action_scale, P.action_scale, sizeof(ap.action_scale));
+  memcpy(ap.action_offset, P.action_offset, sizeof(ap.action_offset));
+  memcpy(ap.action_clip_lo, P.action_clip_lo, sizeof(ap.action_clip_lo));
+  memcpy(ap.action_clip_hi, P.action_clip_hi, sizeof(ap.action_clip_hi));
   ap.raw_env = raw_env;
   ap.raw_mgr = raw_mgr;
   ap.env_actions = static_cast<float*>(b->buf[GFB_B_ENV_ACTIONS]);
@@ -1159,7 +1165,13 @@ int gfb_observe(gfb_handle* h, const gfb_buffers* b, const int64_t* idx, int32_t
   if ((op.plan.needs & NEED_ANG) && !b->buf[GFB_B_ANG]) return fail(h, GFB_ERR_INVALID, "ANG missing");
   rc = upload_table(h, h->observe_slot, table, stream);
   if (rc != GFB_OK) return rc;
-  op.P = P;
+  op.P.n_contact = P.n_contact;
+  op.P.n_obs_groups = P.n_obs_groups;
+  op.P.rng_mode = P.rng_mode;
+  op.P.rng_seed = P.rng_seed;
+  op.P.step_index = P.step_index;
+  for (int m = 0; m < P.n_contact; ++m) op.P.contact_links[m] = P.contact[m].n_links;
+  memcpy(op.P.obs_group, P.obs_group, sizeof(op.P.obs_group));
   op.b = *b;
   op.cols = reinterpret_cast<const DevObsCol*>(h->observe_slot.table_dev);
   op.idx = idx;
