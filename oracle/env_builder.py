@@ -103,6 +103,8 @@ def build_env(spec: dict, ns, num_envs: int, device, **scene_kw):
                 if ref == "fixed_command[:, 2]":
                     return self.fixed_command[:, 2]
                 return getattr(self, ref)
+            if torch.is_tensor(value):  # per-env tensors given in a spec live on the env's device
+                return value.to(device)
             return value
 
         def _params(self, params):

@@ -202,10 +202,12 @@ class ParityRun:
         actions = torch.randn(self.N, self.port.num_actions, generator=self.action_gen)
         if nan_action:
             actions[min(3, self.N - 1), 1] = float("nan")
-        out_p = self.port.step(actions.clone())
+        # (both sides get their own tensor: the within-limits action manager clamps its argument in place)
+        self.last_action_args = (actions.clone(), actions.to(self.device))
+        out_p = self.port.step(self.last_action_args[0])
         self._assert_margins(f"step {i}")
         self._inject_from_log(self.port.reset_idx, self.port.resample_idx)
-        out_e = self.env.step(actions.to(self.device))
+        out_e = self.env.step(self.last_action_args[1])
         where = f"step {i}"
         n_reset = int(self.port.reset_idx.numel())
         self._check(where, "reset_idx", self.env._fused.reset_idx[:n_reset], self.port.reset_idx, exact=True)

@@ -290,3 +290,39 @@ def test_two_launch_step_parity_specialised(name, cuda_device, monkeypatch):
     assert stats["resets"] > 0
     spec_stats = run.env._fused.spec_stats()
     assert spec_stats["specialised_launches"] == 2 * 4 and spec_stats["generic_launches"] == 2, spec_stats
+
+
+def test_within_limits_action_manager(cuda_device):
+    """PositionWithinLimitsActionManager (position_within_limits.py:99-131): clamp to [-1, 1], then the joint-limit map."""
+    from oracle import specs
+    from oracle.parity import ParityRun
+
+    action = dict(specs.get("command_direction")["action"], type="within_limits")
+    for key in ("scale", "use_default_offset"):
+        action.pop(key, None)
+    run = ParityRun("command_direction", num_envs=200, device=cuda_device, seed=31, spec_override={"action": action})
+    assert run.env.action_manager.kernel_mode == 2
+    run.reset()
+    clamped = 0
+    for i in range(40):
+        run.step(nan_action=(i == 4))
+        # clamp_ (:127) acts on the manager's own copy (base.py:76-82), never on the tensor the caller passed
+        given_port, given_env = run.last_action_args
+        assert torch.equal(given_env.cpu().nan_to_num(nan=7.0), given_port.nan_to_num(nan=7.0))
+        clamped += int((given_port.abs() > 1.0).sum())
+    assert clamped > 0 and run.stats["resets"] > 0
+
+
+def test_base_height_with_a_per_env_target_tensor(cuda_device):
+    """rewards.base_height(target_height=<(N,) tensor>) (rewards.py:54-90): GFB_RF_TARGET_FROM_TENSOR."""
+    from oracle import specs
+    from oracle.parity import ParityRun
+
+    n = 160
+    rewards = specs.get("command_direction")["rewards"]
+    name = next(k for k, v in rewards.items() if v["fn"] == "base_height")
+    rewards[name]["params"] = dict(rewards[name]["params"],
+                                   target_height=0.25 + 0.1 * torch.rand(n, generator=torch.Generator().manual_seed(3)))
+    run = ParityRun("command_direction", num_envs=n, device=cuda_device, seed=57, spec_override={"rewards": rewards})
+    stats = run.run(steps=30)
+    assert stats["resets"] > 0
