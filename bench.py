@@ -386,6 +386,7 @@ def run_b200(args, rank, local_rank, world):
     ms, resets_per_step = time_dropin(env, actions, args.steps, args.warmup, dist_on)
     prof = fused.profile_read()
     obs_prof = fused.profile_read_observation_pass()
+    aux_prof = fused.profile_read_aux()
     fused.profile(False)
     launches = env.timed_launches
     clocks = sampler.stop(env.timed_window) if sampler else None
@@ -457,6 +458,7 @@ def run_b200(args, rank, local_rank, world):
                 "peak_source": peak_src,
                 "bytes_per_env": post_bytes, "kernel_us": post_ms * 1e3,
                 "observation_pass": observation_pass,  # only with GFB_OVERLAP_OBS=1 (two-launch step)
+                "small_kernels": aux_prof,  # CUDA-event time per launch: finalize, re-observation, spawn
                 "action_kernel": {"bytes_per_env": roofline.action_kernel_bytes(fused), "kernel_us": act_ms * 1e3,
                                   "achieved": roofline.action_kernel_bytes(fused) * N / max(act_ms, 1e-9) / 1e6,
                                   "frac": roofline.action_kernel_bytes(fused) * N / max(act_ms, 1e-9) / 1e6 / peak},

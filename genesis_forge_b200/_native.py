@@ -165,7 +165,7 @@ EXPORTS = [
     "gfb_abi_version", "gfb_abi_sizeof", "gfb_create", "gfb_destroy", "gfb_last_error", "gfb_set_program",
     "gfb_action_step", "gfb_post_physics", "gfb_read_report", "gfb_observe", "gfb_contact_forces",
     "gfb_rotate", "gfb_spawn_pose", "gfb_peer_export", "gfb_peer_connect", "gfb_peer_disconnect", "gfb_spec_describe", "gfb_spec_attach", "gfb_spec_stats",
-    "gfb_profile_enable", "gfb_profile_read", "gfb_profile_read_observation_pass", "gfb_launch_count",
+    "gfb_profile_enable", "gfb_profile_read", "gfb_profile_read_observation_pass", "gfb_profile_read_aux", "gfb_launch_count",
     "gfb_request_report", "gfb_wait_report",
 ]
 
@@ -234,6 +234,8 @@ def lib() -> C.CDLL:
     L.gfb_profile_read.argtypes = [vp, fp, C.POINTER(i32), fp, C.POINTER(i32)]
     L.gfb_profile_read_observation_pass.restype = C.c_int
     L.gfb_profile_read_observation_pass.argtypes = [vp, fp, C.POINTER(i32)]
+    L.gfb_profile_read_aux.restype = C.c_int
+    L.gfb_profile_read_aux.argtypes = [vp, fp, C.POINTER(i32)]
     L.gfb_request_report.restype = C.c_int
     L.gfb_request_report.argtypes = [vp, vp]
     L.gfb_wait_report.restype = C.c_int

@@ -115,6 +115,12 @@ struct gfb_handle {
   float post_ms = 0.f, action_ms = 0.f, post_obs_ms = 0.f;
   int post_count = 0, action_count = 0, post_obs_count = 0;
   cudaEvent_t report_event = nullptr;  // gfb_request_report / gfb_wait_report
+  // the small kernels: 0 finalize, 1 observe (reset envs), 2 spawn
+  std::vector<cudaEvent_t> ev_aux;
+  std::vector<uint8_t> ev_aux_kind;
+  int n_aux = 0;
+  float aux_ms[3] = {0.f, 0.f, 0.f};
+  int aux_count[3] = {0, 0, 0};
   int smem_attr_post[3] = {0, 0, 0};
   int smem_attr_action[3] = {0, 0, 0};
 };
@@ -566,6 +572,16 @@ bool tma_eligible(const gfb_handle* h, const gfb_buffers& b, const Plan& plan, u
   return true;
 }
 
+// profiling bracket of an auxiliary kernel: records the start event, returns the end event (or null)
+cudaEvent_t aux_begin(gfb_handle* h, int kind, cudaStream_t stream) {
+  if (!h->profiling || h->n_aux + 2 > (int)h->ev_aux.size()) return nullptr;
+  h->ev_aux_kind[h->n_aux / 2] = (uint8_t)kind;
+  cudaEvent_t e0 = h->ev_aux[h->n_aux++];
+  cudaEvent_t e1 = h->ev_aux[h->n_aux++];
+  cudaEventRecord(e0, stream);
+  return e1;
+}
+
 int choose_tile(const gfb_handle* h) {
   if (h->force_tile == 32 || h->force_tile == 64 || h->force_tile == 128) return h->force_tile;
   return h->num_envs >= 32768 ? 128 : 32;
@@ -756,6 +772,7 @@ void gfb_destroy(gfb_handle* h) {
     if (s.table_dev) cudaFree(s.table_dev);
   if (h->observe_slot.table_dev) cudaFree(h->observe_slot.table_dev);
   if (h->report_event) cudaEventDestroy(h->report_event);
+  for (auto e : h->ev_aux) cudaEventDestroy(e);
   for (auto e : h->ev_post) cudaEventDestroy(e);
   for (auto e : h->ev_action) cudaEventDestroy(e);
   delete h;
@@ -1046,8 +1063,10 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
   for (int r = 0; r < P.n_reward; ++r)
     if (P.reward[r].weight != 0.0f) fp.reward_weight_mask |= (1u << r);
   const int n_chunks = std::max(1, std::min(FIN_CHUNK_BLOCKS, (n_tiles + 63) / 64));
+  cudaEvent_t fin_end = aux_begin(h, 0, stream);
   finalize_kernel<<<n_chunks + P.n_termination + P.n_reward + 1, FIN_THREADS, 0, stream>>>(fp, n_chunks);
   CUDA_TRY(cudaGetLastError());
+  if (fin_end) cudaEventRecord(fin_end, stream);
   h->launches += 2;
   return GFB_OK;
 }
@@ -1179,8 +1198,10 @@ int gfb_observe(gfb_handle* h, const gfb_buffers* b, const int64_t* idx, int32_t
   const size_t smem = (size_t)op.plan.stash_stride * OBS_ENVS * 4 + 16 +
                       (size_t)op.plan.n_cols_total * sizeof(DevObsCol);
   const int grid = (n + OBS_ENVS - 1) / OBS_ENVS;
+  cudaEvent_t obs_end = aux_begin(h, 1, stream);
   observe_kernel<<<grid, OBS_THREADS, smem, stream>>>(op);
   CUDA_TRY(cudaGetLastError());
+  if (obs_end) cudaEventRecord(obs_end, stream);
   h->launches += 1;
   return GFB_OK;
 }
@@ -1250,8 +1271,10 @@ int gfb_spawn_pose(gfb_handle* h, const gfb_spawn* cfg, const int64_t* idx, int3
   sp.quat_buffer = quat_buffer;
   sp.pos_out = pos_out;
   sp.quat_out = quat_out;
+  cudaEvent_t spawn_end = aux_begin(h, 2, static_cast<cudaStream_t>(stream_));
   spawn_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream_)>>>(sp);
   CUDA_TRY(cudaGetLastError());
+  if (spawn_end) cudaEventRecord(spawn_end, static_cast<cudaStream_t>(stream_));
   h->launches += 1;
   return GFB_OK;
 }
@@ -1325,13 +1348,20 @@ int gfb_profile_enable(gfb_handle* h, int32_t enabled) {
     h->ev_post.resize(kEventPairs * 2);
     h->ev_post_obs_only.assign(kEventPairs, 0);
     h->ev_action.resize(kEventPairs * 2);
+    h->ev_aux.resize(kEventPairs * 4);
+    h->ev_aux_kind.assign(kEventPairs * 2, 0);
+    for (auto& e : h->ev_aux) CUDA_TRY(cudaEventCreate(&e));
     for (auto& e : h->ev_post) CUDA_TRY(cudaEventCreate(&e));
     for (auto& e : h->ev_action) CUDA_TRY(cudaEventCreate(&e));
   }
   h->profiling = enabled != 0;
-  h->n_post = h->n_action = 0;
+  h->n_post = h->n_action = h->n_aux = 0;
   h->post_ms = h->action_ms = h->post_obs_ms = 0.f;
   h->post_count = h->action_count = h->post_obs_count = 0;
+  for (int k = 0; k < 3; ++k) {
+    h->aux_ms[k] = 0.f;
+    h->aux_count[k] = 0;
+  }
   return GFB_OK;
 }
 
@@ -1358,7 +1388,14 @@ int gfb_profile_read(gfb_handle* h, float* post_ms_total, int32_t* post_launches
       h->action_count += 1;
     }
   }
-  h->n_post = h->n_action = 0;
+  for (int i = 0; i + 1 < h->n_aux; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_aux[i], h->ev_aux[i + 1]) == cudaSuccess) {
+      h->aux_ms[h->ev_aux_kind[i / 2]] += ms;
+      h->aux_count[h->ev_aux_kind[i / 2]] += 1;
+    }
+  }
+  h->n_post = h->n_action = h->n_aux = 0;
   if (post_ms_total) *post_ms_total = h->post_ms;
   if (post_launches) *post_launches = h->post_count;
   if (action_ms_total) *action_ms_total = h->action_ms;
@@ -1372,6 +1409,17 @@ int gfb_profile_read_observation_pass(gfb_handle* h, float* ms_total, int32_t* l
   if (rc != GFB_OK) return rc;
   if (ms_total) *ms_total = h->post_obs_ms;
   if (launches) *launches = h->post_obs_count;
+  return GFB_OK;
+}
+
+int gfb_profile_read_aux(gfb_handle* h, float* ms_total, int32_t* launches) {
+  if (!h || !ms_total || !launches) return GFB_ERR_INVALID;
+  int rc = gfb_profile_read(h, nullptr, nullptr, nullptr, nullptr);  // folds pending event pairs
+  if (rc != GFB_OK) return rc;
+  for (int k = 0; k < 3; ++k) {
+    ms_total[k] = h->aux_ms[k];
+    launches[k] = h->aux_count[k];
+  }
   return GFB_OK;
 }
 

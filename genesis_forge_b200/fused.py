@@ -1111,6 +1111,13 @@ class FusedStep:
     def profile(self, enabled: bool):
         self.handle.check(self.lib.gfb_profile_enable(self.handle.ptr, 1 if enabled else 0), "gfb_profile_enable")
 
+    def profile_read_aux(self) -> dict:
+        """Average device time (us) of the small kernels since profiling was enabled."""
+        ms, n = (C.c_float * 3)(), (C.c_int32 * 3)()
+        self.handle.check(self.lib.gfb_profile_read_aux(self.handle.ptr, ms, n), "gfb_profile_read_aux")
+        return {name: {"kernel_us": ms[k] / max(n[k], 1) * 1e3, "launches": n[k]}
+                for k, name in enumerate(("finalize_kernel", "observe_kernel", "spawn_kernel"))}
+
     def profile_read_observation_pass(self) -> dict:
         ms, n = C.c_float(), C.c_int32()
         self.handle.check(

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GFB_ABI_VERSION 7
+#define GFB_ABI_VERSION 8
 
 /* ---- limits ------------------------------------------------------------------------------- */
 #define GFB_MAX_DOFS 32
@@ -451,6 +451,9 @@ int gfb_profile_read(gfb_handle* h, float* post_ms_total, int32_t* post_launches
 /* Same for the launches of gfb_post_physics that ran GFB_PHASE_OBSERVE alone (they are excluded
  * from the post_* totals of gfb_profile_read).                                                  */
 int gfb_profile_read_observation_pass(gfb_handle* h, float* ms_total, int32_t* launches);
+/* Same for the small kernels; ms_total / launches are arrays of 3: [0] finalize, [1] observe
+ * (gfb_observe), [2] spawn (gfb_spawn_pose).                                                    */
+int gfb_profile_read_aux(gfb_handle* h, float* ms_total, int32_t* launches);
 /* kernels launched by this handle since creation (gfb_action_step: 1, gfb_post_physics: 1-2, ...) */
 int64_t gfb_launch_count(const gfb_handle* h);
 

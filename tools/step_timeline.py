@@ -88,7 +88,8 @@ for k, v in T.items():
     if not k.startswith("    "):
         acc += v / K * 1e6
 print(f"  {'(other python in step)':40s} {total - acc:8.1f} us")
-prof = fused.profile_read(); obs = fused.profile_read_observation_pass()
+prof = fused.profile_read(); obs = fused.profile_read_observation_pass(); aux = fused.profile_read_aux()
+print("  small kernels:", ", ".join(f"{k} {v['kernel_us']:.1f} us x{v['launches']}" for k, v in aux.items()))
 print(f"  kernels: action {prof['action_ms'] / max(prof['action_launches'], 1) * 1e3:.1f} us, post(main) "
       f"{prof['post_ms'] / max(prof['post_launches'], 1) * 1e3:.1f} us, observation pass "
       f"{obs['obs_ms'] / max(obs['obs_launches'], 1) * 1e3:.1f} us ({obs['obs_launches']} launches)")
