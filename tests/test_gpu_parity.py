@@ -326,3 +326,22 @@ def test_base_height_with_a_per_env_target_tensor(cuda_device):
     run = ParityRun("command_direction", num_envs=n, device=cuda_device, seed=57, spec_override={"rewards": rewards})
     stats = run.run(steps=30)
     assert stats["resets"] > 0
+
+
+@pytest.mark.parametrize("switch", ["GFB_DISABLE_TMA=1", "GFB_NO_OVERLAY=1", "GFB_TILE=64", "GFB_STAGES=2"])
+def test_kernel_switches_keep_parity(switch, cuda_device, monkeypatch):
+    """
+    The alternative code paths behind the environment switches (cooperative loads instead of TMA, one
+    load group, another slab size, the persistent two-stage ring) give the same results.  Generic
+    kernels: no specialisation is pre-built for these plans and none is compiled here.
+    """
+    from oracle.parity import ParityRun
+
+    key, value = switch.split("=")
+    monkeypatch.setenv(key, value)
+    monkeypatch.setenv("GFB_SPEC_JIT", "0")
+    # the ring only cycles when there are more slabs than resident blocks: a large batch, few steps
+    n, steps = (150_000, 5) if key == "GFB_STAGES" else (328, 40)
+    run = ParityRun("contacts", num_envs=n, device=cuda_device, seed=404)
+    stats = run.run(steps=steps, nan_step=3)
+    assert stats["resets"] > 0
