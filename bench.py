@@ -377,7 +377,7 @@ def run_b200(args, rank, local_rank, world):
     env = make_dropin_env(spec, N, dev, args.pool, seed)
     fused = env._fused
     if dist_on:
-        fused.shard(dist.group.WORLD, N * world)
+        env.shard()  # logging becomes global over WORLD (in-kernel peer-memory exchange)
     gen = torch.Generator().manual_seed(seed)
     actions_host = [torch.randn(N, fused.D, generator=gen).pin_memory() for _ in range(4)]
     actions = [a.to(dev) for a in actions_host]

@@ -178,6 +178,23 @@ class ManagedEnvironment(GenesisEnv):
         if not self._fused.dry_run:
             self._fused.cache_entity()
 
+    # -- multi-GPU ----------------------------------------------------------------------------------
+    def shard(self, group=None, global_num_envs: int | None = None, peer: bool | None = None):
+        """
+        Declare this environment one shard of a job that runs one process per GPU (torch.distributed
+        initialised, after build()): logged episode means / termination fractions and the decision
+        which keys are published become global over `group` (default: WORLD).  Nothing else is
+        exchanged -- envs are independent rows.  See FusedStep.shard for `peer`.
+        """
+        import torch.distributed as dist
+
+        if self._fused is None:
+            raise RuntimeError("build() the environment before sharding it")
+        group = group if group is not None else dist.group.WORLD
+        if global_num_envs is None:
+            global_num_envs = self.num_envs * dist.get_world_size(group)
+        self._fused.shard(group, global_num_envs, peer=peer)
+
     # -- step -------------------------------------------------------------------------------------
     def step(self, actions: torch.Tensor):
         fused = self._fused
