@@ -204,3 +204,75 @@ def test_program_struct_is_plain_data():
     P = nat.Program()
     assert ctypes.sizeof(P) < 32 * 1024  # travels as a kernel parameter block / one memcpy
     assert ctypes.sizeof(nat.ProgramHead) % 8 == 0
+
+
+# -- slab plans (host-only handle: gfb_spec_describe) -------------------------------------------------
+def _plan(env, phases=None):
+    from genesis_forge_b200 import spec
+
+    fused = env._fused
+    env._allocate_action_buffers(fused.D)
+    fused.bind_action_buffers()
+    fused.prepare_describe(injected=False)
+    canon, words, tile = spec.describe(fused, nat.K["GFB_PHASE_ALL"] if phases is None else phases)
+    names = ["tile", "needs", "n_staged", "n_early", "sums_late"]
+    return dict(zip(names, words[:5]), smem_words=words[-1]), canon, words
+
+
+def test_contact_tables_load_the_slab_in_two_groups(cpu_device, monkeypatch):
+    """Arrays read only after the contact phase are loaded later, over the contact slots."""
+    plain, _, _ = _plan(dry_env("command_direction", n=65536))
+    assert plain["n_early"] == plain["n_staged"] and plain["sums_late"] == 0
+    two, _, _ = _plan(dry_env("berkeley_humanoid", n=65536))
+    assert 0 < two["n_early"] < two["n_staged"] and two["sums_late"] == 1
+    monkeypatch.setenv("GFB_NO_OVERLAY", "1")
+    one, _, _ = _plan(dry_env("berkeley_humanoid", n=65536))
+    assert one["n_early"] == one["n_staged"] and one["sums_late"] == 0
+    assert two["smem_words"] / two["tile"] < 0.8 * one["smem_words"] / one["tile"]  # shared memory per env
+
+
+def test_plan_is_a_function_of_structure_not_of_live_values(cpu_device):
+    """The specialisation key ignores weights / thresholds / step index, but not a zeroed weight's neighbours' layout."""
+    env = dry_env("command_direction", n=65536)
+    _, canon_a, words_a = _plan(env)
+    env.reward_manager.cfg["lin_vel_z"].weight = -3.0
+    env.step_count = 17
+    env._fused._set_program(force=True)
+    _, canon_b, words_b = _plan(env)
+    assert canon_a == canon_b and words_a == words_b
+    env.observation_managers["policy"].cfg["dof_position"].scale = 0.5   # a live value too
+    env._fused._set_program(force=True)
+    _, canon_c, words_c = _plan(env)
+    assert canon_a == canon_c and words_a == words_c
+
+
+def test_two_launch_byte_model_is_consistent(cpu_device):
+    """Main launch + observation pass move at least the fused kernel's bytes; the excess is the re-read sources."""
+    from genesis_forge_b200 import roofline
+
+    for name in ("command_direction", "berkeley_humanoid"):
+        fused = dry_env(name, n=4096)._fused
+        whole = roofline.post_kernel_bytes(fused)
+        main, obs = roofline.two_launch_bytes(fused)
+        assert main < whole and obs < whole
+        assert whole <= main + obs <= 1.4 * whole, (name, whole, main, obs)
+    assert roofline.post_kernel_bytes(dry_env("command_direction")._fused) == 518  # BASELINE.md config 2
+    assert roofline.step_bytes(dry_env("command_direction")._fused) == 710
+
+
+def test_spawn_request_block(cpu_device):
+    """gfb_spawn as TerrainManager fills it (terrain_manager.py:204-229: usable centre of the (sub)terrain)."""
+    env = dry_env("rough_terrain")
+    terrain = env.managers["terrain"][0]
+    cfg = terrain._spawn_config(0.5, None, 0.4, {"z": (0.0, 2 * math.pi)})
+    x_min, x_max, y_min, y_max = terrain.get_bounds()
+    assert cfg.x_lo == np.float32(x_min + (x_max - x_min) / 4) and cfg.x_span == np.float32((x_max - x_min) / 2)
+    assert cfg.y_lo == np.float32(y_min + (y_max - y_min) / 4) and cfg.y_span == np.float32((y_max - y_min) / 2)
+    assert cfg.height_offset == np.float32(0.4) and cfg.with_rotation == 1
+    assert list(cfg.rot_mode) == [0, 0, nat.K["GFB_SPAWN_ROT_DRAW"]]
+    assert cfg.rot_hi[2] == np.float32(2 * math.pi) and cfg.rot_lo[2] == 0.0
+    assert (cfg.height_field_rows, cfg.height_field_cols) == tuple(terrain.height_field.shape)
+    assert terrain._spawn_config(0.5, None, 0.4, {"z": (0.0, 2 * math.pi)}) is cfg          # cached
+    assert terrain._spawn_config(0.5, None, 0.4, None).with_rotation == 0                    # positions only
+    with pytest.raises(nat.NativeLibraryError):
+        terrain.generate_random_env_pos()  # no CUDA device here: loud failure, no host fallback
