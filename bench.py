@@ -434,9 +434,11 @@ def run_b200(args, rank, local_rank, world):
     cpu = None
     if rank == 0 and not dist_on and not args.no_cpu:
         n_cpu = args.cpu_envs or N
-        v, threads, cpu_ms = time_cpu_port(spec, n_cpu, 2, 10, 3, 1234)
+        cpu_steps = 40  # a bounded sample: ~5-20 s of host work at 1M envs depending on the table
+        v, threads, cpu_ms = time_cpu_port(spec, n_cpu, 2, cpu_steps, 3, 1234)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": cpu_ms,
-               "sample": f"10 steps of {n_cpu} envs ({args.config} term table), oracle port on torch-CPU, {cpu_model()}"}
+               "sample": f"{cpu_steps} steps of {n_cpu} envs ({args.config} term table), oracle port on torch-CPU, "
+                         f"{cpu_model()}"}
 
     if rank == 0:
         line = {
