@@ -1052,10 +1052,17 @@ class FusedStep:
         gathered = [torch.empty_like(local) for _ in range(world)]
         dist.all_gather(gathered, local, group=group)
         handles = b"".join(bytes(g.cpu().tolist()) for g in gathered)
-        self.handle.check(
-            self.lib.gfb_peer_connect(self.handle.ptr, rank, world, handles, self.global_num_envs), "gfb_peer_connect"
-        )
-        dist.barrier(group)
+        rc = self.lib.gfb_peer_connect(self.handle.ptr, rank, world, handles, self.global_num_envs)
+        # the decision is collective: if any rank cannot map its peers (ranks on another node, no P2P
+        # path), every rank falls back to the NCCL all-reduce
+        ok = torch.tensor([1 if rc == 0 else 0], device=self.device, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            why = self.lib.gfb_last_error(self.handle.ptr).decode() if rc != 0 else "a peer rank could not connect"
+            self.lib.gfb_peer_disconnect(self.handle.ptr)
+            if rank == 0:
+                print(f"[genesis_forge_b200] peer-memory logging exchange unavailable ({why}); using NCCL all-reduce")
+            return
         self.peer_mode = True
 
     def _allreduce_logging(self):
