@@ -370,12 +370,7 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, i
     plan.sums_off = cursor;
     if (stage_sums) cursor = align4(cursor + P.n_reward * tile);
   }
-  for (int m = 0; m < P.n_contact; ++m) {
-    plan.cout_off[m] = cursor;
-    if (contact) cursor = align4(cursor + 3 * P.contact[m].n_links * tile);
-    plan.cposout_off[m] = cursor;
-    if (contact) cursor = align4(cursor + 3 * P.contact[m].n_links * tile);
-  }
+  for (int m = 0; m < P.n_contact; ++m) plan.cout_off[m] = plan.cposout_off[m] = -1;  // outputs are not staged
 
   // observation columns
   cols.clear();
@@ -596,7 +591,11 @@ int plan_for_launch(gfb_handle* h, const gfb_buffers& b, uint32_t phases, Plan& 
   n_stages = h->force_stages == 2 ? 2 : 1;
   if (h->force_tile == 0 && tile == 128 && n_stages == 1) {
     // big slabs (contact slots staged): pick the slab size that keeps the most warps resident
-    // (shared memory per block vs. the 80-register limit of 6 x 128 threads); ties go to the larger slab
+    // (shared memory per block vs. the 80-register limit of 6 x 128 threads).  Ties go to the larger
+    // slab, except between 128 and 64 when contact slots are staged: those kernels run longer per
+    // slab and the finer grain balances the SMs better at mid batch sizes (config 5 at 262144 envs:
+    // 78 vs 86 us; no difference at 1M)
+    const bool contact_slots = (phases & GFB_PHASE_CONTACT) && h->prog.head.n_contact > 0;
     int best_tile = 128, best_warps = -1;
     for (int t : {128, 64, 32}) {
       int rc = build_plan(h, b, phases, t, 1, plan, table);
@@ -606,7 +605,7 @@ int plan_for_launch(gfb_handle* h, const gfb_buffers& b, uint32_t phases, Plan& 
       const int by_smem = (int)((size_t)(228 * 1024) / bytes);
       const int by_regs = 768 / t;
       const int warps = std::min(std::min(by_smem, by_regs), 32) * (t / 32);
-      if (warps > best_warps) {
+      if (warps > best_warps || (warps == best_warps && t == 64 && best_tile == 128 && contact_slots)) {
         best_warps = warps;
         best_tile = t;
       }

@@ -316,8 +316,10 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
       const gfb_contact_manager& cm = P.contact[m];
       const gfb_contact_manager& cs_ = SP.contact[m];
       const int Lc = cs_.n_links;
-      float* fout = S + plan.cout_off[m] + tid * Lc * 3;
-      float* pout = S + plan.cposout_off[m] + tid * Lc * 3;
+      // results go straight from registers to the (N, Lc, 3) outputs: staging them for a TMA store
+      // would cost 6*Lc words of shared memory per env, i.e. resident warps
+      float* fout = GFB_BUF(float, GFB_B_CONTACTS0 + m) + (size_t)e * Lc * 3;
+      float* pout = GFB_BUF(float, GFB_B_CONTACT_POS0 + m) + (size_t)e * Lc * 3;
       GFB_UNROLL_TERMS
       for (int t = 0; t < Lc; ++t) {
         const int target = cs_.link_ids[t];
@@ -372,8 +374,10 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
         if (cnt > 0.f) {  // kernel.py:85-90
           px = fdiv(px, cnt); py = fdiv(py, cnt); pz = fdiv(pz, cnt);
         }
-        fout[t * 3 + 0] = fx; fout[t * 3 + 1] = fy; fout[t * 3 + 2] = fz;
-        pout[t * 3 + 0] = px; pout[t * 3 + 1] = py; pout[t * 3 + 2] = pz;
+        if (active) {
+          fout[t * 3 + 0] = fx; fout[t * 3 + 1] = fy; fout[t * 3 + 2] = fz;
+          pout[t * 3 + 0] = px; pout[t * 3 + 1] = py; pout[t * 3 + 2] = pz;
+        }
         const float nrm = norm3(fx, fy, fz);
         st[plan.st_cnorm[m] + t] = nrm;
 
@@ -797,26 +801,14 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   __syncthreads();
 
   // ------------------------------------------------------------------------------------------
-  // slab outputs: episode sums, contact forces / positions
+  // slab outputs: episode sums
   // ------------------------------------------------------------------------------------------
-  const bool store_contacts = (ph & GFB_PHASE_CONTACT) && SP.n_contact > 0;
   if (use_tma) {
     if (warp == 0) {
-      const int n_c = store_contacts ? 2 * SP.n_contact : 0;
       bool issued = false;
-      for (int i = lane; i < n_sum_rows + n_c; i += 32) {
-        if (i < n_sum_rows) {
-          bulk_store(GFB_BUF(float, GFB_B_EP_SUMS) + (size_t)i * N + e0, S + plan.sums_off + i * TILE,
-                     (uint32_t)valid * 4u);
-        } else {
-          const int m = (i - n_sum_rows) >> 1;
-          const uint32_t bytes = (uint32_t)SP.contact[m].n_links * 3u * (uint32_t)valid * 4u;
-          const size_t goff = (size_t)e0 * SP.contact[m].n_links * 3;
-          if ((i - n_sum_rows) & 1)
-            bulk_store(GFB_BUF(float, GFB_B_CONTACT_POS0 + m) + goff, S + plan.cposout_off[m], bytes);
-          else
-            bulk_store(GFB_BUF(float, GFB_B_CONTACTS0 + m) + goff, S + plan.cout_off[m], bytes);
-        }
+      for (int i = lane; i < n_sum_rows; i += 32) {
+        bulk_store(GFB_BUF(float, GFB_B_EP_SUMS) + (size_t)i * N + e0, S + plan.sums_off + i * TILE,
+                   (uint32_t)valid * 4u);
         issued = true;
       }
       if (issued) bulk_commit();
@@ -826,17 +818,6 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
       float* sums = GFB_BUF(float, GFB_B_EP_SUMS);
       for (int r = 0; r < SP.n_reward; ++r) sums[(size_t)r * N + e] = S[plan.sums_off + r * TILE + tid];
     }
-    if (store_contacts)
-      for (int m = 0; m < SP.n_contact; ++m) {
-        const int words = SP.contact[m].n_links * 3 * valid;
-        const size_t goff = (size_t)e0 * SP.contact[m].n_links * 3;
-        float* g1 = GFB_BUF(float, GFB_B_CONTACTS0 + m) + goff;
-        float* g2 = GFB_BUF(float, GFB_B_CONTACT_POS0 + m) + goff;
-        for (int w = tid; w < words; w += TILE) {
-          g1[w] = S[plan.cout_off[m] + w];
-          g2[w] = S[plan.cposout_off[m] + w];
-        }
-      }
   }
 
   // ------------------------------------------------------------------------------------------
