@@ -206,6 +206,33 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   if ((ph & GFB_PHASE_REWARD) && K.b.buf[GFB_B_ACTION_RATE])
     action_rate = GFB_BUF(const float, GFB_B_ACTION_RATE)[e];
 
+#ifdef GFB_SPEC
+  // specialised build: the tracked links are compile-time constants, so every link quaternion and
+  // every air-time word of this env is requested here, while the slab is still in flight
+  // (independent loads, their latency hidden behind the slab wait), instead of one dependent global
+  // load per target inside the contact loops
+  float4 tq_all[gfb_spec::N_TARGETS];
+  float air_all[gfb_spec::N_TARGETS][4];
+  if ((ph & GFB_PHASE_CONTACT) && SP.n_contact > 0) {
+    const float4* lq = GFB_BUF(const float4, GFB_B_LINKS_QUAT) + (size_t)e * SP.n_links_total;
+    int k = 0;
+    GFB_UNROLL_TERMS
+    for (int m = 0; m < SP.n_contact; ++m) {
+      const int Lc = SP.contact[m].n_links;
+      GFB_UNROLL_TERMS
+      for (int t = 0; t < Lc; ++t, ++k) {
+        tq_all[k] = lq[SP.contact[m].link_ids[t]];
+        if (SP.contact[m].track_air_time) {
+          const float* air = GFB_BUF(const float, GFB_B_AIR0 + m);
+          const size_t base = (size_t)e * Lc + t, plane = (size_t)N * Lc;
+          air_all[k][0] = air[base]; air_all[k][1] = air[plane + base];
+          air_all[k][2] = air[2 * plane + base]; air_all[k][3] = air[3 * plane + base];
+        }
+      }
+    }
+  }
+#endif
+
   // one warp polls the stage's mbarrier, the block barrier releases the rest
   if (use_tma && warp == 0) mbar_wait(&bars[stage], (uint32_t)((n_stages == 2 ? (it >> 1) : it) & 1));
   __syncthreads();
@@ -286,28 +313,6 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     if (bad && active) status |= GFB_STATUS_BAD_CONTACT;
     const float4* lq = GFB_BUF(const float4, GFB_B_LINKS_QUAT) + (size_t)e * L;
 #ifdef GFB_SPEC
-    // specialised build: the tracked links are compile-time constants, so every link quaternion and
-    // every air-time word of this env is requested up front (independent loads, one latency) instead
-    // of one dependent global load per target inside the loops below
-    float4 tq_all[gfb_spec::N_TARGETS];
-    float air_all[gfb_spec::N_TARGETS][4];
-    {
-      int k = 0;
-      GFB_UNROLL_TERMS
-      for (int m = 0; m < SP.n_contact; ++m) {
-        const int Lc = SP.contact[m].n_links;
-        GFB_UNROLL_TERMS
-        for (int t = 0; t < Lc; ++t, ++k) {
-          tq_all[k] = lq[SP.contact[m].link_ids[t]];
-          if (SP.contact[m].track_air_time) {
-            const float* air = GFB_BUF(const float, GFB_B_AIR0 + m);
-            const size_t base = (size_t)e * Lc + t, plane = (size_t)N * Lc;
-            air_all[k][0] = air[base]; air_all[k][1] = air[plane + base];
-            air_all[k][2] = air[2 * plane + base]; air_all[k][3] = air[3 * plane + base];
-          }
-        }
-      }
-    }
     int k_target = 0;
 #endif
 
