@@ -121,8 +121,8 @@ struct gfb_handle {
   int n_aux = 0;
   float aux_ms[3] = {0.f, 0.f, 0.f};
   int aux_count[3] = {0, 0, 0};
-  int smem_attr_post[3] = {0, 0, 0};
-  int smem_attr_action[3] = {0, 0, 0};
+  int smem_attr_post[4] = {0, 0, 0, 0};
+  int smem_attr_action[4] = {0, 0, 0, 0};
 };
 
 namespace {
@@ -172,7 +172,7 @@ void canonicalize(gfb_program_head& c) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-int tile_index(int tile) { return tile == 32 ? 0 : (tile == 64 ? 1 : 2); }
+int tile_index(int tile) { return tile == 32 ? 0 : (tile == 64 ? 1 : (tile == 128 ? 2 : 3)); }
 
 // ---------------------------------------------------------------------------------------------
 // term-table analysis: which derived vectors / staged slabs does the program need
@@ -578,7 +578,7 @@ cudaEvent_t aux_begin(gfb_handle* h, int kind, cudaStream_t stream) {
 }
 
 int choose_tile(const gfb_handle* h) {
-  if (h->force_tile == 32 || h->force_tile == 64 || h->force_tile == 128) return h->force_tile;
+  if (h->force_tile == 32 || h->force_tile == 64 || h->force_tile == 128 || h->force_tile == 256) return h->force_tile;
   return h->num_envs >= 32768 ? 128 : 32;
 }
 
@@ -628,7 +628,7 @@ int plan_for_launch(gfb_handle* h, const gfb_buffers& b, uint32_t phases, Plan& 
 template <int TILE>
 int launch_post(gfb_handle* h, const KParams& kp, size_t smem, cudaStream_t stream, int grid) {
   int& cur = h->smem_attr_post[tile_index(TILE)];
-  if ((int)smem > 48 * 1024 && (int)smem > cur) {
+  if ((int)smem > 44 * 1024 /* static shared memory counts towards the 48 KB default */ && (int)smem > cur) {
     CUDA_TRY(cudaFuncSetAttribute(post_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cur = (int)smem;
   }
@@ -640,7 +640,7 @@ int launch_post(gfb_handle* h, const KParams& kp, size_t smem, cudaStream_t stre
 template <int TILE>
 int blocks_per_sm(gfb_handle* h, size_t smem) {
   int& cur = h->smem_attr_post[tile_index(TILE)];
-  if ((int)smem > 48 * 1024 && (int)smem > cur) {
+  if ((int)smem > 44 * 1024 /* static shared memory counts towards the 48 KB default */ && (int)smem > cur) {
     if (cudaFuncSetAttribute(post_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess)
       cur = (int)smem;
   }
@@ -652,7 +652,7 @@ int blocks_per_sm(gfb_handle* h, size_t smem) {
 template <int TILE>
 int launch_action(gfb_handle* h, const ActionParams& ap, size_t smem, cudaStream_t stream, int grid) {
   int& cur = h->smem_attr_action[tile_index(TILE)];
-  if ((int)smem > 48 * 1024 && (int)smem > cur) {
+  if ((int)smem > 44 * 1024 /* static shared memory counts towards the 48 KB default */ && (int)smem > cur) {
     CUDA_TRY(cudaFuncSetAttribute(action_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cur = (int)smem;
   }
@@ -879,7 +879,8 @@ int gfb_action_step(gfb_handle* h, const gfb_buffers* b, const float* raw_env, c
   int rc;
   if (tile == 32) rc = launch_action<32>(h, ap, smem, stream, grid);
   else if (tile == 64) rc = launch_action<64>(h, ap, smem, stream, grid);
-  else rc = launch_action<128>(h, ap, smem, stream, grid);
+  else if (tile == 128) rc = launch_action<128>(h, ap, smem, stream, grid);
+  else rc = launch_action<256>(h, ap, smem, stream, grid);
   if (rc != GFB_OK) return rc;
   if (e1) cudaEventRecord(e1, stream);
   h->launches += 1;
@@ -1016,7 +1017,8 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
     int per_sm = 0;
     if (tile == 32) per_sm = blocks_per_sm<32>(h, smem);
     else if (tile == 64) per_sm = blocks_per_sm<64>(h, smem);
-    else per_sm = blocks_per_sm<128>(h, smem);
+    else if (tile == 128) per_sm = blocks_per_sm<128>(h, smem);
+    else per_sm = blocks_per_sm<256>(h, smem);
     if (per_sm > 0 && h->num_sms > 0) grid = std::min(n_tiles, per_sm * h->num_sms);
   }
   const AttachedSpec* spec = lc->spec_index >= 0 ? &h->specs[lc->spec_index] : nullptr;
@@ -1028,7 +1030,8 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
   } else {
     if (tile == 32) rc = launch_post<32>(h, kp, smem, stream, grid);
     else if (tile == 64) rc = launch_post<64>(h, kp, smem, stream, grid);
-    else rc = launch_post<128>(h, kp, smem, stream, grid);
+    else if (tile == 128) rc = launch_post<128>(h, kp, smem, stream, grid);
+    else rc = launch_post<256>(h, kp, smem, stream, grid);
     h->n_generic_launches += 1;
   }
   if (rc != GFB_OK) return rc;

@@ -34,7 +34,7 @@ extern "C" int gfb_spec_info(int* tile, unsigned* phases, const void** canon, co
 }
 
 extern "C" int gfb_spec_launch(const gfb::KParams* kp, int grid, unsigned smem, void* stream) {
-  if ((int)smem > 48 * 1024 && (int)smem > smem_attr) {
+  if ((int)smem > 44 * 1024 && (int)smem > smem_attr) {
     if (cudaFuncSetAttribute(gfb::post_kernel<gfb_spec::TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
         cudaSuccess)
       return 1;
