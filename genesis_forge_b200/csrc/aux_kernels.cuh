@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(TILE) action_kernel(const __grid_constant__ Ac
   }
   int ep_len = 0;
   if (active && A.episode_length) ep_len = A.episode_length[e];  // in flight while the slabs arrive
-  if (use_tma) mbar_wait(&bar, 0);
+  if (use_tma && tid < 32) mbar_wait(&bar, 0);  // one warp polls, the block barrier releases the rest
   __syncthreads();
   if (active && A.episode_length) A.episode_length[e] = ep_len + 1;  // genesis_env.py:195
 

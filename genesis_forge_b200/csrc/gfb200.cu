@@ -710,6 +710,8 @@ int gfb_create(int32_t num_envs, int32_t device, gfb_handle** out) {
     hh->force_tile = env_t ? atoi(env_t) : 0;
     const char* env_o = getenv("GFB_NO_OVERLAY");
     hh->disable_overlay = env_o && env_o[0] == '1';
+    const char* env_s = getenv("GFB_STAGES");
+    hh->force_stages = env_s ? atoi(env_s) : 0;
     *out = hh;
     return GFB_OK;
   }
@@ -955,7 +957,7 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
     c.tma_ok = tma_eligible(h, *b, c.plan, phases) ? 1 : 0;
     // a specialised kernel whose compile-time structure equals this launch's, if one is attached
     c.spec_index = -1;
-    if (!h->specs.empty() && c.tma_ok && c.n_stages == 1) {
+    if (!h->specs.empty() && c.tma_ok) {
       gfb_program_head canon = P;
       canonicalize(canon);
       for (size_t i = 0; i < h->specs.size(); ++i) {
