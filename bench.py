@@ -183,7 +183,6 @@ def time_dropin(env, actions, steps, warmup, dist_on):
     for i in range(warmup):
         env.step(actions[i % len(actions)])
     torch.cuda.synchronize(dev)
-    env._fused.profile(True)  # per-kernel CUDA events only inside the timed region
     if dist_on:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -206,6 +205,13 @@ def time_dropin(env, actions, steps, warmup, dist_on):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    # per-kernel device times (roofline block): the same steps once more, now with a CUDA-event pair
+    # around every launch -- kept out of the timed region above, where the ~10 extra event records per
+    # step would cost host time
+    env._fused.profile(True)
+    for i in range(min(steps, 20)):
+        env.step(actions[i % len(actions)])
+    torch.cuda.synchronize(dev)
     return ms, n_reset / max(steps, 1)
 
 

@@ -1,0 +1,83 @@
+"""
+The stand-alone entry points of the C ABI against the oracle: gfb_contact_forces (the reference's
+Taichi kernel with its own argument list, contact/kernel.py:5-90) and gfb_rotate
+(transform_by_quat(v, inv_quat(q)) of entity_manager.py:130-146 / utils.py:13-55).
+"""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+@pytest.mark.parametrize("with_filter", [False, True])
+@pytest.mark.parametrize("n_envs,n_slots", [(1, 1), (257, 8), (1000, 20)])
+def test_contact_forces_entry_point(n_envs, n_slots, with_filter, cuda_device):
+    from genesis_forge_b200 import _native as nat
+    from oracle.contact_kernel import kernel_get_contact_forces
+
+    lib, handle = nat.lib(), nat.Handle(n_envs, cuda_device.index or 0)
+    g = torch.Generator().manual_seed(1000 * n_envs + n_slots + int(with_filter))
+    L, targets, withs = 14, torch.tensor([3, 6, 9, 12], dtype=torch.int32), torch.tensor([0, 5], dtype=torch.int32)
+    force = 30.0 * torch.randn(n_envs, n_slots, 3, generator=g)
+    pos = torch.rand(n_envs, n_slots, 3, generator=g) * 2 - 1
+    link_a = torch.randint(0, L, (n_envs, n_slots), generator=g, dtype=torch.int32)
+    link_b = torch.randint(0, L, (n_envs, n_slots), generator=g, dtype=torch.int32)
+    # padding slots the way get_contacts(as_tensor=True) returns them: zero force between link 0 and link 0
+    pad = torch.rand(n_envs, n_slots, generator=g) < 0.3
+    link_a[pad], link_b[pad], force[pad], pos[pad] = 0, 0, 0.0, 0.0
+    quat = torch.randn(n_envs, L, 4, generator=g)
+    quat = quat / quat.norm(dim=-1, keepdim=True)
+
+    want_f, want_p = torch.zeros(n_envs, 4, 3), torch.zeros(n_envs, 4, 3)
+    want_c = torch.zeros(n_envs, 4)
+    kernel_get_contact_forces(force, pos, link_a, link_b, quat, targets, withs, want_f, want_p, want_c, int(with_filter))
+
+    dev = cuda_device
+    d = [t.to(dev).contiguous() for t in (force, pos, link_a, link_b, quat, targets, withs)]
+    # the kernel writes every output element: garbage in, results out (the caller zero-fills nothing)
+    out_f = torch.full((n_envs, 4, 3), float("nan"), device=dev)
+    out_p = torch.full((n_envs, 4, 3), float("nan"), device=dev)
+    out_c = torch.full((n_envs, 4), float("nan"), device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    handle.check(
+        lib.gfb_contact_forces(handle.ptr, *(_ptr(t) for t in d), _ptr(out_f), _ptr(out_p), _ptr(out_c),
+                               n_envs, n_slots, L, 4, 2, int(with_filter), stream),
+        "gfb_contact_forces",
+    )
+    # ordered accumulation on both sides: bit-exact
+    assert torch.equal(out_c.cpu(), want_c)
+    assert torch.equal(out_f.cpu(), want_f)
+    assert torch.equal(out_p.cpu(), want_p)
+    assert n_envs < 100 or bool((want_c > 0).any())  # the larger cases do contain hits
+
+
+@pytest.mark.parametrize("n", [1, 33, 4097])
+def test_rotate_entry_point(n, cuda_device):
+    from genesis_forge_b200 import _native as nat
+    from oracle.geom import inv_quat, transform_by_quat
+
+    lib, handle = nat.lib(), nat.Handle(max(n, 1), cuda_device.index or 0)
+    g = torch.Generator().manual_seed(n)
+    vec = torch.randn(n, 3, generator=g)
+    quat = torch.randn(n, 4, generator=g)
+    quat = quat / quat.norm(dim=-1, keepdim=True)
+    stream = C.c_void_p(torch.cuda.current_stream(cuda_device).cuda_stream)
+    dv, dq = vec.to(cuda_device), quat.to(cuda_device)
+    out = torch.empty(n, 3, device=cuda_device)
+    # conjugate = 1: rotate by the inverse of q (what the uncached getters do, utils.py:23-24)
+    handle.check(lib.gfb_rotate(handle.ptr, _ptr(dv), _ptr(dq), _ptr(out), n, 1, stream), "gfb_rotate")
+    assert torch.equal(out.cpu(), transform_by_quat(vec, inv_quat(quat)))
+    # conjugate = 0 with an already inverted quaternion (the cached path, entity_manager.py:134)
+    diq = inv_quat(quat).to(cuda_device).contiguous()
+    handle.check(lib.gfb_rotate(handle.ptr, _ptr(dv), _ptr(diq), _ptr(out), n, 0, stream), "gfb_rotate")
+    assert torch.equal(out.cpu(), transform_by_quat(vec, inv_quat(quat)))
+    # vec == NULL: projected gravity, R(q)^T (0, 0, -1)
+    handle.check(lib.gfb_rotate(handle.ptr, None, _ptr(dq), _ptr(out), n, 1, stream), "gfb_rotate")
+    gravity = torch.tensor([0.0, 0.0, -1.0]).expand(n, 3)
+    assert torch.equal(out.cpu(), transform_by_quat(gravity, inv_quat(quat)))
