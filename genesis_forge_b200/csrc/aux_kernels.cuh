@@ -213,6 +213,7 @@ struct FinalizeParams {
   int32_t n_termination;
   uint32_t phases;
   uint32_t reward_weight_mask;  // bit r set: term r has weight != 0 (mean is logged)
+  gfb_report* report_host;      // device address of the host-mapped report (or null)
 };
 
 constexpr int FIN_THREADS = 256;
@@ -335,58 +336,67 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinalizePar
   if (tid == 0) *F.peer.done_counter = 0u;
   __threadfence();
   const int n_vals = F.n_reward + F.n_termination + 1;
-  if (F.peer.world <= 1 || !F.log_acc) {
+  bool local_only = F.peer.world <= 1 || !F.log_acc;  // (block-uniform from here on)
+  if (!local_only) {
+    // exchange over peer memory: my partials into every rank's inbox, then wait for everyone's
+    const int parity = (int)(F.peer.seq & 1ull);
+    const int me = F.peer.rank, W = F.peer.world;
+    if (tid < n_vals) {
+      const double mine = __ldcg(F.log_acc + tid);
+      for (int p = 0; p < W; ++p) F.peer.inbox[p]->slot[parity][me].vals[tid] = mine;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < W) st_release_sys(&F.peer.inbox[tid]->slot[parity][me].seq, F.peer.seq);
+    int timed_out = 0;
+    if (tid < W) {
+      const unsigned long long* flag = &F.peer.inbox[me]->slot[parity][tid].seq;
+      const unsigned long long t0 = global_timer_ns();
+      while (ld_acquire_sys(flag) != F.peer.seq) {
+        if (global_timer_ns() - t0 > 2000000000ull) {  // ~2 s: a peer never issued this exchange
+          timed_out = 1;
+          break;
+        }
+        __nanosleep(200);
+      }
+    }
+    timed_out = __syncthreads_or(timed_out);
+    __threadfence_system();
+    if (timed_out) {
+      if (tid == 0) atomicOr(&rep->status, GFB_STATUS_PEER_TIMEOUT);
+      local_only = true;
+    } else {
+      if (tid < n_vals) {
+        double g = 0.0;
+        for (int r = 0; r < W; ++r) g += __ldcv(&F.peer.inbox[me]->slot[parity][r].vals[tid]);  // rank order
+        s_global[tid] = g;
+      }
+      __syncthreads();
+      const double g_reset = s_global[n_vals - 1];
+      if (tid == 0) rep->global_n_reset = (int64_t)g_reset;
+      if (tid < F.n_reward) {
+        const bool logged = (F.reward_weight_mask >> tid) & 1u;
+        if (F.log_out) F.log_out[tid] = (g_reset > 0.0 && logged) ? (float)(s_global[tid] / g_reset) : 0.0f;
+      } else if (tid < F.n_reward + F.n_termination) {
+        const int k = tid - F.n_reward;
+        rep->global_termination_count[k] = (int64_t)s_global[tid];
+        if (F.log_out) F.log_out[tid] = fdiv((float)s_global[tid], (float)F.peer.global_num_envs);
+      }
+    }
+  }
+  if (local_only) {
     if (tid == 0) rep->global_n_reset = rep->n_reset;
     if (tid < F.n_termination) rep->global_termination_count[tid] = rep->termination_count[tid];
-    return;
   }
-  // exchange over peer memory: my partials into every rank's inbox, then wait for everyone's
-  const int parity = (int)(F.peer.seq & 1ull);
-  const int me = F.peer.rank, W = F.peer.world;
-  if (tid < n_vals) {
-    const double mine = __ldcg(F.log_acc + tid);
-    for (int p = 0; p < W; ++p) F.peer.inbox[p]->slot[parity][me].vals[tid] = mine;
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (tid < W) st_release_sys(&F.peer.inbox[tid]->slot[parity][me].seq, F.peer.seq);
-  int timed_out = 0;
-  if (tid < W) {
-    const unsigned long long* flag = &F.peer.inbox[me]->slot[parity][tid].seq;
-    const unsigned long long t0 = global_timer_ns();
-    while (ld_acquire_sys(flag) != F.peer.seq) {
-      if (global_timer_ns() - t0 > 2000000000ull) {  // ~2 s: a peer never issued this exchange
-        timed_out = 1;
-        break;
-      }
-      __nanosleep(200);
-    }
-  }
-  timed_out = __syncthreads_or(timed_out);
-  __threadfence_system();
-  if (timed_out) {
-    if (tid == 0) {
-      atomicOr(&rep->status, GFB_STATUS_PEER_TIMEOUT);
-      rep->global_n_reset = rep->n_reset;
-    }
-    if (tid < F.n_termination) rep->global_termination_count[tid] = rep->termination_count[tid];
-    return;
-  }
-  if (tid < n_vals) {
-    double g = 0.0;
-    for (int r = 0; r < W; ++r) g += __ldcv(&F.peer.inbox[me]->slot[parity][r].vals[tid]);  // rank order
-    s_global[tid] = g;
-  }
-  __syncthreads();
-  const double g_reset = s_global[n_vals - 1];
-  if (tid == 0) rep->global_n_reset = (int64_t)g_reset;
-  if (tid < F.n_reward) {
-    const bool logged = (F.reward_weight_mask >> tid) & 1u;
-    if (F.log_out) F.log_out[tid] = (g_reset > 0.0 && logged) ? (float)(s_global[tid] / g_reset) : 0.0f;
-  } else if (tid < F.n_reward + F.n_termination) {
-    const int k = tid - F.n_reward;
-    rep->global_termination_count[k] = (int64_t)s_global[tid];
-    if (F.log_out) F.log_out[tid] = fdiv((float)s_global[tid], (float)F.peer.global_num_envs);
+  // the finished report goes straight into the host's (mapped, pinned) copy: the host only has to
+  // wait for this kernel, no separate device-to-host copy is enqueued
+  if (F.report_host) {
+    __threadfence();
+    __syncthreads();
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(rep);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(F.report_host);
+    for (int w = tid; w < (int)(sizeof(gfb_report) / 4); w += FIN_THREADS) dst[w] = __ldcg(src + w);
+    __threadfence_system();
   }
 }
 

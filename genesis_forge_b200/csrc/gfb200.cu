@@ -86,7 +86,9 @@ struct gfb_handle {
   bool has_prog = false;
   Scratch scratch{};
   int scratch_tiles = 0;
-  gfb_report* report_host = nullptr;  // pinned
+  gfb_report* report_host = nullptr;  // pinned + mapped: the finalize kernel writes the finished report into it
+  gfb_report* report_host_dev = nullptr;  // its device address
+  bool report_in_host = false;        // the last launch's report is already in report_host
   PlanSlot slots[kPlanSlots];
   PlanSlot observe_slot;
   uint64_t prog_epoch = 0;  // bumped when anything but the step index of the term table changes
@@ -734,7 +736,9 @@ int gfb_create(int32_t num_envs, int32_t device, gfb_handle** out) {
   CUDA_TRY(cudaMemset(h->scratch.report, 0, sizeof(gfb_report)));
   CUDA_TRY(cudaMemset(h->scratch.tile_reset_count, 0, (size_t)nt * sizeof(int32_t)));
   CUDA_TRY(cudaMemset(h->scratch.tile_reset_bits, 0, (size_t)nt * sizeof(uint32_t)));
-  CUDA_TRY(cudaMallocHost(&h->report_host, sizeof(gfb_report)));
+  CUDA_TRY(cudaHostAlloc(&h->report_host, sizeof(gfb_report), cudaHostAllocMapped));
+  memset(h->report_host, 0, sizeof(gfb_report));
+  CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->report_host_dev), h->report_host, 0));
   CUDA_TRY(cudaEventCreateWithFlags(&h->report_event, cudaEventDisableTiming));
   CUDA_TRY(cudaMalloc(&h->done_counter, sizeof(uint32_t)));
   CUDA_TRY(cudaMemset(h->done_counter, 0, sizeof(uint32_t)));
@@ -1041,7 +1045,7 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
 
   if (!(phases & (GFB_PHASE_TERMINATION | GFB_PHASE_REWARD | GFB_PHASE_RESET))) {
     h->launches += 1;  // entity / contact / observation phases alone leave nothing to finalize
-    return GFB_OK;
+    return GFB_OK;     // (report_in_host keeps describing the last launch that produced a report)
   }
   FinalizeParams fp{};
   fp.s = kp.s;
@@ -1063,6 +1067,8 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
     fp.peer.seq = ++h->peer_seq;
     fp.peer.global_num_envs = h->global_num_envs;
   }
+  fp.report_host = (phases & GFB_PHASE_RESET) ? h->report_host_dev : nullptr;
+  h->report_in_host = fp.report_host != nullptr;
   fp.reward_weight_mask = 0;
   for (int r = 0; r < P.n_reward; ++r)
     if (P.reward[r].weight != 0.0f) fp.reward_weight_mask |= (1u << r);
@@ -1079,7 +1085,10 @@ int gfb_read_report(gfb_handle* h, gfb_report* out, void* stream_) {
   if (!h || !out) return GFB_ERR_INVALID;
   if (h->host_only) return fail(h, GFB_ERR_NO_DEVICE, "host-only handle has no report");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CUDA_TRY(cudaMemcpyAsync(h->report_host, h->scratch.report, sizeof(gfb_report), cudaMemcpyDeviceToHost, stream));
+  // after a launch with the reset phase the finalize kernel has written the report into the mapped
+  // host copy itself: waiting for the stream is all that is left
+  if (!h->report_in_host)
+    CUDA_TRY(cudaMemcpyAsync(h->report_host, h->scratch.report, sizeof(gfb_report), cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
   *out = *h->report_host;
   return GFB_OK;
@@ -1089,7 +1098,8 @@ int gfb_request_report(gfb_handle* h, void* stream_) {
   if (!h) return GFB_ERR_INVALID;
   if (h->host_only) return fail(h, GFB_ERR_NO_DEVICE, "host-only handle has no report");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CUDA_TRY(cudaMemcpyAsync(h->report_host, h->scratch.report, sizeof(gfb_report), cudaMemcpyDeviceToHost, stream));
+  if (!h->report_in_host)
+    CUDA_TRY(cudaMemcpyAsync(h->report_host, h->scratch.report, sizeof(gfb_report), cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaEventRecord(h->report_event, stream));
   return GFB_OK;
 }
