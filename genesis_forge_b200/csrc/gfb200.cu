@@ -549,6 +549,8 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, i
   plan.n_stages = n_stages;
   plan.cols_off = plan.stage_words * n_stages;
   plan.smem_words = plan.cols_off + align4(plan.table_words);
+  if (const char* pad = getenv("GFB_PAD_SMEM_KB"))  // occupancy experiments: unused shared memory per block
+    plan.smem_words += atoi(pad) * 256;
   return GFB_OK;
 }
 
