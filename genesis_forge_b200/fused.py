@@ -145,6 +145,7 @@ class FusedStep:
         self._spec_checked: set = set()  # phase sets looked at since the last re-pack
         self._eval_handle = None  # second library handle for directly called mdp terms
         self._obs_ptrs = None
+        self._fp_items = None
         self._log_out_handed_out = False
         K = nat.K
         self.PHASES_MAIN = K["GFB_PHASE_ALL"] & ~K["GFB_PHASE_OBSERVE"]
@@ -344,26 +345,28 @@ class FusedStep:
     # pack: live config -> gfb_program
     # ------------------------------------------------------------------------------------------
     def _live_fingerprint(self):
-        fp = [self.env.dt, self.env._base_max_episode_length, self.env._max_episode_random_scaling,
-              self.injected is not None, self.rng_seed, tuple(sorted(self._body_acc_started.items()))]
-        for _, item, _ in self.reward_terms:
-            fp.append(item.weight)
-            fp.append(item.version)
-        for _, item, _ in self.termination_terms:
-            fp.append(item.time_out)
-            fp.append(item.version)
-        for mgr in self.commands:
-            fp.append(tuple(map(tuple, mgr.ranges_list())))
-            fp.append(mgr._resample_steps)
-            fp.append(mgr._external_controller is None)
-        for mgr in self.contacts:
-            fp.append(mgr._air_time_contact_threshold)
-        for om in self.observations:
-            fp.append(om.noise)
-            for item in om.cfg.values():
-                fp.append(item.scale)
-                fp.append(item.noise)
-        return tuple(fp)
+        """Every live value the packed table depends on (one tuple compare per step decides on a re-pack)."""
+        env = self.env
+        items = self._fp_items
+        if items is None:  # the item lists are fixed after _compile()
+            items = self._fp_items = (
+                [item for _, item, _ in self.reward_terms],
+                [item for _, item, _ in self.termination_terms],
+                [item for om in self.observations for item in om.cfg.values()],
+            )
+        rewards, terminations, obs_items = items
+        return (
+            env.dt, env._base_max_episode_length, env._max_episode_random_scaling, self.injected is not None,
+            self.rng_seed, tuple(sorted(self._body_acc_started.items())) if self._body_acc_started else (),
+            [(i.weight, i.version) for i in rewards],
+            [(i.time_out, i.version) for i in terminations],
+            # (range values may be lists the user mutates in place: copied into tuples, never referenced)
+            [(tuple(map(tuple, m.ranges_list())), m._resample_steps, m._external_controller is None)
+             for m in self.commands],
+            [m._air_time_contact_threshold for m in self.contacts],
+            [om.noise for om in self.observations],
+            [(i.scale, i.noise) for i in obs_items],
+        )
 
     def _entity_ok(self, params: dict, what: str):
         em = params.get("entity_manager")

@@ -58,6 +58,7 @@ class ManagedEnvironment(GenesisEnv):
         self._fused: FusedStep | None = None
         self._tracing: dict | None = None
         self._log_key_cache: dict = {}
+        self._reward_log_cache = None
 
     # -- spaces ---------------------------------------------------------------------------------
     @property
@@ -305,15 +306,25 @@ class ManagedEnvironment(GenesisEnv):
                             snapshot = self._log_snapshot()
                         logging[key] = snapshot[n_r + i]
         if rew is not None and rew.enabled and rew.logging_enabled and n_reset_logged > 0:
-            index = {}
-            for (i, key), (name, item, _) in zip(self._log_keys(rew, fused.reward_terms), fused.reward_terms):
-                if item.weight != 0:
-                    if snapshot is None:
-                        snapshot = self._log_snapshot()
+            rows, keys, index = self._reward_log_plan(rew, fused)
+            if rows:
+                if snapshot is None:
+                    snapshot = self._log_snapshot()
+                for i, key in zip(rows, keys):
                     logging[key] = snapshot[i]
-                    index[name] = i
-            if index:
                 rew._last_log = (snapshot[0]._base, index)
+
+    def _reward_log_plan(self, rew, fused):
+        """(rows, keys, {name: row}) of the reward terms that are logged (weight != 0); rebuilt when a weight changes."""
+        weights = [item.weight for _, item, _ in fused.reward_terms]
+        cached = self._reward_log_cache
+        if cached is None or cached[0] != weights or cached[1] != rew.logging_tag:
+            pairs = self._log_keys(rew, fused.reward_terms)
+            rows = [i for (i, _), w in zip(pairs, weights) if w != 0]
+            keys = [pairs[i][1] for i in rows]
+            index = {fused.reward_terms[i][0]: i for i in rows}
+            cached = self._reward_log_cache = (weights, rew.logging_tag, rows, keys, index)
+        return cached[2], cached[3], cached[4]
 
     def _log_keys(self, manager, terms) -> list:
         """[(row, "<tag> / <term>")] of one manager's logged entries (built once per logging tag)."""
