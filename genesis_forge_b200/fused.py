@@ -145,6 +145,8 @@ class FusedStep:
         self._spec_checked: set = set()  # phase sets looked at since the last re-pack
         self._eval_handle = None  # second library handle for directly called mdp terms
         self._obs_ptrs = None
+        self._log_views = None
+        self._log_spare = None
         self._fp_items = None
         self._log_out_handed_out = False
         K = nat.K
@@ -727,13 +729,34 @@ class FusedStep:
         # collects extras["episode"] over a whole iteration): once views were handed out, the next
         # step writes into fresh storage
         if self._log_out_handed_out:
-            self.log_out = torch.empty_like(self.log_out)
+            if self._log_spare is not None:  # prepared while the GPU was busy (prepare_spare_log)
+                self.log_out, self._log_views = self._log_spare
+                self._log_spare = None
+            else:
+                self.log_out, self._log_views = torch.empty_like(self.log_out), None
             self.buffers.buf[self._log_out_id] = self.log_out.data_ptr()
             self._log_out_handed_out = False
 
     # ------------------------------------------------------------------------------------------
     # launches
     # ------------------------------------------------------------------------------------------
+    def log_views(self) -> tuple:
+        """0-dim views of the current logging vector, one per entry (what `extras` hands out)."""
+        if self._log_views is None:
+            self._log_views = self.log_out.unbind(0)
+        self._log_out_handed_out = True  # the next step gets fresh storage
+        return self._log_views
+
+    def prepare_spare_log(self):
+        """
+        Next step's logging vector and its views.  Creating the ~10 view objects costs ~1 us each;
+        called after the step's kernels are enqueued and before the host blocks on the report, i.e.
+        while the GPU is busy, instead of on the critical path between the report and the next launch.
+        """
+        if self._log_spare is None:
+            spare = torch.empty_like(self.log_out)
+            self._log_spare = (spare, spare.unbind(0))
+
     def _set_program(self, force: bool = False):
         """Pack (if a live value changed) and hand the term table to the library; once per step."""
         if self._program_pushed and not force:
@@ -869,6 +892,7 @@ class FusedStep:
             return None
         if self.dist is not None and not self.peer_mode:
             self._allreduce_logging()
+        self.prepare_spare_log()  # host work hidden behind the kernels just enqueued
         self.handle.check(self.lib.gfb_read_report(self.handle.ptr, C.byref(self.report), stream), "gfb_read_report")
         self._after_report()
         return self.report
@@ -890,6 +914,7 @@ class FusedStep:
                 "gfb_post_physics(observe)")
         if self.dist is not None and not self.peer_mode:
             self._allreduce_logging()
+        self.prepare_spare_log()
         h.check(lib.gfb_wait_report(h.ptr, C.byref(self.report)), "gfb_wait_report")
         self._after_report()
         return self.report

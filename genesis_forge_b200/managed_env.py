@@ -338,8 +338,7 @@ class ManagedEnvironment(GenesisEnv):
         """The kernel's logging vector of this step as 0-dim views."""
         fused = self._fused
         if fused.dist is None or fused.peer_mode:
-            fused._log_out_handed_out = True  # the next step gets fresh storage (FusedStep.begin_step)
-            return fused.log_out.unbind(0)
+            return fused.log_views()  # (the next step gets fresh storage, FusedStep.begin_step)
         return fused.global_log_snapshot().unbind(0)
 
     def _host_reset(self, env_ids: torch.Tensor | None):
