@@ -1068,6 +1068,10 @@ class FusedStep:
 
         self.dist = group
         self.global_num_envs = int(global_num_envs)
+        # every shard draws from its own Philox stream (the counters are local env indices)
+        base_seed = getattr(self, "_unsharded_seed", self.rng_seed)
+        self._unsharded_seed = base_seed
+        self.rng_seed = (base_seed ^ ((dist.get_rank(group) + 1) << 40)) & 0xFFFFFFFFFFFFFFFF
         if peer is None:
             peer = os.environ.get("GFB_PEER_LOGGING", "1") != "0" and dist.get_backend(group) == "nccl"
         self.peer_mode = False

@@ -345,3 +345,69 @@ def test_kernel_switches_keep_parity(switch, cuda_device, monkeypatch):
     run = ParityRun("contacts", num_envs=n, device=cuda_device, seed=404)
     stats = run.run(steps=steps, nan_step=3)
     assert stats["resets"] > 0
+
+
+def test_production_draws_philox(cuda_device):
+    """
+    Production mode (nothing injected): the draws made inside the kernels come from Philox4x32-10.
+    Checked: command resample and episode-length draws stay inside their ranges with the moments of
+    a uniform distribution, observation noise is bounded by its scale with uniform spread, the
+    stream is reproducible for a seed and changes with it and with the step.
+    """
+    import copy
+
+    import genesis_forge_b200 as gfb
+    from oracle import specs
+    from oracle.env_builder import build_env, dropin_namespace
+
+    gfb.set_device(cuda_device)
+    n = 1 << 16
+    spec = specs.get("command_direction")
+    spec["observations"]["policy"]["terms"]["dof_position"]["noise"] = 0.02
+
+    def make(seed_offset=0):
+        env = build_env(copy.deepcopy(spec), dropin_namespace(), n, cuda_device, pool=2, seed=9, n_contacts=0,
+                        apply_setters=False)
+        env.build()
+        env._fused.rng_seed += seed_offset
+        env.reset()
+        return env
+
+    env = make()
+    cmd = env.velocity_command.command.clone()
+    ranges = env.velocity_command.ranges_list()
+    for k, (lo, hi) in enumerate(ranges):
+        col = cmd[:, k]
+        assert bool(((col >= lo) & (col <= hi)).all())
+        assert abs(float(col.mean()) - (lo + hi) / 2) < 0.02 * (hi - lo)
+        assert abs(float(col.std()) - (hi - lo) / 12 ** 0.5) < 0.02 * (hi - lo)
+    assert abs(float(torch.corrcoef(cmd.T)[0, 1])) < 0.02  # columns are independent draws
+    # genesis_env.py:246-252: max_episode_length = round(base + U(-1,1) * base * scaling)
+    base, scale = env._base_max_episode_length, env._max_episode_random_scaling
+    max_len = env.max_episode_length.float()
+    assert float(max_len.min()) >= round(base * (1 - scale)) and float(max_len.max()) <= round(base * (1 + scale))
+    assert abs(float(max_len.mean()) - base) < 0.01 * base * scale + 1
+    assert abs(float(max_len.std()) - base * scale / 3 ** 0.5) < 0.05 * base * scale
+    # observation noise on dof_position: obs = q + 0.02 * U(-1, 1)
+    off = 0
+    for name, _, width in env.observation_managers["policy"]._sources:
+        if name == "dof_position":
+            break
+        off += width
+    obs, *_ = env.step(torch.zeros(n, 12, device=cuda_device))
+    q = env.robot.get_dofs_position(env.action_manager.dofs_idx)
+    done = (env.episode_length == 0)
+    noise = (obs[:, off:off + 12] - q)[~done]  # reset envs were re-observed from the reset pose
+    assert float(noise.abs().max()) <= 0.02 * (1 + 1e-5) + 1e-6
+    assert abs(float(noise.std()) - 0.02 / 3 ** 0.5) < 2e-4 and abs(float(noise.mean())) < 2e-4
+    # same seed -> same stream; another seed or step -> another stream
+    twin = make()
+    assert torch.equal(twin.velocity_command.command, cmd)
+    other = make(seed_offset=1)
+    assert not torch.equal(other.velocity_command.command, cmd)
+    obs_twin, *_ = twin.step(torch.zeros(n, 12, device=cuda_device))
+    assert torch.equal(obs_twin, obs)
+    obs2, *_ = env.step(torch.zeros(n, 12, device=cuda_device))
+    q2 = env.robot.get_dofs_position(env.action_manager.dofs_idx)
+    keep = ~(done | (env.episode_length == 0))
+    assert not torch.equal((obs2[:, off:off + 12] - q2)[keep], (obs[:, off:off + 12] - q)[keep])
