@@ -63,7 +63,7 @@ def main(names=None):
     if not ref_harness.reference_available():
         raise SystemExit("needs /root/reference")
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    for name in names or list(specs.ALL):
+    for name in names or list(specs.ALL) + list(specs.VARIANTS):
         spec = specs.get(name)
         env = ref_harness.make_reference_env(spec, NUM_ENVS, seed=SEED)
         trace = trace_of(env, spec, NUM_ENVS, STEPS, SEED, NAN_STEP, compare.extras_to_cpu, compare.reference_snapshot)

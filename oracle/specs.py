@@ -426,5 +426,26 @@ ALL = {
 }
 
 
+def within_limits() -> dict:
+    """
+    Variant of config 2 with the PositionWithinLimitsActionManager (SURVEY.md 8(a) row a4:
+    actions clamped to [-1, 1] and mapped onto each joint's limits, no NaN/Inf check).
+    """
+    s = command_direction()
+    s["name"] = "within_limits"
+    action = dict(s["action"], type="within_limits")
+    for key in ("scale", "use_default_offset"):
+        action.pop(key, None)
+    s["action"] = action
+    return s
+
+
+# variants of the configs above: golden-traced and parity-tested like them, but no specialised
+# kernels are pre-built for them (spec.prebuild walks ALL)
+VARIANTS = {
+    "within_limits": within_limits,
+}
+
+
 def get(name: str) -> dict:
-    return ALL[name]()
+    return (ALL.get(name) or VARIANTS[name])()

@@ -86,7 +86,7 @@ def test_ragged_sizes(num_envs, cuda_device):
     run.run(steps=40)
 
 
-@pytest.mark.parametrize("name", CONFIGS)
+@pytest.mark.parametrize("name", CONFIGS + ["within_limits"])
 def test_cuda_path_reproduces_reference_golden_trace(name, cuda_device):
     """
     The CUDA path against the committed traces of the UNMODIFIED reference (tests/golden/, generated

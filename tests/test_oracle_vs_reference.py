@@ -64,7 +64,7 @@ def _run(name, num_envs, steps, spec_override=None, nan_step=7):
     return resets
 
 
-@pytest.mark.parametrize("name", list(specs.ALL))
+@pytest.mark.parametrize("name", list(specs.ALL) + list(specs.VARIANTS))
 def test_port_is_bit_identical_to_reference(name):
     assert _run(name, 48, 60) > 0
 
