@@ -441,7 +441,7 @@ def within_limits() -> dict:
 
 
 # variants of the configs above: golden-traced and parity-tested like them, but no specialised
-# kernels are pre-built for them (spec.prebuild walks ALL)
+# kernels are pre-built for them (tools/prebuild_specs.py walks ALL)
 VARIANTS = {
     "within_limits": within_limits,
 }

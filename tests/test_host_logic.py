@@ -276,3 +276,17 @@ def test_spawn_request_block(cpu_device):
     assert terrain._spawn_config(0.5, None, 0.4, None).with_rotation == 0                    # positions only
     with pytest.raises(nat.NativeLibraryError):
         terrain.generate_random_env_pos()  # no CUDA device here: loud failure, no host fallback
+
+
+def test_product_code_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under genesis_forge_b200/ may import or execute it."""
+    import pathlib
+    import re
+
+    root = pathlib.Path(gfb.__file__).resolve().parent
+    offenders = []
+    for path in root.rglob("*.py"):
+        text = path.read_text()
+        if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M) or "/root/reference" in text:
+            offenders.append(str(path.relative_to(root)))
+    assert offenders == []

@@ -5,6 +5,4 @@ set -e
 cd "$(dirname "$0")/.."
 python -m genesis_forge_b200.build_native
 rm -rf genesis_forge_b200/_spec
-python -c "
-from genesis_forge_b200 import spec
-print(len(spec.prebuild()), 'specialised kernels')"
+python tools/prebuild_specs.py
