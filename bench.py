@@ -163,7 +163,7 @@ def measured_traffic(config: str, num_envs: int):
 # --------------------------------------------------------------------------------------------------
 def make_dropin_env(spec, num_envs, device, pool, seed):
     import genesis_forge_b200 as gfb
-    from oracle.env_builder import build_env, dropin_namespace
+    from configs.env_builder import build_env, dropin_namespace
 
     gfb.set_device(device)
     # apply_setters=False: see SyntheticScene -- the pool's state sets are reused, so engine-side
@@ -309,7 +309,7 @@ def time_e2e(env, actions_host, steps, warmup, dist_on):
 
 def time_cpu_port(spec, num_envs, pool, steps, warmup, seed):
     """The oracle port (== reference managers, bit for bit) on the host cores."""
-    from oracle.env_builder import make_scene
+    from configs.env_builder import make_scene
     from oracle.manager_port import PortEnv
 
     threads = os.cpu_count() or 1
@@ -343,7 +343,7 @@ def cpu_model() -> str:
 
 # --------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
-    from oracle import specs
+    from configs import specs
 
     if rank != 0:
         return
@@ -369,7 +369,7 @@ def run_b200(args, rank, local_rank, world):
     import torch.distributed as dist
 
     from genesis_forge_b200 import roofline
-    from oracle import specs
+    from configs import specs
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)

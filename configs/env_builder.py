@@ -1,5 +1,5 @@
 """
-TEST INFRASTRUCTURE (oracle).  Builds a ManagedEnvironment from a term-table spec using a given
+Builds a ManagedEnvironment from a term-table spec using a given
 *namespace* of manager classes and mdp functions.
 
 Because the drop-in (genesis_forge_b200) mirrors the reference's manager API, the very same builder
@@ -24,7 +24,7 @@ from genesis_forge_b200.synthetic import ROBOT_MODELS, SyntheticScene
 
 def reference_namespace():
     """Manager classes / mdp modules of the unmodified reference (imports it under the shim)."""
-    from . import shim
+    from oracle import shim
 
     gf = shim.import_reference()
     import genesis_forge.managers as managers

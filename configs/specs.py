@@ -1,9 +1,9 @@
 """
-TEST INFRASTRUCTURE (oracle).  The BASELINE.json configs as term-table specs.
+The BASELINE.json configs as term-table specs (workload definitions; no arithmetic of the path).
 
 Each spec is a plain dict transcribed from the `config()` method of the reference example it names
 (the examples ARE the benchmark definitions).  The same spec drives
-  * oracle/env_builder.py  -> a ManagedEnvironment built from the reference's (or the drop-in's)
+  * configs/env_builder.py  -> a ManagedEnvironment built from the reference's (or the drop-in's)
                               own manager classes and mdp functions,
   * oracle/manager_port.py -> the torch-CPU oracle port.
 Manager references inside params are written "@<manager name>".

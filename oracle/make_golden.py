@@ -3,7 +3,7 @@ TEST INFRASTRUCTURE (oracle).  Regenerates tests/golden/<config>.pt from the UNM
 
     python -m oracle.make_golden            (needs /root/reference; run in the build container)
 
-For every spec in oracle/specs.py the reference's own ManagedEnvironment + managers (imported from
+For every spec in configs/specs.py the reference's own ManagedEnvironment + managers (imported from
 /root/reference under oracle/shim.py, Taichi contact kernel replaced by the ordered restatement) is
 built against the seeded synthetic engine and stepped; the trace records, per step, the actions
 fed in and everything the step returned (obs per group, rewards, terminated, truncated, logged
@@ -58,7 +58,9 @@ def trace_of(env, spec, num_envs: int, steps: int, seed: int, nan_step: int | No
 
 
 def main(names=None):
-    from . import compare, ref_harness, specs
+    from configs import specs
+
+    from . import compare, ref_harness
 
     if not ref_harness.reference_available():
         raise SystemExit("needs /root/reference")

@@ -2,7 +2,7 @@
 TEST INFRASTRUCTURE (oracle) -- the oracle proper.
 
 A torch-CPU, op-for-op restatement of everything `ManagedEnvironment.step / reset / build` does in
-the reference (genesis_forge/managed_env.py:249-398), driven by a term-table spec (oracle/specs.py)
+the reference (genesis_forge/managed_env.py:249-398), driven by a term-table spec (configs/specs.py)
 instead of manager objects.  It exists because the reference itself (pure Python) cannot travel to
 the GPU box; this file can.  It is pinned, bit for bit and step by step (every manager buffer, every
 output, every extras entry, and the global torch RNG stream), against the UNMODIFIED reference on

@@ -20,8 +20,10 @@ import torch
 from genesis_forge_b200.rng import ReplayRng
 from genesis_forge_b200.synthetic import CachedSource, ROBOT_MODELS, StateSource
 
-from . import compare, specs
-from .env_builder import build_env, dropin_namespace, make_scene
+from configs import specs
+
+from . import compare
+from configs.env_builder import build_env, dropin_namespace, make_scene
 from .guard import make_sanitizer
 from .manager_port import PortEnv
 

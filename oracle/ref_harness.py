@@ -20,7 +20,7 @@ import torch
 
 from . import shim
 from .contact_kernel import kernel_get_contact_forces
-from .env_builder import build_env, reference_namespace
+from configs.env_builder import build_env, reference_namespace
 
 
 def reference_available() -> bool:

@@ -125,8 +125,8 @@ def test_million_env_properties(cuda_device):
     the command columns of the observation row equal the command buffer.
     """
     import genesis_forge_b200 as gfb
-    from oracle import specs
-    from oracle.env_builder import build_env, dropin_namespace
+    from configs import specs
+    from configs.env_builder import build_env, dropin_namespace
 
     gfb.set_device(cuda_device)
     n = 1 << 20
@@ -192,8 +192,8 @@ def test_spawn_pose_matches_the_oracle(cuda_device):
 def test_spawn_pose_in_kernel_draws(cuda_device):
     """Production mode (no injected draws): Philox in the kernel; statistical and geometric properties."""
     import genesis_forge_b200 as gfb
-    from oracle import specs
-    from oracle.env_builder import build_env, dropin_namespace
+    from configs import specs
+    from configs.env_builder import build_env, dropin_namespace
 
     gfb.set_device(cuda_device)
     n = 1 << 16
@@ -294,7 +294,7 @@ def test_two_launch_step_parity_specialised(name, cuda_device, monkeypatch):
 
 def test_within_limits_action_manager(cuda_device):
     """PositionWithinLimitsActionManager (position_within_limits.py:99-131): clamp to [-1, 1], then the joint-limit map."""
-    from oracle import specs
+    from configs import specs
     from oracle.parity import ParityRun
 
     action = dict(specs.get("command_direction")["action"], type="within_limits")
@@ -315,7 +315,7 @@ def test_within_limits_action_manager(cuda_device):
 
 def test_base_height_with_a_per_env_target_tensor(cuda_device):
     """rewards.base_height(target_height=<(N,) tensor>) (rewards.py:54-90): GFB_RF_TARGET_FROM_TENSOR."""
-    from oracle import specs
+    from configs import specs
     from oracle.parity import ParityRun
 
     n = 160
@@ -357,8 +357,8 @@ def test_production_draws_philox(cuda_device):
     import copy
 
     import genesis_forge_b200 as gfb
-    from oracle import specs
-    from oracle.env_builder import build_env, dropin_namespace
+    from configs import specs
+    from configs.env_builder import build_env, dropin_namespace
 
     gfb.set_device(cuda_device)
     n = 1 << 16

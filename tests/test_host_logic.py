@@ -16,8 +16,8 @@ from genesis_forge_b200.fused import UnsupportedTermError, asin_tilt_threshold, 
 from genesis_forge_b200.managers import CommandManager, ObservationManager, RewardManager, VelocityCommandManager
 from genesis_forge_b200.mdp import rewards
 from genesis_forge_b200.rng import ReplayRng
-from oracle import specs
-from oracle.env_builder import build_env, dropin_namespace
+from configs import specs
+from configs.env_builder import build_env, dropin_namespace
 
 
 @pytest.fixture()

@@ -6,8 +6,9 @@ torch RNG stream, bit for bit, step by step.  Skipped where /root/reference does
 import pytest
 import torch
 
-from oracle import compare, ref_harness, specs
-from oracle.env_builder import make_scene
+from configs import specs
+from oracle import compare, ref_harness
+from configs.env_builder import make_scene
 from oracle.manager_port import PortEnv
 
 pytestmark = pytest.mark.skipif(not ref_harness.reference_available(), reason="/root/reference not present")

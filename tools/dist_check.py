@@ -7,7 +7,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
 from bench import make_dropin_env
-from oracle import specs
+from configs import specs
 
 rank = int(os.environ["RANK"]); lr = int(os.environ["LOCAL_RANK"]); world = int(os.environ["WORLD_SIZE"])
 dev = torch.device("cuda", lr); torch.cuda.set_device(dev)

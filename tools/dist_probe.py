@@ -3,7 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
 from bench import make_dropin_env
-from oracle import specs
+from configs import specs
 import genesis_forge_b200.fused as F
 rank = int(os.environ.get("RANK", 0)); lr = int(os.environ.get("LOCAL_RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
 dev = torch.device("cuda", lr); torch.cuda.set_device(dev)

@@ -3,7 +3,7 @@ import cProfile, pstats, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bench import make_dropin_env
-from oracle import specs
+from configs import specs
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 dev = torch.device("cuda", 0)
 env = make_dropin_env(specs.get("command_direction"), n, dev, 4, 1)

@@ -1,12 +1,12 @@
 """
 Build-time tooling: ahead-of-time specialisations of the fused kernel for the shipped term tables
-(the BASELINE.json configs + test tables of oracle/specs.py), both slab-size classes, Philox and
+(the BASELINE.json configs + test tables of configs/specs.py), both slab-size classes, Philox and
 injected-draw modes.  Runs without a GPU: a host-only handle describes each table's structure
 (genesis_forge_b200/spec.py), nvcc cross-compiles for sm_100a.
 
     python tools/prebuild_specs.py [config ...]
 
-Kept outside the package: the product code does not import oracle/ (the config definitions live there).
+Kept outside the package: the shipped term tables are workload definitions (configs/), not product code.
 """
 import os
 import sys
@@ -21,8 +21,8 @@ def prebuild(spec_names=None, sizes=(4096, 65536), rng_modes=(1, 0), jobs: int =
 
     import genesis_forge_b200 as gfb
     from genesis_forge_b200 import spec
-    from oracle import specs
-    from oracle.env_builder import build_env, dropin_namespace
+    from configs import specs
+    from configs.env_builder import build_env, dropin_namespace
 
     prev = gfb.gs.device
     gfb.set_device("cpu")

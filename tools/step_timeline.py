@@ -3,7 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bench import make_dropin_env
-from oracle import specs
+from configs import specs
 
 name = sys.argv[1] if len(sys.argv) > 1 else "command_direction"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1048576
