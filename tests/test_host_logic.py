@@ -256,8 +256,14 @@ def test_two_launch_byte_model_is_consistent(cpu_device):
         main, obs = roofline.two_launch_bytes(fused)
         assert main < whole and obs < whole
         assert whole <= main + obs <= 1.4 * whole, (name, whole, main, obs)
-    assert roofline.post_kernel_bytes(dry_env("command_direction")._fused) == 518  # BASELINE.md config 2
-    assert roofline.step_bytes(dry_env("command_direction")._fused) == 710
+    assert roofline.post_kernel_bytes(dry_env("command_direction")._fused) == 518
+    assert roofline.step_bytes(dry_env("command_direction")._fused) == 710      # BASELINE.md, config 2
+    humanoid = build_env(specs.get("berkeley_humanoid"), dropin_namespace(), 32, torch.device("cpu"), n_contacts=8)
+    humanoid._dry_run = True
+    humanoid.build()
+    humanoid._fused._contact_dims = (8, len(humanoid.robot.links) + 1)  # C = 8 synthetic contact slots, plane + links
+    humanoid._fused._set_program(force=True)
+    assert roofline.step_bytes(humanoid._fused) == 1334
 
 
 def test_spawn_request_block(cpu_device):
