@@ -110,6 +110,15 @@ def build_env(spec: dict, ns, num_envs: int, device, **scene_kw):
         def _params(self, params):
             return {k: self._resolve(v) for k, v in (params or {}).items()}
 
+        def _term_fn(self, fn, module):
+            """A term function: a callable, "@<manager>.<method>" (a manager's own term) or an mdp name."""
+            if callable(fn):
+                return fn
+            if fn.startswith("@"):
+                owner, method = fn[1:].split(".")
+                return getattr(getattr(self, owner), method)
+            return getattr(module, fn)
+
         def _obs_fn(self, term):
             kind = term["fn"]
             if callable(kind):  # user-defined observation term
@@ -130,6 +139,8 @@ def build_env(spec: dict, ns, num_envs: int, device, **scene_kw):
                 return (lambda env: self.action_manager.get_dofs_velocity()), {}
             if kind == "dof_force":
                 return (lambda env: self.action_manager.get_dofs_force()), {}
+            if kind == "entity_dofs_force":
+                return ns.observations.entity_dofs_force, {"action_manager": self.action_manager}
             if kind == "actions":
                 return (lambda env: self.action_manager.get_actions()), {}
             if kind == "current_actions":
@@ -168,6 +179,17 @@ def build_env(spec: dict, ns, num_envs: int, device, **scene_kw):
                             _fn(mgr, env_self, env_ids)
 
                     mgr = PythonCommand(self, range=c["range"], resample_time_sec=c["resample_time_sec"])
+                elif ctype == "gait":  # the example's user-level manager (examples/gait_trainer)
+                    from configs import gait
+
+                    if ns.name == "reference":
+                        cls = gait.reference_gait_command_manager()  # the unmodified example class
+                    else:
+                        cls = gait.make_gait_command_manager(M.CommandManager)
+                    mgr = cls(self, foot_names=c["foot_names"], resample_time_sec=c["resample_time_sec"])
+                    for what, times in (c.get("curriculum") or {}).items():
+                        for _ in range(times):
+                            getattr(mgr, f"increment_{what}")()
                 elif ctype == "velocity":
                     mgr = M.VelocityCommandManager(
                         self, range=c["range"], resample_time_sec=c["resample_time_sec"],
@@ -184,7 +206,7 @@ def build_env(spec: dict, ns, num_envs: int, device, **scene_kw):
             for name, item in spec["rewards"].items():
                 cfg[name] = {
                     "weight": item["weight"],
-                    "fn": item["fn"] if callable(item["fn"]) else getattr(ns.rewards, item["fn"]),
+                    "fn": self._term_fn(item["fn"], ns.rewards),
                     "params": self._params(item.get("params")),
                 }
             self.reward_manager = M.RewardManager(self, logging_enabled=True, cfg=cfg)
@@ -192,7 +214,7 @@ def build_env(spec: dict, ns, num_envs: int, device, **scene_kw):
             term_cfg = {}
             for name, item in spec["terminations"].items():
                 term_cfg[name] = {
-                    "fn": item["fn"] if callable(item["fn"]) else getattr(ns.terminations, item["fn"]),
+                    "fn": self._term_fn(item["fn"], ns.terminations),
                     "time_out": item.get("time_out", False),
                     "params": self._params(item.get("params")),
                 }

@@ -184,6 +184,78 @@ def contacts() -> dict:
     }
 
 
+def gait_trainer() -> dict:
+    """
+    examples/gait_trainer/environment.py:94-336 (config 3b): three ContactManagers, the velocity
+    command plus the example's own GaitCommandManager (gait clock, two user-defined reward terms,
+    examples/gait_trainer/gait_command_manager.py:224-345), policy (H=5, O=62) and critic (H=5, O=16)
+    observation groups.  `curriculum` advances the manager's curriculum state before the run the way
+    Go2GaitTrainingEnv.update_curriculum (:359-389) does during training, so that several gaits and
+    non-degenerate period / clearance ranges are sampled.
+    """
+    return {
+        "name": "gait_trainer", "robot": "go2", "dt": 1 / 50,
+        "max_episode_length_sec": 20, "max_episode_random_scaling": 0.4,
+        "entity": {"on_reset": _RESET_FIXED},
+        "action": {
+            "type": "position", "joint_names": GO2_JOINTS, "default_pos": GO2_DEFAULT_POS,
+            "scale": 0.25, "use_default_offset": True, "pd_kp": 20, "pd_kv": 0.5,
+        },
+        "commands": {
+            "velocity_command": {
+                "type": "velocity",
+                "range": {"lin_vel_x": [-1.0, 1.0], "lin_vel_y": [0.0, 0.0], "ang_vel_z": [-1.0, 1.0]},
+                "standing_probability": 0.0, "resample_time_sec": 3.0,
+            },
+            "gait_command_manager": {
+                "type": "gait", "resample_time_sec": 4.0,
+                "foot_names": {"FL": "FL_foot", "FR": "FR_foot", "RL": "RL_foot", "RR": "RR_foot"},
+                "curriculum": {"num_gaits": 2, "gait_period_range": 2, "foot_clearance_range": 3},
+            },
+        },
+        "contacts": {
+            "foot_contact_manager": {"link_names": [".*_foot"], "air_time_contact_threshold": 1.0},
+            "body_contact_manager": {"link_names": ["base"], "air_time_contact_threshold": 1.0},
+            "bad_contact_manager": {"link_names": [".*_thigh", ".*_calf"]},
+        },
+        "rewards": {
+            "gait_phase_reward": {
+                "fn": "@gait_command_manager.gait_phase_reward", "weight": 1.5,
+                "params": {"contact_manager": "@foot_contact_manager"},
+            },
+            "foot_height_reward": {"fn": "@gait_command_manager.foot_height_reward", "weight": 0.9},
+            "base_height_target": {
+                "fn": "base_height", "weight": -25.0, "params": {"target_height": 0.35, "entity_attr": "robot"},
+            },
+            **_track(1.0, 0.5),
+            "body_acceleration": {"fn": "body_acceleration_exp", "weight": -0.1, "params": {"entity_manager": _EM}},
+            "lin_vel_z": {"fn": "lin_vel_z_l2", "weight": -0.1, "params": {"entity_manager": _EM}},
+            "action_rate": {"fn": "action_rate_l2", "weight": -0.01},
+            "bad_contact": {"fn": "contact_force", "weight": -1.0, "params": {"contact_manager": "@bad_contact_manager"}},
+        },
+        "terminations": {
+            "timeout": {"fn": "timeout", "time_out": True},
+            "fall_over": {"fn": "bad_orientation", "params": {"limit_angle": 20.0, "entity_manager": _EM}},
+            "body_contact": {
+                "fn": "contact_force", "params": {"contact_manager": "@body_contact_manager", "threshold": 1.0},
+            },
+        },
+        "observations": {
+            "policy": {
+                "history_len": 5,
+                "terms": {"gait_command": {"fn": "command", "mgr": "gait_command_manager"}, **copy.deepcopy(_OBS_48)},
+            },
+            "critic": {
+                "history_len": 5,
+                "terms": {
+                    "foot_contact_force": {"fn": "contact_force", "mgr": "foot_contact_manager"},
+                    "dof_force": {"fn": "entity_dofs_force", "scale": 0.1},
+                },
+            },
+        },
+    }
+
+
 def rough_terrain() -> dict:
     """examples/rough_terrain/environment.py:86-321 (config 4)."""
     return {
@@ -419,6 +491,7 @@ ALL = {
     "simple": simple,
     "command_direction": command_direction,
     "contacts": contacts,
+    "gait_trainer": gait_trainer,
     "rough_terrain": rough_terrain,
     "berkeley_humanoid": berkeley_humanoid,
     "kitchen_sink": kitchen_sink,

@@ -246,6 +246,7 @@ class FusedStep:
             return True
 
         self.python_commands = [m for m in self.commands if not stock(m)]
+        self._controller_bound = [False] * len(self.commands)  # GFB_B_COMMAND0+k points at a controller's tensor
         # user-defined observation terms: one (N, W) array filled on the host
         self.external_obs: list[tuple[object, str, object, int, int]] = []  # (manager, name, item, col0, width)
         width = 0
@@ -258,7 +259,42 @@ class FusedStep:
         self.ext_obs_width = width
         self.ext_obs = torch.zeros((N, width), device=dev) if width else None
         self.split_mode = bool(self.external_rows or self.python_commands or self.external_obs)
+        self.split_plan = self._make_split_plan() if self.split_mode else []
+        for _, phases, _ in self.split_plan:
+            self._spec_phases.add(phases)
         self._static_buffers()
+
+    def _make_split_plan(self) -> list:
+        """
+        Split execution: the kernel phases as separate launches with the host callbacks of the
+        configuration in between, in the reference's order (managed_env.py:294-326):
+            entity, contacts | user terminations | terminations | user rewards | rewards, stock command
+            resample | user-level command managers' step() | in-library reset (+ report) |
+            engine reset, user-level command managers' reset(idx) | user observation terms | observations
+        Neighbouring phases with no callback between them share a launch.  Returns
+        [(callback name or None, phases, reads_report)].
+        """
+        K = nat.K
+        ext_term = any(kind == "termination" for kind, _, _ in self.external_rows)
+        ext_rew = any(kind == "reward" for kind, _, _ in self.external_rows)
+        stages = [
+            (None, K["GFB_PHASE_ENTITY"] | K["GFB_PHASE_CONTACT"]),
+            ("termination" if ext_term else None, K["GFB_PHASE_TERMINATION"]),
+            ("reward" if ext_rew else None, K["GFB_PHASE_REWARD"] | K["GFB_PHASE_COMMAND"]),
+            ("commands" if self.python_commands else None, K["GFB_PHASE_RESET"]),
+        ]
+        plan: list = []
+        for callback, phases in stages:
+            if callback is None and plan:
+                plan[-1][1] |= phases
+            else:
+                plan.append([callback, phases, False])
+        plan[-1][2] = True  # the launch with the reset phase delivers the report
+        plan.append(["observe", K["GFB_PHASE_OBSERVE"], False])
+        return [tuple(p) for p in plan]
+
+    def split_phase_sets(self) -> list[int]:
+        return [phases for _, phases, _ in self.split_plan]
 
     @staticmethod
     def _opcode_of(fn, kind: str) -> int | None:
@@ -365,8 +401,11 @@ class FusedStep:
             # (range values may be lists the user mutates in place: copied into tuples, never referenced)
             [(tuple(map(tuple, m.ranges_list())), m._resample_steps, m._external_controller is None)
              for m in self.commands],
-            [m._air_time_contact_threshold for m in self.contacts],
-            [om.noise for om in self.observations],
+            [(m._air_time_contact_threshold, m.enabled) for m in self.contacts],
+            (self.reward is None or self.reward.enabled, self.termination is None or self.termination.enabled,
+             self.action is None or self.action.enabled, [m.enabled for m in self.commands],
+             [m.enabled for m in self.entities]),
+            [(om.noise, om.enabled) for om in self.observations],
             [(i.scale, i.noise) for i in obs_items],
         )
 
@@ -415,7 +454,9 @@ class FusedStep:
 
         # action
         if self.action is not None:
-            P.action_mode = self.action.kernel_mode
+            # a disabled action manager returns before anything (position_action_manager.py:383-384):
+            # targets stay as they are and nothing is sent to the actuators; GenesisEnv.step still runs
+            P.action_mode = self.action.kernel_mode if self.action.enabled else 0
             kp = {k: v.detach().cpu().tolist() for k, v in self.action.kernel_params().items()}
             for d in range(self.D):
                 P.action_scale[d] = kp["scale"][d]
@@ -431,6 +472,8 @@ class FusedStep:
             ranges = mgr.ranges_list()
             if len(ranges) > nat.MAX_COMMAND_DIMS:
                 raise UnsupportedTermError("command manager with too many ranges")
+            if not ranges and mgr not in self.python_commands:
+                raise UnsupportedTermError("command manager without a range")
             cm.n_dims = len(ranges)
             cm.resample_steps = mgr._resample_steps
             cm.enabled = 1 if (mgr.enabled and mgr._external_controller is None and mgr not in self.python_commands) else 0
@@ -452,6 +495,7 @@ class FusedStep:
             cm.track_air_time = 1 if mgr._track_air_time else 0
             cm.air_time_threshold = mgr._air_time_contact_threshold
             cm.scene_dt = scene.dt
+            cm.disabled = 0 if mgr.enabled else 1  # contact_manager.py:331-336: nothing is recomputed
             for i, v in enumerate(ids):
                 cm.link_ids[i] = v
                 cm.local_link_ids[i] = local[i]
@@ -459,6 +503,9 @@ class FusedStep:
                 cm.with_ids[i] = v
 
         # rewards
+        P.manager_flags = 0
+        if self.reward is not None and not self.reward.enabled:
+            P.manager_flags |= K["GFB_MF_REWARD_DISABLED"]  # reward_manager.py:172-173, 204: no sums, no logging
         P.n_reward = len(self.reward_terms)
         if P.n_reward > nat.MAX_REWARD:
             raise UnsupportedTermError(f"at most {nat.MAX_REWARD} reward terms are supported")
@@ -468,8 +515,6 @@ class FusedStep:
             t = P.reward[r]
             t.op, t.mgr, t.i0 = opcode, -1, 0
             t.weight = item.weight * env.dt  # reward_manager.py:184
-            if not self.reward.enabled:
-                t.weight = 0.0
             if opcode == K["GFB_R_EXTERNAL"]:
                 t.ext_col = self.ext_row[("reward", name)]
                 continue

@@ -84,6 +84,29 @@ class CommandManager(BaseManager):
             raise ValueError("The range is not a dict")
         return self._range_idx[key]
 
+    # -- lifecycle -------------------------------------------------------------------------------
+    # The stock managers (this class and VelocityCommandManager, neither method overridden) never get
+    # here: their interval / reset resampling is part of the fused post-physics kernel.  A SUBCLASS
+    # that overrides step(), reset() or resample_command() -- the way examples/gait_trainer's
+    # GaitCommandManager does -- is stepped and reset on the host by ManagedEnvironment, and its
+    # super().step() / super().reset(env_ids) calls land here: the host-side equivalents of
+    # command_manager.py:152-170, resampling through the (possibly overridden) resample_command.
+    def step(self):
+        if not self.enabled or self._external_controller is not None:
+            return
+        # the in-library reset runs on the host side of this call in split execution, but the
+        # interval test must see the episode lengths of BEFORE the reset, as in the reference
+        # (managed_env.py:318-323): ManagedEnvironment steps these managers ahead of the reset phase
+        due = (self.env.episode_length % self._resample_steps == 0).nonzero(as_tuple=False).reshape((-1,))
+        self.resample_command(due)
+
+    def reset(self, env_ids=None):
+        if not self.enabled:
+            return
+        if env_ids is None:
+            env_ids = torch.arange(self.env.num_envs, device=gs.device)
+        self.resample_command(env_ids)
+
     def observation(self, env) -> torch.Tensor:
         """Observation term: the current command (command_manager.py:172-174)."""
         return self.env._trace_or(("command", self), lambda: self.command)

@@ -19,6 +19,10 @@ class HostRng:
     def uniform(self, tag: str, like: torch.Tensor, lo: float, hi: float) -> torch.Tensor:
         return torch.empty_like(like).uniform_(lo, hi)
 
+    def multinomial(self, tag: str, weights: torch.Tensor) -> torch.Tensor:
+        """One category per row of `weights` (user-level managers: the gait_trainer example's gait choice)."""
+        return torch.multinomial(weights, 1).squeeze(-1)
+
 
 class ReplayRng(HostRng):
     """Returns recorded draws, in recording order per tag; raises when a tag runs dry."""
@@ -39,4 +43,13 @@ class ReplayRng(HostRng):
         v = q.pop(0).to(like.device, like.dtype)
         if v.shape != like.shape:
             raise RuntimeError(f"ReplayRng: '{tag}' shape {tuple(v.shape)} != {tuple(like.shape)}")
+        return v
+
+    def multinomial(self, tag, weights):
+        q = self.queues.get(tag)
+        if not q:
+            raise RuntimeError(f"ReplayRng: no recorded draw left for '{tag}'")
+        v = q.pop(0).to(weights.device)
+        if v.shape[0] != weights.shape[0]:
+            raise RuntimeError(f"ReplayRng: '{tag}' has {v.shape[0]} rows, {weights.shape[0]} requested")
         return v

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GFB_ABI_VERSION 8
+#define GFB_ABI_VERSION 9
 
 /* ---- limits ------------------------------------------------------------------------------- */
 #define GFB_MAX_DOFS 32
@@ -168,6 +168,10 @@ typedef enum {
   GFB_O_EXTERNAL       /* column `col` of GFB_B_OBS_EXT0, a (N, mgr) array of host-evaluated terms */
 } gfb_obs_src;
 
+/* gfb_program_head.manager_flags */
+#define GFB_MF_REWARD_DISABLED 1u /* RewardManager.enabled == False: the reset phase neither logs nor clears
+                                     the episode sums (reward_manager.py:204); the host drops GFB_PHASE_REWARD */
+
 /* reward-term flag bits */
 #define GFB_RF_TARGET_FROM_COMMAND 1u /* base_height: target = command[mgr][:,0]       */
 #define GFB_RF_TARGET_FROM_TENSOR 2u  /* base_height: target = GFB_B_TARGET_HEIGHT      */
@@ -197,7 +201,8 @@ typedef struct {
 typedef struct {
   int32_t n_dims;
   int32_t resample_steps; /* int(resample_time_sec / dt), command_manager.py:130 */
-  int32_t enabled;        /* 0 when an external controller drives the command    */
+  int32_t enabled;        /* 0: never resampled in the kernel (external controller, user-level
+                             subclass stepped on the host); such a manager may have n_dims == 0 */
   int32_t _pad;
   float lo[GFB_MAX_COMMAND_DIMS];
   float hi[GFB_MAX_COMMAND_DIMS];
@@ -210,7 +215,8 @@ typedef struct {
   int32_t track_air_time;
   float air_time_threshold; /* contact_manager.py:446-449 */
   float scene_dt;           /* contact_manager.py:441     */
-  int32_t _pad[2];
+  int32_t disabled;         /* manager.enabled == False: nothing is recomputed (contact_manager.py:331-336) */
+  int32_t _pad;
   int32_t link_ids[GFB_MAX_CONTACT_LINKS];       /* global link idx */
   int32_t local_link_ids[GFB_MAX_CONTACT_LINKS]; /* for feet_slide  */
   int32_t with_ids[GFB_MAX_WITH_LINKS];
@@ -247,7 +253,8 @@ typedef struct {
   uint64_t rng_seed;
   uint64_t step_index;
 
-  int32_t n_reward, n_termination, n_command, n_contact, n_obs_groups, _pad0;
+  int32_t n_reward, n_termination, n_command, n_contact, n_obs_groups;
+  uint32_t manager_flags; /* GFB_MF_* */
   int32_t height_field_rows, height_field_cols;
   float terrain_bounds[4];
 
@@ -294,19 +301,25 @@ typedef struct {
 #define GFB_STATUS_INF_ACTION 2u   /* position_action_manager.py:405-406 */
 #define GFB_STATUS_BAD_CONTACT 4u  /* contact_manager.py:401-403         */
 #define GFB_STATUS_PEER_TIMEOUT 8u /* a peer rank did not deliver its logging partials in time */
+#define GFB_STATUS_SCAN_TIMEOUT 16u /* internal: a slab waited > 2 s for its predecessors' reset counts */
 
 #define GFB_MAX_PEERS 16           /* ranks of one NVLink domain sharing the logging exchange   */
 #define GFB_IPC_HANDLE_BYTES 64    /* sizeof(cudaIpcMemHandle_t)                                */
 
+/* The step report.  It is written by the post-physics kernel itself, straight into host memory, as
+ * soon as the LAST slab has evaluated its terminations -- i.e. while the final wave of slabs is still
+ * computing rewards and observation rows -- so the host's reset fan-out overlaps the kernel's tail.
+ * Everything the host needs to continue is in it; the logged episode means of the reward terms are
+ * device values (GFB_B_LOG_OUT, complete when the launch has finished in stream order).          */
 typedef struct {
   int32_t n_reset;   /* number of valid entries in GFB_B_RESET_IDX */
   uint32_t status;   /* GFB_STATUS_* seen since the last report    */
   int32_t termination_count[GFB_MAX_TERMINATION_TERMS]; /* envs that fired each term this step */
-  float reward_episode_mean[GFB_MAX_REWARD_TERMS];       /* reward_manager.py:211-216 (n_reset>0) */
   /* envs sharded over ranks (gfb_peer_connect): the same quantities over ALL ranks; on a
    * single-rank handle they repeat the local values                                            */
   int64_t global_n_reset;
   int64_t global_termination_count[GFB_MAX_TERMINATION_TERMS];
+  uint64_t seq;      /* written last: number of the launch (with GFB_PHASE_RESET) this report belongs to */
 } gfb_report;
 
 typedef struct gfb_handle gfb_handle;
@@ -334,22 +347,23 @@ int gfb_set_program(gfb_handle* h, const gfb_program* program);
 int gfb_action_step(gfb_handle* h, const gfb_buffers* b, const float* raw_env, const float* raw_mgr,
                     void* stream);
 
-/* Post-physics launch (one fused kernel + one small finalize kernel).  Replaces, for the phases
- * requested, everything ManagedEnvironment.step does after scene.step()
- * (managed_env.py:294-326): entity cache, contact net forces + air time, terminations, reset mask
- * and ordered index compaction, rewards + episode sums, command resample, the in-library part of
- * reset(), and the observation rows of every env.                                              */
+/* Post-physics launch: ONE persistent kernel.  Replaces, for the phases requested, everything
+ * ManagedEnvironment.step does after scene.step() (managed_env.py:294-326): entity cache, contact
+ * net forces + air time, terminations, reset mask and ordered index compaction (a single-pass
+ * decoupled look-back over the slabs' reset counts: GFB_B_RESET_IDX equals
+ * (terminated | truncated).nonzero()), rewards + episode sums, command resample, the in-library part
+ * of reset(), the logging reductions, the step report, and the observation rows of every env.   */
 int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void* stream);
 
-/* Copy the step report to the host and wait for it (the one blocking point of a step; the
- * reference blocks at the same place, managed_env.py:309,322).                                 */
+/* Wait for the report of the last launch that contained GFB_PHASE_RESET (the one blocking point of a
+ * step; the reference blocks at the same place, managed_env.py:309,322).  The host spins on the
+ * report's sequence word in mapped host memory; the call returns when the report has been DELIVERED,
+ * which is before the kernel has finished (see gfb_report).  Work enqueued afterwards on the same
+ * stream is ordered behind the kernel as usual.                                                 */
 int gfb_read_report(gfb_handle* h, gfb_report* out, void* stream);
 
-/* The same in two halves: gfb_request_report enqueues the copy and marks the stream position,
- * gfb_wait_report blocks until that position is reached.  Work enqueued in between (the separate
- * observation pass of a large batch) runs while the host handles the report.    */
-int gfb_request_report(gfb_handle* h, void* stream);
-int gfb_wait_report(gfb_handle* h, gfb_report* out);
+/* gfb_post_physics + gfb_read_report in one call (one boundary crossing per step).              */
+int gfb_post_physics_report(gfb_handle* h, const gfb_buffers* b, uint32_t phases, gfb_report* out, void* stream);
 
 /* ---- envs sharded over the GPUs of one node ------------------------------------
  * The only exchange between ranks is the logging vector [sum of episode quotients per reward term,
@@ -448,11 +462,8 @@ int gfb_spec_stats(const gfb_handle* h, int64_t* specialised, int64_t* generic);
 int gfb_profile_enable(gfb_handle* h, int32_t enabled);
 int gfb_profile_read(gfb_handle* h, float* post_ms_total, int32_t* post_launches, float* action_ms_total,
                      int32_t* action_launches);
-/* Same for the launches of gfb_post_physics that ran GFB_PHASE_OBSERVE alone (they are excluded
- * from the post_* totals of gfb_profile_read).                                                  */
-int gfb_profile_read_observation_pass(gfb_handle* h, float* ms_total, int32_t* launches);
-/* Same for the small kernels; ms_total / launches are arrays of 3: [0] finalize, [1] observe
- * (gfb_observe), [2] spawn (gfb_spawn_pose).                                                    */
+/* Same for the small kernels; ms_total / launches are arrays of 3: [0] reset scatter
+ * (gfb_reset_rows), [1] observe (gfb_observe), [2] spawn (gfb_spawn_pose).                       */
 int gfb_profile_read_aux(gfb_handle* h, float* ms_total, int32_t* launches);
 /* kernels launched by this handle since creation (gfb_action_step: 1, gfb_post_physics: 1-2, ...) */
 int64_t gfb_launch_count(const gfb_handle* h);

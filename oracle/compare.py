@@ -28,7 +28,12 @@ def reference_snapshot(env) -> dict[str, torch.Tensor]:
     for name, v in env.reward_manager.episode_data.items():
         s[f"episode_data/{name}"] = v
     for name in env.managers_by_name("command"):
-        s[f"command/{name}"] = getattr(env, name)._command
+        mgr = getattr(env, name)
+        s[f"command/{name}"] = mgr._command
+        if hasattr(mgr, "foot_offset"):  # the gait_trainer example's manager: its own state tensors
+            for key in ("foot_offset", "gait_period", "foot_height", "gait_time", "gait_phase", "clock_input"):
+                s[f"gait/{name}/{key}"] = getattr(mgr, key)
+            s[f"gait/{name}/gait_selected"] = mgr._gait_selected
     for name in env.managers_by_name("contact"):
         m = getattr(env, name)
         s[f"contact/{name}/contacts"] = m.contacts

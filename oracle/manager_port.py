@@ -92,6 +92,10 @@ class PortEnv:
         self.rng_log.append((tag, t.clone()))
         return t
 
+    def _draw_max_len(self, idx: torch.Tensor) -> torch.Tensor:
+        """U(-1, 1) draws of genesis_env.py:249 (a hook: the parity harness can transplant the kernel's draws)."""
+        return self._uniform("max_len", (idx.numel(),), -1.0, 1.0)
+
     def _margin(self, what: str, value: torch.Tensor, threshold: float):
         if self.record_margins:
             self.margins.append((what, value.detach().clone(), float(threshold)))
@@ -256,6 +260,14 @@ class PortEnv:
         # --- command_manager.py:66-81, 127-130
         self.command = {}
         for name, c in spec["commands"].items():
+            if c.get("type") == "gait":  # the gait_trainer example's own manager (oracle/gait_port.py)
+                from .gait_port import GaitPort
+
+                gait = GaitPort(self, c)
+                gait.build()
+                self.command[name] = {"gait": gait, "python": None, "command": gait._command}
+                setattr(self, name, gait)
+                continue
             rng = c["range"]
             k = len(rng) if isinstance(rng, dict) else 1
             self.command[name] = {
@@ -418,6 +430,9 @@ class PortEnv:
 
         self.resample_idx = {}
         for name, c in self.command.items():                  # command_manager.py:152-162
+            if c.get("gait") is not None:
+                c["gait"].step()
+                continue
             if c["python"] is not None:  # user-level subclass overriding step()
                 c["python"]["step"](getattr(self, name), self)
                 continue
@@ -548,6 +563,12 @@ class PortEnv:
     def _reward_value(self, fn, p: dict, name: str = "") -> torch.Tensor:
         if callable(fn):  # user-defined term
             return fn(self, **p)
+        if fn.startswith("@"):  # a term that is a method of the gait command manager
+            owner, method = fn[1:].split(".")
+            gait = self.command[owner]["gait"]
+            if method == "gait_phase_reward":
+                return gait.gait_phase_reward(self.contact[p["contact_manager"][1:]])
+            return gait.foot_height_reward(**p)
         if fn == "is_alive":  # :31-37
             return (~self.extras["terminations"]).float().detach()
         if fn == "terminated":  # :40-46
@@ -682,7 +703,7 @@ class PortEnv:
             self.episode_length[idx] = 0
         if len(idx) > 0 and self.max_episode_random_scaling > 0.0 and self.base_max_episode_length is not None:
             max_random_scaling = self.base_max_episode_length * self.max_episode_random_scaling
-            u = self._uniform("max_len", (idx.numel(),), -1.0, 1.0)
+            u = self._draw_max_len(idx)
             randomization = u * max_random_scaling
             self.max_episode_length[idx] = torch.round(self.base_max_episode_length + randomization).to(torch.int32)
 
@@ -760,6 +781,9 @@ class PortEnv:
 
         # -- command_manager.py:164-170
         for name, c in self.command.items():
+            if c.get("gait") is not None:
+                c["gait"].reset(env_ids)
+                continue
             if c["python"] is not None:
                 c["python"]["reset"](getattr(self, name), self, env_ids)
                 continue
@@ -781,7 +805,8 @@ class PortEnv:
         if kind == "ang_vel_uncached":
             return self._ang_vel(False)
         if kind == "command":
-            return self.command[term["mgr"]]["command"]
+            c = self.command[term["mgr"]]
+            return c["gait"].observation() if c.get("gait") is not None else c["command"]
         if kind == "ang_vel":
             return self._ang_vel(True)
         if kind == "lin_vel":
@@ -792,7 +817,7 @@ class PortEnv:
             return self.robot.get_dofs_position(self.dofs_idx)
         if kind == "dof_vel":
             return self.robot.get_dofs_velocity(self.dofs_idx)
-        if kind == "dof_force":
+        if kind in ("dof_force", "entity_dofs_force"):  # mdp/observations.py:133-158 with an action manager
             return self.robot.get_dofs_force(self.dofs_idx)
         if kind in ("actions", "current_actions"):  # base.py:96-102
             if self.targets is None:
@@ -849,6 +874,8 @@ class PortEnv:
             s[f"episode_data/{name}"] = v
         for name, c in self.command.items():
             s[f"command/{name}"] = c["command"]
+            if c.get("gait") is not None:
+                s.update(c["gait"].snapshot(name))
         for name, m in self.contact.items():
             s[f"contact/{name}/contacts"] = m["contacts"]
             s[f"contact/{name}/positions"] = m["positions"]

@@ -53,10 +53,41 @@ def _close(a: torch.Tensor, b: torch.Tensor):
     return ok, err.max().item() if err.numel() else 0.0, rel
 
 
+class _TransplantPort(PortEnv):
+    """
+    Oracle for the PRODUCTION kernels (in-kernel Philox draws, nothing injected): the draws the
+    kernels made are read back from their results and used where the oracle would draw -- the new
+    command of a resampled / reset env, the new maximum episode length of a reset env.  Everything
+    else is computed by the oracle as usual, so every value that is not itself a draw is compared.
+    (The draws' own distribution is covered by test_production_draws_philox.)
+    """
+
+    kernel_results: dict | None = None  # {"command/<name>": (N,K), "max_episode_length": (N,)} on the CPU
+
+    def _resample(self, name, c, env_ids, tag):
+        src = self.kernel_results[f"command/{name}"]
+        for i in range(c["command"].shape[1]):
+            c["command"][env_ids, i] = src[env_ids, i]
+
+    def _draw_max_len(self, idx):
+        # the u for which round(base + u * span) is the kernel's value (the sum lands within 1e-4 of an integer)
+        span = self.base_max_episode_length * self.max_episode_random_scaling
+        got = self.kernel_results["max_episode_length"][idx].float()
+        return (got - self.base_max_episode_length) / span
+
+
 class ParityRun:
     def __init__(self, spec_name: str, num_envs: int, device, seed: int = 1234, n_contacts: int = 8,
-                 spec_override: dict | None = None, sanitize: bool = True):
+                 spec_override: dict | None = None, sanitize: bool = True, philox: bool = False):
+        """
+        `philox=True`: the drop-in runs in production mode (in-kernel Philox draws, the kernel binary
+        bench.py times) and the oracle receives the kernels' draws instead of the other way round.
+        Only for specs without observation noise and without host-side (reset-time) draws that feed
+        compared values.
+        """
         import genesis_forge_b200 as gfb
+
+        self.philox = philox
 
         self.spec = specs.get(spec_name)
         if spec_override:
@@ -77,13 +108,15 @@ class ParityRun:
         torch.manual_seed(seed)
         scene, terrain, robot = make_scene(self.spec, torch.device("cpu"), source=self.source, copy_on_get=True,
                                            n_contacts=n_contacts)
-        self.port = PortEnv(self.spec, num_envs, scene, terrain, robot, record_margins=True)
+        self.port = (_TransplantPort if philox else PortEnv)(self.spec, num_envs, scene, terrain, robot,
+                                                             record_margins=True)
         self.port.build()
 
         gfb.set_device(self.device)
         self.env = build_env(self.spec, dropin_namespace(), num_envs, self.device, source=self.source,
                              n_contacts=n_contacts)
-        self.env.rng = ReplayRng()
+        if not philox:
+            self.env.rng = ReplayRng()
         self.env.build()
         self.action_gen = torch.Generator().manual_seed(seed + 77)
         self.group_names = list(self.spec["observations"].keys())
@@ -192,10 +225,21 @@ class ParityRun:
                 )
 
     # -- drive -----------------------------------------------------------------------------------
+    def _kernel_results(self) -> dict:
+        out = {"max_episode_length": self.env.max_episode_length.cpu()}
+        for name in self.command_names:
+            out[f"command/{name}"] = getattr(self.env, name)._command.cpu()
+        return out
+
     def reset(self):
-        obs_p, extras_p = self.port.reset()
-        self._inject_from_log(None, None)
-        obs_e, extras_e = self.env.reset()
+        if self.philox:  # kernels first, their draws go to the oracle
+            obs_e, extras_e = self.env.reset()
+            self.port.kernel_results = self._kernel_results()
+            obs_p, extras_p = self.port.reset()
+        else:
+            obs_p, extras_p = self.port.reset()
+            self._inject_from_log(None, None)
+            obs_e, extras_e = self.env.reset()
         self._compare_all("reset", extras_p, extras_e)
         self._check("reset", "obs", obs_e, obs_p, exact=False)
 
@@ -206,10 +250,16 @@ class ParityRun:
             actions[min(3, self.N - 1), 1] = float("nan")
         # (both sides get their own tensor: the within-limits action manager clamps its argument in place)
         self.last_action_args = (actions.clone(), actions.to(self.device))
-        out_p = self.port.step(self.last_action_args[0])
-        self._assert_margins(f"step {i}")
-        self._inject_from_log(self.port.reset_idx, self.port.resample_idx)
-        out_e = self.env.step(self.last_action_args[1])
+        if self.philox:
+            out_e = self.env.step(self.last_action_args[1])
+            self.port.kernel_results = self._kernel_results()
+            out_p = self.port.step(self.last_action_args[0])
+            self._assert_margins(f"step {i}")
+        else:
+            out_p = self.port.step(self.last_action_args[0])
+            self._assert_margins(f"step {i}")
+            self._inject_from_log(self.port.reset_idx, self.port.resample_idx)
+            out_e = self.env.step(self.last_action_args[1])
         where = f"step {i}"
         n_reset = int(self.port.reset_idx.numel())
         self._check(where, "reset_idx", self.env._fused.reset_idx[:n_reset], self.port.reset_idx, exact=True)

@@ -47,6 +47,67 @@ def test_step_parity_generic_interpreter(name, cuda_device, monkeypatch):
     assert spec_stats["generic_launches"] == (2 + 4 * 60 if name in SPLIT else 62)
 
 
+def _benchmark_library(fused):
+    """(slab size, library file) of the specialised fused launch this environment's step uses."""
+    from genesis_forge_b200 import _native as nat
+    from genesis_forge_b200 import spec
+
+    phases = nat.K["GFB_PHASE_ALL"]
+    canon, plan, tile = spec.describe(fused, phases)
+    return tile, spec.library_path(spec.key_of(spec.header_text(canon, plan, tile, phases))).name
+
+
+BENCH_SIZES = [("command_direction", 32768), ("command_direction", 65536), ("contacts", 32768), ("contacts", 65536),
+               ("rough_terrain", 32768), ("rough_terrain", 65536), ("berkeley_humanoid", 32768),
+               ("berkeley_humanoid", 65536)]
+
+
+@pytest.mark.parametrize("name,num_envs", BENCH_SIZES)
+def test_step_parity_at_benchmark_slab_sizes(name, num_envs, cuda_device):
+    """
+    Default mode (no switches) at the batch sizes where the library picks the LARGE slabs (128 envs,
+    or 64 with contact slots staged): the specialised one-launch kernels of the BASELINE configs, whose
+    slab plan, row-assembly ownership and late-load overlay all depend on the slab size, against the
+    oracle value by value.
+    """
+    from oracle.parity import ParityRun
+
+    run = ParityRun(name, num_envs=num_envs, device=cuda_device, seed=2025)
+    stats = run.run(steps=4, nan_step=1)
+    fused = run.env._fused
+    spec_stats = fused.spec_stats()
+    tile, library = _benchmark_library(fused)
+    assert tile in (64, 128), tile
+    assert spec_stats["specialised_launches"] == 4 and library in spec_stats["libraries"], (spec_stats, library)
+    assert stats["resets"] > 0
+    print(f"PARITY-VARIANT {name} N={num_envs} slab={tile} draws=injected library={library} stats={stats}")
+
+
+@pytest.mark.parametrize("name,num_envs,steps", [
+    ("command_direction", 65536, 6), ("contacts", 65536, 4), ("rough_terrain", 262144, 3),
+    ("berkeley_humanoid", 65536, 4), ("command_direction", 1 << 20, 2), ("berkeley_humanoid", 1 << 20, 2),
+])
+def test_production_kernel_parity(name, num_envs, steps, cuda_device):
+    """
+    The PRODUCTION binaries -- in-kernel Philox draws, large slabs: exactly the specialised libraries
+    bench.py times (its `kernel_variant.libraries`) -- against the oracle at BASELINE batch sizes up
+    to 1,048,576 envs.  The kernels' draws are transplanted into the oracle (oracle/parity.py,
+    `philox=True`); every other value of the step is compared as in the injected-draw tests.
+    """
+    from oracle.parity import ParityRun
+
+    n_contacts = 8 if name != "command_direction" else 0  # as bench.py builds the workload
+    run = ParityRun(name, num_envs=num_envs, device=cuda_device, seed=11, n_contacts=n_contacts, philox=True)
+    stats = run.run(steps=steps)
+    fused = run.env._fused
+    spec_stats = fused.spec_stats()
+    tile, library = _benchmark_library(fused)
+    assert fused.injected is None and tile in (64, 128)
+    assert spec_stats["specialised_launches"] == steps and library in spec_stats["libraries"], (spec_stats, library)
+    assert stats["resets"] > 0
+    print(f"PARITY-VARIANT {name} N={num_envs} slab={tile} draws=philox library={library} stats={stats}")
+
+
 def test_live_mutation_keeps_the_specialised_kernel(cuda_device):
     """Weights / params / ranges are live values: mutating them must not need a new specialisation."""
     from oracle.parity import ParityRun
