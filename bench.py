@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--num-envs", type=int, default=1 << 20, help="envs per GPU (weak scaling)")
     ap.add_argument("--pool", type=int, default=4, help="pre-generated state sets rotated by scene.step()")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 4096 / 65536 env points")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 3 / 4 / 5 block")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-envs", type=int, default=0, help="envs for the CPU baseline (0 = same as --num-envs)")
@@ -146,14 +147,20 @@ class ClockSampler:
 
 def measured_traffic(config: str, num_envs: int):
     """
-    DRAM bytes (read + write) of ONE post_kernel launch of this workload from the committed
-    `ncu --set full` capture (profiles/traffic.json, written by tools/summarize_profile.py), or None.
+    DRAM bytes (read + write) of ONE post_kernel launch of this workload, measured with
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` by tools/measure_traffic.py and kept in
+    profiles/traffic.json TOGETHER WITH the hash of the kernel sources it was measured on.  An entry
+    whose hash is not the hash of the sources in this tree is stale and refused (None).
     """
+    from genesis_forge_b200 import spec
+
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")
     try:
         with open(path) as f:
             entry = json.load(f).get(f"{config}:{num_envs}")
-        return None if entry is None else entry["dram_bytes"]
+        if entry is None or entry.get("kernel_source_hash") != spec.source_hash():
+            return None
+        return entry["dram_bytes"]
     except (OSError, ValueError):
         return None
 
@@ -307,27 +314,67 @@ def time_e2e(env, actions_host, steps, warmup, dist_on):
     return ms, h2d, d2h
 
 
-def time_cpu_port(spec, num_envs, pool, steps, warmup, seed):
-    """The oracle port (== reference managers, bit for bit) on the host cores."""
+def time_cpu_reference(spec, num_envs, pool, steps, warmup, seed):
+    """
+    The reference's own CPU implementation of the path on the host cores, all threads:
+    the UNMODIFIED reference package (from /root/reference, or its verbatim copy oracle/_ref made by
+    oracle/make_ref.py, which travels to the GPU box) driving the same synthetic engine -- kind
+    "reference" -- or, if neither is present, the oracle port (bit-identical to it) -- kind "port".
+    Returns (env-steps/s, threads, ms per step, kind).
+    """
     from configs.env_builder import make_scene
-    from oracle.manager_port import PortEnv
 
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    scene, terrain, robot = make_scene(spec, torch.device("cpu"), copy_on_get=True, pool=pool, seed=seed,
-                                       n_contacts=8 if spec["contacts"] else 0, apply_setters=False)
-    env = PortEnv(spec, num_envs, scene, terrain, robot)
+    n_contacts = 8 if spec["contacts"] else 0
+    kind = "port"
+    env = None
+    try:
+        from oracle import ref_harness
+
+        if ref_harness.reference_available():
+            env = ref_harness.make_reference_env(spec, num_envs, n_contacts=n_contacts, seed=seed, pool=pool,
+                                                 apply_setters=False)
+            kind = "reference"
+    except Exception as e:  # pragma: no cover - depends on the box
+        print(f"[bench] unmodified reference unavailable ({e}); timing the oracle port", file=sys.stderr)
+        env = None
+    if env is None:
+        from oracle.manager_port import PortEnv
+
+        scene, terrain, robot = make_scene(spec, torch.device("cpu"), copy_on_get=True, pool=pool, seed=seed,
+                                           n_contacts=n_contacts, apply_setters=False)
+        env = PortEnv(spec, num_envs, scene, terrain, robot)
+    import contextlib
+    import io
+
     env.build()
     env.reset()
     gen = torch.Generator().manual_seed(seed)
-    actions = [torch.randn(num_envs, env.num_actions, generator=gen) for _ in range(2)]
-    for i in range(warmup):
-        env.step(actions[i % 2])
-    t0 = time.perf_counter()
-    for i in range(steps):
-        env.step(actions[i % 2])
-    dt = (time.perf_counter() - t0) / steps
-    return num_envs / dt, threads, dt * 1e3
+    n_act = env.action_space.shape[0] if kind == "reference" else env.num_actions
+    actions = [torch.randn(num_envs, n_act, generator=gen) for _ in range(2)]
+    with contextlib.redirect_stdout(io.StringIO()):  # (the reference prints per-step warnings)
+        for i in range(warmup):
+            env.step(actions[i % 2])
+        t0 = time.perf_counter()
+        for i in range(steps):
+            env.step(actions[i % 2])
+        dt = (time.perf_counter() - t0) / steps
+    return num_envs / dt, threads, dt * 1e3, kind
+
+
+def workload_name(config: str, num_envs: int) -> str:
+    return f"{config} manager step (full reward/termination/observation table), num_envs={num_envs} per GPU"
+
+
+def cpu_sample_envs(num_envs: int, steps: int, warmup: int) -> int:
+    """
+    Envs per step of the CPU arm: the workload's own batch when the whole run fits in a few minutes,
+    otherwise a bounded sample (the metric, env-steps/s, does not depend on the batch beyond cache
+    effects; ~1e7 env-steps/s on 16 cores -> 1.2e9 env-steps is about two minutes).
+    """
+    budget = int(1.2e9 // max(steps + warmup, 1))
+    return max(4096, min(num_envs, (budget // 4096) * 4096))
 
 
 def cpu_model() -> str:
@@ -341,24 +388,69 @@ def cpu_model() -> str:
     return "unknown"
 
 
+# the BASELINE.json configs 3 / 4 / 5 at the batch sizes it names (config 2 is the headline workload)
+EXTRA_CONFIGS = [
+    ("contacts", 65536), ("contacts", 1 << 20), ("gait_trainer", 65536), ("rough_terrain", 262144),
+    ("berkeley_humanoid", 4096), ("berkeley_humanoid", 65536), ("berkeley_humanoid", 262144),
+    ("berkeley_humanoid", 1 << 20),
+]
+
+
+def measure_config(name, n, dev, pool, seed, steps, warmup, peak, dist_on=False, shard=False):
+    """One workload through the public API: step time, step / kernel roofline fractions, kernel variant."""
+    from configs import specs
+    from genesis_forge_b200 import roofline
+
+    env = make_dropin_env(specs.get(name), n, dev, pool, seed)
+    fused = env._fused
+    if shard:
+        env.shard()
+    acts = [torch.randn(n, fused.D, device=dev) for _ in range(4)]
+    ms, resets = time_dropin(env, acts, steps, warmup, dist_on)
+    prof = fused.profile_read()
+    fused.profile(False)
+    per_step = len(fused.split_plan) if fused.split_mode else 1
+    post_us = 1e3 * prof["post_ms"] / max(prof["post_launches"], 1) * per_step
+    step_bytes, post_bytes = roofline.step_bytes(fused), roofline.post_kernel_bytes(fused)
+    state_mb = sum(v.numel() * v.element_size() for v in env.scene._pool[0].values()) / 1e6
+    out = {
+        "num_envs": n, "ms_per_step": ms, "value": n / (ms / 1e3), "resets_per_step": resets,
+        "step_bytes_per_env": step_bytes, "step_roofline_frac": step_bytes * n / (ms / 1e3) / 1e9 / peak,
+        "post_kernel_us": post_us, "post_kernel_launches_per_step": per_step, "post_kernel_bytes_per_env": post_bytes,
+        "post_kernel_frac": post_bytes * n / (post_us / 1e6) / 1e9 / peak if post_us > 0 else 0.0,
+        "action_kernel_us": 1e3 * prof["action_ms"] / max(prof["action_launches"], 1),
+        "traffic": measured_traffic(name, n),
+        "l2": f"{pool} state sets of {state_mb:.0f} MB rotated" + ("" if pool * state_mb > 2 * 126 else " (L2-resident: latency point)"),
+        "step_mode": "split execution around user-level Python terms" if fused.split_mode else "fused",
+        "libraries": fused.spec_stats()["libraries"],
+    }
+    del env
+    torch.cuda.empty_cache()
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
+    """
+    `--impl reference`: the reference's CPU implementation of the same workload, same metric / unit /
+    config as the GPU arm, honouring --steps / --warmup; rank 0 only (the other ranks exit).
+    """
     from configs import specs
 
     if rank != 0:
         return
     spec = specs.get(args.config)
-    n = args.cpu_envs or args.num_envs
-    steps = max(3, min(args.steps, 12))
-    warmup = max(3, min(args.warmup, 3))
-    value, threads, ms = time_cpu_port(spec, n, 2, steps, warmup, 1234)
-    sample = f"{steps} steps of {n} envs ({args.config} term table), oracle port on torch-CPU"
+    N = args.num_envs
+    n = args.cpu_envs or cpu_sample_envs(N, args.steps, args.warmup)
+    value, threads, ms, kind = time_cpu_reference(spec, n, args.pool, args.steps, args.warmup, 1234)
+    sample = (f"{args.steps} steps of {n} envs ({args.config} term table) on torch-CPU, {threads} threads, "
+              f"{cpu_model()}; " + ("the unmodified reference package" if kind == "reference" else "oracle port"))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config} Go2 manager step, num_envs={n}", "cpu": cpu_model()},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(args.config, N), "pool": args.pool},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -391,7 +483,6 @@ def run_b200(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms, resets_per_step = time_dropin(env, actions, args.steps, args.warmup, dist_on)
     prof = fused.profile_read()
-    obs_prof = fused.profile_read_observation_pass()
     aux_prof = fused.profile_read_aux()
     fused.profile(False)
     launches = env.timed_launches
@@ -402,14 +493,6 @@ def run_b200(args, rank, local_rank, world):
     post_ms = prof["post_ms"] / max(prof["post_launches"], 1)
     act_ms = prof["action_ms"] / max(prof["action_launches"], 1)
     post_bytes = roofline.post_kernel_bytes(fused)
-    observation_pass = None
-    if fused.overlap_obs:  # opt-in two-launch step: the timed post launches are the main part only
-        post_bytes, obs_bytes = roofline.two_launch_bytes(fused)
-        obs = obs_prof
-        obs_ms = obs["obs_ms"] / max(obs["obs_launches"], 1)
-        observation_pass = {"bytes_per_env": obs_bytes, "kernel_us": obs_ms * 1e3,
-                            "achieved": obs_bytes * N / (obs_ms / 1e3) / 1e9 if obs_ms > 0 else 0.0}
-        observation_pass["frac"] = observation_pass["achieved"] / peak
     achieved = post_bytes * N / (post_ms / 1e3) / 1e9 if post_ms > 0 else 0.0
     step_bytes = roofline.step_bytes(fused)
 
@@ -426,25 +509,35 @@ def run_b200(args, rank, local_rank, world):
         for n_small in (4096, 65536):
             if n_small >= N:
                 continue
-            small = make_dropin_env(spec, n_small, dev, max(args.pool, 4), seed)
-            acts = [torch.randn(n_small, fused.D, device=dev) for _ in range(4)]
-            ms_s, _ = time_dropin(small, acts, max(args.steps, 100), max(args.warmup, 10), False)
-            p = small._fused.profile_read()
-            sweep[str(n_small)] = {
-                "value": n_small / (ms_s / 1e3), "ms_per_step": ms_s,
-                "post_kernel_us": 1e3 * p["post_ms"] / max(p["post_launches"], 1),
-                "action_kernel_us": 1e3 * p["action_ms"] / max(p["action_launches"], 1),
-            }
-            del small
+            m = measure_config(args.config, n_small, dev, max(args.pool, 4), seed, max(args.steps, 100), max(args.warmup, 10), peak)
+            sweep[str(n_small)] = {k: m[k] for k in ("value", "ms_per_step", "post_kernel_us", "action_kernel_us",
+                                                       "step_roofline_frac", "l2")}
+
+    # BASELINE configs 3 / 4 / 5 at their named batch sizes (single GPU); under torchrun the
+    # strong-scaling point of config 4 instead: 262,144 rough_terrain envs in total, sharded over the ranks
+    configs = {}
+    strong = None
+    if dist_on:
+        total = 262144
+        if total % world == 0:
+            m = measure_config("rough_terrain", total // world, dev, args.pool, seed, args.steps, args.warmup, peak,
+                               dist_on=True, shard=True)
+            strong = {"config": "rough_terrain", "total_envs": total, "envs_per_gpu": total // world, "scaling": "strong",
+                      "ms_per_step": m["ms_per_step"], "value": total / (m["ms_per_step"] / 1e3),
+                      "post_kernel_us": m["post_kernel_us"]}
+    elif not args.no_configs:
+        for name, n_cfg in EXTRA_CONFIGS:
+            k_steps = 100 if n_cfg <= 65536 else 20
+            configs[f"{name}:{n_cfg}"] = measure_config(name, n_cfg, dev, 4, seed, k_steps, 5, peak)
 
     cpu = None
     if rank == 0 and not dist_on and not args.no_cpu:
         n_cpu = args.cpu_envs or N
         cpu_steps = 40  # a bounded sample: ~5-20 s of host work at 1M envs depending on the table
-        v, threads, cpu_ms = time_cpu_port(spec, n_cpu, 2, cpu_steps, 3, 1234)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": cpu_ms,
-               "sample": f"{cpu_steps} steps of {n_cpu} envs ({args.config} term table), oracle port on torch-CPU, "
-                         f"{cpu_model()}"}
+        v, threads, cpu_ms, kind = time_cpu_reference(spec, n_cpu, args.pool, cpu_steps, 3, 1234)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "ms_per_step": cpu_ms,
+               "sample": f"{cpu_steps} steps of {n_cpu} envs ({args.config} term table) on torch-CPU, {cpu_model()}; "
+                         + ("the unmodified reference package" if kind == "reference" else "oracle port")}
 
     if rank == 0:
         line = {
@@ -452,24 +545,29 @@ def run_b200(args, rank, local_rank, world):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"{args.config} Go2 manager step (full reward/termination/observation table), "
-                            f"num_envs={N} per GPU",
-                "step_mode": "two launches (GFB_OVERLAP_OBS=1)" if fused.overlap_obs else "one fused launch",
+                "workload": workload_name(args.config, N), "pool": args.pool,
+                "step_mode": "action kernel, one persistent post-physics kernel (compaction + report inside), "
+                             "sparse re-observation of the reset envs",
                 "l2_policy": f"{args.pool} pre-generated state sets rotated per step, each set > L2 at this size",
                 "resets_per_step": resets_per_step,
                 "step_algorithmic_bytes_per_env": step_bytes,
                 "step_roofline_frac": step_bytes * N / (ms / 1e3) / 1e9 / peak,
             },
             "roofline": {
-                "kernel": "post_kernel (gfb_post_physics)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None if fused.overlap_obs else measured_traffic(args.config, N),
+                # whole step first (B_alg * N / t_step), then the dominant kernel
+                "scope": "whole manager step: algorithmic bytes of the step / device time per step (CUDA events)",
+                "bound": "hbm", "achieved": step_bytes * N / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": step_bytes * N / (ms / 1e3) / 1e9 / peak, "bytes_per_env": step_bytes,
                 "peak_source": peak_src,
-                "bytes_per_env": post_bytes, "kernel_us": post_ms * 1e3,
-                "observation_pass": observation_pass,  # only with GFB_OVERLAP_OBS=1 (two-launch step)
-                "small_kernels": aux_prof,  # CUDA-event time per launch: finalize, re-observation, spawn
+                "traffic": measured_traffic(args.config, N),  # DRAM bytes of one post_kernel launch (ncu), or null if stale
+                "kernel": {
+                    "name": "post_kernel (gfb_post_physics)", "bytes_per_env": post_bytes, "kernel_us": post_ms * 1e3,
+                    "achieved": achieved, "frac": achieved / peak,
+                },
                 "action_kernel": {"bytes_per_env": roofline.action_kernel_bytes(fused), "kernel_us": act_ms * 1e3,
                                   "achieved": roofline.action_kernel_bytes(fused) * N / max(act_ms, 1e-9) / 1e6,
                                   "frac": roofline.action_kernel_bytes(fused) * N / max(act_ms, 1e-9) / 1e6 / peak},
+                "small_kernels": aux_prof,  # CUDA-event time per launch: reset rows, re-observation, spawn
             },
             "cpu_baseline": cpu,
             "e2e": e2e,
@@ -477,6 +575,8 @@ def run_b200(args, rank, local_rank, world):
             "kernel_variant": fused.spec_stats(),
             "clocks": clocks,
             "sweep": sweep,
+            "configs": configs,
+            "strong_scaling": strong,
         }
         print(json.dumps(line), flush=True)
     if dist_on:

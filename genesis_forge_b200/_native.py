@@ -91,7 +91,7 @@ class ContactManagerDesc(C.Structure):
     _fields_ = [
         ("n_links", C.c_int32), ("n_with", C.c_int32), ("has_with_filter", C.c_int32),
         ("track_air_time", C.c_int32), ("air_time_threshold", C.c_float), ("scene_dt", C.c_float),
-        ("_pad", C.c_int32 * 2),
+        ("disabled", C.c_int32), ("_pad", C.c_int32),
         ("link_ids", C.c_int32 * MAX_CONTACT_LINKS), ("local_link_ids", C.c_int32 * MAX_CONTACT_LINKS),
         ("with_ids", C.c_int32 * MAX_WITH_LINKS),
     ]
@@ -114,7 +114,7 @@ class ProgramHead(C.Structure):
         ("max_len_random_span", C.c_float), ("rng_mode", C.c_int32),
         ("rng_seed", C.c_uint64), ("step_index", C.c_uint64),
         ("n_reward", C.c_int32), ("n_termination", C.c_int32), ("n_command", C.c_int32),
-        ("n_contact", C.c_int32), ("n_obs_groups", C.c_int32), ("_pad0", C.c_int32),
+        ("n_contact", C.c_int32), ("n_obs_groups", C.c_int32), ("manager_flags", C.c_uint32),
         ("height_field_rows", C.c_int32), ("height_field_cols", C.c_int32),
         ("terrain_bounds", C.c_float * 4),
         ("action_mode", C.c_int32), ("_pad1", C.c_int32),
@@ -151,8 +151,8 @@ class Report(C.Structure):
     _fields_ = [
         ("n_reset", C.c_int32), ("status", C.c_uint32),
         ("termination_count", C.c_int32 * MAX_TERMINATION),
-        ("reward_episode_mean", C.c_float * MAX_REWARD),
         ("global_n_reset", C.c_int64), ("global_termination_count", C.c_int64 * MAX_TERMINATION),
+        ("seq", C.c_uint64),
     ]
 
 
@@ -165,8 +165,8 @@ EXPORTS = [
     "gfb_abi_version", "gfb_abi_sizeof", "gfb_create", "gfb_destroy", "gfb_last_error", "gfb_set_program",
     "gfb_action_step", "gfb_post_physics", "gfb_read_report", "gfb_observe", "gfb_contact_forces",
     "gfb_rotate", "gfb_spawn_pose", "gfb_peer_export", "gfb_peer_connect", "gfb_peer_disconnect", "gfb_spec_describe", "gfb_spec_attach", "gfb_spec_stats",
-    "gfb_profile_enable", "gfb_profile_read", "gfb_profile_read_observation_pass", "gfb_profile_read_aux", "gfb_launch_count",
-    "gfb_request_report", "gfb_wait_report",
+    "gfb_profile_enable", "gfb_profile_read", "gfb_profile_read_aux", "gfb_launch_count",
+    "gfb_post_physics_report",
 ]
 
 
@@ -232,14 +232,10 @@ def lib() -> C.CDLL:
     L.gfb_profile_enable.argtypes = [vp, i32]
     L.gfb_profile_read.restype = C.c_int
     L.gfb_profile_read.argtypes = [vp, fp, C.POINTER(i32), fp, C.POINTER(i32)]
-    L.gfb_profile_read_observation_pass.restype = C.c_int
-    L.gfb_profile_read_observation_pass.argtypes = [vp, fp, C.POINTER(i32)]
     L.gfb_profile_read_aux.restype = C.c_int
     L.gfb_profile_read_aux.argtypes = [vp, fp, C.POINTER(i32)]
-    L.gfb_request_report.restype = C.c_int
-    L.gfb_request_report.argtypes = [vp, vp]
-    L.gfb_wait_report.restype = C.c_int
-    L.gfb_wait_report.argtypes = [vp, C.POINTER(Report)]
+    L.gfb_post_physics_report.restype = C.c_int
+    L.gfb_post_physics_report.argtypes = [vp, C.POINTER(Buffers), u32, C.POINTER(Report), vp]
     L.gfb_launch_count.restype = i64
     L.gfb_launch_count.argtypes = [vp]
 

@@ -1,5 +1,5 @@
-// Pre-physics action kernel, finalize (ordered compaction + logging reductions), the sparse
-// re-observation kernel and the stand-alone contact scatter.
+// Pre-physics action kernel, the sparse re-observation kernel, the reset-side writers (spawn pose,
+// reset rows) and the stand-alone contact scatter / rotation entry points.
 #pragma once
 #include "device_utils.cuh"
 #include "plan.h"
@@ -157,246 +157,64 @@ __global__ void __launch_bounds__(TILE) action_kernel(const __grid_constant__ Ac
 }
 
 // ---------------------------------------------------------------------------------------------
-// finalize_kernel: one block.  Turns the per-slab partials of post_kernel into
-//   * the ascending int64 reset index list, identical to (terminated|truncated).nonzero()
-//     (managed_env.py:308-310)
-//   * per-termination fire counts / fractions (termination_manager.py:178-182)
-//   * per-reward-term episode means over the reset envs (reward_manager.py:205-216)
-//   * the report block (n_reset, status bits)
-// Reductions are fixed-order (lane-strided partial sums in double, then a shuffle tree), so the
-// logged values are run-to-run deterministic.
+// compact_kernel: the ascending int64 list of reset env ids, identical to
+// (terminated | truncated).nonzero() (managed_env.py:308-310), from the reset masks the post-physics
+// kernel left in scratch memory (one 32-env word per warp of a slab, in env order).
+// It is enqueued right behind the post kernel, whose last block has by then told the host how many
+// envs reset: it runs while the host wakes up and walks through its reset fan-out, and whatever
+// reads the list (engine setters, the re-observation) is enqueued behind it.
+// Every block derives the number of reset envs before its own range by summing the population counts
+// of all earlier words (the mask array is 128 KB at 1M envs: L2 hits), then scans its range.
 // ---------------------------------------------------------------------------------------------
-// Logging exchange between the ranks of one NVLink domain (gfb_peer_connect): every rank owns an
-// inbox with one slot per sender and step parity; senders store their partials straight into the
-// peers' inboxes and publish them with a release store of the exchange sequence number.
-constexpr int PEER_VALS = GFB_MAX_REWARD_TERMS + GFB_MAX_TERMINATION_TERMS + 1;
-struct PeerSlot {
-  double vals[PEER_VALS];
-  unsigned long long seq;
-  unsigned long long _pad[64 - PEER_VALS - 1];
-};
-static_assert(sizeof(PeerSlot) == 512, "PeerSlot is padded to 512 bytes");
-struct PeerInbox {
-  PeerSlot slot[2][GFB_MAX_PEERS];
-};
-struct PeerParams {
-  PeerInbox* inbox[GFB_MAX_PEERS];  // [r] = rank r's inbox (own one for r == rank)
-  int32_t rank, world;              // world <= 1: single rank, no exchange
-  unsigned long long seq;           // sequence number of this exchange (same on every rank)
-  int64_t global_num_envs;
-  uint32_t* done_counter;           // blocks of this launch that have written their results
-};
+constexpr int CMP_THREADS = 256;
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
-struct FinalizeParams {
-  Scratch s;
-  PeerParams peer;
-  int64_t* reset_idx;
-  float* log_out;
-  double* log_acc;
-  int32_t tile;
-  int32_t num_envs;
-  int32_t n_reward;
-  int32_t n_termination;
-  uint32_t phases;
-  uint32_t reward_weight_mask;  // bit r set: term r has weight != 0 (mean is logged)
-  gfb_report* report_host;      // device address of the host-mapped report (or null)
-};
-
-constexpr int FIN_THREADS = 256;
-constexpr int FIN_CHUNK_BLOCKS = 128;  // blocks that share the ordered compaction
-
-// deterministic block-wide sum (fixed strided order per thread, shuffle tree, warps in order)
-template <typename T>
-__device__ __forceinline__ T block_sum(T v, T* s_warp) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__global__ void __launch_bounds__(CMP_THREADS) compact_kernel(const uint32_t* __restrict__ words, int n_words,
+                                                               int words_per_block, int64_t* __restrict__ out) {
+  __shared__ int s_warp[CMP_THREADS / 32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int w0 = blockIdx.x * words_per_block;
+  const int w1 = min(w0 + words_per_block, n_words);
+  // reset envs in all words before this block's range
+  int before = 0;
+  for (int w = tid; w < w0; w += CMP_THREADS) before += __popc(words[w]);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if (lane == 0) s_warp[warp] = v;
-  __syncthreads();
-  T total = 0;
-  for (int w = 0; w < FIN_THREADS / 32; ++w) total += s_warp[w];
-  return total;
-}
-
-// Grid layout: blocks [0, n_chunks) each own a contiguous range of slabs of the ordered compaction;
-// blocks [n_chunks, n_chunks + n_termination) reduce one termination counter each; the following
-// n_reward blocks reduce one reward term each; the last block writes n_reset / status.
-__global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinalizeParams F, int n_chunks) {
-  __shared__ int s_iwarp[FIN_THREADS / 32];
-  __shared__ double s_dwarp[FIN_THREADS / 32];
-  __shared__ int s_scan[FIN_THREADS];
-  const int tid = threadIdx.x;
-  const int nt = F.s.n_tiles;
-  const int words = F.tile / 32;
-  const int b = blockIdx.x;
-  gfb_report* rep = F.s.report;
-
-  if (b < n_chunks) {
-    // ---- ordered compaction of this block's slab range -------------------------------------------
-    const int per_block = (nt + n_chunks - 1) / n_chunks;
-    const int c0 = min(b * per_block, nt), c1 = min(c0 + per_block, nt);
-    // resets in all slabs before this range (every block re-reads the short count array: L2 hits)
-    int before = 0;
-    for (int t = tid; t < c0; t += FIN_THREADS) before += F.s.tile_reset_count[t];
-    before = block_sum<int>(before, s_iwarp);
-    if (!F.reset_idx) return;
-    // scan the range in sweeps of FIN_THREADS slabs
-    int base = before;
-    for (int t0 = c0; t0 < c1; t0 += FIN_THREADS) {
-      const int t = t0 + tid;
-      const int cnt = t < c1 ? F.s.tile_reset_count[t] : 0;
-      s_scan[tid] = cnt;
-      __syncthreads();
-      // Hillis-Steele inclusive scan over 256 entries
-      for (int o = 1; o < FIN_THREADS; o <<= 1) {
-        const int v = tid >= o ? s_scan[tid - o] : 0;
-        __syncthreads();
-        s_scan[tid] += v;
-        __syncthreads();
-      }
-      int offset = base + s_scan[tid] - cnt;
-      if (cnt > 0) {
-        for (int w = 0; w < words; ++w) {
-          uint32_t bits = F.s.tile_reset_bits[(size_t)t * words + w];
-          while (bits) {
-            const int bit = __ffs(bits) - 1;
-            bits &= bits - 1;
-            F.reset_idx[offset++] = (int64_t)t * F.tile + w * 32 + bit;
-          }
-        }
-      }
-      base += s_scan[FIN_THREADS - 1];
-      __syncthreads();
-    }
-    return;
-  }
-
-  // total reset count (needed for the means and the report)
-  int n_reset = 0;
-  for (int t = tid; t < nt; t += FIN_THREADS) n_reset += F.s.tile_reset_count[t];
-  n_reset = block_sum<int>(n_reset, s_iwarp);
-
-  const int k = b - n_chunks;
-  if (k < F.n_termination) {
-    int acc = 0;
-    if (F.phases & GFB_PHASE_TERMINATION)
-      for (int t = tid; t < nt; t += FIN_THREADS) acc += F.s.tile_term_count[(size_t)k * nt + t];
-    acc = block_sum<int>(acc, s_iwarp);
-    if (tid == 0 && (F.phases & GFB_PHASE_TERMINATION)) {  // split execution: later launches keep the counts
-      rep->termination_count[k] = acc;
-      if (F.log_out) F.log_out[F.n_reward + k] = fdiv((float)acc, (float)F.num_envs);
-      if (F.log_acc) F.log_acc[F.n_reward + k] = (double)acc;
-    }
-  } else if (k < F.n_termination + F.n_reward) {
-    const int r = k - F.n_termination;
-    double acc = 0.0;
-    if (F.phases & GFB_PHASE_RESET)
-      for (int t = tid; t < nt; t += FIN_THREADS) acc += F.s.tile_rew_sum[(size_t)r * nt + t];
-    acc = block_sum<double>(acc, s_dwarp);
-    if (tid == 0 && (F.phases & GFB_PHASE_RESET)) {
-      const bool logged = (F.reward_weight_mask >> r) & 1u;
-      const float mean = (n_reset > 0 && logged) ? (float)(acc / (double)n_reset) : 0.0f;
-      rep->reward_episode_mean[r] = mean;
-      if (F.log_out) F.log_out[r] = mean;
-      if (F.log_acc) F.log_acc[r] = acc;
-    }
-  } else if (tid == 0 && (F.phases & GFB_PHASE_RESET)) {
-    rep->n_reset = n_reset;
-    rep->status = atomicExch(F.s.status, 0u);
-    if (F.log_acc) F.log_acc[F.n_reward + F.n_termination] = (double)n_reset;
-  }
-  if (!(F.phases & GFB_PHASE_RESET)) return;
-
-  // ---- global view: the LAST of the result blocks publishes counts over all ranks ----------------
-  __shared__ int s_last;
-  __shared__ double s_global[PEER_VALS];
-  __threadfence();
+  for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+  if (lane == 0) s_warp[warp] = before;
   __syncthreads();
   if (tid == 0) {
-    const uint32_t participants = (uint32_t)(F.n_termination + F.n_reward + 1);
-    s_last = (atomicAdd(F.peer.done_counter, 1u) == participants - 1u) ? 1 : 0;
+    int total = 0;
+    for (int k = 0; k < CMP_THREADS / 32; ++k) total += s_warp[k];
+    s_base = total;
   }
   __syncthreads();
-  if (!s_last) return;
-  if (tid == 0) *F.peer.done_counter = 0u;
-  __threadfence();
-  const int n_vals = F.n_reward + F.n_termination + 1;
-  bool local_only = F.peer.world <= 1 || !F.log_acc;  // (block-uniform from here on)
-  if (!local_only) {
-    // exchange over peer memory: my partials into every rank's inbox, then wait for everyone's
-    const int parity = (int)(F.peer.seq & 1ull);
-    const int me = F.peer.rank, W = F.peer.world;
-    if (tid < n_vals) {
-      const double mine = __ldcg(F.log_acc + tid);
-      for (int p = 0; p < W; ++p) F.peer.inbox[p]->slot[parity][me].vals[tid] = mine;
+  int base = s_base;
+  for (int v0 = w0; v0 < w1; v0 += CMP_THREADS) {
+    const int w = v0 + tid;
+    uint32_t bits = w < w1 ? words[w] : 0u;
+    const int mine = __popc(bits);
+    int incl = mine;  // inclusive scan over the sweep: within the warp, then over the warps
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
     }
-    __threadfence_system();
+    __syncthreads();  // (s_warp is free again)
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    if (tid < W) st_release_sys(&F.peer.inbox[tid]->slot[parity][me].seq, F.peer.seq);
-    int timed_out = 0;
-    if (tid < W) {
-      const unsigned long long* flag = &F.peer.inbox[me]->slot[parity][tid].seq;
-      const unsigned long long t0 = global_timer_ns();
-      while (ld_acquire_sys(flag) != F.peer.seq) {
-        if (global_timer_ns() - t0 > 2000000000ull) {  // ~2 s: a peer never issued this exchange
-          timed_out = 1;
-          break;
-        }
-        __nanosleep(200);
-      }
+    int warps_before = 0, sweep_total = 0;
+    for (int k = 0; k < CMP_THREADS / 32; ++k) {
+      const int c = s_warp[k];
+      warps_before += k < warp ? c : 0;
+      sweep_total += c;
     }
-    timed_out = __syncthreads_or(timed_out);
-    __threadfence_system();
-    if (timed_out) {
-      if (tid == 0) atomicOr(&rep->status, GFB_STATUS_PEER_TIMEOUT);
-      local_only = true;
-    } else {
-      if (tid < n_vals) {
-        double g = 0.0;
-        for (int r = 0; r < W; ++r) g += __ldcv(&F.peer.inbox[me]->slot[parity][r].vals[tid]);  // rank order
-        s_global[tid] = g;
-      }
-      __syncthreads();
-      const double g_reset = s_global[n_vals - 1];
-      if (tid == 0) rep->global_n_reset = (int64_t)g_reset;
-      if (tid < F.n_reward) {
-        const bool logged = (F.reward_weight_mask >> tid) & 1u;
-        if (F.log_out) F.log_out[tid] = (g_reset > 0.0 && logged) ? (float)(s_global[tid] / g_reset) : 0.0f;
-      } else if (tid < F.n_reward + F.n_termination) {
-        const int k = tid - F.n_reward;
-        rep->global_termination_count[k] = (int64_t)s_global[tid];
-        if (F.log_out) F.log_out[tid] = fdiv((float)s_global[tid], (float)F.peer.global_num_envs);
-      }
+    int64_t* dst = out + base + warps_before + incl - mine;
+    while (bits) {
+      const int bit = __ffs(bits) - 1;
+      bits &= bits - 1;
+      *dst++ = (int64_t)w * 32 + bit;
     }
-  }
-  if (local_only) {
-    if (tid == 0) rep->global_n_reset = rep->n_reset;
-    if (tid < F.n_termination) rep->global_termination_count[tid] = rep->termination_count[tid];
-  }
-  // the finished report goes straight into the host's (mapped, pinned) copy: the host only has to
-  // wait for this kernel, no separate device-to-host copy is enqueued
-  if (F.report_host) {
-    __threadfence();
-    __syncthreads();
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(rep);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(F.report_host);
-    for (int w = tid; w < (int)(sizeof(gfb_report) / 4); w += FIN_THREADS) dst[w] = __ldcg(src + w);
-    __threadfence_system();
+    base += sweep_total;
   }
 }
 
@@ -405,6 +223,13 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinalizePar
 // current engine state and the CACHED inverse base quaternion.  The reference observes after
 // reset (managed_env.py:322-326) with post-reset engine getters but the pre-reset cached
 // quaternion (entity_manager.py:134-146 vs :189-195; EntityManager.reset does not refresh it).
+//
+// A warp takes OBS_ROWS env rows, no shared memory, no block barrier: the lanes walk the rows' columns
+// (consecutive columns of one source array are consecutive addresses, so loads and stores coalesce),
+// each lane reads its column descriptor once for all rows; the env ids, cached quaternions and base
+// velocities are warp-uniform broadcast loads.  The reset envs are scattered over the batch, so every
+// access is a DRAM miss: the kernel is pure latency, and what matters is that all loads of a level
+// are in flight together -- a row costs two dependent round trips (id -> sources) and the store.
 // ---------------------------------------------------------------------------------------------
 struct ObserveHead {  // the observation part of the term table (instead of the whole 4 KB head)
   int32_t n_contact, n_obs_groups, rng_mode, _pad;
@@ -422,85 +247,102 @@ struct ObserveParams {
   int32_t n;
 };
 
-constexpr int OBS_ENVS = 16;      // envs per block
-constexpr int OBS_THREADS = 128;  // 8 threads per env for the column gather
+constexpr int OBS_WARPS = 4;  // warps per block
+constexpr int OBS_ROWS = 4;   // env rows per warp: their loads are issued together (memory-level parallelism)
 
-__global__ void __launch_bounds__(OBS_THREADS) observe_kernel(const __grid_constant__ ObserveParams K) {
-  extern __shared__ __align__(128) float S[];  // (OBS_ENVS, stash_stride) stash, then the column table
-  __shared__ long long s_env[OBS_ENVS];
+__global__ void __launch_bounds__(OBS_WARPS * 32, 7) observe_kernel(const __grid_constant__ ObserveParams K) {
   const ObserveHead& P = K.P;
   const Plan& plan = K.plan;
-  const int tid = threadIdx.x;
-  const int i0 = blockIdx.x * OBS_ENVS;
-  const int valid = min(OBS_ENVS, K.n - i0);
-  DevObsCol* s_cols = reinterpret_cast<DevObsCol*>(S + OBS_ENVS * plan.stash_stride + 4 - ((OBS_ENVS * plan.stash_stride) & 3));
-  {
-    const int32_t* src = reinterpret_cast<const int32_t*>(K.cols);
-    int32_t* dst = reinterpret_cast<int32_t*>(s_cols);
-    const int words = plan.n_cols_total * (int)(sizeof(DevObsCol) / 4);
-    for (int w = tid; w < words; w += OBS_THREADS) dst[w] = src[w];
+  const int lane = threadIdx.x & 31;
+  const int i0 = (blockIdx.x * OBS_WARPS + (threadIdx.x >> 5)) * OBS_ROWS;
+  if (i0 >= K.n) return;
+  // the rows of this warp: env id, cached inverse quaternion, body-frame vectors -- warp-uniform
+  // broadcast loads, all OBS_ROWS of them in flight at once
+  long long e[OBS_ROWS];
+#pragma unroll
+  for (int r = 0; r < OBS_ROWS; ++r) {
+    const int i = min(i0 + r, K.n - 1);  // (rows past the end repeat the last one and are not stored)
+    e[r] = K.idx ? (long long)K.idx[i] : (long long)i;
   }
-  if (tid < valid) {
-    const long long e = K.idx ? (long long)K.idx[i0 + tid] : (long long)(i0 + tid);
-    s_env[tid] = e;
-    float* st = S + tid * plan.stash_stride;
-    const float4 q = GFB_BUF(const float4, GFB_B_INV_BASE_QUAT)[e];
+  float body[OBS_ROWS][9];  // [ang_b 3][lin_b 3][grav_b 3], the stash layout of the post kernel (plan.h)
+#pragma unroll
+  for (int r = 0; r < OBS_ROWS; ++r) {
+    const float4 q = GFB_BUF(const float4, GFB_B_INV_BASE_QUAT)[e[r]];
     const V3 iq = {q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 9; ++k) body[r][k] = 0.0f;
     if (plan.needs & NEED_ANG) {
-      const float* v = GFB_BUF(const float, GFB_B_ANG) + e * 3;
-      const V3 r = rotate(V3{v[0], v[1], v[2]}, q.x, iq);
-      st[0] = r.x; st[1] = r.y; st[2] = r.z;
+      const float* v = GFB_BUF(const float, GFB_B_ANG) + e[r] * 3;
+      const V3 o = rotate(V3{v[0], v[1], v[2]}, q.x, iq);
+      body[r][0] = o.x; body[r][1] = o.y; body[r][2] = o.z;
     }
     if (plan.needs & NEED_LIN) {
-      const float* v = GFB_BUF(const float, GFB_B_VEL) + e * 3;
-      const V3 r = rotate(V3{v[0], v[1], v[2]}, q.x, iq);
-      st[3] = r.x; st[4] = r.y; st[5] = r.z;
+      const float* v = GFB_BUF(const float, GFB_B_VEL) + e[r] * 3;
+      const V3 o = rotate(V3{v[0], v[1], v[2]}, q.x, iq);
+      body[r][3] = o.x; body[r][4] = o.y; body[r][5] = o.z;
     }
     if (plan.needs & NEED_GRAV) {
-      const V3 r = rotate(V3{0.f, 0.f, -1.f}, q.x, iq);
-      st[6] = r.x; st[7] = r.y; st[8] = r.z;
-    }
-    for (int m = 0; m < P.n_contact; ++m) {
-      const float* cg = GFB_BUF(const float, GFB_B_CONTACTS0 + m);
-      if (!cg) continue;
-      cg += e * P.contact_links[m] * 3;
-      for (int t = 0; t < P.contact_links[m]; ++t)
-        st[plan.st_cnorm[m] + t] = norm3(cg[t * 3], cg[t * 3 + 1], cg[t * 3 + 2]);
+      const V3 o = rotate(V3{0.f, 0.f, -1.f}, q.x, iq);
+      body[r][6] = o.x; body[r][7] = o.y; body[r][8] = o.z;
     }
   }
-  __syncthreads();
   const Philox rng(P.rng_seed);
   for (int g = 0; g < P.n_obs_groups; ++g) {
     const gfb_obs_group& og = P.obs_group[g];
     const int O = og.n_cols, OH = og.n_cols * og.history;
-    const DevObsCol* cols = s_cols + og.col_begin;
     float* out = GFB_BUF(float, GFB_B_OBS_OUT0 + g);
     const float* noise = GFB_BUF(const float, GFB_B_OBS_NOISE0 + g);
-    const int total = valid * O;
-    for (int f = tid; f < total; f += OBS_THREADS) {
-      const int row = f / O, col = f - row * O;
-      const long long e = s_env[row];
-      const DevObsCol d = cols[col];
-      float v = 0.0f;
-      if (d.kind == 1 || d.kind == 2)
-        v = reinterpret_cast<const float*>(K.b.buf[d.gbuf])[e * d.row_words + d.col];
-      else if (d.kind == 3)
-        v = S[row * plan.stash_stride + d.a];
-      v = mul(v, d.scale);
-      if (d.noise != 0.f) {
-        float u;
-        if (P.rng_mode == 0) {
-          u = noise ? noise[e * O + col] : 0.f;
-        } else {
-          const uint4 x = rng((uint32_t)e, (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32),
-                              0x1000u + (uint32_t)(og.col_begin + (col & ~3)));
-          const int j = col & 3;
-          const uint32_t xj = j == 0 ? x.x : (j == 1 ? x.y : (j == 2 ? x.z : x.w));
-          u = sub(mul(u01(xj), 2.f), 1.f);
+    for (int col = lane; col < O; col += 32) {
+      // this lane's column descriptor: two 16-byte loads, shared by the warp's rows
+      const int4* dp = reinterpret_cast<const int4*>(K.cols + og.col_begin + col);
+      const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
+      const int kind = d0.x, a = d0.y, row_words = d0.z, dcol = d0.w, gbuf = d1.z;
+      const float scale = __int_as_float(d1.x), nz = __int_as_float(d1.y);
+      float v[OBS_ROWS];
+#pragma unroll
+      for (int r = 0; r < OBS_ROWS; ++r) v[r] = 0.0f;
+      if (kind == 1 || kind == 2) {
+        const float* src = reinterpret_cast<const float*>(K.b.buf[gbuf]) + dcol;
+#pragma unroll
+        for (int r = 0; r < OBS_ROWS; ++r) v[r] = src[e[r] * row_words];
+      } else if (kind == 3) {
+        if (a < 9) {
+#pragma unroll
+          for (int r = 0; r < OBS_ROWS; ++r)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) v[r] = a == k ? body[r][k] : v[r];
+        } else {  // |net contact force| of one tracked link (mdp/observations.py:181-193)
+          for (int m = 0; m < P.n_contact; ++m) {
+            const int t = a - plan.st_cnorm[m];
+            if (t < 0 || t >= P.contact_links[m]) continue;
+            const float* cg = GFB_BUF(const float, GFB_B_CONTACTS0 + m);
+            if (!cg) continue;
+#pragma unroll
+            for (int r = 0; r < OBS_ROWS; ++r) {
+              const float* c = cg + (e[r] * P.contact_links[m] + t) * 3;
+              v[r] = norm3(c[0], c[1], c[2]);
+            }
+          }
         }
-        v = add(v, mul(u, d.noise));
       }
-      out[e * OH + col] = v;
+#pragma unroll
+      for (int r = 0; r < OBS_ROWS; ++r) {
+        float x = mul(v[r], scale);
+        if (nz != 0.f) {
+          float u;
+          if (P.rng_mode == 0) {
+            u = noise ? noise[e[r] * O + col] : 0.f;
+          } else {
+            const uint4 w = rng((uint32_t)e[r], (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32),
+                                0x1000u + (uint32_t)(og.col_begin + (col & ~3)));
+            const int j = col & 3;
+            const uint32_t wj = j == 0 ? w.x : (j == 1 ? w.y : (j == 2 ? w.z : w.w));
+            u = sub(mul(u01(wj), 2.f), 1.f);
+          }
+          x = add(x, mul(u, nz));
+        }
+        if (i0 + r < K.n) out[e[r] * OH + col] = x;
+      }
     }
   }
 }

@@ -21,7 +21,7 @@ namespace {
 constexpr int kMaxSmemBytes = 227 * 1024;
 constexpr int kPlanSlots = 6;
 constexpr int kEventPairs = 2048;
-constexpr int kObserveTile = OBS_ENVS;
+constexpr int kObserveTile = 32;  // (only sizes the unused slab of the observe-only plan)
 
 inline int align4(int w) { return (w + 3) & ~3; }
 
@@ -63,12 +63,14 @@ struct LaunchCache {
   int tile = 0, n_stages = 1;
   int tma_ok = 0;
   int spec_index = -1;  // index into gfb_handle::specs, -1 = generic kernel
+  int resident_blocks = 0;  // blocks of this kernel / shared-memory size that fit on the device at once
 };
 constexpr int kLaunchCaches = 8;
 
 struct AttachedSpec {
   void* dl = nullptr;
   int (*launch)(const KParams*, int, unsigned, void*) = nullptr;
+  int (*blocks_per_sm)(unsigned) = nullptr;
   int tile = 0;
   uint32_t phases = 0;
   gfb_program_head canon;
@@ -86,9 +88,9 @@ struct gfb_handle {
   bool has_prog = false;
   Scratch scratch{};
   int scratch_tiles = 0;
-  gfb_report* report_host = nullptr;  // pinned + mapped: the finalize kernel writes the finished report into it
-  gfb_report* report_host_dev = nullptr;  // its device address
-  bool report_in_host = false;        // the last launch's report is already in report_host
+  gfb_report* report_host = nullptr;  // pinned + mapped: the post-physics kernel writes the report into it
+  uint32_t epoch = 0;                 // launches of the post-physics kernel so far
+  uint64_t report_seq = 0;            // launches with the reset phase so far (= seq of the latest report)
   PlanSlot slots[kPlanSlots];
   PlanSlot observe_slot;
   uint64_t prog_epoch = 0;  // bumped when anything but the step index of the term table changes
@@ -97,7 +99,6 @@ struct gfb_handle {
   int post_cache_next = 0;
   LaunchCache observe_cache;
   // logging exchange over peer memory (gfb_peer_*)
-  uint32_t* done_counter = nullptr;
   PeerInbox* inbox_own = nullptr;
   PeerInbox* inbox[GFB_MAX_PEERS] = {};
   int peer_rank = 0, peer_world = 0;
@@ -107,6 +108,7 @@ struct gfb_handle {
   bool disable_overlay = false;  // GFB_NO_OVERLAY=1: load every staged array up front
   int force_tile = 0;
   int force_stages = 0;
+  uint32_t debug = 0;
   int num_sms = 0;
   int64_t launches = 0;
   // profiling
@@ -116,8 +118,7 @@ struct gfb_handle {
   int n_post = 0, n_action = 0;
   float post_ms = 0.f, action_ms = 0.f, post_obs_ms = 0.f;
   int post_count = 0, action_count = 0, post_obs_count = 0;
-  cudaEvent_t report_event = nullptr;  // gfb_request_report / gfb_wait_report
-  // the small kernels: 0 finalize, 1 observe (reset envs), 2 spawn
+  // the small kernels: 0 index compaction, 1 observe (reset envs), 2 spawn
   std::vector<cudaEvent_t> ev_aux;
   std::vector<uint8_t> ev_aux_kind;
   int n_aux = 0;
@@ -313,6 +314,7 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, i
   }
   if (phases & (GFB_PHASE_REWARD | GFB_PHASE_COMMAND | GFB_PHASE_RESET | GFB_PHASE_OBSERVE))
     for (int k = 0; k < P.n_command; ++k) {
+      if (P.command[k].n_dims == 0) continue;  // a user-level manager without a command vector of its own
       if (!b.buf[GFB_B_COMMAND0 + k]) return fail(h, GFB_ERR_INVALID, "command buffer missing");
       plan.off_cmd[k] = stage(GFB_B_COMMAND0 + k, P.command[k].n_dims, -1);
     }
@@ -592,7 +594,7 @@ int choose_tile(const gfb_handle* h) {
 int plan_for_launch(gfb_handle* h, const gfb_buffers& b, uint32_t phases, Plan& plan, std::vector<int32_t>& table,
                     int& tile, int& n_stages) {
   tile = choose_tile(h);
-  n_stages = h->force_stages == 2 ? 2 : 1;
+  n_stages = 1;
   if (h->force_tile == 0 && tile == 128 && n_stages == 1) {
     // big slabs (contact slots staged): pick the slab size that keeps the most warps resident
     // (shared memory per block vs. the 80-register limit of 6 x 128 threads).  Ties go to the larger
@@ -728,22 +730,23 @@ int gfb_create(int32_t num_envs, int32_t device, gfb_handle** out) {
   CUDA_TRY(cudaSetDevice(device));
   const int nt = (num_envs + 31) / 32;
   h->scratch_tiles = nt;
-  CUDA_TRY(cudaMalloc(&h->scratch.tile_reset_bits, (size_t)nt * sizeof(uint32_t)));
-  CUDA_TRY(cudaMalloc(&h->scratch.tile_reset_count, (size_t)nt * sizeof(int32_t)));
-  CUDA_TRY(cudaMalloc(&h->scratch.tile_term_count, (size_t)nt * GFB_MAX_TERMINATION_TERMS * sizeof(int32_t)));
-  CUDA_TRY(cudaMalloc(&h->scratch.tile_rew_sum, (size_t)nt * GFB_MAX_REWARD_TERMS * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->scratch.tile_bits, (size_t)(nt + 8) * sizeof(uint32_t)));  // (+ the tail slab's padding)
+  CUDA_TRY(cudaMemset(h->scratch.tile_bits, 0, (size_t)(nt + 8) * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&h->scratch.term_count, GFB_MAX_TERMINATION_TERMS * sizeof(int32_t)));
+  CUDA_TRY(cudaMalloc(&h->scratch.rew_acc, GFB_MAX_REWARD_TERMS * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&h->scratch.rew_flags, GFB_MAX_REWARD_TERMS * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&h->scratch.counters, CTR_COUNT * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&h->scratch.global_reset, sizeof(double)));
   CUDA_TRY(cudaMalloc(&h->scratch.status, sizeof(uint32_t)));
-  CUDA_TRY(cudaMalloc(&h->scratch.report, sizeof(gfb_report)));
+  CUDA_TRY(cudaMemset(h->scratch.term_count, 0, GFB_MAX_TERMINATION_TERMS * sizeof(int32_t)));
+  CUDA_TRY(cudaMemset(h->scratch.rew_acc, 0, GFB_MAX_REWARD_TERMS * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(h->scratch.rew_flags, 0, GFB_MAX_REWARD_TERMS * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemset(h->scratch.counters, 0, CTR_COUNT * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemset(h->scratch.global_reset, 0, sizeof(double)));
   CUDA_TRY(cudaMemset(h->scratch.status, 0, sizeof(uint32_t)));
-  CUDA_TRY(cudaMemset(h->scratch.report, 0, sizeof(gfb_report)));
-  CUDA_TRY(cudaMemset(h->scratch.tile_reset_count, 0, (size_t)nt * sizeof(int32_t)));
-  CUDA_TRY(cudaMemset(h->scratch.tile_reset_bits, 0, (size_t)nt * sizeof(uint32_t)));
   CUDA_TRY(cudaHostAlloc(&h->report_host, sizeof(gfb_report), cudaHostAllocMapped));
   memset(h->report_host, 0, sizeof(gfb_report));
-  CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->report_host_dev), h->report_host, 0));
-  CUDA_TRY(cudaEventCreateWithFlags(&h->report_event, cudaEventDisableTiming));
-  CUDA_TRY(cudaMalloc(&h->done_counter, sizeof(uint32_t)));
-  CUDA_TRY(cudaMemset(h->done_counter, 0, sizeof(uint32_t)));
+  CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->scratch.report_host), h->report_host, 0));
   const char* env = getenv("GFB_DISABLE_TMA");
   h->disable_tma = env && env[0] == '1';
   env = getenv("GFB_NO_OVERLAY");
@@ -752,6 +755,8 @@ int gfb_create(int32_t num_envs, int32_t device, gfb_handle** out) {
   h->force_tile = env ? atoi(env) : 0;
   env = getenv("GFB_STAGES");
   h->force_stages = env ? atoi(env) : 0;
+  env = getenv("GFB_DEBUG");
+  h->debug = env ? (uint32_t)atoi(env) : 0u;
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   return GFB_OK;
 }
@@ -765,20 +770,19 @@ void gfb_destroy(gfb_handle* h) {
     return;
   }
   cudaSetDevice(h->device);
-  cudaFree(h->scratch.tile_reset_bits);
-  cudaFree(h->scratch.tile_reset_count);
-  cudaFree(h->scratch.tile_term_count);
-  cudaFree(h->scratch.tile_rew_sum);
+  cudaFree(h->scratch.tile_bits);
+  cudaFree(h->scratch.term_count);
+  cudaFree(h->scratch.rew_acc);
+  cudaFree(h->scratch.rew_flags);
+  cudaFree(h->scratch.counters);
+  cudaFree(h->scratch.global_reset);
   cudaFree(h->scratch.status);
-  cudaFree(h->scratch.report);
   if (h->report_host) cudaFreeHost(h->report_host);
   gfb_peer_disconnect(h);
   if (h->inbox_own) cudaFree(h->inbox_own);
-  cudaFree(h->done_counter);
   for (auto& s : h->slots)
     if (s.table_dev) cudaFree(s.table_dev);
   if (h->observe_slot.table_dev) cudaFree(h->observe_slot.table_dev);
-  if (h->report_event) cudaEventDestroy(h->report_event);
   for (auto e : h->ev_aux) cudaEventDestroy(e);
   for (auto e : h->ev_post) cudaEventDestroy(e);
   for (auto e : h->ev_action) cudaEventDestroy(e);
@@ -802,7 +806,8 @@ int gfb_set_program(gfb_handle* h, const gfb_program* program) {
   if (P.n_contact < 0 || P.n_contact > GFB_MAX_CONTACT_MANAGERS) return fail(h, GFB_ERR_INVALID, "n_contact out of range");
   if (P.n_obs_groups < 0 || P.n_obs_groups > GFB_MAX_OBS_GROUPS) return fail(h, GFB_ERR_INVALID, "n_obs_groups out of range");
   for (int k = 0; k < P.n_command; ++k) {
-    if (P.command[k].n_dims <= 0 || P.command[k].n_dims > GFB_MAX_COMMAND_DIMS)
+    if (P.command[k].n_dims < 0 || P.command[k].n_dims > GFB_MAX_COMMAND_DIMS ||
+        (P.command[k].n_dims == 0 && P.command[k].enabled))
       return fail(h, GFB_ERR_INVALID, "command n_dims out of range");
     if (P.command[k].enabled && P.command[k].resample_steps <= 0)
       return fail(h, GFB_ERR_INVALID, "command resample_steps must be positive");
@@ -984,7 +989,7 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
   }
   kp.plan = lc->plan;
   const std::vector<int32_t>& table = lc->table;
-  const int tile = lc->tile, n_stages = lc->n_stages;
+  const int tile = lc->tile;
   const size_t smem = (size_t)kp.plan.smem_words * 4;
 
   PlanSlot* slot = nullptr;
@@ -1004,13 +1009,48 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
   if (rc != GFB_OK) return rc;
 
   const int n_tiles = (P.num_envs + tile - 1) / tile;
+  const AttachedSpec* spec = lc->spec_index >= 0 ? &h->specs[lc->spec_index] : nullptr;
+  // persistent grid: every block of the launch is resident from the start (the in-kernel ordered
+  // compaction relies on it: a slab only waits for slabs that are already running)
+  if (lc->resident_blocks == 0) {
+    int per_sm = 0;
+    if (spec && spec->blocks_per_sm) per_sm = spec->blocks_per_sm((unsigned)smem);
+    else if (tile == 32) per_sm = blocks_per_sm<32>(h, smem);
+    else if (tile == 64) per_sm = blocks_per_sm<64>(h, smem);
+    else if (tile == 128) per_sm = blocks_per_sm<128>(h, smem);
+    else per_sm = blocks_per_sm<256>(h, smem);
+    if (per_sm <= 0) return fail(h, GFB_ERR_CUDA, "post kernel: no block fits on an SM with this slab plan");
+    lc->resident_blocks = per_sm * std::max(h->num_sms, 1);
+  }
+  // (single-warp blocks take one slab each: 32-env slabs are the small-batch choice, where there are
+  //  fewer slabs than resident blocks anyway.  Forced onto a large batch -- GFB_TILE=32 -- the
+  //  persistent loop of a 32-thread block failed with cudaErrorLaunchFailure at full speed, clean under
+  //  compute-sanitizer memcheck / racecheck / synccheck and with 64- and 128-env slabs; not understood.)
+  const int grid = ((h->debug & 4u) || tile == 32) ? n_tiles : std::min(n_tiles, lc->resident_blocks);
+
+  const bool reports = (phases & GFB_PHASE_RESET) != 0;
+  if (reports && !b->buf[GFB_B_RESET_IDX]) return fail(h, GFB_ERR_INVALID, "buffer RESET_IDX is NULL");
+  h->epoch += 1;
+  if (reports) h->report_seq += 1;
   kp.P = P;
   kp.b = *b;
   kp.s = h->scratch;
   kp.s.n_tiles = n_tiles;
+  kp.s.epoch = h->epoch;
+  kp.s.report_seq = h->report_seq;
   kp.cols = reinterpret_cast<const DevObsCol*>(slot->table_dev);
   kp.phases = phases;
   kp.tma_ok = lc->tma_ok;
+  kp.debug = h->debug;
+  kp.peer.world = 0;
+  if (h->peer_world > 1 && reports) {
+    if (!b->buf[GFB_B_LOG_ACC]) return fail(h, GFB_ERR_INVALID, "sharded logging needs GFB_B_LOG_ACC");
+    for (int r = 0; r < h->peer_world; ++r) kp.peer.inbox[r] = h->inbox[r];
+    kp.peer.rank = h->peer_rank;
+    kp.peer.world = h->peer_world;
+    kp.peer.seq = ++h->peer_seq;
+    kp.peer.global_num_envs = h->global_num_envs;
+  }
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->profiling && h->n_post + 2 <= (int)h->ev_post.size()) {
@@ -1019,17 +1059,6 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
     e1 = h->ev_post[h->n_post++];
     cudaEventRecord(e0, stream);
   }
-  // persistent grid: as many blocks as can be resident at once (or one per slab if fewer)
-  int grid = n_tiles;
-  if (n_stages == 2) {
-    int per_sm = 0;
-    if (tile == 32) per_sm = blocks_per_sm<32>(h, smem);
-    else if (tile == 64) per_sm = blocks_per_sm<64>(h, smem);
-    else if (tile == 128) per_sm = blocks_per_sm<128>(h, smem);
-    else per_sm = blocks_per_sm<256>(h, smem);
-    if (per_sm > 0 && h->num_sms > 0) grid = std::min(n_tiles, per_sm * h->num_sms);
-  }
-  const AttachedSpec* spec = lc->spec_index >= 0 ? &h->specs[lc->spec_index] : nullptr;
   if (spec) {
     if (spec->launch(&kp, grid, (unsigned)smem, stream) != 0)
       return fail(h, GFB_ERR_CUDA, std::string("specialised kernel launch: ") + cudaGetErrorString(cudaGetLastError()));
@@ -1044,74 +1073,56 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
   }
   if (rc != GFB_OK) return rc;
   if (e1) cudaEventRecord(e1, stream);
-
-  if (!(phases & (GFB_PHASE_TERMINATION | GFB_PHASE_REWARD | GFB_PHASE_RESET))) {
-    h->launches += 1;  // entity / contact / observation phases alone leave nothing to finalize
-    return GFB_OK;     // (report_in_host keeps describing the last launch that produced a report)
+  h->launches += 1;
+  if (reports) {
+    // the ascending index list from the slabs' reset masks: behind the post kernel, which has told the
+    // host the counts by then -- this runs while the host wakes up (see compact_kernel)
+    const int n_words = n_tiles * (tile / 32);
+    const int n_blocks = std::max(1, std::min(128, (n_words + CMP_THREADS - 1) / CMP_THREADS));
+    const int words_per_block = ((n_words + n_blocks - 1) / n_blocks + CMP_THREADS - 1) / CMP_THREADS * CMP_THREADS;
+    cudaEvent_t cmp_end = aux_begin(h, 0, stream);
+    compact_kernel<<<n_blocks, CMP_THREADS, 0, stream>>>(h->scratch.tile_bits, n_words, words_per_block,
+                                                         static_cast<int64_t*>(b->buf[GFB_B_RESET_IDX]));
+    CUDA_TRY(cudaGetLastError());
+    if (cmp_end) cudaEventRecord(cmp_end, stream);
+    h->launches += 1;
   }
-  FinalizeParams fp{};
-  fp.s = kp.s;
-  fp.reset_idx = static_cast<int64_t*>(b->buf[GFB_B_RESET_IDX]);
-  fp.log_out = static_cast<float*>(b->buf[GFB_B_LOG_OUT]);
-  fp.log_acc = static_cast<double*>(b->buf[GFB_B_LOG_ACC]);
-  fp.tile = tile;
-  fp.num_envs = P.num_envs;
-  fp.n_reward = P.n_reward;
-  fp.n_termination = P.n_termination;
-  fp.phases = phases;
-  fp.peer.done_counter = h->done_counter;
-  fp.peer.world = 0;
-  if (h->peer_world > 1 && (phases & GFB_PHASE_RESET)) {
-    if (!fp.log_acc) return fail(h, GFB_ERR_INVALID, "sharded logging needs GFB_B_LOG_ACC");
-    for (int r = 0; r < h->peer_world; ++r) fp.peer.inbox[r] = h->inbox[r];
-    fp.peer.rank = h->peer_rank;
-    fp.peer.world = h->peer_world;
-    fp.peer.seq = ++h->peer_seq;
-    fp.peer.global_num_envs = h->global_num_envs;
-  }
-  fp.report_host = (phases & GFB_PHASE_RESET) ? h->report_host_dev : nullptr;
-  h->report_in_host = fp.report_host != nullptr;
-  fp.reward_weight_mask = 0;
-  for (int r = 0; r < P.n_reward; ++r)
-    if (P.reward[r].weight != 0.0f) fp.reward_weight_mask |= (1u << r);
-  const int n_chunks = std::max(1, std::min(FIN_CHUNK_BLOCKS, (n_tiles + 63) / 64));
-  cudaEvent_t fin_end = aux_begin(h, 0, stream);
-  finalize_kernel<<<n_chunks + P.n_termination + P.n_reward + 1, FIN_THREADS, 0, stream>>>(fp, n_chunks);
-  CUDA_TRY(cudaGetLastError());
-  if (fin_end) cudaEventRecord(fin_end, stream);
-  h->launches += 2;
   return GFB_OK;
 }
 
 int gfb_read_report(gfb_handle* h, gfb_report* out, void* stream_) {
   if (!h || !out) return GFB_ERR_INVALID;
   if (h->host_only) return fail(h, GFB_ERR_NO_DEVICE, "host-only handle has no report");
+  if (h->report_seq == 0) return fail(h, GFB_ERR_INVALID, "no launch with GFB_PHASE_RESET has been issued yet");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  // after a launch with the reset phase the finalize kernel has written the report into the mapped
-  // host copy itself: waiting for the stream is all that is left
-  if (!h->report_in_host)
-    CUDA_TRY(cudaMemcpyAsync(h->report_host, h->scratch.report, sizeof(gfb_report), cudaMemcpyDeviceToHost, stream));
-  CUDA_TRY(cudaStreamSynchronize(stream));
-  *out = *h->report_host;
+  // The kernel stores the report into this (mapped, pinned) block and then its sequence number.
+  // Spinning on that word costs ~1 us after the store; cudaStreamSynchronize would add the driver's
+  // wake-up latency AND wait for the end of the kernel, which comes later than the report.
+  volatile uint64_t* seq = &h->report_host->seq;
+  const uint64_t want = h->report_seq;
+  for (uint64_t spins = 1; *seq != want; ++spins) {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+    if ((spins & 0x3fff) == 0) {  // every ~16 k spins: has the stream died or drained without a report?
+      const cudaError_t q = cudaStreamQuery(stream);
+      if (q == cudaSuccess) {
+        if (*seq == want) break;
+        return fail(h, GFB_ERR_CUDA, "the post-physics launch finished without delivering its report");
+      }
+      if (q != cudaErrorNotReady) return fail(h, GFB_ERR_CUDA, std::string("waiting for the report: ") + cudaGetErrorString(q));
+    }
+  }
+  __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  memcpy(out, h->report_host, sizeof(gfb_report));
   return GFB_OK;
 }
 
-int gfb_request_report(gfb_handle* h, void* stream_) {
-  if (!h) return GFB_ERR_INVALID;
-  if (h->host_only) return fail(h, GFB_ERR_NO_DEVICE, "host-only handle has no report");
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!h->report_in_host)
-    CUDA_TRY(cudaMemcpyAsync(h->report_host, h->scratch.report, sizeof(gfb_report), cudaMemcpyDeviceToHost, stream));
-  CUDA_TRY(cudaEventRecord(h->report_event, stream));
-  return GFB_OK;
-}
-
-int gfb_wait_report(gfb_handle* h, gfb_report* out) {
-  if (!h || !out) return GFB_ERR_INVALID;
-  if (h->host_only) return fail(h, GFB_ERR_NO_DEVICE, "host-only handle has no report");
-  CUDA_TRY(cudaEventSynchronize(h->report_event));
-  *out = *h->report_host;
-  return GFB_OK;
+int gfb_post_physics_report(gfb_handle* h, const gfb_buffers* b, uint32_t phases, gfb_report* out, void* stream) {
+  if (!(phases & GFB_PHASE_RESET)) return fail(h, GFB_ERR_INVALID, "gfb_post_physics_report needs GFB_PHASE_RESET");
+  const int rc = gfb_post_physics(h, b, phases, stream);
+  if (rc != GFB_OK) return rc;
+  return gfb_read_report(h, out, stream);
 }
 
 int gfb_peer_export(gfb_handle* h, void* ipc_handle_out) {
@@ -1211,11 +1222,9 @@ int gfb_observe(gfb_handle* h, const gfb_buffers* b, const int64_t* idx, int32_t
   op.cols = reinterpret_cast<const DevObsCol*>(h->observe_slot.table_dev);
   op.idx = idx;
   op.n = n;
-  const size_t smem = (size_t)op.plan.stash_stride * OBS_ENVS * 4 + 16 +
-                      (size_t)op.plan.n_cols_total * sizeof(DevObsCol);
-  const int grid = (n + OBS_ENVS - 1) / OBS_ENVS;
+  const int grid = (n + OBS_WARPS * OBS_ROWS - 1) / (OBS_WARPS * OBS_ROWS);
   cudaEvent_t obs_end = aux_begin(h, 1, stream);
-  observe_kernel<<<grid, OBS_THREADS, smem, stream>>>(op);
+  observe_kernel<<<grid, OBS_WARPS * 32, 0, stream>>>(op);
   CUDA_TRY(cudaGetLastError());
   if (obs_end) cudaEventRecord(obs_end, stream);
   h->launches += 1;
@@ -1346,6 +1355,7 @@ int gfb_spec_attach(gfb_handle* h, const char* path) {
   memcpy(&sp.plan, plan, sizeof(sp.plan));
   sp.dl = dl;
   sp.launch = launch;
+  sp.blocks_per_sm = reinterpret_cast<int (*)(unsigned)>(dlsym(dl, "gfb_spec_blocks_per_sm"));
   h->specs.push_back(sp);
   h->spec_gen += 1;
   return GFB_OK;
@@ -1416,15 +1426,6 @@ int gfb_profile_read(gfb_handle* h, float* post_ms_total, int32_t* post_launches
   if (post_launches) *post_launches = h->post_count;
   if (action_ms_total) *action_ms_total = h->action_ms;
   if (action_launches) *action_launches = h->action_count;
-  return GFB_OK;
-}
-
-int gfb_profile_read_observation_pass(gfb_handle* h, float* ms_total, int32_t* launches) {
-  if (!h) return GFB_ERR_INVALID;
-  int rc = gfb_profile_read(h, nullptr, nullptr, nullptr, nullptr);  // folds pending event pairs
-  if (rc != GFB_OK) return rc;
-  if (ms_total) *ms_total = h->post_obs_ms;
-  if (launches) *launches = h->post_obs_count;
   return GFB_OK;
 }
 

@@ -82,15 +82,47 @@ struct Plan {
   int32_t smem_words;
 };
 
+// Logging exchange between the ranks of one NVLink domain (gfb_peer_connect): every rank owns an
+// inbox with one slot per sender, exchange kind and step parity; senders store their partials
+// straight into the peers' inboxes and publish them with a release store of the sequence number.
+constexpr int PEER_VALS = GFB_MAX_REWARD_TERMS + GFB_MAX_TERMINATION_TERMS + 1;
+struct PeerSlot {
+  double vals[PEER_VALS];
+  unsigned long long seq;
+  unsigned long long _pad[64 - PEER_VALS - 1];
+};
+static_assert(sizeof(PeerSlot) == 512, "PeerSlot is padded to 512 bytes");
+enum : int { PEER_KIND_COUNTS = 0, PEER_KIND_SUMS = 1 };
+struct PeerInbox {
+  PeerSlot slot[2][2][GFB_MAX_PEERS];  // [parity][kind][sender]
+};
+struct PeerParams {
+  PeerInbox* inbox[GFB_MAX_PEERS];  // [r] = rank r's inbox (own one for r == rank)
+  int32_t rank, world;              // world <= 1: single rank, no exchange
+  unsigned long long seq;           // sequence number of this exchange (same on every rank)
+  int64_t global_num_envs;
+};
+
+// Scratch owned by the handle.  All counters are left at zero by the launch that used them.
+enum : int {
+  CTR_TICKET = 0,      // next slab to hand out (slabs [0, gridDim.x) belong to the blocks by index)
+  CTR_COMPACT_DONE = 1,  // blocks of compact_kernel that have written their indices
+  CTR_BLOCKS_DONE = 2, // blocks that have left the kernel (late logging at gridDim.x)
+  CTR_TOTAL_RESET = 3, // number of reset envs of this launch
+  CTR_COUNT = 8
+};
 struct Scratch {
-  uint32_t* tile_reset_bits;  // (n_tiles, tile/32)
-  int32_t* tile_reset_count;  // (n_tiles)
-  int32_t* tile_term_count;   // (GFB_MAX_TERMINATION_TERMS, n_tiles)
-  double* tile_rew_sum;       // (GFB_MAX_REWARD_TERMS, n_tiles)
-  uint32_t* status;           // sticky status bits
-  gfb_report* report;         // device copy of the report
+  uint32_t* tile_bits;             // (ceil(N / 32) words, in env order) reset masks, 32 envs per word
+  int32_t* term_count;             // (GFB_MAX_TERMINATION_TERMS) fire counts since the last report
+  unsigned long long* rew_acc;     // (GFB_MAX_REWARD_TERMS) signed 64-bit fixed-point sums (tail.cuh)
+  uint32_t* rew_flags;             // (GFB_MAX_REWARD_TERMS) non-finite episode quotients seen
+  uint32_t* counters;              // CTR_*
+  double* global_reset;            // global number of reset envs (after the count exchange)
+  uint32_t* status;                // sticky status bits
+  gfb_report* report_host;         // device address of the host's mapped report
   int32_t n_tiles;
-  int32_t _pad;
+  uint32_t epoch;                  // launch number
+  unsigned long long report_seq;   // value of gfb_report.seq that announces this launch's report
 };
 
 struct KParams {
@@ -98,9 +130,11 @@ struct KParams {
   gfb_buffers b;
   Plan plan;
   Scratch s;
+  PeerParams peer;
   const DevObsCol* cols;
   uint32_t phases;
   int32_t tma_ok;
+  uint32_t debug;  // GFB_DEBUG experiments (0 in production): 1 no fences in the scan, 2 no scan, 4 one slab per block
 };
 
 }  // namespace gfb

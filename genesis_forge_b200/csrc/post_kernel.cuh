@@ -18,9 +18,15 @@
 // each staged array is ONE cp.async.bulk (TMA) transfer into shared memory, completion on one
 // mbarrier; slab outputs go back with cp.async.bulk stores; (N,) arrays are plain coalesced
 // accesses; observation rows are written with coalesced 16-byte stores straight from the gather.
+//
+// Persistent grid: as many blocks as are resident at once (or one per slab if fewer); a block takes
+// slab blockIdx.x first and then draws further slabs from a ticket counter.  The logging reductions
+// and the step report are part of this kernel (tail.cuh): its last block to finish writes the report
+// into the host's mapped memory.
 #pragma once
 #include "device_utils.cuh"
 #include "plan.h"
+#include "tail.cuh"
 
 // In a specialised build the term loops have compile-time trip counts and are fully unrolled.
 #ifdef GFB_SPEC
@@ -78,11 +84,12 @@ __device__ __forceinline__ void issue_slab_loads(const KParams& K, const Plan& p
   const uint32_t valid = (uint32_t)min(TILE, N - e0);
   const int n_arrays = a_end - a_begin;
   if (lane == 0) {
-    uint32_t total = (with_table ? (uint32_t)plan.table_words * 4u : 0u) + (uint32_t)n_sum_rows * valid * 4u;
+    uint32_t total = ((with_table && plan.table_words > 0) ? (uint32_t)plan.table_words * 4u : 0u) + (uint32_t)n_sum_rows * valid * 4u;
     for (int i = a_begin; i < a_end; ++i) total += (uint32_t)plan.staged_words[i] * valid * 4u;
     mbar_expect_tx(bar, total);
   }
   __syncwarp();
+  with_table = with_table && plan.table_words > 0;  // (phase sets without observation rows have no table)
   const int n_ops = n_arrays + n_sum_rows + (with_table ? 1 : 0);
   for (int op = lane; op < n_ops; op += 32) {
     if (op < n_arrays) {
@@ -100,17 +107,17 @@ __device__ __forceinline__ void issue_slab_loads(const KParams& K, const Plan& p
   }
 }
 
-// Persistent kernel: each block walks slabs blockIdx.x, blockIdx.x + gridDim.x, ... with a two-stage
-// shared-memory ring -- the TMA loads of the next slab are in flight while the current one is
-// processed, and the stores of the previous one drain in the background.
 template <int TILE>
 __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_constant__ KParams K) {
   extern __shared__ __align__(128) float Sbase[];
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ int32_t s_term_count[GFB_MAX_TERMINATION_TERMS];
-  __shared__ double s_rew_part[GFB_MAX_REWARD_TERMS][TILE / 32];
+  __shared__ unsigned long long s_rew_acc[GFB_MAX_REWARD_TERMS];  // fixed-point sums of the slab (tail.cuh)
+  __shared__ uint32_t s_rew_flags[GFB_MAX_REWARD_TERMS];
   __shared__ uint32_t s_reset_bits[TILE / 32];
   __shared__ uint32_t s_status;
+  __shared__ int s_arrived;    // warps of this slab that are past the termination phase
+  __shared__ int s_next_tile;  // the ticket drawn for the block's next slab
 
   // P: live values (weights, thresholds, ranges, dt, seeds) -- always the kernel parameters.
   // SP / plan / ph: the STRUCTURE of the term table and of the slab.  In the generic build they are
@@ -129,19 +136,23 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   const uint32_t ph = K.phases;
   const bool use_tma = K.tma_ok != 0;
 #endif
+  constexpr int NW = TILE / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = P.num_envs;
   const int D = SP.num_dofs;
   const bool stage_sums = (ph & (GFB_PHASE_REWARD | GFB_PHASE_RESET)) != 0 && SP.n_reward > 0;
   const int n_sum_rows = stage_sums ? SP.n_reward : 0;
   const int n_tiles = K.s.n_tiles;
-  const int n_stages = plan.n_stages;
   // two load groups (plan.h): the late one follows the contact phase into the contact slots' memory
   const bool two_groups = plan.n_early < plan.n_staged || plan.sums_late != 0;
   const int n_sum_rows_early = plan.sums_late ? 0 : n_sum_rows;
+  float* const S = Sbase;
   float* const Tbl = Sbase + plan.cols_off;  // descriptor table, loaded once per block
   const Philox rng(P.rng_seed);
+  // reset_reward_log: the reset phase logs and clears the episode sums (reward manager enabled)
+  const bool reward_log = SP.n_reward > 0 && !(SP.manager_flags & GFB_MF_REWARD_DISABLED);
 
+  if (tid == 0) s_arrived = 0;
   if (use_tma) {
     if (tid == 0) {
       mbar_init(&bars[0], 1);
@@ -158,30 +169,24 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   }
 
   int it = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-  const int stage = n_stages == 2 ? (it & 1) : 0;
-  float* const S = Sbase + stage * plan.stage_words;
+  for (int tile = blockIdx.x; tile < n_tiles; ++it) {
   const int e0 = tile * TILE;
   const int valid = min(TILE, N - e0);
   const bool active = tid < valid;
   const int e = active ? e0 + tid : N - 1;  // inactive lanes shadow the last env and never write
-  const int next_tile = tile + gridDim.x;
 
   if (tid < GFB_MAX_TERMINATION_TERMS) s_term_count[tid] = 0;
   if (tid == 0) s_status = 0;
-  for (int i = tid; i < GFB_MAX_REWARD_TERMS * (TILE / 32); i += TILE) (&s_rew_part[0][0])[i] = 0.0;
+  for (int i = tid; i < GFB_MAX_REWARD_TERMS; i += TILE) {
+    s_rew_acc[i] = 0ull;
+    s_rew_flags[i] = 0u;
+  }
 
   // ------------------------------------------------------------------------------------------
   // slab loads: every staged array and the episode-sum rows are single cp.async.bulk transfers;
   // the lanes of warp 0 issue them in parallel, all complete on the stage's mbarrier
   // ------------------------------------------------------------------------------------------
-  if (use_tma) {
-    if (warp == 0 && n_stages == 2 && next_tile < n_tiles) {
-      bulk_wait_all_read();  // the other stage's outgoing stores have left shared memory
-      issue_slab_loads<TILE>(K, plan, Sbase + (stage ^ 1) * plan.stage_words, Tbl, &bars[stage ^ 1], next_tile,
-                             0, plan.n_early, n_sum_rows_early, false, lane);
-    }
-  } else {
+  if (!use_tma) {
     for (int i = 0; i < plan.n_early; ++i) {
       const int words = plan.staged_words[i] * valid;
       const float* src = reinterpret_cast<const float*>(K.b.buf[plan.staged_buf[i]]) +
@@ -233,13 +238,14 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   }
 #endif
 
-  // one warp polls the stage's mbarrier, the block barrier releases the rest
-  if (use_tma && warp == 0) mbar_wait(&bars[stage], (uint32_t)((n_stages == 2 ? (it >> 1) : it) & 1));
+  // one warp polls the slab's mbarrier, the block barrier releases the rest
+  if (use_tma && warp == 0) mbar_wait(&bars[0], (uint32_t)(it & 1));
   __syncthreads();
+  uint32_t ticket = 0;
 
   // slab copies that need no arithmetic (entity cache: base_pos / base_quat are copies of pos / quat)
   if (ph & GFB_PHASE_ENTITY) {
-    if (use_tma) {
+    if (use_tma && !(K.debug & 16u)) {
       if (warp == 0 && lane < plan.n_staged) {
         const int i = lane;
         if (plan.staged_store[i] >= 0 && K.b.buf[plan.staged_store[i]]) {
@@ -321,6 +327,22 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
       const gfb_contact_manager& cm = P.contact[m];
       const gfb_contact_manager& cs_ = SP.contact[m];
       const int Lc = cs_.n_links;
+      if (cs_.disabled) {  // contact_manager.py:331-336: a disabled manager keeps its last results
+        const float* cg = GFB_BUF(const float, GFB_B_CONTACTS0 + m) + (size_t)e * Lc * 3;
+        for (int t = 0; t < Lc; ++t) {
+          st[plan.st_cnorm[m] + t] = norm3(cg[t * 3], cg[t * 3 + 1], cg[t * 3 + 2]);
+          if (cs_.track_air_time) {
+            const float* air = GFB_BUF(const float, GFB_B_AIR0 + m);
+            const size_t base = (size_t)e * Lc + t, plane = (size_t)N * Lc;
+            float* sa = st + plan.st_air[m] + t * 4;
+            sa[0] = air[base]; sa[1] = air[plane + base]; sa[2] = air[2 * plane + base]; sa[3] = air[3 * plane + base];
+          }
+        }
+#ifdef GFB_SPEC
+        k_target += Lc;
+#endif
+        continue;
+      }
       // results go straight from registers to the (N, Lc, 3) outputs: staging them for a TMA store
       // would cost 6*Lc words of shared memory per env, i.e. resident warps
       float* fout = GFB_BUF(float, GFB_B_CONTACTS0 + m) + (size_t)e * Lc * 3;
@@ -427,6 +449,11 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     }
   }
 
+  {
+    const uint32_t warp_status = __reduce_or_sync(0xffffffffu, status);
+    if (lane == 0 && warp_status) atomicOr(&s_status, warp_status);
+  }
+
   // ------------------------------------------------------------------------------------------
   // late load group: the arrays that only rewards / resample / reset / observations read (joint
   // state, targets, commands, episode-sum rows) now replace the contact slots in shared memory;
@@ -471,8 +498,9 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
           v = P.base_max_episode_length > 0 && ep_len > max_len;
           break;
         case GFB_T_BAD_ORIENTATION: {
-          const float tilt = fminf(norm2(grav_b.x, grav_b.y), 0.99f);
-          v = !(ep_len <= ts.i0) && (tilt >= tt.p[0]);
+          // asin(clamp(NaN, max=0.99)) > limit is False in the reference; fminf would drop the NaN
+          const float tilt = norm2(grav_b.x, grav_b.y);
+          v = !(ep_len <= ts.i0) && (tilt == tilt) && (fminf(tilt, 0.99f) >= tt.p[0]);
         } break;
         case GFB_T_BASE_HEIGHT_MIN:
           v = S[plan.off_pos + tid * 3 + 2] < tt.p[0];
@@ -517,6 +545,44 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
       reset = terminated | truncated;  // managed_env.py:308-310
     }
     reset = reset && active;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // the slab's terminations are final: fire counts, ordered reset indices, step report (tail.cuh).
+  // The LAST warp of the slab to get here does this for the whole slab; the others carry on.
+  // ------------------------------------------------------------------------------------------
+  const uint32_t reset_votes = __ballot_sync(0xffffffffu, reset);
+  int last = 0;  // this warp is the slab's last one past the terminations
+  if (ph & (GFB_PHASE_TERMINATION | GFB_PHASE_RESET)) {
+    if (lane == 0) {
+      s_reset_bits[warp] = reset_votes;
+      __threadfence_block();
+      last = atomicAdd(&s_arrived, 1) == NW - 1;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      __threadfence_block();
+      if (lane == 0) s_arrived = 0;
+      if ((ph & GFB_PHASE_TERMINATION) && lane < SP.n_termination) {
+        const int fired = atomicAdd(&s_term_count[lane], 0);
+        if (fired) atomicAdd(K.s.term_count + lane, fired);
+      }
+      if (lane == 0) {
+        const uint32_t slab_status = atomicOr(&s_status, 0u);
+        if (slab_status) atomicOr(K.s.status, slab_status);
+      }
+      if (ph & GFB_PHASE_RESET) {
+        // Nothing here waits for memory: the number of reset envs is a sum (fire-and-forget integer
+        // atomic), and the slab's reset mask goes to the scratch array from which compact_kernel,
+        // enqueued right behind this kernel, expands the ascending index list (aux_kernels.cuh).
+        const uint32_t bits = lane < NW ? atomicOr(&s_reset_bits[lane], 0u) : 0u;
+        if (lane < NW) K.s.tile_bits[(size_t)tile * NW + lane] = bits;
+        int slab_resets = __popc(bits);
+#pragma unroll
+        for (int o = NW / 2; o > 0; o >>= 1) slab_resets += __shfl_xor_sync(0xffffffffu, slab_resets, o);
+        if (lane == 0 && slab_resets) atomicAdd(K.s.counters + CTR_TOTAL_RESET, (uint32_t)slab_resets);
+      }
+    }
   }
 
   if (two_groups) {  // the late group has landed
@@ -702,8 +768,6 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   // ------------------------------------------------------------------------------------------
   // in-library part of reset() for the envs that terminated / truncated
   // ------------------------------------------------------------------------------------------
-  const uint32_t reset_votes = __ballot_sync(0xffffffffu, reset);
-  if (lane == 0) s_reset_bits[warp] = reset_votes;
   if (ph & GFB_PHASE_RESET) {
     if (reset) {
       // genesis_env.py:233-252
@@ -751,25 +815,23 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
         if (SP.contact[m].track_air_time)
           for (int k = 0; k < SP.contact[m].n_links * 4; ++k) st[plan.st_air[m] + k] = 0.0f;
     }
-    // reward_manager.py:197-222: per-term episode mean over the reset envs, then clear.
-    // Resets are sparse: lane 0 visits the reset lanes of its warp in ascending order (fixed order,
-    // double accumulation -> deterministic logging).
-    if (SP.n_reward > 0 && reset_votes) {
-      for (int r = 0; r < SP.n_reward; ++r) {
-        float* sum = S + plan.sums_off + r * TILE + tid;
-        float q = 0.0f;
-        if (reset) {
-          if (P.reward[r].weight != 0.0f) q = fdiv(*sum, ep_secs);
+    // reward_manager.py:197-222: per-term episode mean over the reset envs, then clear.  Resets are
+    // sparse: every reset env adds its quotient to the slab's exact fixed-point sums (tail.cuh).
+    if (reset) {
+      if (reward_log) {
+        GFB_UNROLL_TERMS
+        for (int r = 0; r < SP.n_reward; ++r) {
+          float* sum = S + plan.sums_off + r * TILE + tid;
+          if (P.reward[r].weight != 0.0f) {
+            uint32_t fl = 0;
+            const long long f = to_fixed(fdiv(*sum, ep_secs), fl);
+            if (f) atomicAdd(&s_rew_acc[r], (unsigned long long)f);
+            if (fl) atomicOr(&s_rew_flags[r], fl);
+          }
           *sum = 0.0f;
         }
-        double acc = 0.0;
-        for (uint32_t bits = reset_votes; bits; bits &= bits - 1) {
-          const float qb = __shfl_sync(0xffffffffu, q, __ffs(bits) - 1);
-          acc += (double)qb;
-        }
-        if (lane == 0) s_rew_part[r][warp] = acc;
       }
-      if (reset) ep_secs = 1e-10f;
+      ep_secs = 1e-10f;
     }
   }
 
@@ -800,10 +862,12 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
       }
     }
   }
-  if (status) atomicOr(&s_status, status);
-
   if (use_tma) fence_async_smem();
   __syncthreads();
+  // The ticket of the block's NEXT slab is drawn here and looked at when the row assembly below is
+  // done: a returning atomic takes microseconds while the memory system is saturated, and nothing a
+  // slab does may wait for a global round trip (tail.cuh).
+  if (tid == 0) ticket = atomicAdd(K.s.counters + CTR_TICKET, 1u);
 
   // ------------------------------------------------------------------------------------------
   // slab outputs: episode sums
@@ -826,26 +890,13 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   }
 
   // ------------------------------------------------------------------------------------------
-  // slab partials for the finalize kernel (ordered compaction + logging reductions)
+  // the slab's logging partials -> the launch's accumulators (integer atomics: order-independent)
   // ------------------------------------------------------------------------------------------
-  {
-    const Scratch& sc = K.s;
-    const int nt = sc.n_tiles;
-    if (tid < TILE / 32) sc.tile_reset_bits[(size_t)tile * (TILE / 32) + tid] = s_reset_bits[tid];
-    if (tid == 0) {
-      int n = 0;
-      for (int w = 0; w < TILE / 32; ++w) n += __popc(s_reset_bits[w]);
-      sc.tile_reset_count[tile] = n;
-      if (s_status) atomicOr(sc.status, s_status);
-    }
-    if ((ph & GFB_PHASE_TERMINATION) && tid < SP.n_termination)
-      sc.tile_term_count[(size_t)tid * nt + tile] = s_term_count[tid];
-    if ((ph & GFB_PHASE_RESET) && tid < SP.n_reward) {
-      double acc = 0.0;
-      for (int w = 0; w < TILE / 32; ++w) acc += s_rew_part[tid][w];
-      sc.tile_rew_sum[(size_t)tid * nt + tile] = acc;
-    }
+  if ((ph & GFB_PHASE_RESET) && reward_log && tid < SP.n_reward) {
+    if (s_rew_acc[tid]) atomicAdd(K.s.rew_acc + tid, s_rew_acc[tid]);  // (no return value: RED, fire and forget)
+    if (s_rew_flags[tid]) atomicOr(K.s.rew_flags + tid, s_rew_flags[tid]);
   }
+  if (!(ph & (GFB_PHASE_TERMINATION | GFB_PHASE_RESET)) && tid == 0 && s_status) atomicOr(K.s.status, s_status);
 
   // ------------------------------------------------------------------------------------------
   // observations: every thread assembles 16-byte pieces of the slab's rows
@@ -968,15 +1019,45 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     }
   }
 
-  // everyone is done with this stage's shared memory before it is refilled
-  if (next_tile < n_tiles) __syncthreads();
-  if (use_tma && n_stages == 1 && next_tile < n_tiles && warp == 0) {
+  // everyone is done with the slab's shared memory before it is refilled
+  if (tid == 0) s_next_tile = (int)gridDim.x + (int)ticket;
+  __syncthreads();
+  const int next_tile = s_next_tile;
+  if (use_tma && next_tile < n_tiles && warp == 0) {
     bulk_wait_all_read();
+    fence_async_smem();  // the slab's generic-proxy reads above, the async-proxy refill below
     issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], next_tile, 0, plan.n_early, n_sum_rows_early, false, lane);
   }
+
+  tile = next_tile;
   }  // slab loop
 
   if (use_tma && warp == 0) bulk_wait_all();
+
+  // ------------------------------------------------------------------------------------------
+  // the last block to leave turns the reward sums into logged means and re-arms the counters
+  // ------------------------------------------------------------------------------------------
+  __shared__ int s_last_block;
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last_block = atomicAdd(K.s.counters + CTR_BLOCKS_DONE, 1u) == gridDim.x - 1u;
+  }
+  __syncthreads();
+  if (s_last_block && warp == 0) {
+    __threadfence();
+    if (ph & GFB_PHASE_RESET) {
+      write_report(K, lane);        // counts (exchanged with the peer ranks when sharded)
+      write_reward_means(K, lane);  // logged episode means
+      publish_report(K, lane);      // everything is in place: the host may go on
+    }
+    __syncwarp();
+    if (lane == 0) {
+      K.s.counters[CTR_TICKET] = 0u;
+      K.s.counters[CTR_BLOCKS_DONE] = 0u;
+      K.s.counters[CTR_TOTAL_RESET] = 0u;
+    }
+  }
 }
 
 }  // namespace gfb

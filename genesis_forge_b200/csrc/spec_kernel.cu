@@ -33,6 +33,19 @@ extern "C" int gfb_spec_info(int* tile, unsigned* phases, const void** canon, co
   return 0;
 }
 
+extern "C" int gfb_spec_blocks_per_sm(unsigned smem) {
+  if ((int)smem > 44 * 1024 && (int)smem > smem_attr) {
+    if (cudaFuncSetAttribute(gfb::post_kernel<gfb_spec::TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return 0;
+    smem_attr = (int)smem;
+  }
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gfb::post_kernel<gfb_spec::TILE>, gfb_spec::TILE, smem) != cudaSuccess)
+    n = 0;
+  return n;
+}
+
 extern "C" int gfb_spec_launch(const gfb::KParams* kp, int grid, unsigned smem, void* stream) {
   if ((int)smem > 44 * 1024 && (int)smem > smem_attr) {
     if (cudaFuncSetAttribute(gfb::post_kernel<gfb_spec::TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=

@@ -140,6 +140,7 @@ class FusedStep:
         self._log_pending = False
         self._stream_ptr = None
         self._program_pushed = False
+        self._program_ever_pushed = False
         self._injected_bound = object()
         self._spec_tried: set = set()
         self._spec_checked: set = set()  # phase sets looked at since the last re-pack
@@ -150,14 +151,15 @@ class FusedStep:
         self._fp_items = None
         self._log_out_handed_out = False
         K = nat.K
-        self.PHASES_MAIN = K["GFB_PHASE_ALL"] & ~K["GFB_PHASE_OBSERVE"]
-        self._spec_phases = {K["GFB_PHASE_ALL"], self.PHASES_MAIN, K["GFB_PHASE_OBSERVE"]}
-        # Option for large batches (GFB_OVERLAP_OBS=1, off by default): the observation rows of all
-        # envs are written by a SEPARATE launch enqueued behind the report copy, so that it runs while
-        # the host handles the report and the reset fan-out, where the GPU otherwise idles.  Measured
-        # at 1M envs: step 245 -> 224 us, paid with a re-read of the observation sources (+19 % DRAM
-        # traffic per step, two kernels at 71 % / 76 % of the HBM peak instead of one at 81 %).
-        self.overlap_obs = os.environ.get("GFB_OVERLAP_OBS", "0") == "1"
+        self._spec_phases = {K["GFB_PHASE_ALL"], K["GFB_PHASE_OBSERVE"]}
+        self.step_phases = K["GFB_PHASE_ALL"]  # minus the phases of disabled managers (pack)
+        self._buffers_ref = C.byref(self.buffers)
+        self._report_ref = C.byref(self.report)
+        self._h = self.handle.ptr
+        self._engine_cache: dict = {}  # buffer id -> (tensor, data_ptr) of the last bound engine tensor
+        self._action_enabled_packed = True
+        self._PHASE_REWARD = K["GFB_PHASE_REWARD"]
+        self._phase_mask = 0xFFFFFFFF  # phases of disabled managers are dropped from every launch (pack)
         self.spec_paths: list = []
         self._body_acc_prev = None
         self._body_acc_started: dict[str, bool] = {}
@@ -325,10 +327,24 @@ class FusedStep:
 
     def _set_engine(self, buf_id: int, tensor: torch.Tensor, dtype):
         """Pointer of an engine getter's tensor (kept alive until the next launch group)."""
+        seen = self._engine_cache.get(buf_id)
+        if seen is None:
+            seen = self._engine_cache[buf_id] = {}
+        hit = seen.get(id(tensor))
+        if hit is not None:  # a tensor object validated before (engines that hand out views of solver state)
+            self.buffers.buf[buf_id] = hit[1]
+            return
+        given = tensor
         if tensor.dtype is not dtype or not tensor.is_contiguous() or tensor.get_device() != self.index:
             tensor = tensor.to(self.device, dtype).contiguous()
-        self._keepalive.append(tensor)
-        self.buffers.buf[buf_id] = tensor.data_ptr()
+        ptr = tensor.data_ptr()
+        if tensor is given:
+            if len(seen) >= 8:  # engines that return fresh tensors every call: nothing to remember
+                seen.clear()
+            seen[id(tensor)] = (tensor, ptr)  # (the reference held here keeps the id unique)
+        else:
+            self._keepalive.append(tensor)
+        self.buffers.buf[buf_id] = ptr
 
     def _static_buffers(self):
         """Pointers that never change: tensors owned by the env / managers / this object."""
@@ -403,8 +419,7 @@ class FusedStep:
              for m in self.commands],
             [(m._air_time_contact_threshold, m.enabled) for m in self.contacts],
             (self.reward is None or self.reward.enabled, self.termination is None or self.termination.enabled,
-             self.action is None or self.action.enabled, [m.enabled for m in self.commands],
-             [m.enabled for m in self.entities]),
+             self.action is None or self.action.enabled, [m.enabled for m in self.commands]),
             [(om.noise, om.enabled) for om in self.observations],
             [(i.scale, i.noise) for i in obs_items],
         )
@@ -457,6 +472,7 @@ class FusedStep:
             # a disabled action manager returns before anything (position_action_manager.py:383-384):
             # targets stay as they are and nothing is sent to the actuators; GenesisEnv.step still runs
             P.action_mode = self.action.kernel_mode if self.action.enabled else 0
+            self._action_enabled_packed = self.action.enabled
             kp = {k: v.detach().cpu().tolist() for k, v in self.action.kernel_params().items()}
             for d in range(self.D):
                 P.action_scale[d] = kp["scale"][d]
@@ -502,10 +518,17 @@ class FusedStep:
             for i, v in enumerate(withs):
                 cm.with_ids[i] = v
 
+        # phases of disabled managers are not launched: their step() returns before touching anything
+        # (termination_manager.py:159-160, reward_manager.py:172-173)
+        mask = 0xFFFFFFFF
+        if self.termination is not None and not self.termination.enabled:
+            mask &= ~K["GFB_PHASE_TERMINATION"]
         # rewards
         P.manager_flags = 0
         if self.reward is not None and not self.reward.enabled:
-            P.manager_flags |= K["GFB_MF_REWARD_DISABLED"]  # reward_manager.py:172-173, 204: no sums, no logging
+            mask &= ~K["GFB_PHASE_REWARD"]
+            P.manager_flags |= K["GFB_MF_REWARD_DISABLED"]  # reward_manager.py:204: no logging, sums kept
+        self._phase_mask = mask
         P.n_reward = len(self.reward_terms)
         if P.n_reward > nat.MAX_REWARD:
             raise UnsupportedTermError(f"at most {nat.MAX_REWARD} reward terms are supported")
@@ -673,6 +696,15 @@ class FusedStep:
             s(K["GFB_B_DOF_VEL"], robot.get_dofs_velocity(idx), f32)
             if self._uses_dof_force:
                 s(K["GFB_B_DOF_FORCE"], robot.get_dofs_force(idx), f32)
+        # a command manager driven by an external controller / gamepad: the terms read what its
+        # `command` property returns -- the controller's tensor for this step (command_manager.py:85-90)
+        for k, mgr in enumerate(self.commands):
+            if mgr._external_controller is not None:
+                s(K["GFB_B_COMMAND0"] + k, mgr._external_controller(self.env.step_count), f32)
+                self._controller_bound[k] = True
+            elif self._controller_bound[k]:
+                self._set(K["GFB_B_COMMAND0"] + k, mgr._command)
+                self._controller_bound[k] = False
         if self.contacts and not post_reset:
             solver = self.env.scene.rigid_solver
             c = solver.collider.get_contacts(as_tensor=True, to_torch=True)
@@ -763,11 +795,11 @@ class FusedStep:
 
     def _stream(self):
         if self._stream_ptr is None:
-            self._stream_ptr = C.c_void_p(torch._C._cuda_getCurrentRawStream(self.index))
+            self._stream_ptr = torch._C._cuda_getCurrentRawStream(self.index)
         return self._stream_ptr
 
     def begin_step(self):
-        """Per-step caches: the caller's current stream, one live-config check."""
+        """Per-step caches: the caller's current stream; fresh logging storage once views were handed out."""
         self._stream_ptr = None
         self._program_pushed = False
         # logged means are handed out as views of this vector and may be kept by the caller (rsl_rl
@@ -817,6 +849,7 @@ class FusedStep:
             P.n_contact_slots, P.n_links_total = self._contact_dims
         self.handle.check(self.lib.gfb_set_program(self.handle.ptr, C.byref(self.program)), "gfb_set_program")
         self._program_pushed = not self.dry_run
+        self._program_ever_pushed = True
 
     def cache_entity(self):
         """Entity phase alone (EntityManager.build() caches the pose before the first reset)."""
@@ -828,23 +861,28 @@ class FusedStep:
         )
 
     def action_step(self, actions: torch.Tensor):
-        env = self.env
-        if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
+        """
+        Pre-physics launch + the engine's PD-target write.  This is on the host's critical path (the
+        GPU idles until the launch is issued), so nothing that can wait is done here: the live-config
+        check / re-pack happens in the shadow of this kernel (post_physics).  The launch only reads the
+        action part of the table, which is fixed at build time -- except for `action.enabled`.
+        """
+        if actions.dtype is not torch.float32 or not actions.is_contiguous() or actions.device != self.device:
             actions = actions.to(self.device, torch.float32).contiguous()
-        raw_mgr = self.action._delayed(actions) if self.action is not None else actions
-        if raw_mgr is not actions and (raw_mgr.dtype != torch.float32 or not raw_mgr.is_contiguous()):
+        action = self.action
+        enabled = action is None or action.enabled
+        # (a disabled manager's step() returns before its delay FIFO moves, position_action_manager.py:383-384)
+        raw_mgr = action._delayed(actions) if action is not None and enabled else actions
+        if raw_mgr is not actions and (raw_mgr.dtype is not torch.float32 or not raw_mgr.is_contiguous()):
             raw_mgr = raw_mgr.to(self.device, torch.float32).contiguous()
         self._action_keep = (actions, raw_mgr)
-        self._set_program()
-        self.handle.check(
-            self.lib.gfb_action_step(
-                self.handle.ptr, C.byref(self.buffers), C.c_void_p(actions.data_ptr()),
-                C.c_void_p(raw_mgr.data_ptr()), self._stream(),
-            ),
-            "gfb_action_step",
-        )
-        if self.action is not None:
-            env.robot.control_dofs_position(self.action._actions, self.action.dofs_idx)
+        if not self._program_ever_pushed or enabled != self._action_enabled_packed:
+            self._set_program()
+        rc = self.lib.gfb_action_step(self._h, self._buffers_ref, actions.data_ptr(), raw_mgr.data_ptr(), self._stream())
+        if rc:
+            self.handle.check(rc, "gfb_action_step")
+        if action is not None and enabled:  # position_action_manager.py:383-384: a disabled manager sends nothing
+            self.env.robot.control_dofs_position(action._actions, action.dofs_idx)
 
     # ------------------------------------------------------------------------------------------
     # specialised kernels (spec.py)
@@ -918,49 +956,36 @@ class FusedStep:
             self.ext_obs[:, col0:col0 + width].copy_(value.reshape(self.N, width))
 
     def post_physics(self, phases: int, read_report: bool = True) -> nat.Report | None:
+        """
+        The post-physics launch.  Everything up to the launch call runs in the shadow of the action
+        kernel (which the GPU is still executing); the host then prepares the next step's logging
+        storage while the kernel runs and finally spins on the report, which the kernel delivers as
+        soon as the last slab's terminations are final -- before it has finished (include/gfb200.h).
+        """
         self._engine_buffers()
         self._obs_buffers()
         self._injection_buffers()
         self._set_program()
+        phases &= self._phase_mask
         if phases in self._spec_phases:
             self._maybe_specialise(phases)
-        if phases & nat.K["GFB_PHASE_REWARD"]:
+        if phases & self._PHASE_REWARD:
             self._after_launch_started = [
                 name for name in self._body_acc_terms
                 if not self._body_acc_started.get(name, False) and self.reward.cfg[name].weight != 0
-            ]
+            ] if self._body_acc_terms else []
         stream = self._stream()
-        self.handle.check(
-            self.lib.gfb_post_physics(self.handle.ptr, C.byref(self.buffers), phases, stream), "gfb_post_physics"
-        )
+        rc = self.lib.gfb_post_physics(self._h, self._buffers_ref, phases, stream)
+        if rc:
+            self.handle.check(rc, "gfb_post_physics")
         if not read_report:
             return None
         if self.dist is not None and not self.peer_mode:
             self._allreduce_logging()
-        self.prepare_spare_log()  # host work hidden behind the kernels just enqueued
-        self.handle.check(self.lib.gfb_read_report(self.handle.ptr, C.byref(self.report), stream), "gfb_read_report")
-        self._after_report()
-        return self.report
-
-    def post_physics_overlapped(self) -> nat.Report:
-        """
-        The fused step in two launches for large batches: everything except the observation rows
-        (+ finalize), the report copy, then the observation rows of all envs.  The host waits for
-        the report only, so the observation pass runs while Python walks through the reset fan-out.
-        Same results as `post_physics(GFB_PHASE_ALL)`: the observation phase reads what the main
-        launch left in global memory (cached inverse quaternion, contact forces, resampled commands).
-        """
-        K, lib, h = nat.K, self.lib, self.handle
-        self.post_physics(self.PHASES_MAIN, read_report=False)
-        stream = self._stream()
-        h.check(lib.gfb_request_report(h.ptr, stream), "gfb_request_report")
-        self._maybe_specialise(K["GFB_PHASE_OBSERVE"])
-        h.check(lib.gfb_post_physics(h.ptr, C.byref(self.buffers), K["GFB_PHASE_OBSERVE"], stream),
-                "gfb_post_physics(observe)")
-        if self.dist is not None and not self.peer_mode:
-            self._allreduce_logging()
-        self.prepare_spare_log()
-        h.check(lib.gfb_wait_report(h.ptr, C.byref(self.report)), "gfb_wait_report")
+        self.prepare_spare_log()  # host work hidden behind the kernel just enqueued
+        rc = self.lib.gfb_read_report(self._h, self._report_ref, stream)
+        if rc:
+            self.handle.check(rc, "gfb_read_report")
         self._after_report()
         return self.report
 
@@ -971,6 +996,8 @@ class FusedStep:
                 "sharded logging: a peer rank did not take part in this step's exchange within 2 s "
                 "(every rank must issue the same sequence of env.step / env.reset calls)"
             )
+        if self.report.status & nat.K["GFB_STATUS_SCAN_TIMEOUT"]:
+            raise nat.NativeLibraryError("post-physics kernel: the ordered reset-index scan stalled (internal error)")
         for name in self._after_launch_started:  # the term now has a previous velocity to difference
             self._body_acc_started[name] = True
         self._after_launch_started = []
@@ -980,10 +1007,9 @@ class FusedStep:
         self._obs_buffers()
         self._injection_buffers()
         self._set_program()
-        ptr = C.c_void_p(idx.data_ptr()) if idx is not None else None
-        self.handle.check(
-            self.lib.gfb_observe(self.handle.ptr, C.byref(self.buffers), ptr, n, self._stream()), "gfb_observe"
-        )
+        rc = self.lib.gfb_observe(self._h, self._buffers_ref, idx.data_ptr() if idx is not None else None, n, self._stream())
+        if rc:
+            self.handle.check(rc, "gfb_observe")
 
     def rotate_by_inv_base_quat(self, vec: torch.Tensor | None) -> torch.Tensor:
         quat = self.entity_manager._inv_base_quat if self.entity_manager is not None else self._inv_base_quat
@@ -1200,15 +1226,7 @@ class FusedStep:
         ms, n = (C.c_float * 3)(), (C.c_int32 * 3)()
         self.handle.check(self.lib.gfb_profile_read_aux(self.handle.ptr, ms, n), "gfb_profile_read_aux")
         return {name: {"kernel_us": ms[k] / max(n[k], 1) * 1e3, "launches": n[k]}
-                for k, name in enumerate(("finalize_kernel", "observe_kernel", "spawn_kernel"))}
-
-    def profile_read_observation_pass(self) -> dict:
-        ms, n = C.c_float(), C.c_int32()
-        self.handle.check(
-            self.lib.gfb_profile_read_observation_pass(self.handle.ptr, C.byref(ms), C.byref(n)),
-            "gfb_profile_read_observation_pass",
-        )
-        return {"obs_ms": ms.value, "obs_launches": n.value}
+                for k, name in enumerate(("compact_kernel", "observe_kernel", "spawn_kernel"))}
 
     def profile_read(self) -> dict:
         post_ms, act_ms = C.c_float(), C.c_float()

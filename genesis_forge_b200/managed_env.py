@@ -19,6 +19,7 @@ the engine reset but with the pre-reset cached quaternion; ...).
 """
 from __future__ import annotations
 
+import os
 from typing import Any
 
 import torch
@@ -31,6 +32,14 @@ from .managers.base import BaseManager, ManagerType
 
 
 class ManagedEnvironment(GenesisEnv):
+    # The observation tensors returned by step() / get_observations() are the manager's own
+    # double-buffered storage: the tensor handed out by step t is rewritten in place by step t+2 (the
+    # reference returns a fresh torch.cat every step).  Callers that keep observations across more
+    # than one step without copying them (rollout lists of raw references) set this to True -- or
+    # GFB_COPY_OBSERVATIONS=1 in the environment -- to get a private copy per step (one extra
+    # (N, O*H) device copy).
+    copy_observations = os.environ.get("GFB_COPY_OBSERVATIONS", "0") == "1"
+
     def __init__(
         self,
         num_envs: int = 1,
@@ -147,8 +156,6 @@ class ManagedEnvironment(GenesisEnv):
     # -- build ------------------------------------------------------------------------------------
     def build(self):
         super().build()
-        if hasattr(self.scene, "_env"):
-            pass
         try:
             self.scene._env = self
         except Exception:
@@ -212,10 +219,7 @@ class ManagedEnvironment(GenesisEnv):
         self.scene.step()
         if fused.split_mode:
             return self._finish_step_split()
-        if fused.overlap_obs:  # large batch: observation rows by a second launch behind the report copy
-            report = fused.post_physics_overlapped()
-        else:
-            report = fused.post_physics(nat.K["GFB_PHASE_ALL"])
+        report = fused.post_physics(fused.step_phases)
 
         n_reset = report.n_reset
         if n_reset > 0:
@@ -230,43 +234,50 @@ class ManagedEnvironment(GenesisEnv):
     def _finish_step_split(self):
         """
         Post-physics part of a step when the configuration contains user-defined (Python) terms or
-        command managers with overridden behaviour.  The kernel phases run as separate launches with
-        the Python callbacks in between, in the reference's order (managed_env.py:294-326):
-            entity + contacts | user terminations | terminations | user rewards |
-            rewards + command resample + in-library reset | python command managers, engine reset |
-            user observation terms | observations of every env (taken after the reset, so no patch).
+        user-level command managers.  The kernel phases run as separate launches with the Python
+        callbacks in between, in the reference's order (managed_env.py:294-326); which phases share
+        a launch is decided once (FusedStep._make_split_plan).  User-level command managers step
+        BEFORE the in-library reset, so that their interval test sees the episode lengths the
+        reference's does (command_manager.py:152-162 runs ahead of managed_env.py:322-323).
         """
-        fused, K = self._fused, nat.K
-        term, rew = self.managers["termination"], self.managers["reward"]
-        fused.post_physics(K["GFB_PHASE_ENTITY"] | K["GFB_PHASE_CONTACT"], read_report=False)
-        fused.evaluate_external("termination")
-        fused.post_physics(K["GFB_PHASE_TERMINATION"], read_report=False)
-        if term is not None:
-            self.extras["terminations"] = term._terminated_buf
-            self.extras["time_outs"] = term._truncated_buf
-        fused.evaluate_external("reward")
-        report = fused.post_physics(K["GFB_PHASE_REWARD"] | K["GFB_PHASE_COMMAND"] | K["GFB_PHASE_RESET"])
-        for mgr in fused.python_commands:
-            mgr.step()
-        n_reset = report.n_reset
-        if n_reset > 0:
-            reset_idx = fused.reset_idx[:n_reset]
-            self._host_reset(reset_idx)
-            for mgr in fused.python_commands:
-                mgr.reset(reset_idx)
-        fused.evaluate_external_obs()
-        fused.post_physics(K["GFB_PHASE_OBSERVE"], read_report=False)
+        fused = self._fused
+        term = self.managers["termination"]
+        report = None
+        for callback, phases, reads_report in fused.split_plan:
+            if callback == "observe":
+                n_reset = report.n_reset
+                if n_reset > 0:
+                    reset_idx = fused.reset_idx[:n_reset]
+                    self._host_reset(reset_idx)
+                    for mgr in fused.python_commands:
+                        mgr.reset(reset_idx)
+                fused.evaluate_external_obs()
+            elif callback == "commands":
+                for mgr in fused.python_commands:
+                    mgr.step()
+            elif callback is not None:
+                if callback == "reward" and term is not None and term.enabled:
+                    self.extras["terminations"] = term._terminated_buf  # user rewards may read them
+                    self.extras["time_outs"] = term._truncated_buf
+                fused.evaluate_external(callback)
+            out = fused.post_physics(phases, read_report=reads_report)
+            if reads_report:
+                report = out
         fused.finish_logging()
         self._publish(report, step=True)
         return self._step_outputs()
 
     def _step_outputs(self):
         obs = None
+        obs_dict = self.extras["observations"]
         for om in self.managers["observation"]:
             om._current = 1 - om._current
-            self.extras["observations"][om.name] = om.get_observations()
+            value = om.get_observations()
+            if self.copy_observations:  # see the class attribute
+                value = value.clone()
+            obs_dict[om.name] = value
             if om.name == "policy":
-                obs = om.get_observations()
+                obs = value
         term = self.managers["termination"]
         terminated = term._terminated_buf if term is not None else self._terminated_buf
         truncated = term._truncated_buf if term is not None else self._truncated_buf
@@ -296,7 +307,7 @@ class ManagedEnvironment(GenesisEnv):
         acc = fused.global_acc
         term_count = (lambda i: acc[n_r + i]) if acc is not None else (lambda i: report.global_termination_count[i])
         n_reset_logged = acc[-1] if acc is not None else report.global_n_reset
-        if step and term is not None:
+        if step and term is not None and term.enabled:  # (a disabled manager publishes nothing, :159-160)
             self.extras["terminations"] = term._terminated_buf
             self.extras["time_outs"] = term._truncated_buf
             if term.logging_enabled:
@@ -347,6 +358,12 @@ class ManagedEnvironment(GenesisEnv):
             self.managers["action"].reset(env_ids)
         for entity_manager in self.managers["entity"]:
             entity_manager.reset(env_ids)
+        for mgr in self._fused.commands:
+            # command_manager.py:164-170: reset() resamples `_command` even while an external controller
+            # supplies `command`; the kernel skips such managers, so it is done here (rare: teleoperation)
+            if mgr._external_controller is not None and mgr.enabled and mgr not in self._fused.python_commands:
+                mgr.resample_command(
+                    env_ids if env_ids is not None else torch.arange(self.num_envs, device=gs.device))
 
     # -- reset ------------------------------------------------------------------------------------
     def reset(self, env_ids=None):

@@ -115,6 +115,7 @@ class PositionActionManager(BaseActionManager):
         self._max_force_cfg = _ensure_dof_pattern(max_force)
         self._quiet_action_errors = quiet_action_errors
         self._enabled_dof = None
+        self._dofs_idx_list = None
         self._noise_scale = noise_scale
         self._reset_plan = None  # (robot, [(gain key, draw tag, engine setter)], default pose row), built on first reset
         self._use_default_offset = use_default_offset
@@ -136,7 +137,10 @@ class PositionActionManager(BaseActionManager):
 
     @property
     def dofs_idx(self) -> list[int]:
-        return list(self._enabled_dof.values())
+        idx = self._dofs_idx_list
+        if idx is None:  # (fixed once build() has resolved the joint patterns)
+            idx = self._dofs_idx_list = list(self._enabled_dof.values())
+        return idx
 
     @property
     def default_dofs_pos(self) -> torch.Tensor:
@@ -173,6 +177,7 @@ class PositionActionManager(BaseActionManager):
         """Resolve joint-name patterns to per-DOF parameter vectors."""
         robot = self.env.robot
         self._enabled_dof = {}
+        self._dofs_idx_list = None
         for joint in robot.joints:
             if joint.type != gs.JOINT_TYPE.REVOLUTE:
                 continue

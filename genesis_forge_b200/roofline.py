@@ -94,46 +94,6 @@ def post_kernel_bytes(fused) -> int:
     return 4 * (read + write) + 2
 
 
-def two_launch_bytes(fused) -> tuple[int, int]:
-    """
-    (main launch, observation pass) bytes per env when the step runs as two launches
-    (GFB_OVERLAP_OBS=1): the main launch neither reads observation-only sources nor writes rows; the
-    observation pass re-reads the cached inverse quaternion, the velocity vectors it rotates and
-    every observation source.
-    """
-    f = _program_facts(fused)
-    P, K, D = fused.program.head, nat.K, f["D"]
-    ops = {P.reward[r].op for r in range(P.n_reward) if P.reward[r].weight != 0.0}
-    tops = {P.termination[t].op for t in range(P.n_termination)}
-    srcs = set()
-    contact_norm_words = 0
-    for g in range(P.n_obs_groups):
-        og = P.obs_group[g]
-        for c in range(og.n_cols):
-            oc = fused.program.obs_cols[og.col_begin + c]
-            srcs.add(oc.src)
-    for m in range(P.n_contact):
-        if any(fused.program.obs_cols[P.obs_group[g].col_begin + c].src == K["GFB_O_CONTACT_NORM"]
-               and fused.program.obs_cols[P.obs_group[g].col_begin + c].mgr == m
-               for g in range(P.n_obs_groups) for c in range(P.obs_group[g].n_cols)):
-            contact_norm_words += 3 * P.contact[m].n_links
-    main_vel = bool(ops & {K["GFB_R_LIN_VEL_Z"], K["GFB_R_TRACK_LIN_VEL"]})
-    main_ang = bool(ops & {K["GFB_R_ANG_VEL_XY"], K["GFB_R_TRACK_ANG_VEL"]})
-    main_dof = bool(ops & {K["GFB_R_DOF_SIMILAR"], K["GFB_R_STAND_STILL"]})
-    main_pos = bool(ops & {K["GFB_R_BASE_HEIGHT"]}) or bool(tops & {K["GFB_T_BASE_HEIGHT_MIN"], K["GFB_T_OUT_OF_BOUNDS"]}) \
-        or f["entity"]
-    read = 4 + 3 * main_pos + 3 * main_vel + 3 * main_ang + D * main_dof
-    read += f["cmd"] + 1 + f["has_max"] + f["uses"]["action_rate"] + (1 + f["n_reward"] if f["n_reward"] else 0)
-    read += f["contact_in"] + f["air"] + f["feet_slide"]
-    write = 1 + ((1 + f["n_reward"]) if f["n_reward"] else 0) + 11 * f["entity"] + f["contact_out"] + f["air"]
-    main = 4 * (read + write) + 2
-    obs_read = 4 + 3 * (K["GFB_O_LIN_VEL_B"] in srcs) + 3 * (K["GFB_O_ANG_VEL_B"] in srcs)
-    obs_read += D * sum(k in srcs for k in (K["GFB_O_DOF_POS"], K["GFB_O_DOF_VEL"], K["GFB_O_DOF_FORCE"],
-                                            K["GFB_O_TARGETS"], K["GFB_O_ENV_ACTIONS"]))
-    obs_read += (f["cmd"] if K["GFB_O_COMMAND"] in srcs else 0) + contact_norm_words + f["obs_hist"] + f["noise"]
-    return main, 4 * (obs_read + f["obs_out"])
-
-
 def action_kernel_bytes(fused) -> int:
     """Bytes the pre-physics kernel moves per env."""
     D = fused.program.head.num_dofs

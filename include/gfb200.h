@@ -347,19 +347,20 @@ int gfb_set_program(gfb_handle* h, const gfb_program* program);
 int gfb_action_step(gfb_handle* h, const gfb_buffers* b, const float* raw_env, const float* raw_mgr,
                     void* stream);
 
-/* Post-physics launch: ONE persistent kernel.  Replaces, for the phases requested, everything
+/* Post-physics launch: one persistent kernel.  Replaces, for the phases requested, everything
  * ManagedEnvironment.step does after scene.step() (managed_env.py:294-326): entity cache, contact
- * net forces + air time, terminations, reset mask and ordered index compaction (a single-pass
- * decoupled look-back over the slabs' reset counts: GFB_B_RESET_IDX equals
- * (terminated | truncated).nonzero()), rewards + episode sums, command resample, the in-library part
- * of reset(), the logging reductions, the step report, and the observation rows of every env.   */
+ * net forces + air time, terminations, reset mask, rewards + episode sums, command resample, the
+ * in-library part of reset(), the logging reductions, the step report, and the observation rows of
+ * every env.  With GFB_PHASE_RESET a small second kernel is enqueued behind it that expands the
+ * slabs' reset masks into GFB_B_RESET_IDX == (terminated | truncated).nonzero(), ascending; the
+ * host does not wait for it (the report has the count), only later work on the stream does.    */
 int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void* stream);
 
 /* Wait for the report of the last launch that contained GFB_PHASE_RESET (the one blocking point of a
  * step; the reference blocks at the same place, managed_env.py:309,322).  The host spins on the
- * report's sequence word in mapped host memory; the call returns when the report has been DELIVERED,
- * which is before the kernel has finished (see gfb_report).  Work enqueued afterwards on the same
- * stream is ordered behind the kernel as usual.                                                 */
+ * report's sequence word in mapped host memory, which the kernel's last block stores after
+ * everything else: ~1 us after the store, without the driver's wake-up latency of a stream
+ * synchronisation.                                                                              */
 int gfb_read_report(gfb_handle* h, gfb_report* out, void* stream);
 
 /* gfb_post_physics + gfb_read_report in one call (one boundary crossing per step).              */
@@ -462,8 +463,8 @@ int gfb_spec_stats(const gfb_handle* h, int64_t* specialised, int64_t* generic);
 int gfb_profile_enable(gfb_handle* h, int32_t enabled);
 int gfb_profile_read(gfb_handle* h, float* post_ms_total, int32_t* post_launches, float* action_ms_total,
                      int32_t* action_launches);
-/* Same for the small kernels; ms_total / launches are arrays of 3: [0] reset scatter
- * (gfb_reset_rows), [1] observe (gfb_observe), [2] spawn (gfb_spawn_pose).                       */
+/* Same for the small kernels; ms_total / launches are arrays of 3: [0] index compaction (behind
+ * the post kernel), [1] observe (gfb_observe), [2] spawn (gfb_spawn_pose).                       */
 int gfb_profile_read_aux(gfb_handle* h, float* ms_total, int32_t* launches);
 /* kernels launched by this handle since creation (gfb_action_step: 1, gfb_post_physics: 1-2, ...) */
 int64_t gfb_launch_count(const gfb_handle* h);

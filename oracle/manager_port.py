@@ -63,6 +63,10 @@ class PortEnv:
         self.record_margins = record_margins
         self.printed: list[str] = []
         self.body_acc_state: dict[str, dict] = {}
+        # manager kinds whose `enabled` flag is off ("action", "termination", "reward"): their step()
+        # returns before touching anything (position_action_manager.py:383-384,
+        # termination_manager.py:159-160, reward_manager.py:172-173)
+        self.disabled: set[str] = set()
 
         # genesis_env.py:60-93
         self.extras = {"episode": {}}
@@ -404,16 +408,17 @@ class PortEnv:
         self.extras["observations"] = {}
 
         # -- action manager: base.py:67-82, position_action_manager.py:376-419
-        a = actions
-        if self.delay_step > 0:
-            self.action_delay_buffer.insert(0, a)
-            a = self.action_delay_buffer.pop()
-        self.raw_actions = a
-        if self.targets is None:
-            self.targets = a.clone()
-        else:
-            self.targets[:] = a[:]
-        self.targets = self._handle_actions(self.targets)
+        if "action" not in self.disabled:
+            a = actions
+            if self.delay_step > 0:
+                self.action_delay_buffer.insert(0, a)
+                a = self.action_delay_buffer.pop()
+            self.raw_actions = a
+            if self.targets is None:
+                self.targets = a.clone()
+            else:
+                self.targets[:] = a[:]
+            self.targets = self._handle_actions(self.targets)
 
         self.scene.step()
 
@@ -540,6 +545,8 @@ class PortEnv:
         raise KeyError(fn)
 
     def _terminations(self):
+        if "termination" in self.disabled:
+            return self.terminated, self.truncated
         self.terminated[:] = False
         self.truncated[:] = False
         logging = self.extras["episode"]
@@ -661,6 +668,8 @@ class PortEnv:
         raise KeyError(fn)
 
     def _rewards(self):
+        if "reward" in self.disabled:
+            return self.reward_buf
         dt = self.dt
         self.reward_buf[:] = 0.0
         self.episode_seconds += dt
@@ -720,15 +729,16 @@ class PortEnv:
 
         setters = {"pd_kp": "set_dofs_kp", "pd_kv": "set_dofs_kv", "damping": "set_dofs_damping",
                    "stiffness": "set_dofs_stiffness", "frictionloss": "set_dofs_frictionloss"}
-        for key, setter in setters.items():
-            if key in self.gain_values:
-                getattr(self.robot, setter)(noisy(key, self.gain_values[key]), self.dofs_idx, aidx)
-        if self.force_range is not None:
-            lower = noisy("force_lower", self.force_range[0])
-            upper = noisy("force_upper", self.force_range[1])
-            self.robot.set_dofs_force_range(lower, upper, self.dofs_idx, aidx)
-        position = noisy("position", self.default_dofs_pos[aidx])
-        self.robot.set_dofs_position(position=position, dofs_idx_local=self.dofs_idx, envs_idx=aidx)
+        if "action" not in self.disabled:  # position_action_manager.py:426-427
+            for key, setter in setters.items():
+                if key in self.gain_values:
+                    getattr(self.robot, setter)(noisy(key, self.gain_values[key]), self.dofs_idx, aidx)
+            if self.force_range is not None:
+                lower = noisy("force_lower", self.force_range[0])
+                upper = noisy("force_upper", self.force_range[1])
+                self.robot.set_dofs_force_range(lower, upper, self.dofs_idx, aidx)
+            position = noisy("position", self.default_dofs_pos[aidx])
+            self.robot.set_dofs_position(position=position, dofs_idx_local=self.dofs_idx, envs_idx=aidx)
 
         # -- entity_manager.py:169-183 + mdp/reset.py
         eidx = torch.arange(N) if env_ids is None else env_ids
@@ -769,14 +779,15 @@ class PortEnv:
         # -- reward_manager.py:197-222
         ridx = torch.arange(N) if env_ids is None else env_ids
         logging = self.extras["episode"]
-        episode_seconds = self.episode_seconds[ridx]
-        for name, value in self.episode_data.items():
-            if self.spec["rewards"][name]["weight"] != 0:
-                value[ridx] /= episode_seconds
-                episode_mean = torch.mean(value[ridx])
-                self.episode_mean[name] = episode_mean.item()
-                logging[f"Rewards / {name}"] = episode_mean
-            self.episode_data[name][ridx] = 0.0
+        if "reward" not in self.disabled:
+            episode_seconds = self.episode_seconds[ridx]
+            for name, value in self.episode_data.items():
+                if self.spec["rewards"][name]["weight"] != 0:
+                    value[ridx] /= episode_seconds
+                    episode_mean = torch.mean(value[ridx])
+                    self.episode_mean[name] = episode_mean.item()
+                    logging[f"Rewards / {name}"] = episode_mean
+                self.episode_data[name][ridx] = 0.0
         self.episode_seconds[ridx] = 1e-10
 
         # -- command_manager.py:164-170

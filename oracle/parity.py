@@ -158,7 +158,7 @@ class ParityRun:
                 g = self.group_names.index(parts[1])
                 off = offsets[parts[1]][parts[2]]
                 draws[f"obs_noise{g}"][:, off:off + value.shape[1]] = value
-            else:  # host-side draws: action_dr:*, spawn_x, spawn_y, spawn_rot_*
+            else:  # host-side draws: action_dr:*, spawn_x, spawn_y, spawn_rot_*, gait_* (user-level manager)
                 replay.push(tag, value)
         self.env._fused.inject({k: v.to(dev).contiguous() for k, v in draws.items()})
 
@@ -169,7 +169,8 @@ class ParityRun:
         if kind == "ang_vel_uncached":
             return 3
         if kind == "command":
-            return self.port.command[term["mgr"]]["command"].shape[1]
+            c = self.port.command[term["mgr"]]
+            return (c["gait"].observation() if c.get("gait") is not None else c["command"]).shape[1]
         if kind in ("ang_vel", "lin_vel", "gravity"):
             return 3
         if kind == "contact_force":
@@ -217,6 +218,8 @@ class ParityRun:
         from .guard import BAND
 
         for what, value, thr in self.port.margins:
+            if self.philox and what in ("feet_air_cmd", "stand_still_cmd"):
+                continue  # thresholds on the kernels' own command draws: nothing to keep clear of in advance
             near = (value - thr).abs() <= 0.25 * BAND * max(abs(thr), 1e-3)
             if bool(near.any()):
                 raise ParityFailure(

@@ -33,13 +33,13 @@ def install_contact_kernel():
     cm.kernel_get_contact_forces = kernel_get_contact_forces
 
 
-def make_reference_env(spec: dict, num_envs: int, source=None, n_contacts: int = 8, seed: int = 1234):
+def make_reference_env(spec: dict, num_envs: int, source=None, n_contacts: int = 8, seed: int = 1234, **scene_kw):
     """Reference ManagedEnvironment (torch-CPU) for `spec`, not yet built."""
     shim.install("cpu")
     ns = reference_namespace()
     install_contact_kernel()
     env = build_env(
         spec, ns, num_envs, torch.device("cpu"),
-        source=source, copy_on_get=True, n_contacts=n_contacts, seed=seed,
+        source=source, copy_on_get=True, n_contacts=n_contacts, seed=seed, **scene_kw,
     )
     return env

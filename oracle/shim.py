@@ -27,7 +27,11 @@ from genesis_forge_b200._gs import gs as _engine_gs
 
 from . import geom as _geom
 
-REFERENCE_ROOT = "/root/reference"
+import os as _os
+
+# the reference itself (build container), else the verbatim copy made by oracle/make_ref.py (GPU box)
+_COPY = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = "/root/reference" if _os.path.isdir("/root/reference/genesis_forge") else _COPY
 _INSTALLED = False
 
 

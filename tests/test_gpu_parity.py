@@ -8,9 +8,9 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-CONFIGS = ["simple", "command_direction", "contacts", "rough_terrain", "berkeley_humanoid", "kitchen_sink",
-           "custom_terms"]
-SPLIT = {"custom_terms"}  # user-defined Python terms: kernel phases run as separate (generic) launches
+CONFIGS = ["simple", "command_direction", "contacts", "gait_trainer", "rough_terrain", "berkeley_humanoid",
+           "kitchen_sink", "custom_terms"]
+SPLIT = {"custom_terms", "gait_trainer"}  # user-defined Python terms / managers: kernel phases as separate launches
 
 
 @pytest.mark.parametrize("name", CONFIGS)
@@ -24,9 +24,10 @@ def test_step_parity(name, cuda_device):
     assert stats["resets"] > 0
     spec_stats = run.env._fused.spec_stats()
     if name in SPLIT:
-        # four launches per step with the Python callbacks in between; the observation pass is specialised
+        # several launches per step with the Python callbacks in between, every one of them specialised
         assert run.env._fused.split_mode, spec_stats
-        assert spec_stats["generic_launches"] == 2 + 3 * 120 and spec_stats["specialised_launches"] == 120, spec_stats
+        per_step = len(run.env._fused.split_plan)
+        assert spec_stats["generic_launches"] == 2 and spec_stats["specialised_launches"] == per_step * 120, spec_stats
     else:
         # (the two generic launches are the build-time entity phase and the initial reset phase)
         assert spec_stats["specialised_launches"] == 120 and spec_stats["generic_launches"] == 2, spec_stats
@@ -44,7 +45,8 @@ def test_step_parity_generic_interpreter(name, cuda_device, monkeypatch):
     assert stats["resets"] > 0
     spec_stats = run.env._fused.spec_stats()
     assert spec_stats["specialised_launches"] == 0
-    assert spec_stats["generic_launches"] == (2 + 4 * 60 if name in SPLIT else 62)
+    per_step = len(run.env._fused.split_plan) if name in SPLIT else 1
+    assert spec_stats["generic_launches"] == 2 + per_step * 60
 
 
 def _benchmark_library(fused):
@@ -106,6 +108,70 @@ def test_production_kernel_parity(name, num_envs, steps, cuda_device):
     assert spec_stats["specialised_launches"] == steps and library in spec_stats["libraries"], (spec_stats, library)
     assert stats["resets"] > 0
     print(f"PARITY-VARIANT {name} N={num_envs} slab={tile} draws=philox library={library} stats={stats}")
+
+
+def test_disabled_managers(cuda_device):
+    """
+    `manager.enabled = False` (action / termination / reward): the manager's step() returns before it
+    touches anything in the reference (position_action_manager.py:383-384, termination_manager.py:159-160,
+    reward_manager.py:172-173, :204) -- stale masks keep resetting the same envs, episode sums are neither
+    advanced nor logged nor cleared, targets stay put and nothing is sent to the actuators.
+    """
+    from oracle.parity import ParityRun
+
+    run = ParityRun("contacts", num_envs=256, device=cuda_device, seed=21)
+    run.reset()
+    toggles = {5: {"reward": False}, 12: {"reward": True, "termination": False},
+               20: {"termination": True, "action": False}, 27: {"action": True}}
+    for i in range(40):
+        for kind, enabled in toggles.get(i, {}).items():
+            getattr(run.env, f"{kind}_manager").enabled = enabled
+            (run.port.disabled.discard if enabled else run.port.disabled.add)(kind)
+        out_e, out_p = run.step()
+        assert ("terminations" in out_e[4]) == ("terminations" in out_p[4]), i
+    assert run.stats["resets"] > 0
+
+
+def test_external_controller_feeds_the_fused_terms(cuda_device):
+    """
+    CommandManager.use_external_controller (command_manager.py:85-90, 176-180): while a controller is
+    attached, every term that reads the manager's `command` -- the observation column, the tracking
+    rewards -- sees the controller's tensor, the interval resample is skipped, and reset() still
+    resamples the manager's own buffer.
+    """
+    import genesis_forge_b200 as gfb
+    from configs import specs
+    from configs.env_builder import build_env, dropin_namespace
+
+    gfb.set_device(cuda_device)
+    n = 512
+
+    def make():
+        env = build_env(specs.get("command_direction"), dropin_namespace(), n, cuda_device, seed=3, n_contacts=0)
+        env.build()
+        env.reset()
+        return env
+
+    env, twin = make(), make()
+    ctrl = torch.rand(n, 3, device=cuda_device) * 2 - 1
+    env.velocity_command.use_external_controller(lambda step_count: ctrl)
+    twin.velocity_command._command.copy_(ctrl)  # same commands, the ordinary way
+    own = env.velocity_command._command.clone()
+    actions = torch.randn(n, 12, device=cuda_device)
+    obs, rew, term, trunc, _ = env.step(actions)
+    obs_t, rew_t, term_t, trunc_t, _ = twin.step(actions)
+    done = term | trunc
+    assert bool(done.any()) and torch.equal(done, term_t | trunc_t)
+    assert torch.equal(obs[:, :3], ctrl)                       # every env observes the controller's command
+    assert torch.equal(rew, rew_t)                             # rewards were computed from it
+    assert torch.equal(obs[~done], obs_t[~done])
+    mine = env.velocity_command._command
+    assert torch.equal(mine[~done], own[~done])                # no interval resample ...
+    assert not torch.equal(mine[done], own[done])              # ... but reset() resampled the manager's own buffer
+    env.velocity_command.use_external_controller(None)        # detach: the manager's buffer is used again
+    obs2, *_ = env.step(actions)
+    done2 = env.termination_manager.terminated | env.termination_manager.truncated
+    assert torch.equal(obs2[~done2][:, :3], env.velocity_command._command[~done2])
 
 
 def test_live_mutation_keeps_the_specialised_kernel(cuda_device):
@@ -320,39 +386,6 @@ def test_direct_term_calls_match_the_oracle(name, cuda_device):
         run.step()
 
 
-@pytest.mark.parametrize("name", ["command_direction", "contacts", "rough_terrain", "kitchen_sink"])
-def test_two_launch_step_parity(name, cuda_device, monkeypatch):
-    """
-    Optional large-batch mode (GFB_OVERLAP_OBS=1): the step as main launch + report copy + separate
-    observation pass (FusedStep.post_physics_overlapped) must reproduce the oracle like the single
-    fused launch does.  (No specialisations are pre-built for this slab size: generic kernels.)
-    """
-    from oracle.parity import ParityRun
-
-    monkeypatch.setenv("GFB_OVERLAP_OBS", "1")
-    monkeypatch.setenv("GFB_SPEC_JIT", "0")
-    run = ParityRun(name, num_envs=200, device=cuda_device, seed=2024)
-    assert run.env._fused.overlap_obs
-    stats = run.run(steps=60, nan_step=5)
-    assert stats["resets"] > 0
-    spec_stats = run.env._fused.spec_stats()
-    assert spec_stats["generic_launches"] + spec_stats["specialised_launches"] == 2 + 2 * 60, spec_stats
-
-
-@pytest.mark.parametrize("name", ["command_direction", "berkeley_humanoid"])
-def test_two_launch_step_parity_specialised(name, cuda_device, monkeypatch):
-    """The same at a large-slab batch size, where both launches have pre-built specialisations."""
-    from oracle.parity import ParityRun
-
-    monkeypatch.setenv("GFB_OVERLAP_OBS", "1")
-    run = ParityRun(name, num_envs=131072, device=cuda_device, seed=8)
-    assert run.env._fused.overlap_obs
-    stats = run.run(steps=4)
-    assert stats["resets"] > 0
-    spec_stats = run.env._fused.spec_stats()
-    assert spec_stats["specialised_launches"] == 2 * 4 and spec_stats["generic_launches"] == 2, spec_stats
-
-
 def test_within_limits_action_manager(cuda_device):
     """PositionWithinLimitsActionManager (position_within_limits.py:99-131): clamp to [-1, 1], then the joint-limit map."""
     from configs import specs
@@ -389,20 +422,23 @@ def test_base_height_with_a_per_env_target_tensor(cuda_device):
     assert stats["resets"] > 0
 
 
-@pytest.mark.parametrize("switch", ["GFB_DISABLE_TMA=1", "GFB_NO_OVERLAY=1", "GFB_TILE=64", "GFB_STAGES=2"])
+@pytest.mark.parametrize("switch", ["GFB_DISABLE_TMA=1", "GFB_NO_OVERLAY=1", "GFB_TILE=64", "GFB_TILE=64:persistent"])
 def test_kernel_switches_keep_parity(switch, cuda_device, monkeypatch):
     """
     The alternative code paths behind the environment switches (cooperative loads instead of TMA, one
-    load group, another slab size, the persistent two-stage ring) give the same results.  Generic
-    kernels: no specialisation is pre-built for these plans and none is compiled here.
+    load group, another slab size) give the same results, and so does the persistent loop of the
+    GENERIC kernel when there are more slabs than resident blocks (every block draws several tickets).
+    Generic kernels: no specialisation is pre-built for these plans and none is compiled here.
     """
     from oracle.parity import ParityRun
 
+    switch, _, mode = switch.partition(":")
     key, value = switch.split("=")
     monkeypatch.setenv(key, value)
     monkeypatch.setenv("GFB_SPEC_JIT", "0")
-    # the ring only cycles when there are more slabs than resident blocks: a large batch, few steps
-    n, steps = (150_000, 5) if key == "GFB_STAGES" else (328, 40)
+    n, steps = (400_000, 3) if mode == "persistent" else (328, 40)
+    if mode == "persistent":
+        monkeypatch.setenv("GFB_NO_SPEC", "1")
     run = ParityRun("contacts", num_envs=n, device=cuda_device, seed=404)
     stats = run.run(steps=steps, nan_step=3)
     assert stats["resets"] > 0

@@ -246,26 +246,6 @@ def test_plan_is_a_function_of_structure_not_of_live_values(cpu_device):
     assert canon_a == canon_c and words_a == words_c
 
 
-def test_two_launch_byte_model_is_consistent(cpu_device):
-    """Main launch + observation pass move at least the fused kernel's bytes; the excess is the re-read sources."""
-    from genesis_forge_b200 import roofline
-
-    for name in ("command_direction", "berkeley_humanoid"):
-        fused = dry_env(name, n=4096)._fused
-        whole = roofline.post_kernel_bytes(fused)
-        main, obs = roofline.two_launch_bytes(fused)
-        assert main < whole and obs < whole
-        assert whole <= main + obs <= 1.4 * whole, (name, whole, main, obs)
-    assert roofline.post_kernel_bytes(dry_env("command_direction")._fused) == 518
-    assert roofline.step_bytes(dry_env("command_direction")._fused) == 710      # BASELINE.md, config 2
-    humanoid = build_env(specs.get("berkeley_humanoid"), dropin_namespace(), 32, torch.device("cpu"), n_contacts=8)
-    humanoid._dry_run = True
-    humanoid.build()
-    humanoid._fused._contact_dims = (8, len(humanoid.robot.links) + 1)  # C = 8 synthetic contact slots, plane + links
-    humanoid._fused._set_program(force=True)
-    assert roofline.step_bytes(humanoid._fused) == 1334                         # BASELINE.md, config 5
-
-
 def test_spawn_request_block(cpu_device):
     """gfb_spawn as TerrainManager fills it (terrain_manager.py:204-229: usable centre of the (sub)terrain)."""
     env = dry_env("rough_terrain")

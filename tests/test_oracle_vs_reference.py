@@ -18,7 +18,8 @@ def _same(x, y):
     return bool(((x == y) | (x.isnan() & y.isnan())).all()) if x.is_floating_point() else bool(torch.equal(x, y))
 
 
-def _run(name, num_envs, steps, spec_override=None, nan_step=7):
+def _run(name, num_envs, steps, spec_override=None, nan_step=7, toggles=None):
+    """`toggles`: {step: {manager kind: enabled}} flips `enabled` flags on both sides before that step."""
     spec = specs.get(name)
     if spec_override:
         spec.update(spec_override)
@@ -51,6 +52,9 @@ def _run(name, num_envs, steps, spec_override=None, nan_step=7):
         a = torch.randn(num_envs, 12, generator=gen)
         if i == nan_step:
             a[3, 2] = float("nan")
+        for kind, enabled in (toggles or {}).get(i, {}).items():
+            getattr(ref, f"{kind}_manager").enabled = enabled
+            (port.disabled.discard if enabled else port.disabled.add)(kind)
         torch.set_rng_state(rng_r)
         o_r = ref.step(a.clone())
         rng_r = torch.get_rng_state()
@@ -60,6 +64,7 @@ def _run(name, num_envs, steps, spec_override=None, nan_step=7):
         assert torch.equal(rng_r, rng_p), f"RNG stream diverged at step {i}"
         for j in range(4):
             assert _same(o_r[j], o_p[j]), f"step {i} output {j}"
+        assert ("terminations" in o_r[4]) == ("terminations" in o_p[4]), f"step {i} extras keys"
         check(f"step {i}", o_r[4], o_p[4])
         resets += int((o_r[2] | o_r[3]).sum())
     return resets
@@ -81,3 +86,10 @@ def test_port_matches_reference_within_limits_action_manager():
     for key in ("scale", "use_default_offset"):
         action.pop(key, None)
     assert _run("command_direction", 16, 30, {"action": action}) >= 0
+
+
+def test_port_matches_reference_with_managers_disabled():
+    """`enabled = False` on the action / termination / reward managers: their step() returns early."""
+    toggles = {5: {"reward": False}, 12: {"reward": True, "termination": False}, 20: {"termination": True, "action": False},
+               27: {"action": True}}
+    assert _run("contacts", 32, 40, toggles=toggles, nan_step=None) > 0

@@ -63,8 +63,7 @@ wrap(env, "_begin_step", "_begin_step")
 wrap(fused, "begin_step", "begin_step")
 wrap(fused, "action_step", "action_step (launch)")
 wrap(env.scene, "step", "scene.step")
-wrap(fused, "post_physics", "post_physics (launch + report sync)" if not fused.overlap_obs else "    post_physics main (launch)")
-wrap(fused, "post_physics_overlapped", "post_physics_overlapped (2 launches + report wait)")
+wrap(fused, "post_physics", "post_physics (launch + report wait)")
 wrap(env, "_host_reset", "host reset handlers")
 wrap(fused, "observe", "observe (launch)")
 wrap(fused, "finish_logging", "finish_logging")
@@ -88,8 +87,7 @@ for k, v in T.items():
     if not k.startswith("    "):
         acc += v / K * 1e6
 print(f"  {'(other python in step)':40s} {total - acc:8.1f} us")
-prof = fused.profile_read(); obs = fused.profile_read_observation_pass(); aux = fused.profile_read_aux()
+prof = fused.profile_read(); aux = fused.profile_read_aux()
 print("  small kernels:", ", ".join(f"{k} {v['kernel_us']:.1f} us x{v['launches']}" for k, v in aux.items()))
-print(f"  kernels: action {prof['action_ms'] / max(prof['action_launches'], 1) * 1e3:.1f} us, post(main) "
-      f"{prof['post_ms'] / max(prof['post_launches'], 1) * 1e3:.1f} us, observation pass "
-      f"{obs['obs_ms'] / max(obs['obs_launches'], 1) * 1e3:.1f} us ({obs['obs_launches']} launches)")
+print(f"  kernels: action {prof['action_ms'] / max(prof['action_launches'], 1) * 1e3:.1f} us, post "
+      f"{prof['post_ms'] / max(prof['post_launches'], 1) * 1e3:.1f} us")
