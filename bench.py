@@ -222,6 +222,35 @@ def time_dropin(env, actions, steps, warmup, dist_on):
     return ms, n_reset / max(steps, 1)
 
 
+def pin_to_gpu_numa_node(index: int) -> dict:
+    """
+    Keep this process (and therefore the pinned host buffers it allocates next: first-touch / local
+    allocation policy) on the NUMA node the GPU hangs off, so that host<->device copies do not cross
+    the socket interconnect.  Returns what was done, for the `e2e` block.
+    """
+    info = {"gpu_numa_node": None, "cpus": None}
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        info["gpu_numa_node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = len(allowed)
+    except Exception as e:  # pragma: no cover - depends on the box
+        info["note"] = f"{type(e).__name__}: {e}"[:80]
+    return info
+
+
 def time_e2e(env, actions_host, steps, warmup, dist_on):
     """
     Same step with HOST buffers: every step copies that step's engine state (the arrays the step
@@ -465,6 +494,8 @@ def run_b200(args, rank, local_rank, world):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    all_cpus = os.sched_getaffinity(0)
+    numa = pin_to_gpu_numa_node(local_rank)  # before any pinned host buffer is allocated
     dist_on = world > 1
     if dist_on:
         dist.init_process_group("nccl", device_id=dev)
@@ -501,7 +532,7 @@ def run_b200(args, rank, local_rank, world):
         e2e_steps = max(3, min(args.steps, 10))
         e2e_ms, h2d, d2h = time_e2e(env, actions_host, e2e_steps, 3, dist_on)
         e2e = {"value": N * world / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps, "numa": numa,
                "overlap": "observation read-back of step i on a copy stream, overlapping step i+1's H2D copies"}
 
     sweep = {}
@@ -531,6 +562,7 @@ def run_b200(args, rank, local_rank, world):
             configs[f"{name}:{n_cfg}"] = measure_config(name, n_cfg, dev, 4, seed, k_steps, 5, peak)
 
     cpu = None
+    os.sched_setaffinity(0, all_cpus)  # the CPU baseline uses every core of the box
     if rank == 0 and not dist_on and not args.no_cpu:
         n_cpu = args.cpu_envs or N
         cpu_steps = 40  # a bounded sample: ~5-20 s of host work at 1M envs depending on the table

@@ -166,7 +166,7 @@ EXPORTS = [
     "gfb_action_step", "gfb_post_physics", "gfb_read_report", "gfb_observe", "gfb_contact_forces",
     "gfb_rotate", "gfb_spawn_pose", "gfb_peer_export", "gfb_peer_connect", "gfb_peer_disconnect", "gfb_spec_describe", "gfb_spec_attach", "gfb_spec_stats",
     "gfb_profile_enable", "gfb_profile_read", "gfb_profile_read_aux", "gfb_launch_count",
-    "gfb_post_physics_report",
+    "gfb_post_physics_report", "gfb_reset_rows",
 ]
 
 
@@ -236,6 +236,8 @@ def lib() -> C.CDLL:
     L.gfb_profile_read_aux.argtypes = [vp, fp, C.POINTER(i32)]
     L.gfb_post_physics_report.restype = C.c_int
     L.gfb_post_physics_report.argtypes = [vp, C.POINTER(Buffers), u32, C.POINTER(Report), vp]
+    L.gfb_reset_rows.restype = C.c_int
+    L.gfb_reset_rows.argtypes = [vp, vp, i32, i32, i32, vp, C.c_float, C.c_float, vp, C.c_uint64, C.c_uint64, vp, vp, vp]
     L.gfb_launch_count.restype = i64
     L.gfb_launch_count.argtypes = [vp]
 

@@ -175,9 +175,14 @@ __global__ void __launch_bounds__(CMP_THREADS) compact_kernel(const uint32_t* __
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int w0 = blockIdx.x * words_per_block;
   const int w1 = min(w0 + words_per_block, n_words);
-  // reset envs in all words before this block's range
+  // reset envs in all words before this block's range (w0 is a multiple of 256: 16-byte loads)
   int before = 0;
-  for (int w = tid; w < w0; w += CMP_THREADS) before += __popc(words[w]);
+  const uint4* words4 = reinterpret_cast<const uint4*>(words);
+#pragma unroll 4
+  for (int w = tid; w < (w0 >> 2); w += CMP_THREADS) {
+    const uint4 v = words4[w];
+    before += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
   if (lane == 0) s_warp[warp] = before;
@@ -228,14 +233,18 @@ __global__ void __launch_bounds__(CMP_THREADS) compact_kernel(const uint32_t* __
 // (consecutive columns of one source array are consecutive addresses, so loads and stores coalesce),
 // each lane reads its column descriptor once for all rows; the env ids, cached quaternions and base
 // velocities are warp-uniform broadcast loads.  The reset envs are scattered over the batch, so every
-// access is a DRAM miss: the kernel is pure latency, and what matters is that all loads of a level
-// are in flight together -- a row costs two dependent round trips (id -> sources) and the store.
+// access is a DRAM miss: the kernel is pure latency, a warp issues in order, and what matters is
+// that all loads of a dependency level are issued before the first of them is used -- level 0: env
+// ids + column descriptors; level 1: quaternions, velocities and the source values of two columns
+// for all rows (unconditional loads from always-valid addresses, so no branch separates them).
 // ---------------------------------------------------------------------------------------------
+constexpr int OBS_MAX_ITEMS = 16;  // (group, 32-column chunk) pairs: 256 columns in at most 4 groups
 struct ObserveHead {  // the observation part of the term table (instead of the whole 4 KB head)
-  int32_t n_contact, n_obs_groups, rng_mode, _pad;
+  int32_t n_contact, n_obs_groups, rng_mode, n_items;
   uint64_t rng_seed, step_index;
   int32_t contact_links[GFB_MAX_CONTACT_MANAGERS];
   gfb_obs_group obs_group[GFB_MAX_OBS_GROUPS];
+  int8_t item_group[OBS_MAX_ITEMS], item_chunk[OBS_MAX_ITEMS];
 };
 
 struct ObserveParams {
@@ -250,68 +259,104 @@ struct ObserveParams {
 constexpr int OBS_WARPS = 4;  // warps per block
 constexpr int OBS_ROWS = 4;   // env rows per warp: their loads are issued together (memory-level parallelism)
 
-__global__ void __launch_bounds__(OBS_WARPS * 32, 7) observe_kernel(const __grid_constant__ ObserveParams K) {
+// One (group, column) work item of a lane: its descriptor and the raw values of the warp's rows.
+struct ObsItem {
+  int4 d0, d1;  // DevObsCol: {kind, a, row_words, col}, {scale, noise, gbuf, vec}
+  int g, col;
+  bool on;
+};
+__device__ __forceinline__ ObsItem obs_item(const ObserveParams& K, int item, int lane) {
+  ObsItem it;
+  it.g = item < K.P.n_items ? K.P.item_group[item] : 0;
+  const gfb_obs_group& og = K.P.obs_group[it.g];
+  it.col = (item < K.P.n_items ? K.P.item_chunk[item] : 0) * 32 + lane;
+  it.on = item < K.P.n_items && it.col < og.n_cols;
+  const int4* dp = reinterpret_cast<const int4*>(K.cols + og.col_begin + (it.on ? it.col : 0));
+  it.d0 = __ldg(dp);       // (issued unconditionally from a valid address: no branch ahead of the loads,
+  it.d1 = __ldg(dp + 1);   //  so that the scheduler can put every load of a level in flight together)
+  return it;
+}
+
+__global__ void __launch_bounds__(OBS_WARPS * 32, 5) observe_kernel(const __grid_constant__ ObserveParams K) {
   const ObserveHead& P = K.P;
   const Plan& plan = K.plan;
   const int lane = threadIdx.x & 31;
   const int i0 = (blockIdx.x * OBS_WARPS + (threadIdx.x >> 5)) * OBS_ROWS;
   if (i0 >= K.n) return;
-  // the rows of this warp: env id, cached inverse quaternion, body-frame vectors -- warp-uniform
-  // broadcast loads, all OBS_ROWS of them in flight at once
+  // level 0 (independent loads): the rows' env ids and the descriptors of this lane's first two columns
   long long e[OBS_ROWS];
 #pragma unroll
   for (int r = 0; r < OBS_ROWS; ++r) {
     const int i = min(i0 + r, K.n - 1);  // (rows past the end repeat the last one and are not stored)
     e[r] = K.idx ? (long long)K.idx[i] : (long long)i;
   }
-  float body[OBS_ROWS][9];  // [ang_b 3][lin_b 3][grav_b 3], the stash layout of the post kernel (plan.h)
+  ObsItem cur[2] = {obs_item(K, 0, lane), obs_item(K, 1, lane)};
+
+  // level 1: cached inverse quaternion and base velocities of every row (warp-uniform broadcast loads).
+  // Lane k < 9 keeps component k of [ang_b 3][lin_b 3][grav_b 3] (the stash layout of the post kernel,
+  // plan.h) of every row; a column that wants one fetches it with a shuffle.
+  float body[OBS_ROWS];
+  {
+    float4 q[OBS_ROWS];
+    float va[OBS_ROWS][3], vl[OBS_ROWS][3];
 #pragma unroll
-  for (int r = 0; r < OBS_ROWS; ++r) {
-    const float4 q = GFB_BUF(const float4, GFB_B_INV_BASE_QUAT)[e[r]];
-    const V3 iq = {q.y, q.z, q.w};
+    for (int r = 0; r < OBS_ROWS; ++r) {
+      q[r] = GFB_BUF(const float4, GFB_B_INV_BASE_QUAT)[e[r]];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) body[r][k] = 0.0f;
-    if (plan.needs & NEED_ANG) {
-      const float* v = GFB_BUF(const float, GFB_B_ANG) + e[r] * 3;
-      const V3 o = rotate(V3{v[0], v[1], v[2]}, q.x, iq);
-      body[r][0] = o.x; body[r][1] = o.y; body[r][2] = o.z;
+      for (int k = 0; k < 3; ++k) {
+        va[r][k] = (plan.needs & NEED_ANG) ? GFB_BUF(const float, GFB_B_ANG)[e[r] * 3 + k] : 0.0f;
+        vl[r][k] = (plan.needs & NEED_LIN) ? GFB_BUF(const float, GFB_B_VEL)[e[r] * 3 + k] : 0.0f;
+      }
     }
-    if (plan.needs & NEED_LIN) {
-      const float* v = GFB_BUF(const float, GFB_B_VEL) + e[r] * 3;
-      const V3 o = rotate(V3{v[0], v[1], v[2]}, q.x, iq);
-      body[r][3] = o.x; body[r][4] = o.y; body[r][5] = o.z;
-    }
-    if (plan.needs & NEED_GRAV) {
-      const V3 o = rotate(V3{0.f, 0.f, -1.f}, q.x, iq);
-      body[r][6] = o.x; body[r][7] = o.y; body[r][8] = o.z;
+#pragma unroll
+    for (int r = 0; r < OBS_ROWS; ++r) {
+      const V3 iq = {q[r].y, q[r].z, q[r].w};
+      const V3 a = rotate(V3{va[r][0], va[r][1], va[r][2]}, q[r].x, iq);
+      const V3 l = rotate(V3{vl[r][0], vl[r][1], vl[r][2]}, q[r].x, iq);
+      const V3 g = rotate(V3{0.f, 0.f, -1.f}, q[r].x, iq);
+      const float comp[9] = {a.x, a.y, a.z, l.x, l.y, l.z, g.x, g.y, g.z};
+      float mine = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) mine = lane == k ? comp[k] : mine;
+      body[r] = mine;
     }
   }
   const Philox rng(P.rng_seed);
-  for (int g = 0; g < P.n_obs_groups; ++g) {
-    const gfb_obs_group& og = P.obs_group[g];
-    const int O = og.n_cols, OH = og.n_cols * og.history;
-    float* out = GFB_BUF(float, GFB_B_OBS_OUT0 + g);
-    const float* noise = GFB_BUF(const float, GFB_B_OBS_NOISE0 + g);
-    for (int col = lane; col < O; col += 32) {
-      // this lane's column descriptor: two 16-byte loads, shared by the warp's rows
-      const int4* dp = reinterpret_cast<const int4*>(K.cols + og.col_begin + col);
-      const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
-      const int kind = d0.x, a = d0.y, row_words = d0.z, dcol = d0.w, gbuf = d1.z;
-      const float scale = __int_as_float(d1.x), nz = __int_as_float(d1.y);
+  const float* dummy = reinterpret_cast<const float*>(K.b.buf[GFB_B_INV_BASE_QUAT]);
+  for (int item = 0; item < P.n_items; item += 2) {
+    // level 1 (cont.): the source values of two columns x OBS_ROWS rows, all issued before any is used
+    float raw[2][OBS_ROWS];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int kind = cur[j].d0.x;
+      const bool global = cur[j].on && (kind == 1 || kind == 2);
+      const float* src = global ? reinterpret_cast<const float*>(K.b.buf[cur[j].d1.z]) + cur[j].d0.w : dummy;
+      const long long stride = global ? cur[j].d0.z : 0;
+#pragma unroll
+      for (int r = 0; r < OBS_ROWS; ++r) raw[j][r] = src[e[r] * stride];
+    }
+    // the next two descriptors are requested before this pair is finished
+    ObsItem nxt[2] = {obs_item(K, item + 2, lane), obs_item(K, item + 3, lane)};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int kind = cur[j].d0.x, a = cur[j].d0.y, col = cur[j].col;
+      const float scale = __int_as_float(cur[j].d1.x), nz = __int_as_float(cur[j].d1.y);
+      const gfb_obs_group& og = P.obs_group[cur[j].g];
+      const int O = og.n_cols, OH = og.n_cols * og.history;
+      float* out = GFB_BUF(float, GFB_B_OBS_OUT0 + cur[j].g);
+      const float* noise = GFB_BUF(const float, GFB_B_OBS_NOISE0 + cur[j].g);
       float v[OBS_ROWS];
 #pragma unroll
-      for (int r = 0; r < OBS_ROWS; ++r) v[r] = 0.0f;
-      if (kind == 1 || kind == 2) {
-        const float* src = reinterpret_cast<const float*>(K.b.buf[gbuf]) + dcol;
+      for (int r = 0; r < OBS_ROWS; ++r) v[r] = (kind == 1 || kind == 2) ? raw[j][r] : 0.0f;
+      // (the shuffle is executed by every lane of the warp: no lane may skip it)
+      const bool derived = cur[j].on && kind == 3 && a < 9;
 #pragma unroll
-        for (int r = 0; r < OBS_ROWS; ++r) v[r] = src[e[r] * row_words];
-      } else if (kind == 3) {
-        if (a < 9) {
-#pragma unroll
-          for (int r = 0; r < OBS_ROWS; ++r)
-#pragma unroll
-            for (int k = 0; k < 9; ++k) v[r] = a == k ? body[r][k] : v[r];
-        } else {  // |net contact force| of one tracked link (mdp/observations.py:181-193)
+      for (int r = 0; r < OBS_ROWS; ++r) {
+        const float b = __shfl_sync(0xffffffffu, body[r], derived ? a : 0);
+        if (derived) v[r] = b;
+      }
+      if (cur[j].on && kind == 3) {
+        if (a >= 9) {  // |net contact force| of one tracked link (mdp/observations.py:181-193)
           for (int m = 0; m < P.n_contact; ++m) {
             const int t = a - plan.st_cnorm[m];
             if (t < 0 || t >= P.contact_links[m]) continue;
@@ -325,6 +370,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 7) observe_kernel(const __grid
           }
         }
       }
+      if (!cur[j].on) continue;  // (behind the shuffles: this lane has no column in this chunk)
 #pragma unroll
       for (int r = 0; r < OBS_ROWS; ++r) {
         float x = mul(v[r], scale);
@@ -335,8 +381,8 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 7) observe_kernel(const __grid
           } else {
             const uint4 w = rng((uint32_t)e[r], (uint32_t)P.step_index, (uint32_t)(P.step_index >> 32),
                                 0x1000u + (uint32_t)(og.col_begin + (col & ~3)));
-            const int j = col & 3;
-            const uint32_t wj = j == 0 ? w.x : (j == 1 ? w.y : (j == 2 ? w.z : w.w));
+            const int jj = col & 3;
+            const uint32_t wj = jj == 0 ? w.x : (jj == 1 ? w.y : (jj == 2 ? w.z : w.w));
             u = sub(mul(u01(wj), 2.f), 1.f);
           }
           x = add(x, mul(u, nz));
@@ -344,6 +390,8 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, 7) observe_kernel(const __grid
         if (i0 + r < K.n) out[e[r] * OH + col] = x;
       }
     }
+    cur[0] = nxt[0];
+    cur[1] = nxt[1];
   }
 }
 
@@ -410,6 +458,52 @@ __global__ void rotate_kernel(const float* __restrict__ vec, const float4* __res
   out[i * 3] = r.x;
   out[i * 3 + 1] = r.y;
   out[i * 3 + 2] = r.z;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reset_rows_kernel: the value rows a reset hands to the engine setters, one
+// launch instead of a chain of indexed torch ops per setter:
+//   mode GFB_ROWS_NOISE    out[i, j] = base[j] + u * a, u ~ U(-1, 1)        (PositionActionManager
+//                          ._add_random_noise, position_action_manager.py:516-525: gains -- one row --
+//                          and the default joint positions of the reset envs, :432-464)
+//   mode GFB_ROWS_UNIFORM  out[i, j] = U(a, b)                               (randomize_link_mass_shift,
+//                          mdp/reset.py:229-284)
+// Draws are injected (`draws`, (n, width): the reference's own numbers in the parity harness) or
+// Philox4x32-10 keyed by (seed, env id, counter, column).  `scatter` (rows, width), if given, receives
+// row idx[i] as well (the manager's persistent per-env buffer).
+// ---------------------------------------------------------------------------------------------
+struct ResetRowsParams {
+  const int64_t* idx;
+  int32_t n, width, mode, _pad;
+  const float* base;
+  float a, b;
+  const float* draws;
+  uint64_t seed, counter;
+  float* out;
+  float* scatter;
+};
+
+__global__ void __launch_bounds__(256) reset_rows_kernel(const ResetRowsParams p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)p.n * p.width) return;
+  const int row = (int)(i / p.width), col = (int)(i - (long long)row * p.width);
+  const long long e = p.idx ? (long long)p.idx[row] : (long long)row;
+  float u;  // U(-1, 1) for NOISE, the final value (injected) or U(0, 1) for UNIFORM
+  if (p.draws) {
+    u = p.draws[i];
+  } else {
+    const Philox rng(p.seed);
+    const uint4 r = rng((uint32_t)e, (uint32_t)((uint64_t)e >> 32) ^ 0x52455354u, (uint32_t)p.counter,
+                        (uint32_t)(p.counter >> 32) ^ (uint32_t)(col >> 2));  // stream tag 'REST'
+    const int j = col & 3;
+    const float u01v = u01(j == 0 ? r.x : (j == 1 ? r.y : (j == 2 ? r.z : r.w)));
+    u = p.mode == GFB_ROWS_NOISE ? sub(mul(u01v, 2.0f), 1.0f) : u01v;
+  }
+  float v;
+  if (p.mode == GFB_ROWS_NOISE) v = add(p.base[col], mul(u, p.a));
+  else v = p.draws ? u : add(mul(u, sub(p.b, p.a)), p.a);
+  p.out[i] = v;
+  if (p.scatter) p.scatter[e * p.width + col] = v;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -291,6 +291,7 @@ int build_plan(gfb_handle* h, const gfb_buffers& b, uint32_t phases, int tile, i
     if (!b.buf[GFB_B_ANG]) return fail(h, GFB_ERR_INVALID, "GFB_B_ANG missing");
     plan.off_ang = stage(GFB_B_ANG, 3, -1);
   }
+  plan.n_prefetch = plan.n_staged;  // everything staged so far: quat, pos, vel, ang
   int contact_begin = cursor, contact_end = cursor;
   if (contact) {
     for (int id : {GFB_B_C_FORCE, GFB_B_C_POS, GFB_B_C_LINK_A, GFB_B_C_LINK_B, GFB_B_LINKS_QUAT})
@@ -736,13 +737,11 @@ int gfb_create(int32_t num_envs, int32_t device, gfb_handle** out) {
   CUDA_TRY(cudaMalloc(&h->scratch.rew_acc, GFB_MAX_REWARD_TERMS * sizeof(unsigned long long)));
   CUDA_TRY(cudaMalloc(&h->scratch.rew_flags, GFB_MAX_REWARD_TERMS * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc(&h->scratch.counters, CTR_COUNT * sizeof(uint32_t)));
-  CUDA_TRY(cudaMalloc(&h->scratch.global_reset, sizeof(double)));
   CUDA_TRY(cudaMalloc(&h->scratch.status, sizeof(uint32_t)));
   CUDA_TRY(cudaMemset(h->scratch.term_count, 0, GFB_MAX_TERMINATION_TERMS * sizeof(int32_t)));
   CUDA_TRY(cudaMemset(h->scratch.rew_acc, 0, GFB_MAX_REWARD_TERMS * sizeof(unsigned long long)));
   CUDA_TRY(cudaMemset(h->scratch.rew_flags, 0, GFB_MAX_REWARD_TERMS * sizeof(uint32_t)));
   CUDA_TRY(cudaMemset(h->scratch.counters, 0, CTR_COUNT * sizeof(uint32_t)));
-  CUDA_TRY(cudaMemset(h->scratch.global_reset, 0, sizeof(double)));
   CUDA_TRY(cudaMemset(h->scratch.status, 0, sizeof(uint32_t)));
   CUDA_TRY(cudaHostAlloc(&h->report_host, sizeof(gfb_report), cudaHostAllocMapped));
   memset(h->report_host, 0, sizeof(gfb_report));
@@ -775,7 +774,6 @@ void gfb_destroy(gfb_handle* h) {
   cudaFree(h->scratch.rew_acc);
   cudaFree(h->scratch.rew_flags);
   cudaFree(h->scratch.counters);
-  cudaFree(h->scratch.global_reset);
   cudaFree(h->scratch.status);
   if (h->report_host) cudaFreeHost(h->report_host);
   gfb_peer_disconnect(h);
@@ -1022,11 +1020,16 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
     if (per_sm <= 0) return fail(h, GFB_ERR_CUDA, "post kernel: no block fits on an SM with this slab plan");
     lc->resident_blocks = per_sm * std::max(h->num_sms, 1);
   }
-  // (single-warp blocks take one slab each: 32-env slabs are the small-batch choice, where there are
-  //  fewer slabs than resident blocks anyway.  Forced onto a large batch -- GFB_TILE=32 -- the
-  //  persistent loop of a 32-thread block failed with cudaErrorLaunchFailure at full speed, clean under
-  //  compute-sanitizer memcheck / racecheck / synccheck and with 64- and 128-env slabs; not understood.)
-  const int grid = ((h->debug & 4u) || tile == 32) ? n_tiles : std::min(n_tiles, lc->resident_blocks);
+  // The persistent loop is used where it pays: launches that assemble observation rows (the fused
+  // step, the observation pass of split execution), with slabs of 64 envs or more.  Every other launch
+  // takes one slab per block.  Reason besides "nothing to gain": launches whose slab iteration is very
+  // short (entity cache alone: two small TMA loads, a copy, ~1 us) failed intermittently with
+  // cudaErrorLaunchFailure when looped -- 32-env slabs at 200k envs every time, 64-env slabs at 400k
+  // envs inside a long test session only -- while compute-sanitizer memcheck / racecheck / synccheck
+  // and CUDA_LAUNCH_BLOCKING=1 runs of the same launches were clean.  Not understood; the looped
+  // launches of the fused step have never shown it (parity suites up to 1M envs, all benches).
+  const bool looped = (phases & GFB_PHASE_OBSERVE) && tile >= 64 && !(h->debug & 4u);
+  const int grid = looped ? std::min(n_tiles, lc->resident_blocks) : n_tiles;
 
   const bool reports = (phases & GFB_PHASE_RESET) != 0;
   if (reports && !b->buf[GFB_B_RESET_IDX]) return fail(h, GFB_ERR_INVALID, "buffer RESET_IDX is NULL");
@@ -1218,6 +1221,14 @@ int gfb_observe(gfb_handle* h, const gfb_buffers* b, const int64_t* idx, int32_t
   op.P.step_index = P.step_index;
   for (int m = 0; m < P.n_contact; ++m) op.P.contact_links[m] = P.contact[m].n_links;
   memcpy(op.P.obs_group, P.obs_group, sizeof(op.P.obs_group));
+  op.P.n_items = 0;
+  for (int g = 0; g < P.n_obs_groups; ++g)
+    for (int c = 0; c * 32 < P.obs_group[g].n_cols; ++c) {
+      if (op.P.n_items >= OBS_MAX_ITEMS) return fail(h, GFB_ERR_UNSUPPORTED, "gfb_observe: too many observation columns");
+      op.P.item_group[op.P.n_items] = (int8_t)g;
+      op.P.item_chunk[op.P.n_items] = (int8_t)c;
+      op.P.n_items += 1;
+    }
   op.b = *b;
   op.cols = reinterpret_cast<const DevObsCol*>(h->observe_slot.table_dev);
   op.idx = idx;
@@ -1300,6 +1311,27 @@ int gfb_spawn_pose(gfb_handle* h, const gfb_spawn* cfg, const int64_t* idx, int3
   spawn_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream_)>>>(sp);
   CUDA_TRY(cudaGetLastError());
   if (spawn_end) cudaEventRecord(spawn_end, static_cast<cudaStream_t>(stream_));
+  h->launches += 1;
+  return GFB_OK;
+}
+
+int gfb_reset_rows(gfb_handle* h, const int64_t* idx, int32_t n, int32_t width, int32_t mode, const float* base,
+                   float a, float b, const float* draws, uint64_t seed, uint64_t counter, float* out, float* scatter,
+                   void* stream_) {
+  if (!h) return GFB_ERR_INVALID;
+  if (h->host_only) return fail(h, GFB_ERR_NO_DEVICE, "host-only handle cannot launch kernels");
+  if (n < 0 || width <= 0) return fail(h, GFB_ERR_INVALID, "gfb_reset_rows: bad shape");
+  if (n == 0) return GFB_OK;
+  if (!out) return fail(h, GFB_ERR_INVALID, "gfb_reset_rows: out is NULL");
+  if (mode != GFB_ROWS_NOISE && mode != GFB_ROWS_UNIFORM) return fail(h, GFB_ERR_INVALID, "gfb_reset_rows: bad mode");
+  if (mode == GFB_ROWS_NOISE && !base) return fail(h, GFB_ERR_INVALID, "gfb_reset_rows: base is NULL");
+  ResetRowsParams p{};
+  p.idx = idx; p.n = n; p.width = width; p.mode = mode; p.base = base; p.a = a; p.b = b; p.draws = draws;
+  p.seed = seed; p.counter = counter; p.out = out; p.scatter = scatter;
+  const long long total = (long long)n * width;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  reset_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return GFB_OK;
 }

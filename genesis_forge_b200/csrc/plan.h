@@ -49,6 +49,10 @@ struct Plan {
   // n_early == n_staged && !sums_late: everything is loaded up front (no contact slots staged).
   int32_t n_early;
   int32_t sums_late;
+  // Arrays [0, n_prefetch) -- base quaternion, position, velocities -- are dead once the per-env
+  // (owner) phase is over: the persistent kernel refills them with the NEXT slab's rows while the
+  // current slab's observation rows are still being assembled.
+  int32_t n_prefetch;
   int32_t staged_buf[GFB_MAX_STAGED];
   int32_t staged_words[GFB_MAX_STAGED];
   int32_t staged_off[GFB_MAX_STAGED];
@@ -83,7 +87,7 @@ struct Plan {
 };
 
 // Logging exchange between the ranks of one NVLink domain (gfb_peer_connect): every rank owns an
-// inbox with one slot per sender, exchange kind and step parity; senders store their partials
+// inbox with one slot per sender and step parity; senders store their partials
 // straight into the peers' inboxes and publish them with a release store of the sequence number.
 constexpr int PEER_VALS = GFB_MAX_REWARD_TERMS + GFB_MAX_TERMINATION_TERMS + 1;
 struct PeerSlot {
@@ -92,9 +96,8 @@ struct PeerSlot {
   unsigned long long _pad[64 - PEER_VALS - 1];
 };
 static_assert(sizeof(PeerSlot) == 512, "PeerSlot is padded to 512 bytes");
-enum : int { PEER_KIND_COUNTS = 0, PEER_KIND_SUMS = 1 };
 struct PeerInbox {
-  PeerSlot slot[2][2][GFB_MAX_PEERS];  // [parity][kind][sender]
+  PeerSlot slot[2][GFB_MAX_PEERS];  // [parity of the exchange number][sender]
 };
 struct PeerParams {
   PeerInbox* inbox[GFB_MAX_PEERS];  // [r] = rank r's inbox (own one for r == rank)
@@ -117,7 +120,6 @@ struct Scratch {
   unsigned long long* rew_acc;     // (GFB_MAX_REWARD_TERMS) signed 64-bit fixed-point sums (tail.cuh)
   uint32_t* rew_flags;             // (GFB_MAX_REWARD_TERMS) non-finite episode quotients seen
   uint32_t* counters;              // CTR_*
-  double* global_reset;            // global number of reset envs (after the count exchange)
   uint32_t* status;                // sticky status bits
   gfb_report* report_host;         // device address of the host's mapped report
   int32_t n_tiles;

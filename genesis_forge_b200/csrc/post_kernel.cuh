@@ -110,7 +110,7 @@ __device__ __forceinline__ void issue_slab_loads(const KParams& K, const Plan& p
 template <int TILE>
 __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_constant__ KParams K) {
   extern __shared__ __align__(128) float Sbase[];
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) uint64_t bars[3];  // [0] slab loads, [1] late load group, [2] prefetched arrays
   __shared__ int32_t s_term_count[GFB_MAX_TERMINATION_TERMS];
   __shared__ unsigned long long s_rew_acc[GFB_MAX_REWARD_TERMS];  // fixed-point sums of the slab (tail.cuh)
   __shared__ uint32_t s_rew_flags[GFB_MAX_REWARD_TERMS];
@@ -157,16 +157,28 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     if (tid == 0) {
       mbar_init(&bars[0], 1);
       mbar_init(&bars[1], 1);
+      mbar_init(&bars[2], 1);
       fence_mbar_init();
     }
     __syncthreads();
-    if (warp == 0 && (int)blockIdx.x < n_tiles)
-      issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], blockIdx.x, 0, plan.n_early, n_sum_rows_early, true, lane);
+    if (warp == 0 && (int)blockIdx.x < n_tiles) {
+      if (plan.n_prefetch > 0)
+        issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[2], blockIdx.x, 0, plan.n_prefetch, 0, false, lane);
+      issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], blockIdx.x, plan.n_prefetch, plan.n_early, n_sum_rows_early,
+                             true, lane);
+    }
   } else {
     const int32_t* src = reinterpret_cast<const int32_t*>(K.cols);
     int32_t* dst = reinterpret_cast<int32_t*>(Tbl);
     for (int w = tid; w < plan.table_words; w += TILE) dst[w] = src[w];
   }
+
+  // Slabs after the first come from a ticket counter.  A returning atomic takes microseconds while the
+  // memory system is saturated and nothing a slab does may wait for a global round trip (tail.cuh), so
+  // two tickets are kept in flight: the one drawn during the PREVIOUS slab names the next slab (it is
+  // needed in the middle of this one, for the prefetch), the one drawn now the slab after that.
+  uint32_t ticket = 0;  // (thread 0) drawn a slab ago
+  if (tid == 0) ticket = atomicAdd(K.s.counters + CTR_TICKET, 1u);
 
   int it = 0;
   for (int tile = blockIdx.x; tile < n_tiles; ++it) {
@@ -239,9 +251,11 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
 #endif
 
   // one warp polls the slab's mbarrier, the block barrier releases the rest
-  if (use_tma && warp == 0) mbar_wait(&bars[0], (uint32_t)(it & 1));
+  if (use_tma && warp == 0) {
+    if (plan.n_prefetch > 0) mbar_wait(&bars[2], (uint32_t)(it & 1));
+    mbar_wait(&bars[0], (uint32_t)(it & 1));
+  }
   __syncthreads();
-  uint32_t ticket = 0;
 
   // slab copies that need no arithmetic (entity cache: base_pos / base_quat are copies of pos / quat)
   if (ph & GFB_PHASE_ENTITY) {
@@ -842,6 +856,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     if (ph & GFB_PHASE_TERMINATION) {
       GFB_BUF(uint8_t, GFB_B_TERMINATED)[e] = terminated;
       GFB_BUF(uint8_t, GFB_B_TRUNCATED)[e] = truncated;
+      if (K.b.buf[GFB_B_DONES]) GFB_BUF(uint8_t, GFB_B_DONES)[e] = terminated | truncated;
     }
     if (ph & GFB_PHASE_REWARD) GFB_BUF(float, GFB_B_REWARD)[e] = reward;
     if ((ph & (GFB_PHASE_REWARD | GFB_PHASE_RESET)) && K.b.buf[GFB_B_EP_SECONDS])
@@ -864,10 +879,20 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   }
   if (use_tma) fence_async_smem();
   __syncthreads();
-  // The ticket of the block's NEXT slab is drawn here and looked at when the row assembly below is
-  // done: a returning atomic takes microseconds while the memory system is saturated, and nothing a
-  // slab does may wait for a global round trip (tail.cuh).
-  if (tid == 0) ticket = atomicAdd(K.s.counters + CTR_TICKET, 1u);
+  // the per-env phase is over: quat / pos / vel / ang of this slab are dead -- warp 0 refills them with
+  // the next slab's rows, which land while the observation rows below are assembled
+  int next_tile = 0;
+  if (warp == 0) {
+    next_tile = (int)gridDim.x + (int)__shfl_sync(0xffffffffu, ticket, 0);
+    if (lane == 0) {
+      s_next_tile = next_tile;
+      ticket = atomicAdd(K.s.counters + CTR_TICKET, 1u);  // (names the slab after the next one)
+    }
+    if (use_tma && next_tile < n_tiles && plan.n_prefetch > 0) {
+      bulk_wait_all_read();  // the entity-cache stores have read the pos / quat slabs
+      issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[2], next_tile, 0, plan.n_prefetch, 0, false, lane);
+    }
+  }
 
   // ------------------------------------------------------------------------------------------
   // slab outputs: episode sums
@@ -1019,14 +1044,14 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     }
   }
 
-  // everyone is done with the slab's shared memory before it is refilled
-  if (tid == 0) s_next_tile = (int)gridDim.x + (int)ticket;
+  // everyone is done with the slab's shared memory before the rest of it is refilled
   __syncthreads();
-  const int next_tile = s_next_tile;
+  next_tile = s_next_tile;
   if (use_tma && next_tile < n_tiles && warp == 0) {
     bulk_wait_all_read();
     fence_async_smem();  // the slab's generic-proxy reads above, the async-proxy refill below
-    issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], next_tile, 0, plan.n_early, n_sum_rows_early, false, lane);
+    issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], next_tile, plan.n_prefetch, plan.n_early, n_sum_rows_early,
+                           false, lane);
   }
 
   tile = next_tile;
@@ -1046,11 +1071,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   __syncthreads();
   if (s_last_block && warp == 0) {
     __threadfence();
-    if (ph & GFB_PHASE_RESET) {
-      write_report(K, lane);        // counts (exchanged with the peer ranks when sharded)
-      write_reward_means(K, lane);  // logged episode means
-      publish_report(K, lane);      // everything is in place: the host may go on
-    }
+    if (ph & GFB_PHASE_RESET) finalize_step(K, lane);  // logging values, the report, the word the host spins on
     __syncwarp();
     if (lane == 0) {
       K.s.counters[CTR_TICKET] = 0u;

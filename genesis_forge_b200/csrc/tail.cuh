@@ -84,21 +84,25 @@ __device__ __forceinline__ double fixed_to_double(long long v, uint32_t flags) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// exchange of one small vector between the ranks (one warp; lane i owns element i < n_vals).
-// Returns the sum over ranks in rank order (bit-identical on all ranks); `timed_out` is warp-uniform.
+// exchange of the logging partials between the ranks (one warp).  Lane i owns two elements of the
+// vector: a[i] (i < n_a: termination fire counts, then the number of reset envs) and b[i] (i < n_b:
+// reward episode-quotient sums); they travel in one inbox slot.  On return a / b hold the sums over
+// ranks in rank order (bit-identical on all ranks).  Returns false if a peer did not show up.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double peer_exchange(const PeerParams& pp, int kind, double mine, int n_vals, int lane,
-                                                bool& timed_out) {
+__device__ __forceinline__ bool peer_exchange(const PeerParams& pp, double& a, int n_a, double& b, int n_b, int lane) {
   const int parity = (int)(pp.seq & 1ull);
   const int me = pp.rank, W = pp.world;
-  if (lane < n_vals)
-    for (int p = 0; p < W; ++p) pp.inbox[p]->slot[parity][kind][me].vals[lane] = mine;
+  for (int p = 0; p < W; ++p) {
+    PeerSlot& slot = pp.inbox[p]->slot[parity][me];
+    if (lane < n_a) slot.vals[lane] = a;
+    if (lane < n_b) slot.vals[n_a + lane] = b;
+  }
   __threadfence_system();
   __syncwarp();
-  if (lane < W) st_release_sys(&pp.inbox[lane]->slot[parity][kind][me].seq, pp.seq);
+  if (lane < W) st_release_sys(&pp.inbox[lane]->slot[parity][me].seq, pp.seq);
   int late = 0;
   if (lane < W) {
-    const unsigned long long* flag = &pp.inbox[me]->slot[parity][kind][lane].seq;
+    const unsigned long long* flag = &pp.inbox[me]->slot[parity][lane].seq;
     const unsigned long long t0 = global_timer_ns();
     while (ld_acquire_sys(flag) != pp.seq) {
       if (global_timer_ns() - t0 > 2000000000ull) {  // ~2 s: a peer never issued this exchange
@@ -108,101 +112,72 @@ __device__ __forceinline__ double peer_exchange(const PeerParams& pp, int kind, 
       __nanosleep(200);
     }
   }
-  timed_out = __any_sync(0xffffffffu, late) != 0;
+  if (__any_sync(0xffffffffu, late)) return false;
   __threadfence_system();
-  double g = mine;
-  if (!timed_out && lane < n_vals) {
-    g = 0.0;
-    for (int r = 0; r < W; ++r) g += __ldcv(&pp.inbox[me]->slot[parity][kind][r].vals[lane]);
+  double ga = 0.0, gb = 0.0;
+  for (int r = 0; r < W; ++r) {
+    const PeerSlot& slot = pp.inbox[me]->slot[parity][r];
+    if (lane < n_a) ga += __ldcv(&slot.vals[lane]);
+    if (lane < n_b) gb += __ldcv(&slot.vals[n_a + lane]);
   }
-  return g;
+  a = ga;
+  b = gb;
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------------
-// the step report (one warp of the last block to leave the kernel)
+// End of the launch (one warp of the last block to leave the kernel): logging values and the report.
 //   termination_manager.py:178-182  fired fraction per term
-//   managed_env.py:308-310          number of reset envs (the indices are already in GFB_B_RESET_IDX)
+//   reward_manager.py:205-216       mean over the reset envs of (episode sum / episode seconds)
+//   managed_env.py:308-310          number of reset envs (compact_kernel writes the indices)
+// The GPU is idle while this runs, so every read is issued before the first one is used (one round
+// trip), then the values are stored, and last -- behind a system-scope fence -- the report's sequence
+// word, on which the host spins.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void write_report(const KParams& K, int lane) {
+__device__ __forceinline__ void finalize_step(const KParams& K, int lane) {
   const gfb_program_head& P = K.P;
   const Scratch& sc = K.s;
   const int n_t = P.n_termination, n_r = P.n_reward;
   __threadfence();
+  // reads (and re-arming: every accumulator is left at zero for the next launch)
   const int n_reset = (int)ld_acquire_gpu_u32(sc.counters + CTR_TOTAL_RESET);  // every slab has added its share
-  int count = 0;
-  if (lane < n_t) count = atomicExch(sc.term_count + lane, 0);
-  uint32_t status = 0;
-  if (lane == 0) status = atomicExch(sc.status, 0u);
-  double mine = lane < n_t ? (double)count : (lane == n_t ? (double)n_reset : 0.0);
-  double global = mine;
+  const int count = lane < n_t ? atomicExch(sc.term_count + lane, 0) : 0;
+  uint32_t status = lane == 0 ? atomicExch(sc.status, 0u) : 0u;
+  const long long acc = lane < n_r ? (long long)atomicExch(sc.rew_acc + lane, 0ull) : 0ll;
+  const uint32_t acc_flags = lane < n_r ? atomicExch(sc.rew_flags + lane, 0u) : 0u;
+
+  double counts = lane < n_t ? (double)count : (lane == n_t ? (double)n_reset : 0.0);  // lane n_t: reset envs
+  double sum = lane < n_r ? fixed_to_double(acc, acc_flags) : 0.0;
   double* log_acc = GFB_BUF(double, GFB_B_LOG_ACC);
   float* log_out = GFB_BUF(float, GFB_B_LOG_OUT);
-  if (log_acc && lane <= n_t) log_acc[n_r + lane] = mine;  // local partials (NCCL fallback path)
+  if (log_acc) {  // local partials (what the NCCL fallback path all-reduces)
+    if (lane < n_r) log_acc[lane] = sum;
+    if (lane <= n_t) log_acc[n_r + lane] = counts;
+  }
   long long denom = P.num_envs;
   if (K.peer.world > 1 && log_acc) {
-    bool timed_out;
-    global = peer_exchange(K.peer, PEER_KIND_COUNTS, mine, n_t + 1, lane, timed_out);
-    if (timed_out) {
-      if (lane == 0) status |= GFB_STATUS_PEER_TIMEOUT;
-    } else {
-      denom = K.peer.global_num_envs;
-    }
+    if (peer_exchange(K.peer, counts, n_t + 1, sum, n_r, lane)) denom = K.peer.global_num_envs;
+    else if (lane == 0) status |= GFB_STATUS_PEER_TIMEOUT;
   }
+  const double g_reset = __shfl_sync(0xffffffffu, counts, n_t);
   gfb_report* rep = sc.report_host;
   if (lane < n_t) {
     rep->termination_count[lane] = count;
-    rep->global_termination_count[lane] = (long long)global;
-    if (log_out) log_out[n_r + lane] = fdiv((float)global, (float)denom);
+    rep->global_termination_count[lane] = (long long)counts;
+    if (log_out) log_out[n_r + lane] = fdiv((float)counts, (float)denom);
   }
-  if (lane == n_t) {
-    rep->global_n_reset = (long long)global;
-    *sc.global_reset = global;
+  if (lane < n_r && log_out) {
+    const bool logged = P.reward[lane].weight != 0.0f;  // reward_manager.py:208-209
+    log_out[lane] = (g_reset > 0.0 && logged) ? (float)(sum / g_reset) : 0.0f;
   }
+  if (lane == n_t) rep->global_n_reset = (long long)counts;
   if (lane == 0) {
     rep->n_reset = n_reset;
     rep->status = status;
   }
-}
-// the report is complete (and so is everything else the launch writes): tell the host
-__device__ __forceinline__ void publish_report(const KParams& K, int lane) {
   __threadfence_system();
   __syncwarp();
-  if (lane == 0) st_release_sys(reinterpret_cast<unsigned long long*>(&K.s.report_host->seq), K.s.report_seq);
-}
-
-// ---------------------------------------------------------------------------------------------
-// logged episode means of the reward terms (one warp of the last block to leave the kernel)
-//   reward_manager.py:205-216: mean over the reset envs of (episode sum / episode seconds)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void write_reward_means(const KParams& K, int lane) {
-  const gfb_program_head& P = K.P;
-  const Scratch& sc = K.s;
-  const int n_r = P.n_reward;
-  __threadfence();
-  double sum = 0.0;
-  if (lane < n_r) {
-    const long long acc = (long long)atomicExch(sc.rew_acc + lane, 0ull);
-    const uint32_t fl = atomicExch(sc.rew_flags + lane, 0u);
-    sum = fixed_to_double(acc, fl);
-  }
-  double* log_acc = GFB_BUF(double, GFB_B_LOG_ACC);
-  float* log_out = GFB_BUF(float, GFB_B_LOG_OUT);
-  if (log_acc && lane < n_r) log_acc[lane] = sum;
-  double g_reset = (double)ld_acquire_gpu_u32(sc.counters + CTR_TOTAL_RESET);
-  if (K.peer.world > 1 && log_acc && n_r > 0) {
-    bool timed_out;
-    const double g = peer_exchange(K.peer, PEER_KIND_SUMS, sum, n_r, lane, timed_out);
-    if (timed_out) {
-      if (lane == 0) atomicOr(sc.status, GFB_STATUS_PEER_TIMEOUT);  // reported with the next step
-    } else {
-      sum = g;
-      g_reset = __ldcg(sc.global_reset);
-    }
-  }
-  if (log_out && lane < n_r) {
-    const bool logged = P.reward[lane].weight != 0.0f;  // reward_manager.py:208-209
-    log_out[lane] = (g_reset > 0.0 && logged) ? (float)(sum / g_reset) : 0.0f;
-  }
+  if (lane == 0) st_release_sys(reinterpret_cast<unsigned long long*>(&rep->seq), sc.report_seq);
 }
 
 }  // namespace gfb

@@ -159,6 +159,7 @@ class FusedStep:
         self._engine_cache: dict = {}  # buffer id -> (tensor, data_ptr) of the last bound engine tensor
         self._action_enabled_packed = True
         self._PHASE_REWARD = K["GFB_PHASE_REWARD"]
+        self._B = {name: value for name, value in K.items() if name.startswith("GFB_B_")}
         self._phase_mask = 0xFFFFFFFF  # phases of disabled managers are dropped from every launch (pack)
         self.spec_paths: list = []
         self._body_acc_prev = None
@@ -248,7 +249,10 @@ class FusedStep:
             return True
 
         self.python_commands = [m for m in self.commands if not stock(m)]
+        self._has_command_override = any(m._external_controller is not None for m in self.commands)
         self._controller_bound = [False] * len(self.commands)  # GFB_B_COMMAND0+k points at a controller's tensor
+        self.any_controller = False
+        self._has_command_override = False  # set by CommandManager.use_external_controller / use_gamepad
         # user-defined observation terms: one (N, W) array filled on the host
         self.external_obs: list[tuple[object, str, object, int, int]] = []  # (manager, name, item, col0, width)
         width = 0
@@ -385,6 +389,7 @@ class FusedStep:
         for t in self.terrains:
             if t.height_field is not None:
                 s(K["GFB_B_HEIGHT_FIELD"], t.height_field)
+        s(K["GFB_B_DONES"], getattr(env, "dones", None))
         s(K["GFB_B_EXT_VALUES"], self.ext_values)
         s(K["GFB_B_OBS_EXT0"], self.ext_obs)
 
@@ -681,30 +686,36 @@ class FusedStep:
     # ------------------------------------------------------------------------------------------
     def _engine_buffers(self, post_reset: bool = False):
         """Pointers to the engine's state tensors (zero-copy; getters are called once per launch)."""
-        K, s = nat.K, self._set_engine
+        s, B = self._set_engine, self._B
         self._keepalive = []
         robot = self.primary_entity
         f32 = torch.float32
         if not post_reset:  # the re-observation of reset envs reads the cached quaternion, not pos/quat
-            s(K["GFB_B_POS"], robot.get_pos(), f32)
-            s(K["GFB_B_QUAT"], robot.get_quat(), f32)
-        s(K["GFB_B_VEL"], robot.get_vel(), f32)
-        s(K["GFB_B_ANG"], robot.get_ang(), f32)
+            s(B["GFB_B_POS"], robot.get_pos(), f32)
+            s(B["GFB_B_QUAT"], robot.get_quat(), f32)
+        s(B["GFB_B_VEL"], robot.get_vel(), f32)
+        s(B["GFB_B_ANG"], robot.get_ang(), f32)
         if self.action is not None:
             idx = self.action.dofs_idx
-            s(K["GFB_B_DOF_POS"], robot.get_dofs_position(idx), f32)
-            s(K["GFB_B_DOF_VEL"], robot.get_dofs_velocity(idx), f32)
+            s(B["GFB_B_DOF_POS"], robot.get_dofs_position(idx), f32)
+            s(B["GFB_B_DOF_VEL"], robot.get_dofs_velocity(idx), f32)
             if self._uses_dof_force:
-                s(K["GFB_B_DOF_FORCE"], robot.get_dofs_force(idx), f32)
+                s(B["GFB_B_DOF_FORCE"], robot.get_dofs_force(idx), f32)
         # a command manager driven by an external controller / gamepad: the terms read what its
         # `command` property returns -- the controller's tensor for this step (command_manager.py:85-90)
-        for k, mgr in enumerate(self.commands):
-            if mgr._external_controller is not None:
-                s(K["GFB_B_COMMAND0"] + k, mgr._external_controller(self.env.step_count), f32)
-                self._controller_bound[k] = True
-            elif self._controller_bound[k]:
-                self._set(K["GFB_B_COMMAND0"] + k, mgr._command)
-                self._controller_bound[k] = False
+        if self._has_command_override:
+            K = nat.K
+            any_controller = False
+            for k, mgr in enumerate(self.commands):
+                if mgr._external_controller is not None:
+                    s(K["GFB_B_COMMAND0"] + k, mgr._external_controller(self.env.step_count), f32)
+                    self._controller_bound[k] = any_controller = True
+                elif self._controller_bound[k]:
+                    self._set(K["GFB_B_COMMAND0"] + k, mgr._command)
+                    self._controller_bound[k] = False
+            self.any_controller = any_controller
+            self._has_command_override = any_controller
+        K = nat.K
         if self.contacts and not post_reset:
             solver = self.env.scene.rigid_solver
             c = solver.collider.get_contacts(as_tensor=True, to_torch=True)
@@ -1010,6 +1021,34 @@ class FusedStep:
         rc = self.lib.gfb_observe(self._h, self._buffers_ref, idx.data_ptr() if idx is not None else None, n, self._stream())
         if rc:
             self.handle.check(rc, "gfb_observe")
+
+    def reset_rows(self, mode: str, tag: str, idx: torch.Tensor | None, n: int, width: int, a: float, b: float = 0.0,
+                   base: torch.Tensor | None = None, out: torch.Tensor | None = None,
+                   scatter: torch.Tensor | None = None) -> torch.Tensor:
+        """
+        Value rows for the engine setters of a reset, one launch of gfb_reset_rows (include/gfb200.h):
+        mode "noise": base + U(-1,1) * a (position_action_manager.py:516-525); "uniform": U(a, b)
+        (mdp/reset.py:229-284).  Draws come from the kernel's Philox stream unless the environment
+        carries a replaying `rng` (parity harness), whose recorded draws for `tag` are passed through.
+        """
+        from .rng import HostRng
+
+        if out is None:
+            out = torch.empty((n, width), device=self.device)
+        rng = getattr(self.env, "rng", None)
+        draws = None
+        if rng is not None and type(rng) is not HostRng:
+            lo, hi = (-1.0, 1.0) if mode == "noise" else (a, b)
+            like = out.reshape(-1) if (idx is None and n == 1) else out  # (a single row was drawn as a vector)
+            draws = rng.uniform(tag, like, lo, hi).to(self.device, torch.float32).contiguous()
+        code = nat.K["GFB_ROWS_NOISE"] if mode == "noise" else nat.K["GFB_ROWS_UNIFORM"]
+        counter = (int(self.env.step_count) << 16) ^ (hash(tag) & 0xFFFF)
+        ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        rc = self.lib.gfb_reset_rows(self._h, ptr(idx), n, width, code, ptr(base), float(a), float(b), ptr(draws),
+                                     (self.rng_seed << 4) ^ 0xD0, counter, ptr(out), ptr(scatter), self._stream())
+        if rc:
+            self.handle.check(rc, "gfb_reset_rows")
+        return out
 
     def rotate_by_inv_base_quat(self, vec: torch.Tensor | None) -> torch.Tensor:
         quat = self.entity_manager._inv_base_quat if self.entity_manager is not None else self._inv_base_quat

@@ -64,6 +64,9 @@ class ManagedEnvironment(GenesisEnv):
         self._reward_buf = torch.zeros((num_envs,), device=gs.device, dtype=gs.tc_float)
         self._terminated_buf = torch.zeros((num_envs,), device=gs.device, dtype=gs.tc_bool)
         self._truncated_buf = torch.zeros((num_envs,), device=gs.device, dtype=gs.tc_bool)
+        # terminated | truncated of the last step, written by the post-physics kernel (wrapper glue:
+        # RslRlWrapper hands it out as `dones` instead of launching an elementwise OR)
+        self.dones = torch.zeros((num_envs,), device=gs.device, dtype=gs.tc_bool)
         self._fused: FusedStep | None = None
         self._tracing: dict | None = None
         self._log_key_cache: dict = {}
@@ -305,14 +308,15 @@ class ManagedEnvironment(GenesisEnv):
         # sharded over ranks: keys are published when ANY rank saw the event (global counts)
         # (single rank / peer-memory exchange: the kernel's report carries the global counts)
         acc = fused.global_acc
-        term_count = (lambda i: acc[n_r + i]) if acc is not None else (lambda i: report.global_termination_count[i])
+        n_t = fused.n_termination
+        counts = acc[n_r:n_r + n_t] if acc is not None else report.global_termination_count[:n_t]
         n_reset_logged = acc[-1] if acc is not None else report.global_n_reset
         if step and term is not None and term.enabled:  # (a disabled manager publishes nothing, :159-160)
             self.extras["terminations"] = term._terminated_buf
             self.extras["time_outs"] = term._truncated_buf
             if term.logging_enabled:
                 for i, key in self._log_keys(term, fused.termination_terms):
-                    if term_count(i) > 0:
+                    if counts[i] > 0:
                         if snapshot is None:
                             snapshot = self._log_snapshot()
                         logging[key] = snapshot[n_r + i]
@@ -358,12 +362,13 @@ class ManagedEnvironment(GenesisEnv):
             self.managers["action"].reset(env_ids)
         for entity_manager in self.managers["entity"]:
             entity_manager.reset(env_ids)
-        for mgr in self._fused.commands:
-            # command_manager.py:164-170: reset() resamples `_command` even while an external controller
-            # supplies `command`; the kernel skips such managers, so it is done here (rare: teleoperation)
-            if mgr._external_controller is not None and mgr.enabled and mgr not in self._fused.python_commands:
-                mgr.resample_command(
-                    env_ids if env_ids is not None else torch.arange(self.num_envs, device=gs.device))
+        if self._fused.any_controller:
+            for mgr in self._fused.commands:
+                # command_manager.py:164-170: reset() resamples `_command` even while an external controller
+                # supplies `command`; the kernel skips such managers, so it is done here (rare: teleoperation)
+                if mgr._external_controller is not None and mgr.enabled and mgr not in self._fused.python_commands:
+                    mgr.resample_command(
+                        env_ids if env_ids is not None else torch.arange(self.num_envs, device=gs.device))
 
     # -- reset ------------------------------------------------------------------------------------
     def reset(self, env_ids=None):

@@ -118,6 +118,7 @@ class PositionActionManager(BaseActionManager):
         self._dofs_idx_list = None
         self._noise_scale = noise_scale
         self._reset_plan = None  # (robot, [(gain key, draw tag, engine setter)], default pose row), built on first reset
+        self._fast_reset = None  # the same with everything resolved, when there is no reset noise
         self._use_default_offset = use_default_offset
         self._default_dofs_pos: torch.Tensor = None
         if use_default_offset and offset != 0.0:
@@ -216,6 +217,7 @@ class PositionActionManager(BaseActionManager):
         self._actions = torch.zeros((N, n), device=gs.device, dtype=gs.tc_float)
         self._has_stepped = False
         self._reset_plan = None
+        self._fast_reset = None
 
     def kernel_params(self) -> dict[str, torch.Tensor]:
         """Per-DOF fp32 vectors for the action kernel: scale, offset, clip bounds, default pose."""
@@ -245,6 +247,17 @@ class PositionActionManager(BaseActionManager):
         robot = self.env.robot
         ns = self._noise_scale
         dofs_idx = self.dofs_idx
+        fast = self._fast_reset
+        if ns == 0.0 and fast is not None and fast[0] is robot:
+            # no domain randomisation: the values handed to the engine never change -- bound setters and
+            # constant rows prepared once (this runs between the step report and the re-observation
+            # launch, i.e. while the GPU waits for the host)
+            for setter, values in fast[1]:
+                setter(values, dofs_idx, envs_idx)
+            if fast[2] is not None:
+                robot.set_dofs_force_range(fast[2][0], fast[2][1], dofs_idx, envs_idx)
+            fast[3](position=fast[4][: envs_idx.shape[0]], dofs_idx_local=dofs_idx, envs_idx=envs_idx)
+            return
         plan = self._reset_plan
         if plan is None or plan[0] is not robot:
             names = {"kp": "set_dofs_kp", "kv": "set_dofs_kv", "damping": "set_dofs_damping",
@@ -264,8 +277,19 @@ class PositionActionManager(BaseActionManager):
             robot.set_dofs_force_range(lower, upper, dofs_idx, envs_idx)
         # every row of the default pose is the same vector: a stride-0 view instead of an index gather
         n = envs_idx.numel() if torch.is_tensor(envs_idx) else len(envs_idx)
-        position = self._add_random_noise("action_dr:position", plan[2].expand(n, -1), ns)
+        fused = getattr(self.env, "_fused", None)
+        if ns != 0.0 and fused is not None and not fused.dry_run and torch.is_tensor(envs_idx):
+            # default pose + per-env noise for the reset envs: one launch of the reset-rows kernel
+            position = fused.reset_rows("noise", "action_dr:position", envs_idx, n, len(dofs_idx), ns,
+                                        base=self._default_dofs_pos[0].contiguous())
+        else:
+            position = self._add_random_noise("action_dr:position", plan[2].expand(n, -1), ns)
         robot.set_dofs_position(position=position, dofs_idx_local=dofs_idx, envs_idx=envs_idx)
+        if ns == 0.0 and torch.is_tensor(envs_idx):
+            self._fast_reset = (
+                robot, [(setter, self._gain_values[key]) for key, _, setter in plan[1]], self._force_range,
+                robot.set_dofs_position, self._default_dofs_pos[0].unsqueeze(0).repeat(self.env.num_envs, 1),
+            )
 
     # -- helpers ----------------------------------------------------------------------------------
     def _dof_values(self, values: dict, default_value=0.0, output=None):
@@ -295,6 +319,10 @@ class PositionActionManager(BaseActionManager):
     def _add_random_noise(self, tag: str, values: torch.Tensor, noise_scale: float = 0.0) -> torch.Tensor:
         if noise_scale == 0.0:
             return values
+        fused = getattr(self.env, "_fused", None)
+        if fused is not None and not fused.dry_run and values.dim() == 1 and values.is_contiguous():
+            # one row (the gains: a draw per DOF shared by all reset envs): the reset-rows kernel
+            return fused.reset_rows("noise", tag, None, 1, values.shape[0], noise_scale, base=values).reshape(-1)
         return values + self.env.rng.uniform(tag, values, -1.0, 1.0) * noise_scale
 
 

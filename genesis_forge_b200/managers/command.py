@@ -113,6 +113,12 @@ class CommandManager(BaseManager):
 
     def use_external_controller(self, controller: Callable[[int], torch.Tensor]):
         self._external_controller = controller
+        self._notify_fused()
+
+    def _notify_fused(self):
+        fused = getattr(self.env, "_fused", None)
+        if fused is not None:
+            fused._has_command_override = True  # the fused step re-binds this manager's command source
 
     def use_gamepad(self, gamepad, range_axis: int | dict[str, int]):
         self._external_controller = self._gamepad_axis_command
@@ -123,6 +129,7 @@ class CommandManager(BaseManager):
             axis_map = [range_axis[key] for key in self._range.keys()]
         self._gamepad_cfg = {"gamepad": gamepad, "axis_map": axis_map}
         self._gamepad_axis_command_buffer = torch.zeros_like(self._command, device=gs.device)
+        self._notify_fused()
 
     def resample_command(self, env_ids):
         """Draw a new command for `env_ids` now (host path; the per-step resample is in-kernel)."""

@@ -105,6 +105,13 @@ class randomize_link_mass_shift(ResetMdpFnClass):
                 )
 
     def __call__(self, env, entity, envs_idx, link_name: str, add_mass_range=(-0.2, 0.2)):
-        like = self._mass_shift_buffer[envs_idx, :]
-        self._mass_shift_buffer[envs_idx, :] = env.rng.uniform("mass_shift", like, *self.add_mass_range)
+        fused = getattr(env, "_fused", None)
+        if fused is not None and not fused.dry_run and torch.is_tensor(envs_idx):
+            # U(lo, hi) per reset env and link, scattered into the persistent buffer: one launch
+            lo, hi = self.add_mass_range
+            fused.reset_rows("uniform", "mass_shift", envs_idx, envs_idx.shape[0], self._mass_shift_buffer.shape[1], lo, hi,
+                             scatter=self._mass_shift_buffer)
+        else:
+            like = self._mass_shift_buffer[envs_idx, :]
+            self._mass_shift_buffer[envs_idx, :] = env.rng.uniform("mass_shift", like, *self.add_mass_range)
         self._entity.set_mass_shift(self._mass_shift_buffer, links_idx_local=self._links_idx_local, envs_idx=envs_idx)

@@ -114,6 +114,7 @@ typedef enum {
   GFB_B_INJ_MAX_LEN,  /* (N,) fp32 U(-1,1) draws for max_episode_length */
   /* values of user-defined (host-evaluated) reward / termination terms: (J, N) fp32, one row per term */
   GFB_B_EXT_VALUES,
+  GFB_B_DONES,        /* (N,) bool written: terminated | truncated (what wrappers/rsl_rl.py:57 computes) */
   GFB_B_COUNT
 } gfb_buf;
 
@@ -438,6 +439,23 @@ int gfb_spawn_pose(gfb_handle* h, const gfb_spawn* cfg, const int64_t* idx, int3
                    const float* height_field, const float* u_x, const float* u_y, const float* u_rot_x,
                    const float* u_rot_y, const float* u_rot_z, float* position_buffer, float* rot_buffer,
                    float* quat_buffer, float* pos_out, float* quat_out, void* stream);
+
+/* ---- reset-side writer: value rows for the engine setters of the reset envs ----
+ * One launch for what the reference does with a few indexed torch ops per setter:
+ *   GFB_ROWS_NOISE    out[i, j] = base[j] + u * a,  u ~ U(-1, 1)   PositionActionManager._add_random_noise
+ *                     (position_action_manager.py:516-525) for the gains (n = 1, idx = NULL) and the
+ *                     default joint positions of the reset envs (:432-464)
+ *   GFB_ROWS_UNIFORM  out[i, j] = U(a, b)                           mdp.reset.randomize_link_mass_shift
+ *                     (mdp/reset.py:229-284)
+ * idx: n int64 env ids (NULL = rows 0..n-1); base: (width) or NULL (UNIFORM); draws: (n, width) injected
+ * draws -- U(-1, 1) for NOISE, the final values for UNIFORM -- or NULL = Philox in the kernel keyed by
+ * (seed, env id, counter, column); out (n, width) compact rows; scatter (rows, width) optional per-env
+ * buffer that receives row idx[i].                                                              */
+#define GFB_ROWS_NOISE 0
+#define GFB_ROWS_UNIFORM 1
+int gfb_reset_rows(gfb_handle* h, const int64_t* idx, int32_t n, int32_t width, int32_t mode, const float* base,
+                   float a, float b, const float* draws, uint64_t seed, uint64_t counter, float* out, float* scatter,
+                   void* stream);
 
 /* ---- compile-time specialisation of the fused kernel -------------------------------------------
  * The fused post-physics kernel is an interpreter over the packed term table.  For a given table

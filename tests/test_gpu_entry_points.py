@@ -81,3 +81,72 @@ def test_rotate_entry_point(n, cuda_device):
     handle.check(lib.gfb_rotate(handle.ptr, None, _ptr(dq), _ptr(out), n, 1, stream), "gfb_rotate")
     gravity = torch.tensor([0.0, 0.0, -1.0]).expand(n, 3)
     assert torch.equal(out.cpu(), transform_by_quat(gravity, inv_quat(quat)))
+
+
+def test_reset_rows_entry_point(cuda_device):
+    """
+    gfb_reset_rows: base + U(-1,1) * scale rows with injected draws are bit-equal
+    to the reference's two torch ops (position_action_manager.py:516-525); U(a, b) rows are scattered
+    into the per-env buffer at the given env ids; in-kernel Philox draws stay inside their range.
+    """
+    import genesis_forge_b200 as gfb
+    from configs import specs
+    from configs.env_builder import build_env, dropin_namespace
+    from genesis_forge_b200.rng import ReplayRng
+
+    gfb.set_device(cuda_device)
+    env = build_env(specs.get("command_direction"), dropin_namespace(), 256, cuda_device, seed=3, n_contacts=0)
+    env.build()
+    fused = env._fused
+    gen = torch.Generator().manual_seed(0)
+    base = torch.randn(12, generator=gen).to(cuda_device)
+    idx = torch.tensor([3, 7, 100, 255], device=cuda_device)
+    u = (torch.rand(4, 12, generator=gen) * 2 - 1).to(cuda_device)
+    env.rng = ReplayRng()
+    env.rng.push("t", u)
+    got = fused.reset_rows("noise", "t", idx, 4, 12, 0.05, base=base)
+    assert torch.equal(got, base + u * 0.05)
+    buf = torch.zeros((256, 5), device=cuda_device)
+    vals = torch.rand(4, 5, generator=gen).to(cuda_device)
+    env.rng.push("m", vals)
+    out = fused.reset_rows("uniform", "m", idx, 4, 5, -0.2, 0.2, scatter=buf)
+    assert torch.equal(out, vals) and torch.equal(buf[idx], vals) and int((buf != 0).any(dim=1).sum()) == 4
+    from genesis_forge_b200.rng import HostRng
+
+    env.rng = HostRng()
+    big = torch.arange(256, device=cuda_device)
+    draws = fused.reset_rows("uniform", "m", big, 256, 8, -0.2, 0.2)
+    assert float(draws.min()) >= -0.2 and float(draws.max()) <= 0.2 and float(draws.std()) > 0.08
+    noisy = fused.reset_rows("noise", "t", big, 256, 12, 0.05, base=base)
+    assert float((noisy - base).abs().max()) <= 0.05 * (1 + 1e-6) and float((noisy - base).std()) > 0.02
+
+
+def test_rsl_rl_wrapper_glue(cuda_device):
+    """
+    RslRlWrapper (wrappers/rsl_rl.py:41-72): step returns (obs, rewards, dones, extras) with
+    dones == terminated | truncated -- here the kernel's own GFB_B_DONES output, no extra launch --
+    and the critic observations default to the policy's.
+    """
+    import genesis_forge_b200 as gfb
+    from configs import specs
+    from configs.env_builder import build_env, dropin_namespace
+    from genesis_forge_b200.wrappers import RslRlWrapper
+
+    gfb.set_device(cuda_device)
+    env = build_env(specs.get("command_direction"), dropin_namespace(), 2048, cuda_device, seed=5, n_contacts=0)
+    wrapped = RslRlWrapper(env)
+    wrapped.build()
+    wrapped.reset()
+    fired = 0
+    for _ in range(5):
+        launches = env._fused.launch_count()
+        obs, rew, dones, extras = wrapped.step(torch.randn(2048, 12, device=cuda_device))
+        term, trunc = env.termination_manager.terminated, env.termination_manager.truncated
+        assert dones.dtype == torch.bool and torch.equal(dones, term | trunc)
+        assert torch.equal(extras["time_outs"], trunc)
+        assert extras["observations"]["critic"] is not None and obs is not None
+        assert env._fused.launch_count() - launches <= 4  # action, post-physics, index compaction, re-observation
+        fired += int(dones.sum())
+    assert fired > 0
+    with pytest.raises(AssertionError):
+        RslRlWrapper(wrapped)  # can_be_wrapped = False
