@@ -54,17 +54,18 @@ __global__ void __launch_bounds__(TILE) action_kernel(const __grid_constant__ Ac
   const uint32_t slab_bytes = (uint32_t)TILE * D * 4u;
   const size_t goff = (size_t)e0 * D;
 
+  // (thread 0 is selected by predicate inside the wrappers, never by a branch: uniform-datapath rule,
+  //  device_utils.cuh)
+  mbar_init(tid == 0, &bar, 1);
+  fence_mbar_init();
+  __syncthreads();
   if (use_tma) {
-    if (tid == 0) {
-      mbar_init(&bar, 1);
-      fence_mbar_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-      mbar_expect_tx(&bar, slab_bytes * (two_raw ? 3u : 2u));
-      bulk_load(s_raw, A.raw_env + goff, slab_bytes, &bar);
-      bulk_load(s_prev, A.env_actions + goff, slab_bytes, &bar);
-      if (two_raw) bulk_load(s_rawm, A.raw_mgr + goff, slab_bytes, &bar);
+    if (tid < 32) {
+      mbar_expect_tx(tid == 0, &bar, slab_bytes * (two_raw ? 3u : 2u));
+      bulk_load(tid == 0, s_raw, A.raw_env + goff, slab_bytes, &bar);
+      bulk_load(tid == 0, s_prev, A.env_actions + goff, slab_bytes, &bar);
+      bulk_load(tid == 0 && two_raw, s_rawm, A.raw_mgr + goff, slab_bytes, &bar);
+      __syncwarp();
     }
   } else {
     const int words = valid * D;
@@ -82,10 +83,11 @@ __global__ void __launch_bounds__(TILE) action_kernel(const __grid_constant__ Ac
 
   // pure copies first: last_actions <- previous actions, actions <- raw
   if (use_tma) {
-    if (tid == 0) {
-      bulk_store(A.env_last_actions + goff, s_prev, slab_bytes);
-      bulk_store(A.env_actions + goff, s_raw, slab_bytes);
+    if (tid < 32) {
+      bulk_store(tid == 0, A.env_last_actions + goff, s_prev, slab_bytes);
+      bulk_store(tid == 0, A.env_actions + goff, s_raw, slab_bytes);
       bulk_commit();
+      __syncwarp();
     }
   } else {
     const int words = valid * D;
@@ -143,9 +145,10 @@ __global__ void __launch_bounds__(TILE) action_kernel(const __grid_constant__ Ac
     if (use_tma) {
       fence_async_smem();
       __syncthreads();
-      if (tid == 0) {
-        bulk_store(A.targets + goff, s_tgt, slab_bytes);
+      if (tid < 32) {
+        bulk_store(tid == 0, A.targets + goff, s_tgt, slab_bytes);
         bulk_commit();
+        __syncwarp();
       }
     } else {
       __syncthreads();
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(TILE) action_kernel(const __grid_constant__ Ac
       for (int w = tid; w < words; w += TILE) A.targets[goff + w] = s_tgt[w];
     }
   }
-  if (use_tma && tid == 0) bulk_wait_all();
+  if (use_tma && tid < 32) bulk_wait_all();
 }
 
 // ---------------------------------------------------------------------------------------------

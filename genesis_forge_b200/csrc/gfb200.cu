@@ -1020,15 +1020,10 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
     if (per_sm <= 0) return fail(h, GFB_ERR_CUDA, "post kernel: no block fits on an SM with this slab plan");
     lc->resident_blocks = per_sm * std::max(h->num_sms, 1);
   }
-  // The persistent loop is used where it pays: launches that assemble observation rows (the fused
-  // step, the observation pass of split execution), with slabs of 64 envs or more.  Every other launch
-  // takes one slab per block.  Reason besides "nothing to gain": launches whose slab iteration is very
-  // short (entity cache alone: two small TMA loads, a copy, ~1 us) failed intermittently with
-  // cudaErrorLaunchFailure when looped -- 32-env slabs at 200k envs every time, 64-env slabs at 400k
-  // envs inside a long test session only -- while compute-sanitizer memcheck / racecheck / synccheck
-  // and CUDA_LAUNCH_BLOCKING=1 runs of the same launches were clean.  Not understood; the looped
-  // launches of the fused step have never shown it (parity suites up to 1M envs, all benches).
-  const bool looped = (phases & GFB_PHASE_OBSERVE) && tile >= 64 && !(h->debug & 4u);
+  // Persistent loop: launches with 64-env slabs or more; debug bit 8 forces it (tests), bit 4 disables it.
+  // (The intermittent "unspecified launch failure" of looped launches with short slab iterations was a
+  //  corrupted mbarrier init value -- see the uniform-datapath note at the top of post_kernel.)
+  const bool looped = (tile >= 64 || (h->debug & 8u)) && !(h->debug & 4u);
   const int grid = looped ? std::min(n_tiles, lc->resident_blocks) : n_tiles;
 
   const bool reports = (phases & GFB_PHASE_RESET) != 0;

@@ -72,9 +72,12 @@ __device__ __forceinline__ float4 add_noise(float4 v, const float4 nz, const flo
   return v;
 }
 
-// Issue the TMA loads of one slab (warp 0 only): staged arrays + episode-sum rows, optionally the
-// descriptor table.  All complete on `bar` (one arrival with the expected byte count by lane 0).
-// Staged arrays [a_begin, a_end) of the plan take part (the early or the late load group).
+// Issue the TMA loads of one slab: staged arrays [a_begin, a_end) of the plan (the early, the late or
+// the prefetched group), `n_sum_rows` episode-sum rows, optionally the descriptor table.  All complete
+// on `bar` (one arrival with the expected byte count).  Called by ALL lanes of warp 0, convergent: lane
+// k describes transfer k (address arithmetic in parallel), the byte counts are summed across the warp
+// for the expect-tx, and each lane's transfer is issued under a predicate -- no per-lane branch around
+// an mbarrier / bulk-copy instruction (uniform-datapath rule, device_utils.cuh).
 template <int TILE>
 __device__ __forceinline__ void issue_slab_loads(const KParams& K, const Plan& plan, float* S, float* table_dst,
                                                  uint64_t* bar, int tile, int a_begin, int a_end, int n_sum_rows,
@@ -83,28 +86,45 @@ __device__ __forceinline__ void issue_slab_loads(const KParams& K, const Plan& p
   const int e0 = tile * TILE;
   const uint32_t valid = (uint32_t)min(TILE, N - e0);
   const int n_arrays = a_end - a_begin;
-  if (lane == 0) {
-    uint32_t total = ((with_table && plan.table_words > 0) ? (uint32_t)plan.table_words * 4u : 0u) + (uint32_t)n_sum_rows * valid * 4u;
-    for (int i = a_begin; i < a_end; ++i) total += (uint32_t)plan.staged_words[i] * valid * 4u;
-    mbar_expect_tx(bar, total);
-  }
-  __syncwarp();
   with_table = with_table && plan.table_words > 0;  // (phase sets without observation rows have no table)
   const int n_ops = n_arrays + n_sum_rows + (with_table ? 1 : 0);
-  for (int op = lane; op < n_ops; op += 32) {
+  // (at most GFB_MAX_STAGED + GFB_MAX_REWARD_TERMS + 1 transfers: two sweeps of the warp)
+  float* dst[2];
+  const float* src[2];
+  uint32_t bytes[2];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int sweep = 0; sweep < 2; ++sweep) {
+    const int op = sweep * 32 + lane;
+    dst[sweep] = S;
+    src[sweep] = nullptr;
+    bytes[sweep] = 0;
     if (op < n_arrays) {
       const int i = a_begin + op;
-      const float* src = reinterpret_cast<const float*>(K.b.buf[plan.staged_buf[i]]) +
-                         (size_t)e0 * plan.staged_words[i];
-      bulk_load(S + plan.staged_off[i], src, (uint32_t)plan.staged_words[i] * valid * 4u, bar);
+      dst[sweep] = S + plan.staged_off[i];
+      src[sweep] = reinterpret_cast<const float*>(K.b.buf[plan.staged_buf[i]]) + (size_t)e0 * plan.staged_words[i];
+      bytes[sweep] = (uint32_t)plan.staged_words[i] * valid * 4u;
     } else if (op < n_arrays + n_sum_rows) {
       const int r = op - n_arrays;
-      bulk_load(S + plan.sums_off + r * TILE, GFB_BUF(const float, GFB_B_EP_SUMS) + (size_t)r * N + e0,
-                valid * 4u, bar);
-    } else {
-      bulk_load(table_dst, K.cols, (uint32_t)plan.table_words * 4u, bar);
+      dst[sweep] = S + plan.sums_off + r * TILE;
+      src[sweep] = GFB_BUF(const float, GFB_B_EP_SUMS) + (size_t)r * N + e0;
+      bytes[sweep] = valid * 4u;
+    } else if (op < n_ops) {
+      dst[sweep] = table_dst;
+      src[sweep] = reinterpret_cast<const float*>(K.cols);
+      bytes[sweep] = (uint32_t)plan.table_words * 4u;
     }
+    mine += bytes[sweep];
   }
+  const uint32_t total = __reduce_add_sync(0xffffffffu, mine);
+  mbar_expect_tx(lane == 0, bar, total);  // (also with total == 0: the phase then completes at once)
+  __syncwarp();
+#pragma unroll
+  for (int sweep = 0; sweep < 2; ++sweep) {
+    if (sweep * 32 < n_ops)  // (warp-uniform)
+      bulk_load(bytes[sweep] != 0u, dst[sweep], src[sweep], bytes[sweep], bar);
+  }
+  __syncwarp();
 }
 
 template <int TILE>
@@ -153,14 +173,13 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   const bool reward_log = SP.n_reward > 0 && !(SP.manager_flags & GFB_MF_REWARD_DISABLED);
 
   if (tid == 0) s_arrived = 0;
+  // barrier setup in straight-line code (thread 0 selected by predicate: uniform-datapath rule)
+  mbar_init(tid == 0, &bars[0], 1);
+  mbar_init(tid == 0, &bars[1], 1);
+  mbar_init(tid == 0, &bars[2], 1);
+  fence_mbar_init();
+  __syncthreads();
   if (use_tma) {
-    if (tid == 0) {
-      mbar_init(&bars[0], 1);
-      mbar_init(&bars[1], 1);
-      mbar_init(&bars[2], 1);
-      fence_mbar_init();
-    }
-    __syncthreads();
     if (warp == 0 && (int)blockIdx.x < n_tiles) {
       if (plan.n_prefetch > 0)
         issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[2], blockIdx.x, 0, plan.n_prefetch, 0, false, lane);
@@ -260,13 +279,13 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   // slab copies that need no arithmetic (entity cache: base_pos / base_quat are copies of pos / quat)
   if (ph & GFB_PHASE_ENTITY) {
     if (use_tma && !(K.debug & 16u)) {
-      if (warp == 0 && lane < plan.n_staged) {
-        const int i = lane;
-        if (plan.staged_store[i] >= 0 && K.b.buf[plan.staged_store[i]]) {
-          float* dst = reinterpret_cast<float*>(K.b.buf[plan.staged_store[i]]) + (size_t)e0 * plan.staged_words[i];
-          bulk_store(dst, S + plan.staged_off[i], (uint32_t)plan.staged_words[i] * (uint32_t)valid * 4u);
-          bulk_commit();
-        }
+      if (warp == 0) {  // lane i copies staged array i (predicated issue, every lane commits)
+        const int i = min(lane, GFB_MAX_STAGED - 1);
+        const bool mine = lane < plan.n_staged && plan.staged_store[i] >= 0 && K.b.buf[max(plan.staged_store[i], 0)] != nullptr;
+        float* dst = mine ? reinterpret_cast<float*>(K.b.buf[plan.staged_store[i]]) + (size_t)e0 * plan.staged_words[i] : nullptr;
+        bulk_store(mine, dst, S + plan.staged_off[i], (uint32_t)plan.staged_words[i] * (uint32_t)valid * 4u);
+        bulk_commit();
+        __syncwarp();
       }
     } else {
       for (int i = 0; i < plan.n_staged; ++i)
@@ -898,14 +917,13 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   // slab outputs: episode sums
   // ------------------------------------------------------------------------------------------
   if (use_tma) {
-    if (warp == 0) {
-      bool issued = false;
-      for (int i = lane; i < n_sum_rows; i += 32) {
-        bulk_store(GFB_BUF(float, GFB_B_EP_SUMS) + (size_t)i * N + e0, S + plan.sums_off + i * TILE,
-                   (uint32_t)valid * 4u);
-        issued = true;
-      }
-      if (issued) bulk_commit();
+    if (warp == 0 && n_sum_rows > 0) {  // lane i stores row i (GFB_MAX_REWARD_TERMS <= 32)
+      const bool mine = lane < n_sum_rows;
+      const int i = mine ? lane : 0;
+      bulk_store(mine, GFB_BUF(float, GFB_B_EP_SUMS) + (size_t)i * N + e0, S + plan.sums_off + i * TILE,
+                 (uint32_t)valid * 4u);
+      bulk_commit();
+      __syncwarp();
     }
   } else {
     if (stage_sums && active) {

@@ -79,3 +79,48 @@ def test_sm100a_code_is_what_was_built():
     assert "UBLKCP" in sass, "no bulk async copy (TMA) instructions in the SASS"
     assert "SYNCS" in sass, "no mbarrier instructions in the SASS"
     assert "HMMA" not in sass and "UTCHMMA" not in sass  # nothing here is a dense contraction
+
+
+def test_sass_obeys_the_uniform_datapath_rule():
+    """No mbarrier / bulk-copy instruction sits in a lane-divergent region whose sibling lanes write a
+    uniform register before the warp reconverges (csrc/device_utils.cuh; the bug it guards against --
+    an mbarrier init value overwritten in ~15 % of the blocks -- is recorded in
+    profiles/r2_01_mbarrier_init_clobber_evidence.txt).  The main library and a sample of the
+    specialised kernels are checked."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    sys.path.insert(0, str(ROOT / "tools"))
+    import sass_lint
+    assert sass_lint.lint(_native.LIB_PATH) == []
+    specs = sorted((ROOT / "genesis_forge_b200" / "_spec").glob("spec_*.so"))[:3]
+    for so in specs:
+        assert sass_lint.lint(so) == [], so.name
+
+
+def test_sass_lint_recognises_the_hazard():
+    """The lint flags the shape that failed on the GPU: thread 0 alone executes SYNCS.EXCH with uniform
+    operands while the sibling lanes' path reloads one of those uniform registers."""
+    import sys
+    sys.path.insert(0, str(ROOT / "tools"))
+    import sass_lint
+    code = [
+        (0x00, "S2R R0, SR_TID.X"),
+        (0x10, "ISETP.NE.AND P1, PT, R0, RZ, PT"),
+        (0x20, "@P1 BRA 0x70"),
+        (0x30, "UMOV UR4, 0x1ffffe"),
+        (0x40, "FENCE.VIEW.ASYNC.S"),
+        (0x50, "SYNCS.EXCH.64 URZ, [UR6], UR4"),
+        (0x60, "BRA 0xa0"),
+        (0x70, "LDCU UR4, c[0x0][0x1944]"),
+        (0x80, "UISETP.NE.AND UP0, UPT, UR4, URZ, UPT"),
+        (0x90, "BRA.U UP0, 0xa0"),
+        (0xa0, "BAR.SYNC.DEFER_BLOCKING 0x0"),
+    ]
+    problems = sass_lint.lint_kernel("k", code)
+    assert len(problems) == 1 and "UR4" in problems[0]
+    safe = code[:7] + [(0x70, "BSYNC.RECONVERGENT B0"), (0x80, "LDCU UR4, c[0x0][0x1944]"), (0xa0, "BAR.SYNC.DEFER_BLOCKING 0x0")]
+    assert sass_lint.lint_kernel("k", safe) == []
+    warp_uniform = [(0x00, "S2R R0, SR_TID.X"), (0x10, "ISETP.GT.U32.AND P1, PT, R0, 0x1f, PT")] + code[2:]
+    assert sass_lint.lint_kernel("k", warp_uniform) == []

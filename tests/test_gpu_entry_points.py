@@ -150,3 +150,20 @@ def test_rsl_rl_wrapper_glue(cuda_device):
     assert fired > 0
     with pytest.raises(AssertionError):
         RslRlWrapper(wrapped)  # can_be_wrapped = False
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tile,num_envs", [(32, 200_000), (64, 400_000), (128, 400_000)])
+def test_persistent_loop_with_short_slabs(tile, num_envs):
+    """The slab loop with the shortest possible iteration (entity phase alone), forced for every slab
+    size (GFB_DEBUG=8), generic kernel: the launch shape that failed with "unspecified launch failure"
+    before the uniform-datapath rule (csrc/device_utils.cuh).  Own process: a faulting kernel would
+    poison this one's CUDA context."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GFB_DEBUG="8", GFB_NO_SPEC="1", GFB_TILE=str(tile))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "loop_stress.py"), str(num_envs), "20"],
+                         capture_output=True, text=True, env=env, timeout=600, cwd=root)
+    assert out.returncode == 0 and "ok, copies equal: True" in out.stdout, out.stdout[-400:] + out.stderr[-400:]
