@@ -1,13 +1,19 @@
+#!/bin/bash
+# (under gpurun) GPU tests + the experiment list of the main configs; args: <tag>
+TAG=${1:-r2x}
 mkdir -p gpurun_out
-for cfg in "32 200000" "32 400000" "64 200000" "64 400000" "128 400000" "128 2000000"; do
-  set -- $cfg
-  GFB_DEBUG=8 GFB_NO_SPEC=1 GFB_TILE=$1 timeout 120 python tools/loop_stress.py $2 40 2>&1 | tail -1
-done | tee gpurun_out/r2p_loop_stress.txt
-(timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | grep -vE "UserWarning|torch.tensor\(|^  warnings" | tail -15 | cut -c1-250) | tee gpurun_out/r2p_tests.log
-python bench.py --steps 20 --warmup 5 --no-cpu --no-e2e --no-configs > gpurun_out/r2p_bench.json 2> gpurun_out/r2p_bench.err; tail -c 1500 gpurun_out/r2p_bench.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r2p_bench.json').read().strip().splitlines()[-1])
-r=d['roofline']
-print('step %.1f us frac %.3f post %.1f action %.1f small %s sweep %s' % (d['ms_per_step']*1e3, r['frac'], r['kernel']['kernel_us'], r['action_kernel']['kernel_us'], {k:(v['kernel_us'] if isinstance(v,dict) else v) for k,v in r['small_kernels'].items()}, {k:round(v['ms_per_step']*1e3,1) for k,v in d['sweep'].items()}))
-PY
+(timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | grep -vE "UserWarning|torch.tensor\(|^  warnings" | tail -12 | cut -c1-250) | tee gpurun_out/${TAG}_tests.log
+one() {  # label, env..., -- bench args
+  label=$1; shift
+  envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
+  env "${envs[@]}" timeout 300 python bench.py --no-cpu --no-e2e --no-configs --steps 20 --warmup 5 "$@" 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
+print('$label: step %.1f us (%.3f) post %.1f us (%.3f) action %.1f us small %s sweep %s' % (d['ms_per_step']*1e3, r['frac'], r['kernel']['kernel_us'], r['kernel']['frac'], r['action_kernel']['kernel_us'], {k:round(v['kernel_us'],1) for k,v in r['small_kernels'].items() if isinstance(v,dict)}, {k:round(v['ms_per_step']*1e3,1) for k,v in d.get('sweep',{}).items()}))" 2>&1 | tail -1
+}
+{
+one "cd 1M" X=1 --
+one "contacts 1M" X=1 -- --config contacts --no-sweep
+one "humanoid 1M" X=1 -- --config berkeley_humanoid --no-sweep
+one "rough 262144" X=1 -- --config rough_terrain --num-envs 262144 --no-sweep
+} | tee gpurun_out/${TAG}_exp.txt
