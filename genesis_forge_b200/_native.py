@@ -163,7 +163,7 @@ _LIB = None
 
 EXPORTS = [
     "gfb_abi_version", "gfb_abi_sizeof", "gfb_create", "gfb_destroy", "gfb_last_error", "gfb_set_program",
-    "gfb_action_step", "gfb_post_physics", "gfb_read_report", "gfb_observe", "gfb_contact_forces",
+    "gfb_action_step", "gfb_action_step_ring", "gfb_post_physics", "gfb_read_report", "gfb_observe", "gfb_contact_forces",
     "gfb_rotate", "gfb_spawn_pose", "gfb_peer_export", "gfb_peer_connect", "gfb_peer_disconnect", "gfb_spec_describe", "gfb_spec_attach", "gfb_spec_stats",
     "gfb_profile_enable", "gfb_profile_read", "gfb_profile_read_aux", "gfb_launch_count",
     "gfb_post_physics_report", "gfb_reset_rows",
@@ -204,6 +204,8 @@ def lib() -> C.CDLL:
     L.gfb_set_program.argtypes = [vp, C.POINTER(Program)]
     L.gfb_action_step.restype = C.c_int
     L.gfb_action_step.argtypes = [vp, C.POINTER(Buffers), vp, vp, vp]
+    L.gfb_action_step_ring.restype = C.c_int
+    L.gfb_action_step_ring.argtypes = [vp, C.POINTER(Buffers), vp, vp, vp]
     L.gfb_post_physics.restype = C.c_int
     L.gfb_post_physics.argtypes = [vp, C.POINTER(Buffers), u32, vp]
     L.gfb_read_report.restype = C.c_int

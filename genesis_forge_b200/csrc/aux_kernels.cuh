@@ -9,7 +9,8 @@ namespace gfb {
 // ---------------------------------------------------------------------------------------------
 // action_kernel: GenesisEnv.step bookkeeping + action manager (pre-physics)
 //   genesis_env.py:196       episode_length += 1
-//   genesis_env.py:202-203   last_actions <- actions ; actions <- raw
+//   genesis_env.py:202-203   last_actions <- actions ; actions <- raw   (ring mode: the caller has
+//                            exchanged the two buffers, only actions <- raw is left to do)
 //   position_action_manager.py:402-414   NaN/Inf flags; t = a*scale + offset; clamp(lo, hi)
 //   position_within_limits.py:125-126    clamp(a,-1,1) * scale + offset
 //   rewards.py:267-271       action_rate = sum((last_actions - actions)^2)   (consumed post-physics)
@@ -31,6 +32,7 @@ struct ActionParams {
   uint32_t* status;
   int32_t tma_ok;
   int32_t check_finite;
+  int32_t ring;  // gfb_action_step_ring: env_last_actions already holds the previous actions (read only)
 };
 
 template <int TILE>
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(TILE) action_kernel(const __grid_constant__ Ac
     if (tid < 32) {
       mbar_expect_tx(tid == 0, &bar, slab_bytes * (two_raw ? 3u : 2u));
       bulk_load(tid == 0, s_raw, A.raw_env + goff, slab_bytes, &bar);
-      bulk_load(tid == 0, s_prev, A.env_actions + goff, slab_bytes, &bar);
+      bulk_load(tid == 0, s_prev, (A.ring ? A.env_last_actions : A.env_actions) + goff, slab_bytes, &bar);
       bulk_load(tid == 0 && two_raw, s_rawm, A.raw_mgr + goff, slab_bytes, &bar);
       __syncwarp();
     }
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(TILE) action_kernel(const __grid_constant__ Ac
     const int words = valid * D;
     for (int w = tid; w < words; w += TILE) {
       s_raw[w] = A.raw_env[goff + w];
-      s_prev[w] = A.env_actions[goff + w];
+      s_prev[w] = (A.ring ? A.env_last_actions : A.env_actions)[goff + w];
       if (two_raw) s_rawm[w] = A.raw_mgr[goff + w];
     }
   }
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(TILE) action_kernel(const __grid_constant__ Ac
   // pure copies first: last_actions <- previous actions, actions <- raw
   if (use_tma) {
     if (tid < 32) {
-      bulk_store(tid == 0, A.env_last_actions + goff, s_prev, slab_bytes);
+      bulk_store(tid == 0 && !A.ring, A.env_last_actions + goff, s_prev, slab_bytes);
       bulk_store(tid == 0, A.env_actions + goff, s_raw, slab_bytes);
       bulk_commit();
       __syncwarp();
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(TILE) action_kernel(const __grid_constant__ Ac
   } else {
     const int words = valid * D;
     for (int w = tid; w < words; w += TILE) {
-      A.env_last_actions[goff + w] = s_prev[w];
+      if (!A.ring) A.env_last_actions[goff + w] = s_prev[w];
       A.env_actions[goff + w] = s_raw[w];
     }
   }

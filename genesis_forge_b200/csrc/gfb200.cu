@@ -849,7 +849,8 @@ int gfb_set_program(gfb_handle* h, const gfb_program* program) {
   return GFB_OK;
 }
 
-int gfb_action_step(gfb_handle* h, const gfb_buffers* b, const float* raw_env, const float* raw_mgr, void* stream_) {
+static int action_step_impl(gfb_handle* h, const gfb_buffers* b, const float* raw_env, const float* raw_mgr,
+                            void* stream_, int ring) {
   if (!h || !b || !raw_env) return GFB_ERR_INVALID;
   if (h->host_only) return fail(h, GFB_ERR_NO_DEVICE, "host-only handle cannot launch kernels");
   if (!h->has_prog) return fail(h, GFB_ERR_INVALID, "gfb_set_program() first");
@@ -873,6 +874,7 @@ int gfb_action_step(gfb_handle* h, const gfb_buffers* b, const float* raw_env, c
   ap.episode_length = static_cast<int32_t*>(b->buf[GFB_B_EPISODE_LENGTH]);
   ap.status = h->scratch.status;
   ap.check_finite = P.action_mode == 2 ? 0 : 1;  // position_within_limits.py:113-131 overrides the checks away
+  ap.ring = ring;
   if (!ap.env_actions || !ap.env_last_actions) return fail(h, GFB_ERR_INVALID, "env action buffers missing");
   if (P.action_mode != 0 && !ap.targets) return fail(h, GFB_ERR_INVALID, "GFB_B_TARGETS missing");
   const int tile = choose_tile(h);
@@ -896,6 +898,17 @@ int gfb_action_step(gfb_handle* h, const gfb_buffers* b, const float* raw_env, c
   if (e1) cudaEventRecord(e1, stream);
   h->launches += 1;
   return GFB_OK;
+}
+
+int gfb_action_step(gfb_handle* h, const gfb_buffers* b, const float* raw_env, const float* raw_mgr, void* stream) {
+  return action_step_impl(h, b, raw_env, raw_mgr, stream, 0);
+}
+
+int gfb_action_step_ring(gfb_handle* h, const gfb_buffers* b, const float* raw_env, const float* raw_mgr,
+                         void* stream) {
+  if (b && b->buf[GFB_B_ENV_ACTIONS] == b->buf[GFB_B_ENV_LAST_ACTIONS])
+    return h ? fail(h, GFB_ERR_INVALID, "gfb_action_step_ring: the two action buffers must differ") : GFB_ERR_INVALID;
+  return action_step_impl(h, b, raw_env, raw_mgr, stream, 1);
 }
 
 int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void* stream_) {

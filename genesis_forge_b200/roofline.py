@@ -95,6 +95,9 @@ def post_kernel_bytes(fused) -> int:
 
 
 def action_kernel_bytes(fused) -> int:
-    """Bytes the pre-physics kernel moves per env."""
+    """Bytes the pre-physics kernel moves per env.  env.actions / env.last_actions are a ring
+    (gfb_action_step_ring): the copy last_actions <- actions of the reference is a buffer exchange, so
+    the kernel writes 2*D words, not the 3*D the whole-step model (`step_bytes`, the reference's
+    semantics) counts."""
     D = fused.program.head.num_dofs
-    return 4 * (2 * D + 1 + 3 * D + 1 + 1)  # raw, prev, ep_len | last, actions, targets, ep_len, action_rate
+    return 4 * (2 * D + 1 + 2 * D + 1 + 1)  # raw, prev, ep_len | actions, targets, ep_len, action_rate

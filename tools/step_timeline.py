@@ -73,7 +73,9 @@ for i in range(20):
     env.step(acts[i % 4])
 torch.cuda.synchronize()
 T.clear()
-fused.profile(True)
+PROFILE = os.environ.get('GFB_TIMELINE_PROFILE', '0') == '1'  # (per-kernel events cost ~2 us of host time per launch)
+if PROFILE:
+    fused.profile(True)
 K = 100
 t0 = time.perf_counter()
 for i in range(K):
@@ -87,7 +89,8 @@ for k, v in T.items():
     if not k.startswith("    "):
         acc += v / K * 1e6
 print(f"  {'(other python in step)':40s} {total - acc:8.1f} us")
-prof = fused.profile_read(); aux = fused.profile_read_aux()
-print("  small kernels:", ", ".join(f"{k} {v['kernel_us']:.1f} us x{v['launches']}" for k, v in aux.items()))
-print(f"  kernels: action {prof['action_ms'] / max(prof['action_launches'], 1) * 1e3:.1f} us, post "
-      f"{prof['post_ms'] / max(prof['post_launches'], 1) * 1e3:.1f} us")
+if PROFILE:
+    prof = fused.profile_read(); aux = fused.profile_read_aux()
+    print("  small kernels:", ", ".join(f"{k} {v['kernel_us']:.1f} us x{v['launches']}" for k, v in aux.items()))
+    print(f"  kernels: action {prof['action_ms'] / max(prof['action_launches'], 1) * 1e3:.1f} us, post "
+          f"{prof['post_ms'] / max(prof['post_launches'], 1) * 1e3:.1f} us")
