@@ -73,8 +73,7 @@ __device__ __forceinline__ float4 add_noise(float4 v, const float4 nz, const flo
 }
 
 // Issue the TMA loads of one slab: staged arrays [a_begin, a_end) of the plan (the early, the late or
-// the prefetched group), `n_sum_rows` episode-sum rows (unused by the step: the sums are private slots
-// of their owner threads), optionally the descriptor table.  All complete
+// the prefetched group), `n_sum_rows` episode-sum rows, optionally the descriptor table.  All complete
 // on `bar` (one arrival with the expected byte count).  Called by ALL lanes of warp 0, convergent: lane
 // k describes transfer k (address arithmetic in parallel), the byte counts are summed across the warp
 // for the expect-tx, and each lane's transfer is issued under a predicate -- no per-lane branch around
@@ -102,13 +101,9 @@ __device__ __forceinline__ void issue_slab_loads(const KParams& K, const Plan& p
     bytes[sweep] = 0;
     if (op < n_arrays) {
       const int i = a_begin + op;
-      const int buf = plan.staged_buf[i];
-      // (command vectors have a slot in the slab but are not transferred: their owner threads load and
-      //  rewrite them, see "private slots" in post_kernel)
-      const bool is_cmd = buf >= GFB_B_COMMAND0 && buf < GFB_B_COMMAND0 + GFB_MAX_COMMANDS;
       dst[sweep] = S + plan.staged_off[i];
-      src[sweep] = reinterpret_cast<const float*>(K.b.buf[buf]) + (size_t)e0 * plan.staged_words[i];
-      bytes[sweep] = is_cmd ? 0u : (uint32_t)plan.staged_words[i] * valid * 4u;
+      src[sweep] = reinterpret_cast<const float*>(K.b.buf[plan.staged_buf[i]]) + (size_t)e0 * plan.staged_words[i];
+      bytes[sweep] = (uint32_t)plan.staged_words[i] * valid * 4u;
     } else if (op < n_arrays + n_sum_rows) {
       const int r = op - n_arrays;
       dst[sweep] = S + plan.sums_off + r * TILE;
@@ -166,9 +161,11 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   const int N = P.num_envs;
   const int D = SP.num_dofs;
   const bool stage_sums = (ph & (GFB_PHASE_REWARD | GFB_PHASE_RESET)) != 0 && SP.n_reward > 0;
+  const int n_sum_rows = stage_sums ? SP.n_reward : 0;
   const int n_tiles = K.s.n_tiles;
   // two load groups (plan.h): the late one follows the contact phase into the contact slots' memory
   const bool two_groups = plan.n_early < plan.n_staged || plan.sums_late != 0;
+  const int n_sum_rows_early = plan.sums_late ? 0 : n_sum_rows;
   float* const S = Sbase;
   float* const Tbl = Sbase + plan.cols_off;  // descriptor table, loaded once per block
   const Philox rng(P.rng_seed);
@@ -186,7 +183,8 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     if (warp == 0 && (int)blockIdx.x < n_tiles) {
       if (plan.n_prefetch > 0)
         issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[2], blockIdx.x, 0, plan.n_prefetch, 0, false, lane);
-      issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], blockIdx.x, plan.n_prefetch, plan.n_early, 0, true, lane);
+      issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], blockIdx.x, plan.n_prefetch, plan.n_early, n_sum_rows_early,
+                             true, lane);
     }
   } else {
     const int32_t* src = reinterpret_cast<const int32_t*>(K.cols);
@@ -227,31 +225,12 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
       float* dst = S + plan.staged_off[i];
       for (int w = tid; w < words; w += TILE) dst[w] = src[w];
     }
-  }
-  // Private slots: the command vector and the episode sums of an env are read and written by its owner
-  // thread only (the observation rows read the commands after the block barrier that ends the per-env
-  // phase).  Each thread loads its own slots with plain coalesced loads -- issued here, together with
-  // the per-env scalars, while the slab's transfers are in flight -- and stores the sums back itself,
-  // so neither array sits on an mbarrier.  With contact slots staged their memory is still occupied at
-  // this point: the loads then follow the contact phase (below).
-  auto load_private_slots = [&]() {
-    if (ph & (GFB_PHASE_REWARD | GFB_PHASE_COMMAND | GFB_PHASE_RESET | GFB_PHASE_OBSERVE)) {
-      GFB_UNROLL_TERMS
-      for (int k = 0; k < SP.n_command; ++k) {
-        const int nd = SP.command[k].n_dims;
-        if (nd == 0 || plan.off_cmd[k] < 0) continue;
-        const float* cg = GFB_BUF(const float, GFB_B_COMMAND0 + k) + (size_t)e * nd;
-        float* cs = S + plan.off_cmd[k] + tid * nd;
-        for (int i = 0; i < nd; ++i) cs[i] = cg[i];
-      }
-    }
-    if (stage_sums) {
+    if (stage_sums && !plan.sums_late) {
       const float* sums = GFB_BUF(const float, GFB_B_EP_SUMS);
-      GFB_UNROLL_TERMS
-      for (int r = 0; r < SP.n_reward; ++r) S[plan.sums_off + r * TILE + tid] = sums[(size_t)r * N + e];
+      for (int r = 0; r < SP.n_reward; ++r)
+        if (active) S[plan.sums_off + r * TILE + tid] = sums[(size_t)r * N + e];
     }
-  };
-  if (!two_groups) load_private_slots();
+  }
 
   // per-env scalars straight into registers while the slab is in flight
   int ep_len = GFB_BUF(const int32_t, GFB_B_EPISODE_LENGTH)[e];
@@ -292,13 +271,8 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
 
   // one warp polls the slab's mbarrier, the block barrier releases the rest
   if (use_tma && warp == 0) {
-    // The per-env phase reads quat / pos / vel / ang (the prefetched group, requested in the middle of
-    // the previous slab) and, if staged, the contact slots (bars[0]).  The arrays that only the
-    // observation rows read -- joint state, targets: bars[0] without contact slots, else the late group
-    // on bars[1] -- are awaited just before the rows are assembled: their latency hides behind the
-    // per-env phase instead of stalling the whole block here.
     if (plan.n_prefetch > 0) mbar_wait(&bars[2], (uint32_t)(it & 1));
-    if (two_groups || plan.n_prefetch == 0) mbar_wait(&bars[0], (uint32_t)(it & 1));
+    mbar_wait(&bars[0], (uint32_t)(it & 1));
   }
   __syncthreads();
 
@@ -523,7 +497,8 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     if (use_tma) {
       if (warp == 0) {
         fence_async_smem();  // generic-proxy reads above, async-proxy writes below
-        issue_slab_loads<TILE>(K, plan, S, Tbl, &bars[1], tile, plan.n_early, plan.n_staged, 0, false, lane);
+        issue_slab_loads<TILE>(K, plan, S, Tbl, &bars[1], tile, plan.n_early, plan.n_staged,
+                               plan.sums_late ? n_sum_rows : 0, false, lane);
       }
     } else {
       for (int i = plan.n_early; i < plan.n_staged; ++i) {
@@ -533,8 +508,12 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
         float* dst = S + plan.staged_off[i];
         for (int w = tid; w < words; w += TILE) dst[w] = src[w];
       }
+      if (stage_sums && plan.sums_late) {
+        const float* sums = GFB_BUF(const float, GFB_B_EP_SUMS);
+        for (int r = 0; r < SP.n_reward; ++r)
+          if (active) S[plan.sums_off + r * TILE + tid] = sums[(size_t)r * N + e];
+      }
     }
-    load_private_slots();  // (their slots lie in the memory the contact slots occupied)
   }
 
   // ------------------------------------------------------------------------------------------
@@ -639,6 +618,11 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     }
   }
 
+  if (two_groups) {  // the late group has landed
+    if (use_tma && warp == 0) mbar_wait(&bars[1], (uint32_t)(it & 1));
+    __syncthreads();
+  }
+
   // ------------------------------------------------------------------------------------------
   // rewards
   // ------------------------------------------------------------------------------------------
@@ -677,9 +661,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
         case GFB_R_DOF_SIMILAR:
         case GFB_R_STAND_STILL: {
           if (!have_dof_dev) {
-            // (own row straight from global memory -- an L2 hit, the slab transfer of the same rows is
-            //  in flight or done: the staged copy is only awaited for the observation rows)
-            const float* q = GFB_BUF(const float, GFB_B_DOF_POS) + (size_t)e * D;
+            const float* q = S + plan.off_dof_pos + tid * D;
             if ((D & 3) == 0) {
               for (int d4 = 0; d4 < D; d4 += 4) {
                 const float4 qv = *reinterpret_cast<const float4*>(q + d4);
@@ -914,16 +896,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
       }
     }
   }
-  if (stage_sums && active) {
-    float* sums = GFB_BUF(float, GFB_B_EP_SUMS);
-    GFB_UNROLL_TERMS
-    for (int r = 0; r < SP.n_reward; ++r) sums[(size_t)r * N + e] = S[plan.sums_off + r * TILE + tid];
-  }
-  if (use_tma) {
-    fence_async_smem();
-    // the arrays only the observation rows read have had the whole per-env phase to land
-    if (warp == 0) mbar_wait(two_groups ? &bars[1] : &bars[0], (uint32_t)(it & 1));
-  }
+  if (use_tma) fence_async_smem();
   __syncthreads();
   // the per-env phase is over: quat / pos / vel / ang of this slab are dead -- warp 0 refills them with
   // the next slab's rows, which land while the observation rows below are assembled
@@ -937,6 +910,25 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     if (use_tma && next_tile < n_tiles && plan.n_prefetch > 0) {
       bulk_wait_all_read();  // the entity-cache stores have read the pos / quat slabs
       issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[2], next_tile, 0, plan.n_prefetch, 0, false, lane);
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // slab outputs: episode sums
+  // ------------------------------------------------------------------------------------------
+  if (use_tma) {
+    if (warp == 0 && n_sum_rows > 0) {  // lane i stores row i (GFB_MAX_REWARD_TERMS <= 32)
+      const bool mine = lane < n_sum_rows;
+      const int i = mine ? lane : 0;
+      bulk_store(mine, GFB_BUF(float, GFB_B_EP_SUMS) + (size_t)i * N + e0, S + plan.sums_off + i * TILE,
+                 (uint32_t)valid * 4u);
+      bulk_commit();
+      __syncwarp();
+    }
+  } else {
+    if (stage_sums && active) {
+      float* sums = GFB_BUF(float, GFB_B_EP_SUMS);
+      for (int r = 0; r < SP.n_reward; ++r) sums[(size_t)r * N + e] = S[plan.sums_off + r * TILE + tid];
     }
   }
 
@@ -1076,7 +1068,8 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   if (use_tma && next_tile < n_tiles && warp == 0) {
     bulk_wait_all_read();
     fence_async_smem();  // the slab's generic-proxy reads above, the async-proxy refill below
-    issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], next_tile, plan.n_prefetch, plan.n_early, 0, false, lane);
+    issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], next_tile, plan.n_prefetch, plan.n_early, n_sum_rows_early,
+                           false, lane);
   }
 
   tile = next_tile;

@@ -2,7 +2,7 @@
 # (under gpurun) GPU tests + the experiment list of the main configs; args: <tag>
 TAG=${1:-r2x}
 mkdir -p gpurun_out
-(timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | grep -vE "UserWarning|torch.tensor\(|^  warnings" | tail -12 | cut -c1-250) | tee gpurun_out/${TAG}_tests.log
+[ -n "$SKIP_TESTS" ] || (timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | grep -vE "UserWarning|torch.tensor\(|^  warnings" | tail -12 | cut -c1-250) | tee gpurun_out/${TAG}_tests.log
 one() {  # label, env..., -- bench args
   label=$1; shift
   envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
