@@ -57,16 +57,9 @@ if rep.exists():
                 return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
 
             traffic = _bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum")
-            grid = int(r[hdr.index("launch__grid_size")].replace(",", ""))
-            block = int(r[hdr.index("launch__block_size")].replace(",", ""))
-            tpath = ROOT / "profiles" / "traffic.json"
-            table = json.loads(tpath.read_text()) if tpath.exists() else {}
-            key = sys.argv[3] if len(sys.argv) > 3 else "command_direction"
-            table[f"{key}:{grid * block}"] = {
-                "dram_bytes": traffic, "kernel": r[hdr.index("Kernel Name")][:60], "capture": f"{out_name} (post_{tag}.ncu-rep)",
-            }
-            tpath.write_text(json.dumps(table, indent=1, sort_keys=True) + "\n")
-            out.append(f"  DRAM traffic of the launch (read + write): {traffic / 1e6:.1f} MB -> profiles/traffic.json[{key}:{grid * block}]")
+            # (profiles/traffic.json itself is written by tools/measure_traffic.py, stamped with the hash of
+            #  the kernel sources; this summary only states the figure of this capture)
+            out.append(f"  DRAM traffic of the launch (read + write): {traffic / 1e6:.1f} MB")
         except (ValueError, KeyError) as e:
             out.append(f"  (traffic not recorded: {e})")
     cs = subprocess.run(["ncu", "-i", str(rep), "--page", "source", "--csv", "--print-source", "cuda,sass"],
