@@ -282,7 +282,7 @@ __device__ __forceinline__ ObsItem obs_item(const ObserveParams& K, int item, in
   return it;
 }
 
-__global__ void __launch_bounds__(OBS_WARPS * 32, 5) observe_kernel(const __grid_constant__ ObserveParams K) {
+__global__ void __launch_bounds__(OBS_WARPS * 32, 7) observe_kernel(const __grid_constant__ ObserveParams K) {
   const ObserveHead& P = K.P;
   const Plan& plan = K.plan;
   const int lane = threadIdx.x & 31;
