@@ -877,11 +877,17 @@ static int action_step_impl(gfb_handle* h, const gfb_buffers* b, const float* ra
   ap.ring = ring;
   if (!ap.env_actions || !ap.env_last_actions) return fail(h, GFB_ERR_INVALID, "env action buffers missing");
   if (P.action_mode != 0 && !ap.targets) return fail(h, GFB_ERR_INVALID, "GFB_B_TARGETS missing");
-  const int tile = choose_tile(h);
+  int tile = choose_tile(h);
+  if (const char* at = getenv("GFB_ACTION_TILE")) {  // experiments: slab size of the action kernel alone
+    const int t = atoi(at);
+    if (t == 32 || t == 64 || t == 128 || t == 256) tile = t;
+  }
   const int D = P.num_dofs;
   ap.tma_ok = !h->disable_tma && ((tile * D) % 4 == 0) && aligned16(raw_env) && aligned16(raw_mgr) &&
               aligned16(ap.env_actions) && aligned16(ap.env_last_actions) && (!ap.targets || aligned16(ap.targets));
-  const size_t smem = (size_t)tile * D * 4 * 4;
+  // raw, previous, targets (+ the delayed raw slab only with a delay FIFO): fewer bytes per block = more
+  // blocks -- and more bytes in flight -- per SM
+  const size_t smem = (size_t)tile * D * 4 * (raw_mgr != raw_env ? 4 : 3);
   const int grid = (P.num_envs + tile - 1) / tile;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->profiling && h->n_action + 2 <= (int)h->ev_action.size()) {
