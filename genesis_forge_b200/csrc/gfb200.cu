@@ -107,7 +107,6 @@ struct gfb_handle {
   bool disable_tma = false;
   bool disable_overlay = false;  // GFB_NO_OVERLAY=1: load every staged array up front
   int force_tile = 0;
-  int force_stages = 0;
   uint32_t debug = 0;
   int num_sms = 0;
   int64_t launches = 0;
@@ -589,9 +588,9 @@ int choose_tile(const gfb_handle* h) {
   return h->num_envs >= 32768 ? 128 : 32;
 }
 
-// Slab size / ring depth for a launch: shrink the slab until it fits comfortably.
-// (GFB_STAGES=2 selects the persistent two-stage ring; measured slower on B200 because only 3
-//  blocks fit per SM and the per-env arithmetic becomes latency-bound -- see DESIGN.md)
+// Slab size for a launch: shrink the slab until it fits comfortably.  (n_stages stays 1: the two-stage
+// ring of round 1 was measured slower on B200 -- only 3 blocks fit per SM -- and has been removed from
+// the kernel; the plan keeps the field for the layout arithmetic.)
 int plan_for_launch(gfb_handle* h, const gfb_buffers& b, uint32_t phases, Plan& plan, std::vector<int32_t>& table,
                     int& tile, int& n_stages) {
   tile = choose_tile(h);
@@ -717,8 +716,6 @@ int gfb_create(int32_t num_envs, int32_t device, gfb_handle** out) {
     hh->force_tile = env_t ? atoi(env_t) : 0;
     const char* env_o = getenv("GFB_NO_OVERLAY");
     hh->disable_overlay = env_o && env_o[0] == '1';
-    const char* env_s = getenv("GFB_STAGES");
-    hh->force_stages = env_s ? atoi(env_s) : 0;
     *out = hh;
     return GFB_OK;
   }
@@ -752,8 +749,6 @@ int gfb_create(int32_t num_envs, int32_t device, gfb_handle** out) {
   h->disable_overlay = env && env[0] == '1';
   env = getenv("GFB_TILE");
   h->force_tile = env ? atoi(env) : 0;
-  env = getenv("GFB_STAGES");
-  h->force_stages = env ? atoi(env) : 0;
   env = getenv("GFB_DEBUG");
   h->debug = env ? (uint32_t)atoi(env) : 0u;
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);

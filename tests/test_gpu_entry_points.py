@@ -167,3 +167,45 @@ def test_persistent_loop_with_short_slabs(tile, num_envs):
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "loop_stress.py"), str(num_envs), "20"],
                          capture_output=True, text=True, env=env, timeout=600, cwd=root)
     assert out.returncode == 0 and "ok, copies equal: True" in out.stdout, out.stdout[-400:] + out.stderr[-400:]
+
+
+@pytest.mark.parametrize("num_envs", [300, 4096 + 4, 333])
+def test_action_step_ring_equals_the_copying_entry_point(num_envs, cuda_device):
+    """gfb_action_step_ring (the caller exchanges its two action buffers, nothing is copied into
+    last_actions) leaves the same values in env.actions / env.last_actions / targets / action-rate /
+    episode_length as gfb_action_step (genesis_env.py:195-203 with the copy), TMA and fallback paths."""
+    import genesis_forge_b200 as gfb
+    from configs import specs
+    from configs.env_builder import build_env, dropin_namespace
+
+    dev = cuda_device
+    gfb.set_device(dev)
+    env = build_env(specs.get("command_direction"), dropin_namespace(), num_envs, dev, pool=2, seed=7)
+    env.build()
+    env.reset()
+    fused, action = env._fused, env.managers["action"]
+    g = torch.Generator().manual_seed(3)
+    for _ in range(2):  # fill both buffers of the ring with history
+        env.step(torch.randn(num_envs, fused.D, generator=g).to(dev))
+    a0, l0, ep0 = env.actions.clone(), env.last_actions.clone(), env.episode_length.clone()
+    raw = torch.randn(num_envs, fused.D, generator=g).to(dev)
+
+    fused.action_step(raw)  # ring: exchanges env._actions / env._last_actions, then launches
+    torch.cuda.synchronize(dev)
+    ring = [t.clone() for t in (env.actions, env.last_actions, action._actions, fused.action_rate, env.episode_length)]
+    assert torch.equal(ring[0], raw) and torch.equal(ring[1], a0)
+    assert torch.equal(ring[4], ep0 + 1)
+
+    # the same inputs through the copying entry point
+    env._actions.copy_(a0)
+    env._last_actions.copy_(l0)
+    env.episode_length.copy_(ep0)
+    action._actions.fill_(float("nan"))
+    fused.action_rate.fill_(float("nan"))
+    fused.bind_action_buffers()
+    rc = fused.lib.gfb_action_step(fused._h, fused._buffers_ref, raw.data_ptr(), raw.data_ptr(), fused._stream())
+    assert rc == 0
+    torch.cuda.synchronize(dev)
+    copy = (env.actions, env.last_actions, action._actions, fused.action_rate, env.episode_length)
+    for r, c, what in zip(ring, copy, ("actions", "last_actions", "targets", "action_rate", "episode_length")):
+        assert torch.equal(r, c), what
