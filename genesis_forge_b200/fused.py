@@ -975,8 +975,8 @@ class FusedStep:
         """
         The post-physics launch.  Everything up to the launch call runs in the shadow of the action
         kernel (which the GPU is still executing); the host then prepares the next step's logging
-        storage while the kernel runs and finally spins on the report, which the kernel delivers as
-        soon as the last slab's terminations are final -- before it has finished (include/gfb200.h).
+        storage while the kernel runs and finally spins on the report, which the kernel's last block
+        writes into mapped host memory (include/gfb200.h).
         """
         self._engine_buffers()
         self._obs_buffers()

@@ -307,11 +307,14 @@ typedef struct {
 #define GFB_MAX_PEERS 16           /* ranks of one NVLink domain sharing the logging exchange   */
 #define GFB_IPC_HANDLE_BYTES 64    /* sizeof(cudaIpcMemHandle_t)                                */
 
-/* The step report.  It is written by the post-physics kernel itself, straight into host memory, as
- * soon as the LAST slab has evaluated its terminations -- i.e. while the final wave of slabs is still
- * computing rewards and observation rows -- so the host's reset fan-out overlaps the kernel's tail.
- * Everything the host needs to continue is in it; the logged episode means of the reward terms are
- * device values (GFB_B_LOG_OUT, complete when the launch has finished in stream order).          */
+/* The step report.  It is written by the post-physics kernel itself -- by its last block to leave,
+ * once the launch-wide accumulators are final -- straight into mapped pinned host memory: every field,
+ * then (behind a system-scope fence) `seq`, the word gfb_read_report() spins on.  No copy is enqueued
+ * and the host does not wait for the stream.  Everything the host needs to continue is in it; the
+ * logged episode means of the reward terms are device values (GFB_B_LOG_OUT, complete when the
+ * launch has finished in stream order).  (A two-stage variant that delivered the reset count as soon
+ * as the last slab had evaluated its terminations was measured in round 2 and not kept:
+ * profiles/r2_02_post_kernel_experiments.txt.)                                                  */
 typedef struct {
   int32_t n_reset;   /* number of valid entries in GFB_B_RESET_IDX */
   uint32_t status;   /* GFB_STATUS_* seen since the last report    */
