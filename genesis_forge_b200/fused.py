@@ -893,7 +893,8 @@ class FusedStep:
         # exchange of the two buffers instead of a copy: 4*D bytes per env less traffic per step)
         env = self.env
         env._actions, env._last_actions = env._last_actions, env._actions
-        self.bind_action_buffers()
+        buf, ia, il = self.buffers.buf, self._B["GFB_B_ENV_ACTIONS"], self._B["GFB_B_ENV_LAST_ACTIONS"]
+        buf[ia], buf[il] = buf[il], buf[ia]  # (both tensors were validated when they were first bound)
         rc = self.lib.gfb_action_step_ring(self._h, self._buffers_ref, actions.data_ptr(), raw_mgr.data_ptr(), self._stream())
         if rc:
             self.handle.check(rc, "gfb_action_step_ring")
