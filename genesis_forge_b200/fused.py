@@ -896,7 +896,9 @@ class FusedStep:
         buf, ia, il = self.buffers.buf, self._B["GFB_B_ENV_ACTIONS"], self._B["GFB_B_ENV_LAST_ACTIONS"]
         buf[ia], buf[il] = buf[il], buf[ia]  # (both tensors were validated when they were first bound)
         rc = self.lib.gfb_action_step_ring(self._h, self._buffers_ref, actions.data_ptr(), raw_mgr.data_ptr(), self._stream())
-        if rc:
+        if rc:  # nothing was launched: undo the exchange before raising
+            env._actions, env._last_actions = env._last_actions, env._actions
+            buf[ia], buf[il] = buf[il], buf[ia]
             self.handle.check(rc, "gfb_action_step_ring")
         if action is not None and enabled:  # position_action_manager.py:383-384: a disabled manager sends nothing
             self.env.robot.control_dofs_position(action._actions, action.dofs_idx)
