@@ -81,7 +81,7 @@ __device__ __forceinline__ float4 add_noise(float4 v, const float4 nz, const flo
 template <int TILE>
 __device__ __forceinline__ void issue_slab_loads(const KParams& K, const Plan& plan, float* S, float* table_dst,
                                                  uint64_t* bar, int tile, int a_begin, int a_end, int n_sum_rows,
-                                                 bool with_table, int lane) {
+                                                 bool with_table, int lane, bool skip_cmd = false) {
   const int N = K.P.num_envs;
   const int e0 = tile * TILE;
   const uint32_t valid = (uint32_t)min(TILE, N - e0);
@@ -101,9 +101,13 @@ __device__ __forceinline__ void issue_slab_loads(const KParams& K, const Plan& p
     bytes[sweep] = 0;
     if (op < n_arrays) {
       const int i = a_begin + op;
+      const int buf = plan.staged_buf[i];
+      // (skip_cmd: the command vectors keep their slot in the slab but are loaded and rewritten by their
+      //  owner threads -- "split groups" in post_kernel)
+      const bool skip = skip_cmd && buf >= GFB_B_COMMAND0 && buf < GFB_B_COMMAND0 + GFB_MAX_COMMANDS;
       dst[sweep] = S + plan.staged_off[i];
-      src[sweep] = reinterpret_cast<const float*>(K.b.buf[plan.staged_buf[i]]) + (size_t)e0 * plan.staged_words[i];
-      bytes[sweep] = (uint32_t)plan.staged_words[i] * valid * 4u;
+      src[sweep] = reinterpret_cast<const float*>(K.b.buf[buf]) + (size_t)e0 * plan.staged_words[i];
+      bytes[sweep] = skip ? 0u : (uint32_t)plan.staged_words[i] * valid * 4u;
     } else if (op < n_arrays + n_sum_rows) {
       const int r = op - n_arrays;
       dst[sweep] = S + plan.sums_off + r * TILE;
@@ -166,6 +170,16 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   // two load groups (plan.h): the late one follows the contact phase into the contact slots' memory
   const bool two_groups = plan.n_early < plan.n_staged || plan.sums_late != 0;
   const int n_sum_rows_early = plan.sums_late ? 0 : n_sum_rows;
+  // Split groups (no contact slots staged): what the per-env phase reads -- quat / pos / vel / ang and the
+  // episode-sum rows -- is the PREFETCHED group (requested in the middle of the previous slab, bars[2]);
+  // what only the observation rows read -- joint state, targets (bars[0], requested when the previous
+  // slab was finished) -- is awaited just before the rows are assembled, so its latency hides behind the
+  // per-env phase.  The command vectors (read by both) are loaded by their owner threads into registers
+  // at the top of the slab and written to their slots before the rewards; the rewards read their own
+  // joint positions from global memory.
+  const bool split_x = !two_groups && plan.n_prefetch > 0;
+  const int n_sum_rows_pf = split_x ? n_sum_rows : 0;
+  const int n_sum_rows_main = split_x ? 0 : n_sum_rows_early;
   float* const S = Sbase;
   float* const Tbl = Sbase + plan.cols_off;  // descriptor table, loaded once per block
   const Philox rng(P.rng_seed);
@@ -182,9 +196,9 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   if (use_tma) {
     if (warp == 0 && (int)blockIdx.x < n_tiles) {
       if (plan.n_prefetch > 0)
-        issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[2], blockIdx.x, 0, plan.n_prefetch, 0, false, lane);
-      issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], blockIdx.x, plan.n_prefetch, plan.n_early, n_sum_rows_early,
-                             true, lane);
+        issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[2], blockIdx.x, 0, plan.n_prefetch, n_sum_rows_pf, false, lane);
+      issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], blockIdx.x, plan.n_prefetch, plan.n_early, n_sum_rows_main,
+                             true, lane, split_x);
     }
   } else {
     const int32_t* src = reinterpret_cast<const int32_t*>(K.cols);
@@ -269,10 +283,24 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   }
 #endif
 
+#ifdef GFB_SPEC
+  float cmd_r[GFB_MAX_COMMANDS][GFB_MAX_COMMAND_DIMS];  // split groups: own command vectors, requested here
+  if (split_x && (ph & (GFB_PHASE_REWARD | GFB_PHASE_COMMAND | GFB_PHASE_RESET | GFB_PHASE_OBSERVE))) {
+    GFB_UNROLL_TERMS
+    for (int k = 0; k < SP.n_command; ++k) {
+      const int nd = SP.command[k].n_dims;
+      if (nd == 0 || plan.off_cmd[k] < 0) continue;
+      const float* cg = GFB_BUF(const float, GFB_B_COMMAND0 + k) + (size_t)e * nd;
+      GFB_UNROLL_TERMS
+      for (int i = 0; i < nd; ++i) cmd_r[k][i] = cg[i];
+    }
+  }
+#endif
+
   // one warp polls the slab's mbarrier, the block barrier releases the rest
   if (use_tma && warp == 0) {
     if (plan.n_prefetch > 0) mbar_wait(&bars[2], (uint32_t)(it & 1));
-    mbar_wait(&bars[0], (uint32_t)(it & 1));
+    if (!split_x) mbar_wait(&bars[0], (uint32_t)(it & 1));
   }
   __syncthreads();
 
@@ -623,6 +651,23 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
     __syncthreads();
   }
 
+  // split groups: the owner threads' command vectors -> their slots (the transfer group skips them)
+  if (split_x && (ph & (GFB_PHASE_REWARD | GFB_PHASE_COMMAND | GFB_PHASE_RESET | GFB_PHASE_OBSERVE))) {
+    GFB_UNROLL_TERMS
+    for (int k = 0; k < SP.n_command; ++k) {
+      const int nd = SP.command[k].n_dims;
+      if (nd == 0 || plan.off_cmd[k] < 0) continue;
+      float* cs = S + plan.off_cmd[k] + tid * nd;
+#ifdef GFB_SPEC
+      GFB_UNROLL_TERMS
+      for (int i = 0; i < nd; ++i) cs[i] = cmd_r[k][i];
+#else
+      const float* cg = GFB_BUF(const float, GFB_B_COMMAND0 + k) + (size_t)e * nd;
+      for (int i = 0; i < nd; ++i) cs[i] = cg[i];
+#endif
+    }
+  }
+
   // ------------------------------------------------------------------------------------------
   // rewards
   // ------------------------------------------------------------------------------------------
@@ -661,7 +706,10 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
         case GFB_R_DOF_SIMILAR:
         case GFB_R_STAND_STILL: {
           if (!have_dof_dev) {
-            const float* q = S + plan.off_dof_pos + tid * D;
+            // (split groups: own row from global memory -- an L2 hit, the slab transfer of the same rows
+            //  is in flight or done; the staged copy is only awaited for the observation rows)
+            const float* q = split_x ? GFB_BUF(const float, GFB_B_DOF_POS) + (size_t)e * D
+                                     : S + plan.off_dof_pos + tid * D;
             if ((D & 3) == 0) {
               for (int d4 = 0; d4 < D; d4 += 4) {
                 const float4 qv = *reinterpret_cast<const float4*>(q + d4);
@@ -896,8 +944,21 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
       }
     }
   }
-  if (use_tma) fence_async_smem();
+  if (use_tma) {
+    fence_async_smem();
+    // split groups: the arrays only the observation rows read have had the whole per-env phase to land
+    if (split_x && warp == 0) mbar_wait(&bars[0], (uint32_t)(it & 1));
+  }
   __syncthreads();
+  // split groups: the episode sums leave first -- their rows are refilled by the prefetch below
+  if (use_tma && split_x && warp == 0 && n_sum_rows > 0) {
+    const bool mine = lane < n_sum_rows;
+    const int i = mine ? lane : 0;
+    bulk_store(mine, GFB_BUF(float, GFB_B_EP_SUMS) + (size_t)i * N + e0, S + plan.sums_off + i * TILE,
+               (uint32_t)valid * 4u);
+    bulk_commit();
+    __syncwarp();
+  }
   // the per-env phase is over: quat / pos / vel / ang of this slab are dead -- warp 0 refills them with
   // the next slab's rows, which land while the observation rows below are assembled
   int next_tile = 0;
@@ -908,8 +969,8 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
       ticket = atomicAdd(K.s.counters + CTR_TICKET, 1u);  // (names the slab after the next one)
     }
     if (use_tma && next_tile < n_tiles && plan.n_prefetch > 0) {
-      bulk_wait_all_read();  // the entity-cache stores have read the pos / quat slabs
-      issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[2], next_tile, 0, plan.n_prefetch, 0, false, lane);
+      bulk_wait_all_read();  // the entity-cache (and episode-sum) stores have read their slabs
+      issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[2], next_tile, 0, plan.n_prefetch, n_sum_rows_pf, false, lane);
     }
   }
 
@@ -917,7 +978,7 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   // slab outputs: episode sums
   // ------------------------------------------------------------------------------------------
   if (use_tma) {
-    if (warp == 0 && n_sum_rows > 0) {  // lane i stores row i (GFB_MAX_REWARD_TERMS <= 32)
+    if (!split_x && warp == 0 && n_sum_rows > 0) {  // lane i stores row i (GFB_MAX_REWARD_TERMS <= 32)
       const bool mine = lane < n_sum_rows;
       const int i = mine ? lane : 0;
       bulk_store(mine, GFB_BUF(float, GFB_B_EP_SUMS) + (size_t)i * N + e0, S + plan.sums_off + i * TILE,
@@ -1068,8 +1129,8 @@ __global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_con
   if (use_tma && next_tile < n_tiles && warp == 0) {
     bulk_wait_all_read();
     fence_async_smem();  // the slab's generic-proxy reads above, the async-proxy refill below
-    issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], next_tile, plan.n_prefetch, plan.n_early, n_sum_rows_early,
-                           false, lane);
+    issue_slab_loads<TILE>(K, plan, Sbase, Tbl, &bars[0], next_tile, plan.n_prefetch, plan.n_early, n_sum_rows_main,
+                           false, lane, split_x);
   }
 
   tile = next_tile;
