@@ -131,8 +131,16 @@ __device__ __forceinline__ void issue_slab_loads(const KParams& K, const Plan& p
   __syncwarp();
 }
 
+// Blocks per SM promised to the register allocator: the generic build assumes 768 threads per SM; a
+// specialised build knows its slab's shared memory and promises only what that admits (spec.py)
+#ifdef GFB_SPEC
+#define GFB_MIN_BLOCKS(TILE_) (gfb_spec::MIN_BLOCKS)
+#else
+#define GFB_MIN_BLOCKS(TILE_) (768 / (TILE_))
+#endif
+
 template <int TILE>
-__global__ void __launch_bounds__(TILE, 768 / TILE) post_kernel(const __grid_constant__ KParams K) {
+__global__ void __launch_bounds__(TILE, GFB_MIN_BLOCKS(TILE)) post_kernel(const __grid_constant__ KParams K) {
   extern __shared__ __align__(128) float Sbase[];
   __shared__ __align__(8) uint64_t bars[3];  // [0] slab loads, [1] late load group, [2] prefetched arrays
   __shared__ int32_t s_term_count[GFB_MAX_TERMINATION_TERMS];
