@@ -152,7 +152,7 @@ class Report(C.Structure):
         ("n_reset", C.c_int32), ("status", C.c_uint32),
         ("termination_count", C.c_int32 * MAX_TERMINATION),
         ("global_n_reset", C.c_int64), ("global_termination_count", C.c_int64 * MAX_TERMINATION),
-        ("seq", C.c_uint64),
+        ("seq", C.c_uint64), ("local_seq", C.c_uint64),
     ]
 
 
@@ -163,7 +163,7 @@ _LIB = None
 
 EXPORTS = [
     "gfb_abi_version", "gfb_abi_sizeof", "gfb_create", "gfb_destroy", "gfb_last_error", "gfb_set_program",
-    "gfb_action_step", "gfb_action_step_ring", "gfb_post_physics", "gfb_read_report", "gfb_observe", "gfb_contact_forces",
+    "gfb_action_step", "gfb_action_step_ring", "gfb_post_physics", "gfb_read_report", "gfb_read_report_local", "gfb_observe", "gfb_contact_forces",
     "gfb_rotate", "gfb_spawn_pose", "gfb_peer_export", "gfb_peer_connect", "gfb_peer_disconnect", "gfb_spec_describe", "gfb_spec_attach", "gfb_spec_stats",
     "gfb_profile_enable", "gfb_profile_read", "gfb_profile_read_aux", "gfb_launch_count",
     "gfb_post_physics_report", "gfb_reset_rows",
@@ -210,6 +210,8 @@ def lib() -> C.CDLL:
     L.gfb_post_physics.argtypes = [vp, C.POINTER(Buffers), u32, vp]
     L.gfb_read_report.restype = C.c_int
     L.gfb_read_report.argtypes = [vp, C.POINTER(Report), vp]
+    L.gfb_read_report_local.restype = C.c_int
+    L.gfb_read_report_local.argtypes = [vp, C.POINTER(C.c_int32), vp]
     L.gfb_observe.restype = C.c_int
     L.gfb_observe.argtypes = [vp, C.POINTER(Buffers), vp, i32, vp]
     L.gfb_contact_forces.restype = C.c_int

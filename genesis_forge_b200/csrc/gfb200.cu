@@ -1130,6 +1130,31 @@ int gfb_read_report(gfb_handle* h, gfb_report* out, void* stream_) {
   return GFB_OK;
 }
 
+int gfb_read_report_local(gfb_handle* h, int32_t* n_reset, void* stream_) {
+  if (!h || !n_reset) return GFB_ERR_INVALID;
+  if (h->host_only) return fail(h, GFB_ERR_NO_DEVICE, "host-only handle has no report");
+  if (h->report_seq == 0) return fail(h, GFB_ERR_INVALID, "no launch with GFB_PHASE_RESET has been issued yet");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  volatile uint64_t* seq = &h->report_host->local_seq;
+  const uint64_t want = h->report_seq;
+  for (uint64_t spins = 1; *seq != want; ++spins) {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+    if ((spins & 0x3fff) == 0) {  // has the stream died or drained without a report?
+      const cudaError_t q = cudaStreamQuery(stream);
+      if (q == cudaSuccess) {
+        if (*seq == want) break;
+        return fail(h, GFB_ERR_CUDA, "the post-physics launch finished without delivering its report");
+      }
+      if (q != cudaErrorNotReady) return fail(h, GFB_ERR_CUDA, std::string("waiting for the report: ") + cudaGetErrorString(q));
+    }
+  }
+  __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  *n_reset = h->report_host->n_reset;
+  return GFB_OK;
+}
+
 int gfb_post_physics_report(gfb_handle* h, const gfb_buffers* b, uint32_t phases, gfb_report* out, void* stream) {
   if (!(phases & GFB_PHASE_RESET)) return fail(h, GFB_ERR_INVALID, "gfb_post_physics_report needs GFB_PHASE_RESET");
   const int rc = gfb_post_physics(h, b, phases, stream);

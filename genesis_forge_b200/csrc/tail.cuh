@@ -154,15 +154,28 @@ __device__ __forceinline__ void finalize_step(const KParams& K, int lane) {
     if (lane < n_r) log_acc[lane] = sum;
     if (lane <= n_t) log_acc[n_r + lane] = counts;
   }
+  // first stage of the report: the rank's own counts -- all the host needs to start its reset fan-out --
+  // before the exchange below waits for the slowest peer
+  gfb_report* rep = sc.report_host;
+  if (lane < n_t) rep->termination_count[lane] = count;
+  if (lane == 0) {
+    rep->n_reset = n_reset;
+    rep->status = status;
+  }
+  const bool staged = K.peer.world > 1 && log_acc;  // single rank: both stages are released together below
+  if (staged) {
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) st_release_sys(reinterpret_cast<unsigned long long*>(&rep->local_seq), sc.report_seq);
+  }
+
   long long denom = P.num_envs;
   if (K.peer.world > 1 && log_acc) {
     if (peer_exchange(K.peer, counts, n_t + 1, sum, n_r, lane)) denom = K.peer.global_num_envs;
     else if (lane == 0) status |= GFB_STATUS_PEER_TIMEOUT;
   }
   const double g_reset = __shfl_sync(0xffffffffu, counts, n_t);
-  gfb_report* rep = sc.report_host;
   if (lane < n_t) {
-    rep->termination_count[lane] = count;
     rep->global_termination_count[lane] = (long long)counts;
     if (log_out) log_out[n_r + lane] = fdiv((float)counts, (float)denom);
   }
@@ -171,13 +184,13 @@ __device__ __forceinline__ void finalize_step(const KParams& K, int lane) {
     log_out[lane] = (g_reset > 0.0 && logged) ? (float)(sum / g_reset) : 0.0f;
   }
   if (lane == n_t) rep->global_n_reset = (long long)counts;
-  if (lane == 0) {
-    rep->n_reset = n_reset;
-    rep->status = status;
-  }
+  if (lane == 0) rep->status = status;  // (again: the exchange may have added GFB_STATUS_PEER_TIMEOUT)
   __threadfence_system();
   __syncwarp();
-  if (lane == 0) st_release_sys(reinterpret_cast<unsigned long long*>(&rep->seq), sc.report_seq);
+  if (lane == 0) {
+    if (!staged) st_release_sys(reinterpret_cast<unsigned long long*>(&rep->local_seq), sc.report_seq);
+    st_release_sys(reinterpret_cast<unsigned long long*>(&rep->seq), sc.report_seq);
+  }
 }
 
 }  // namespace gfb

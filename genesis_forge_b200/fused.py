@@ -155,6 +155,8 @@ class FusedStep:
         self.step_phases = K["GFB_PHASE_ALL"]  # minus the phases of disabled managers (pack)
         self._buffers_ref = C.byref(self.buffers)
         self._report_ref = C.byref(self.report)
+        self._local_n = C.c_int32(0)
+        self._local_n_ref = C.byref(self._local_n)
         self._h = self.handle.ptr
         self._engine_cache: dict = {}  # buffer id -> (tensor, data_ptr) of the last bound engine tensor
         self._action_enabled_packed = True
@@ -973,6 +975,29 @@ class FusedStep:
         for om, name, item, col0, width in self.external_obs:
             value = item.fn(env=self.env, **item.params)
             self.ext_obs[:, col0:col0 + width].copy_(value.reshape(self.N, width))
+
+    def post_physics_local(self, phases: int) -> int:
+        """
+        The post-physics launch of the one-launch step; returns the rank's number of reset envs as soon as
+        the FIRST stage of the report arrives (gfb_report.local_seq: before the kernel's last block waits
+        for the peers' logging partials).  `finish_report()` completes the report before it is published.
+        On a single rank the two stages arrive together.
+        """
+        self.post_physics(phases, read_report=False)
+        if self.dist is not None and not self.peer_mode:
+            self._allreduce_logging()
+        self.prepare_spare_log()  # host work hidden behind the kernel just enqueued
+        rc = self.lib.gfb_read_report_local(self._h, self._local_n_ref, self._stream())
+        if rc:
+            self.handle.check(rc, "gfb_read_report_local")
+        return self._local_n.value
+
+    def finish_report(self) -> nat.Report:
+        rc = self.lib.gfb_read_report(self._h, self._report_ref, self._stream())
+        if rc:
+            self.handle.check(rc, "gfb_read_report")
+        self._after_report()
+        return self.report
 
     def post_physics(self, phases: int, read_report: bool = True) -> nat.Report | None:
         """

@@ -222,13 +222,15 @@ class ManagedEnvironment(GenesisEnv):
         self.scene.step()
         if fused.split_mode:
             return self._finish_step_split()
-        report = fused.post_physics(fused.step_phases)
-
-        n_reset = report.n_reset
+        # two-stage report: the rank's own reset count first -- on a sharded env the kernel's last block
+        # then still waits for the slowest peer's logging partials, and that wait now overlaps the reset
+        # fan-out and the re-observation launch below instead of preceding them
+        n_reset = fused.post_physics_local(fused.step_phases)
         if n_reset > 0:
             reset_idx = fused.reset_idx[:n_reset]
             self._host_reset(reset_idx)
             fused.observe(reset_idx, n_reset)
+        report = fused.finish_report()  # status bits, per-term counts (global when sharded)
         fused.finish_logging()  # sharded envs: joins the logging all-reduce issued on a side stream
         self._publish(report, step=True)
 

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GFB_ABI_VERSION 10
+#define GFB_ABI_VERSION 11
 
 /* ---- limits ------------------------------------------------------------------------------- */
 #define GFB_MAX_DOFS 32
@@ -324,6 +324,12 @@ typedef struct {
   int64_t global_n_reset;
   int64_t global_termination_count[GFB_MAX_TERMINATION_TERMS];
   uint64_t seq;      /* written last: number of the launch (with GFB_PHASE_RESET) this report belongs to */
+  /* Sharded handles: n_reset (the rank's own count -- all the host needs to start its reset fan-out) is
+   * complete as soon as the rank's kernel has finished its slabs; the global_* fields additionally
+   * wait for the slowest peer's partials.  `local_seq` (same numbering as `seq`) is released right after
+   * n_reset / status / termination_count, BEFORE the exchange: gfb_read_report_local() returns then, and
+   * the wait for the peers overlaps the host's work instead of preceding it.                    */
+  uint64_t local_seq;
 } gfb_report;
 
 typedef struct gfb_handle gfb_handle;
@@ -374,6 +380,10 @@ int gfb_post_physics(gfb_handle* h, const gfb_buffers* b, uint32_t phases, void*
  * everything else: ~1 us after the store, without the driver's wake-up latency of a stream
  * synchronisation.                                                                              */
 int gfb_read_report(gfb_handle* h, gfb_report* out, void* stream);
+/* First stage of the report (see gfb_report.local_seq): blocks -- spinning on mapped memory -- until the
+ * rank's own counts are final and returns the number of reset envs.  gfb_read_report() of the same launch
+ * must still be called for the rest (status bits, global counts).                                */
+int gfb_read_report_local(gfb_handle* h, int32_t* n_reset, void* stream);
 
 /* gfb_post_physics + gfb_read_report in one call (one boundary crossing per step).              */
 int gfb_post_physics_report(gfb_handle* h, const gfb_buffers* b, uint32_t phases, gfb_report* out, void* stream);
