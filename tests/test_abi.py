@@ -36,6 +36,18 @@ def test_dynamic_symbol_table_matches_header():
     assert set(declared_functions()) <= exported
 
 
+def test_documents_track_the_header():
+    """DESIGN.md / INTEGRATION.md quote the ABI version and name every entry point of the header."""
+    declared = declared_functions()
+    version = _native.K["GFB_ABI_VERSION"]
+    design = (ROOT / "DESIGN.md").read_text()
+    integration = (ROOT / "INTEGRATION.md").read_text()
+    assert f"{len(declared)} entry points, ABI v{version}" in design
+    assert f"gfb_abi_version() == {version}" in integration
+    missing = [name for name in declared if name not in integration]
+    assert not missing, f"entry points without a row in INTEGRATION.md: {missing}"
+
+
 def test_abi_version_and_struct_layouts():
     lib = _native.lib()
     assert lib.gfb_abi_version() == _native.K["GFB_ABI_VERSION"]
