@@ -170,6 +170,7 @@ class FusedStep:
         self._body_acc_terms: set = set()
         self.entities = list(env.managers["entity"])
         self.entity_manager = self.entities[0] if self.entities else None
+        self.secondary_entities = self.entities[1:]
         if self.entity_manager is None:
             self._inv_base_quat = torch.zeros((self.N, 4), device=self.device)
         self.global_num_envs = self.N
@@ -197,10 +198,12 @@ class FusedStep:
             raise UnsupportedTermError(f"at most {nat.MAX_OBS_GROUPS} observation managers are supported")
         self.primary_entity = self.entities[0].entity if self.entities else getattr(env, "robot", None)
         self.entity_manager = self.entities[0] if self.entities else None
-        if len(self.entities) > 1:
-            others = {id(e.entity) for e in self.entities}
-            if len(others) > 1:
-                raise UnsupportedTermError("the fused step supports EntityManagers of a single entity")
+        # Further EntityManagers (the registry is a list, managed_env.py:200-220): a prop, a second robot.
+        # The kernel caches the pose of the FIRST manager's entity and lowers the mdp terms of that
+        # entity; the others keep their cache on the host side of the step (EntityManager._cached_calcs,
+        # device copies) and their body-frame getters go through the rotation entry point, so terms
+        # reading them run as host-evaluated columns (split execution).
+        self.secondary_entities = self.entities[1:]
         self.D = self.action.num_actions if self.action is not None else 0
         if self.D > nat.MAX_DOFS:
             raise UnsupportedTermError(f"at most {nat.MAX_DOFS} controlled DOFs are supported")
@@ -435,7 +438,10 @@ class FusedStep:
         em = params.get("entity_manager")
         if em is not None:
             if em.entity is not self.primary_entity:
-                raise UnsupportedTermError(f"{what}: entity_manager of a second entity is not supported")
+                raise UnsupportedTermError(
+                    f"{what}: stock mdp terms are lowered for the first EntityManager's entity only; wrap a term "
+                    "of another entity in a user-defined function around that manager's getters"
+                )
             return
         attr = params.get("entity_attr", "robot")
         if getattr(self.env, attr, None) is not self.primary_entity:

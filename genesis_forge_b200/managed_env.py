@@ -122,6 +122,8 @@ class ManagedEnvironment(GenesisEnv):
                 return mgr._command.shape[1]
             if kind == "contact_norm":
                 return mgr._link_ids.shape[0]
+            if kind.startswith("entity_"):  # body-frame vector of a further EntityManager
+                return 3
         if key in ("lin_vel_b", "ang_vel_b", "gravity_b", "lin_vel_uncached", "ang_vel_uncached", "gravity_uncached"):
             return 3
         return self.managers["action"].num_actions
@@ -145,6 +147,11 @@ class ManagedEnvironment(GenesisEnv):
                         # without an entity_manager the term inverts the CURRENT (post-reset) quaternion
                         # (utils.py:13-55); it runs as a host-evaluated term through the rotation kernel
                         err = UnsupportedTermError(f"{what}: body-frame term without an entity_manager")
+                        err.width = 3
+                        raise err
+                    if isinstance(key, tuple) and key[0].startswith("entity_"):
+                        # the kernel holds the pose of the first EntityManager's entity only
+                        err = UnsupportedTermError(f"{what}: body-frame term of a further EntityManager")
                         err.width = 3
                         raise err
                     return key, sentinel.shape[1]
@@ -220,6 +227,8 @@ class ManagedEnvironment(GenesisEnv):
 
         fused.action_step(actions)
         self.scene.step()
+        for entity_manager in fused.secondary_entities:  # (the first one's step is the kernel's entity phase)
+            entity_manager.step()
         if fused.split_mode:
             return self._finish_step_split()
         # two-stage report: the rank's own reset count first -- on a sharded env the kernel's last block

@@ -28,7 +28,8 @@ def state_checksum(scene) -> float:
     return float(sum(v.double().sum() for k, v in sorted(scene.state.items()) if v.is_floating_point()))
 
 
-def trace_of(env, spec, num_envs: int, steps: int, seed: int, nan_step: int | None, logging_of, snapshot_of):
+def trace_of(env, spec, num_envs: int, steps: int, seed: int, nan_step: int | None, logging_of, snapshot_of,
+             extra_of=None):
     """Drive `env` (any implementation with the reference API) and record the golden trace."""
     torch.manual_seed(seed)
     env.build()
@@ -53,6 +54,8 @@ def trace_of(env, spec, num_envs: int, steps: int, seed: int, nan_step: int | No
             "logging": logging_of(out[4]),
             "state_checksum": state_checksum(env.scene),
         })
+        if extra_of is not None:
+            trace["step"][-1]["extra"] = extra_of(env)
     trace["final"] = snapshot_of(env)
     return trace
 
@@ -65,7 +68,7 @@ def main(names=None):
     if not ref_harness.reference_available():
         raise SystemExit("needs /root/reference")
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    for name in names or list(specs.ALL) + list(specs.VARIANTS):
+    for name in (n for n in names if n != "second_entity") if names else list(specs.ALL) + list(specs.VARIANTS):
         spec = specs.get(name)
         env = ref_harness.make_reference_env(spec, NUM_ENVS, seed=SEED)
         trace = trace_of(env, spec, NUM_ENVS, STEPS, SEED, NAN_STEP, compare.extras_to_cpu, compare.reference_snapshot)
@@ -73,6 +76,25 @@ def main(names=None):
         torch.save(trace, path)
         n_reset = sum(int(s["reset_idx"].numel()) for s in trace["step"])
         print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB, {n_reset} resets in {STEPS} steps")
+    if not names or "second_entity" in names:
+        second_entity_trace()
+
+
+def second_entity_trace():
+    """Two EntityManagers (configs/second_entity.py): the reference's trace incl. the prop manager's cache."""
+    from configs import second_entity
+    from configs.env_builder import reference_namespace
+
+    from . import compare, ref_harness
+
+    spec = second_entity.spec()
+    env = second_entity.add_prop(ref_harness.make_reference_env(spec, NUM_ENVS, seed=SEED), reference_namespace())
+    trace = trace_of(env, spec, NUM_ENVS, STEPS, SEED, None, compare.extras_to_cpu, lambda env: {},
+                     extra_of=second_entity.prop_cache)
+    path = os.path.join(GOLDEN_DIR, "second_entity.pt")
+    torch.save(trace, path)
+    n_reset = sum(int(s["reset_idx"].numel()) for s in trace["step"])
+    print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB, {n_reset} resets in {STEPS} steps")
 
 
 if __name__ == "__main__":

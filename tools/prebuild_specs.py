@@ -28,7 +28,17 @@ def prebuild(spec_names=None, sizes=(4096, 65536), rng_modes=(1, 0), jobs: int =
     gfb.set_device("cpu")
     todo: dict[str, str] = {}
     try:
-        for name in spec_names or list(specs.ALL):
+        names = list(spec_names or list(specs.ALL) + ["second_entity"])
+        if "second_entity" in names:  # two EntityManagers (configs/second_entity.py), at its test's size
+            from configs import second_entity
+
+            names.remove("second_entity")
+            ns = dropin_namespace()
+            env = second_entity.add_prop(build_env(second_entity.spec(), ns, 16, torch.device("cpu"), n_contacts=8), ns)
+            env._dry_run = True
+            env.build()
+            todo.update(spec.collect(env, rng_modes))
+        for name in names:
             table = specs.get(name)
             for n in sizes:
                 for n_contacts in {8 if table["contacts"] else 0, 8}:
