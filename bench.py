@@ -595,6 +595,9 @@ def run_b200(args, rank, local_rank, world):
                 "kernel": {
                     "name": "post_kernel (gfb_post_physics)", "bytes_per_env": post_bytes, "kernel_us": post_ms * 1e3,
                     "achieved": achieved, "frac": achieved / peak,
+                    # sharded envs: the kernel's last block waits inside the launch for the slowest peer's
+                    # logging partials (csrc/tail.cuh), so this duration includes the ranks' skew
+                    **({"includes_peer_wait": True} if world > 1 else {}),
                 },
                 "action_kernel": {"bytes_per_env": roofline.action_kernel_bytes(fused), "kernel_us": act_ms * 1e3,
                                   "achieved": roofline.action_kernel_bytes(fused) * N / max(act_ms, 1e-9) / 1e6,
