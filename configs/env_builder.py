@@ -159,6 +159,8 @@ def build_env(spec: dict, ns, num_envs: int, device, **scene_kw):
             for name, item in spec["entity"]["on_reset"].items():
                 on_reset[name] = {"fn": getattr(ns.reset, item["fn"]), "params": self._params(item.get("params"))}
             self.robot_manager = M.EntityManager(self, entity_attr="robot", on_reset=on_reset)
+            if hasattr(self, "after_entity_manager"):  # workloads with further entities (configs/second_entity.py)
+                self.after_entity_manager()
 
             a = dict(spec["action"])
             kind = a.pop("type")

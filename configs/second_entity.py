@@ -15,12 +15,22 @@ PROP_RESET_POS = [0.5, -0.25, 0.1]
 PROP_RESET_QUAT = [1.0, 0.0, 0.0, 0.0]
 
 
-def spec():
+def spec(stock_terms: bool = False):
+    """`stock_terms`: also stock mdp reward / termination terms that refer to the prop -- through its manager
+    (cached pose) and through `entity_attr` (current pose)."""
     from . import specs
 
     s = specs.get("simple")
-    s["name"] = "second_entity"
+    s["name"] = "second_entity_terms" if stock_terms else "second_entity"
     s["max_episode_random_scaling"] = 0.0  # nothing in this workload depends on a random draw
+    if stock_terms:
+        prop = {"entity_manager": "@prop_manager"}
+        s["rewards"].update({
+            "prop_lin_vel_z": {"fn": "lin_vel_z_l2", "weight": -0.5, "params": dict(prop)},
+            "prop_flat": {"fn": "flat_orientation_l2", "weight": -0.25, "params": dict(prop)},
+            "prop_height": {"fn": "base_height", "weight": -2.0, "params": {"target_height": 1.3, "entity_attr": "prop"}},
+        })
+        s["terminations"]["prop_tilt"] = {"fn": "bad_orientation", "params": {"limit_angle": 4.5, **prop}}
     return s
 
 
@@ -80,19 +90,21 @@ class Prop:
 
 
 def add_prop(env, ns):
-    """Extend env.config(): a prop entity, its EntityManager and an observation group around its getters."""
+    """Extend env.config(): a prop entity, its EntityManager (registered right after the robot's, before the
+    term managers that may refer to it) and an observation group around its getters."""
     base_config = env.config
 
-    def config():
-        base_config()
-        M = ns.managers
+    def after_entity_manager():
         env.prop = Prop(env.scene)
-        env.prop_manager = M.EntityManager(
+        env.prop_manager = ns.managers.EntityManager(
             env, entity_attr="prop",
             on_reset={"position": {"fn": ns.reset.position,
                                    "params": {"position": PROP_RESET_POS, "quat": PROP_RESET_QUAT, "zero_velocity": True}}},
         )
-        env.observation_managers["prop"] = M.ObservationManager(
+
+    def config():
+        base_config()
+        env.observation_managers["prop"] = ns.managers.ObservationManager(
             env, name="prop",
             cfg={
                 "prop_linear_velocity": {"fn": lambda env: env.prop_manager.get_linear_velocity(), "scale": 2.0},
@@ -103,6 +115,7 @@ def add_prop(env, ns):
             },
         )
 
+    env.after_entity_manager = after_entity_manager
     env.config = config
     return env
 

@@ -197,12 +197,13 @@ class FusedStep:
         if len(self.observations) > nat.MAX_OBS_GROUPS:
             raise UnsupportedTermError(f"at most {nat.MAX_OBS_GROUPS} observation managers are supported")
         self.primary_entity = self.entities[0].entity if self.entities else getattr(env, "robot", None)
+        self._dof_entity = self.primary_entity
         self.entity_manager = self.entities[0] if self.entities else None
         # Further EntityManagers (the registry is a list, managed_env.py:200-220): a prop, a second robot.
         # The kernel caches the pose of the FIRST manager's entity and lowers the mdp terms of that
         # entity; the others keep their cache on the host side of the step (EntityManager._cached_calcs,
         # device copies) and their body-frame getters go through the rotation entry point, so terms
-        # reading them run as host-evaluated columns (split execution).
+        # reading them run as host-evaluated columns / rows (split execution, `_other_entity`).
         self.secondary_entities = self.entities[1:]
         self.D = self.action.num_actions if self.action is not None else 0
         if self.D > nat.MAX_DOFS:
@@ -227,7 +228,7 @@ class FusedStep:
         if self.reward is not None:
             for name, item in self.reward.cfg.items():
                 opcode = self._opcode_of(item.fn, "reward")
-                if opcode is None:
+                if opcode is None or self._other_entity(item, f"reward '{name}'") is not None:
                     opcode = nat.K["GFB_R_EXTERNAL"]
                     self.external_rows.append(("reward", name, item))
                 self.reward_terms.append((name, item, opcode))
@@ -235,7 +236,7 @@ class FusedStep:
         if self.termination is not None:
             for name, item in self.termination.term_cfg.items():
                 opcode = self._opcode_of(item.fn, "termination")
-                if opcode is None:
+                if opcode is None or self._other_entity(item, f"termination '{name}'") is not None:
                     opcode = nat.K["GFB_T_EXTERNAL"]
                     self.external_rows.append(("termination", name, item))
                 self.termination_terms.append((name, item, opcode))
@@ -433,6 +434,33 @@ class FusedStep:
             [(om.noise, om.enabled) for om in self.observations],
             [(i.scale, i.noise) for i in obs_items],
         )
+
+    def _entity_of(self, params: dict):
+        """The entity a term's (bound) parameters refer to, or None when the term takes no entity."""
+        em = params.get("entity_manager")
+        if em is not None:
+            return em.entity
+        if "entity_attr" in params:
+            return getattr(self.env, params["entity_attr"], None)
+        return None
+
+    def _other_entity(self, item, what: str):
+        """
+        A stock mdp term that refers to an entity other than the kernel's (a further EntityManager, another
+        `entity_attr`): the step's kernel holds one entity's state, so the term is evaluated like a
+        user-defined one -- a host callback between the kernel phases -- through the one-term path of
+        `evaluate_single_term`, bound to that entity's state and to its manager's cache.
+        """
+        sig = getattr(item.fn, "gfb_signature", None)
+        if sig is None or getattr(item.fn, "__self__", None) is not None:  # user function / a manager's own term
+            return None
+        entity = self._entity_of(sig(self.env, **(item.params or {})))
+        if entity is None or entity is self.primary_entity:
+            return None
+        if item.fn.gfb_opcode == "GFB_R_BODY_ACC_EXP":
+            raise UnsupportedTermError(f"{what}: body_acceleration_exp keeps per-term state in the kernel and is "
+                                       "lowered for the first EntityManager's entity only")
+        return entity
 
     def _entity_ok(self, params: dict, what: str):
         em = params.get("entity_manager")
@@ -705,10 +733,11 @@ class FusedStep:
         s(B["GFB_B_ANG"], robot.get_ang(), f32)
         if self.action is not None:
             idx = self.action.dofs_idx
-            s(B["GFB_B_DOF_POS"], robot.get_dofs_position(idx), f32)
-            s(B["GFB_B_DOF_VEL"], robot.get_dofs_velocity(idx), f32)
+            jointed = self._dof_entity  # (a one-term evaluation may point `primary_entity` at another entity)
+            s(B["GFB_B_DOF_POS"], jointed.get_dofs_position(idx), f32)
+            s(B["GFB_B_DOF_VEL"], jointed.get_dofs_velocity(idx), f32)
             if self._uses_dof_force:
-                s(B["GFB_B_DOF_FORCE"], robot.get_dofs_force(idx), f32)
+                s(B["GFB_B_DOF_FORCE"], jointed.get_dofs_force(idx), f32)
         # a command manager driven by an external controller / gamepad: the terms read what its
         # `command` property returns -- the controller's tensor for this step (command_manager.py:85-90)
         if self._has_command_override:
@@ -1138,6 +1167,7 @@ class FusedStep:
         saved = {k: getattr(self, k) for k in (
             "program", "buffers", "handle", "_fingerprint", "_program_pushed", "reward_terms", "termination_terms",
             "_feet_slide_manager", "_fixed_command_parts", "_keepalive", "_body_acc_terms", "_spec_checked",
+            "primary_entity",
         )}
         N, dev = self.N, self.device
         try:
@@ -1147,6 +1177,15 @@ class FusedStep:
             self._fingerprint = None
             self._program_pushed = False
             self._keepalive = []
+            entity = self._entity_of(params)
+            if entity is not None and entity is not self.primary_entity:
+                # a term of another entity: that entity's state arrays, and its manager's cached pose
+                self.primary_entity = entity
+                other = params.get("entity_manager")
+                if other is not None:
+                    self._set(K["GFB_B_BASE_POS"], other._base_pos)
+                    self._set(K["GFB_B_BASE_QUAT"], other._base_quat)
+                    self._set(K["GFB_B_INV_BASE_QUAT"], other._inv_base_quat)
             if kind == "reward":
                 self.reward_terms, self.termination_terms = [("direct", item, opcode)], []
                 phase = K["GFB_PHASE_REWARD"]

@@ -68,7 +68,7 @@ def main(names=None):
     if not ref_harness.reference_available():
         raise SystemExit("needs /root/reference")
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    for name in (n for n in names if n != "second_entity") if names else list(specs.ALL) + list(specs.VARIANTS):
+    for name in (n for n in names if not n.startswith("second_entity")) if names else list(specs.ALL) + list(specs.VARIANTS):
         spec = specs.get(name)
         env = ref_harness.make_reference_env(spec, NUM_ENVS, seed=SEED)
         trace = trace_of(env, spec, NUM_ENVS, STEPS, SEED, NAN_STEP, compare.extras_to_cpu, compare.reference_snapshot)
@@ -76,22 +76,24 @@ def main(names=None):
         torch.save(trace, path)
         n_reset = sum(int(s["reset_idx"].numel()) for s in trace["step"])
         print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB, {n_reset} resets in {STEPS} steps")
-    if not names or "second_entity" in names:
-        second_entity_trace()
+    for stock_terms in (False, True):
+        name = "second_entity_terms" if stock_terms else "second_entity"
+        if not names or name in names:
+            second_entity_trace(stock_terms)
 
 
-def second_entity_trace():
+def second_entity_trace(stock_terms: bool = False):
     """Two EntityManagers (configs/second_entity.py): the reference's trace incl. the prop manager's cache."""
     from configs import second_entity
     from configs.env_builder import reference_namespace
 
     from . import compare, ref_harness
 
-    spec = second_entity.spec()
+    spec = second_entity.spec(stock_terms)
     env = second_entity.add_prop(ref_harness.make_reference_env(spec, NUM_ENVS, seed=SEED), reference_namespace())
     trace = trace_of(env, spec, NUM_ENVS, STEPS, SEED, None, compare.extras_to_cpu, lambda env: {},
                      extra_of=second_entity.prop_cache)
-    path = os.path.join(GOLDEN_DIR, "second_entity.pt")
+    path = os.path.join(GOLDEN_DIR, f"{spec['name']}.pt")
     torch.save(trace, path)
     n_reset = sum(int(s["reset_idx"].numel()) for s in trace["step"])
     print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB, {n_reset} resets in {STEPS} steps")

@@ -18,6 +18,7 @@ import torch
 import genesis_forge_b200 as gfb
 from configs import second_entity
 from configs.env_builder import build_env, dropin_namespace
+from genesis_forge_b200 import _native as nat
 from genesis_forge_b200.fused import UnsupportedTermError
 from genesis_forge_b200.synthetic import ROBOT_MODELS, StateSource
 from oracle import geom
@@ -25,6 +26,7 @@ from oracle.make_golden import GOLDEN_DIR
 from oracle.parity import _close
 
 GOLD = os.path.join(GOLDEN_DIR, "second_entity.pt")
+GOLD_TERMS = os.path.join(GOLDEN_DIR, "second_entity_terms.pt")
 
 
 def test_reference_trace_of_the_second_manager():
@@ -66,9 +68,9 @@ def cpu_device():
     gfb.gs.device = prev
 
 
-def _dropin(n, device, **kw):
+def _dropin(n, device, stock_terms=False, **kw):
     ns = dropin_namespace()
-    return second_entity.add_prop(build_env(second_entity.spec(), ns, n, device, **kw), ns)
+    return second_entity.add_prop(build_env(second_entity.spec(stock_terms), ns, n, device, **kw), ns)
 
 
 def test_dropin_accepts_further_entity_managers(cpu_device):
@@ -91,29 +93,42 @@ def test_dropin_accepts_further_entity_managers(cpu_device):
     assert torch.equal(env.prop_manager.inv_base_quat, geom.inv_quat(env.prop.get_quat()))
 
 
-def test_stock_terms_of_a_further_entity_are_refused(cpu_device):
+def test_stock_terms_of_a_further_entity_become_host_callbacks(cpu_device):
+    """Stock mdp terms that refer to the prop are evaluated between the kernel phases (one-term path bound
+    to the prop's state); the robot's stay in the kernel."""
+    env = _dropin(32, cpu_device, stock_terms=True)
+    env._dry_run = True
+    env.build()
+    fused = env._fused
+    fused._set_program()
+    external = {(kind, name) for kind, name, _ in fused.external_rows}
+    assert external == {("reward", "prop_lin_vel_z"), ("reward", "prop_flat"), ("reward", "prop_height"),
+                        ("termination", "prop_tilt")}
+    K = nat.K
+    ops = {name: op for name, _, op in fused.reward_terms}
+    assert ops["prop_flat"] == K["GFB_R_EXTERNAL"] and ops["lin_vel_z"] == K["GFB_R_LIN_VEL_Z"]
+    assert {name: op for name, _, op in fused.termination_terms}["fall_over"] == K["GFB_T_BAD_ORIENTATION"]
+    assert [callback for callback, _, _ in fused.split_plan] == [None, "termination", "reward", "observe"]
+
+
+def test_body_acceleration_of_a_further_entity_is_refused(cpu_device):
     ns = dropin_namespace()
-    env = _dropin(32, cpu_device)
-    prop_config = env.config
-
-    def config():
-        prop_config()
-        env.reward_manager.cfg["prop_lin_vel_z"] = type(next(iter(env.reward_manager.cfg.values())))(
-            {"weight": -1.0, "fn": ns.rewards.lin_vel_z_l2, "params": {"entity_manager": env.prop_manager}}, env)
-
-    env.config = config
+    spec = second_entity.spec()
+    spec["rewards"]["prop_acc"] = {"fn": "body_acceleration_exp", "weight": 1.0,
+                                   "params": {"entity_manager": "@prop_manager"}}
+    env = second_entity.add_prop(build_env(spec, ns, 32, cpu_device), ns)
     env._dry_run = True
     with pytest.raises(UnsupportedTermError, match="first EntityManager"):
         env.build()
-        env._fused._set_program()
 
 
 @pytest.mark.gpu
-def test_cuda_path_reproduces_reference_trace_with_two_entity_managers(cuda_device):
-    gold = torch.load(GOLD, weights_only=False)
+@pytest.mark.parametrize("stock_terms", [False, True], ids=["getters", "stock_terms"])
+def test_cuda_path_reproduces_reference_trace_with_two_entity_managers(stock_terms, cuda_device):
+    gold = torch.load(GOLD_TERMS if stock_terms else GOLD, weights_only=False)
     n = gold["num_envs"]
     gfb.set_device(cuda_device)
-    env = _dropin(n, cuda_device, seed=gold["seed"])
+    env = _dropin(n, cuda_device, stock_terms=stock_terms, seed=gold["seed"])
     torch.manual_seed(gold["seed"])
     env.build()
     assert env._fused.split_mode and env._fused.secondary_entities == [env.prop_manager]
@@ -135,6 +150,9 @@ def test_cuda_path_reproduces_reference_trace_with_two_entity_managers(cuda_devi
         for group, want in g["obs"].items():
             ok, err, _ = _close(out[4]["observations"][group], want)
             assert ok, f"step {i} obs[{group}] err {err}"
+        for key, want in g["logging"].items():
+            ok, err, _ = _close(torch.as_tensor(out[4]["episode"][key]).reshape(()), want)
+            assert ok, f"step {i} extras[{key}] err {err}"
         for key, want in second_entity.prop_cache(env).items():
             assert torch.equal(want, g["extra"][key]), f"step {i} prop {key}"  # copies and sign flips: exact
     assert ("set_pos", 1) in env.prop.calls or any(c[0] == "set_pos" for c in env.prop.calls)

@@ -34,10 +34,12 @@ def prebuild(spec_names=None, sizes=(4096, 65536), rng_modes=(1, 0), jobs: int =
 
             names.remove("second_entity")
             ns = dropin_namespace()
-            env = second_entity.add_prop(build_env(second_entity.spec(), ns, 16, torch.device("cpu"), n_contacts=8), ns)
-            env._dry_run = True
-            env.build()
-            todo.update(spec.collect(env, rng_modes))
+            for stock_terms in (False, True):
+                env = second_entity.add_prop(
+                    build_env(second_entity.spec(stock_terms), ns, 16, torch.device("cpu"), n_contacts=8), ns)
+                env._dry_run = True
+                env.build()
+                todo.update(spec.collect(env, rng_modes))
         for name in names:
             table = specs.get(name)
             for n in sizes:
